@@ -1,0 +1,110 @@
+"""The oracle (oracle/) against the golden vectors generated from the live reference
+(tools/make_golden.py).  CPU only.  Bit-exact everywhere except k-means (1e-3, the tolerance
+BASELINE.json's north_star states)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+from oracle import dither_oracle as O
+
+
+def test_versions_match_golden():
+    """Results depend on the numeric libraries; flag drift loudly instead of failing mysteriously."""
+    import PIL
+    import scipy
+    import sklearn
+    v = json.load(open(os.path.join(GOLDEN, "VERSIONS.json")))
+    assert v["numba_path_used"] is True
+    assert scipy.__version__ == v["scipy"]
+    assert np.__version__ == v["numpy"]
+    assert PIL.__version__ == v["Pillow"]
+    assert sklearn.__version__ == v["scikit-learn"]
+
+
+def test_threshold_sources():
+    g = load_golden("threshold_sources.npz")
+    for s in ("2x2", "4x4", "8x8", "16x16", "psx4x4"):
+        assert np.array_equal(O.bayer_matrix(s), g["bayer_" + s]), s
+    assert np.array_equal(O.bayer_matrix("psx"), g["bayer_psx4x4"])
+    assert np.array_equal(O.bayer_matrix("bogus"), g["bayer_4x4"])
+    assert np.array_equal(O.blue_noise_matrix(64, 42), g["blue_64_42"])
+    assert np.array_equal(O.blue_noise_matrix(32, 5), g["blue_32_5"])
+    assert np.array_equal(O.polka_dot_matrix(8, 1.5), g["polka_8_1.5"])
+    assert np.array_equal(O.polka_dot_matrix(5, 0.7), g["polka_5_0.7"])
+    assert np.array_equal(O.ign_thresholds(33, 47, 1.0, 0), g["ign_1_0"])
+    assert np.array_equal(O.ign_thresholds(33, 47, 2.5, 17), g["ign_2.5_17"])
+    assert np.array_equal(O.ostromoukhov_coeffs(), g["ostro_coeffs"])
+    assert np.array_equal(O.halftone_screen(40, 56)[0], g["halftone_default_screen"])
+    assert np.array_equal(O.halftone_screen(40, 56, cell_size=6, angle=30.0, shape="diamond")[0],
+                          g["halftone_diamond_screen"])
+
+
+def test_kdtree_c_restatement_matches_scipy_golden():
+    g = load_golden("kdtree_queries.npz")
+    t = 0
+    while f"pal_{t}" in g:
+        pal = g[f"pal_{t}"]
+        pts = g[f"pts_{t}"].astype(np.float64)
+        tree = O.export_kdtree(pal)
+        d2a, i1 = O.kdtree_query_c(tree, pts, 1)
+        d2b, i2 = O.kdtree_query_c(tree, pts, 2)
+        assert np.array_equal(i1[:, 0], g[f"i1_{t}"]), t
+        assert np.array_equal(i2, g[f"i2_{t}"]), t
+        assert np.array_equal(np.sqrt(d2b), g[f"d2_{t}"]), t
+        t += 1
+    assert t >= 10
+
+
+def test_dither_cases_bit_exact(golden_cases):
+    data, meta = golden_cases
+    bad = []
+    for n, m in enumerate(meta):
+        out = O.apply_dithering(data["img_" + m["image"]], data["pal_" + m["palette"]],
+                                m["mode"], m["params"], m["gamma"])
+        if not np.array_equal(out, data[f"out_{n}"]):
+            bad.append((n, m))
+    assert not bad, bad[:5]
+
+
+def test_diffusion_big():
+    g = load_golden("diffusion_big.npz")
+    for v in ("floyd_steinberg", "atkinson", "jjn", "sierra"):
+        out = O.apply_dithering(g["img"], g["pal"], "error_diffusion", {"variant": v})
+        assert np.array_equal(out, g["ed_" + v]), v
+    out = O.apply_dithering(g["img"], g["pal16"], "ostromoukhov", {})
+    assert np.array_equal(out, g["ostro"])
+
+
+def test_pixelize_tables():
+    g = load_golden("pixelize.npz")
+    meta = json.load(open(os.path.join(GOLDEN, "pixelize.json")))
+    for m in meta:
+        tw, th = O.even_dimensions(m["w"], m["h"], m["max_size"])
+        assert (tw, th) == (m["tw"], m["th"]), m
+        key = f"{m['w']}x{m['h']}_{m['max_size']}"
+        assert np.array_equal(O.nearest_table(m["w"], tw), g["xt_" + key]), key
+        assert np.array_equal(O.nearest_table(m["h"], th), g["yt_" + key]), key
+    small = g["small"]
+    for mult in (2, 3, 5):
+        assert np.array_equal(O.final_resize(small, mult, True), g[f"small_x{mult}_even"])
+        assert np.array_equal(O.final_resize(small, mult, False), g[f"small_x{mult}_cli"])
+
+
+def test_kmeans_centers():
+    g = load_golden("kmeans.npz")
+    for t, k in enumerate((16, 8, 5)):
+        c = O.kmeans_centers(g[f"sample_{t}"], k, 42)
+        assert np.abs(c - g[f"centers_{t}"]).max() <= 1e-3  # north_star tolerance
+        assert np.array_equal(c.astype(int), g[f"palette_{t}"])
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_kdtree_single_colour_palette(k):
+    pal = np.array([[10, 20, 30]], np.float32)
+    d2, idx = O.kdtree_query_c(O.export_kdtree(pal), np.array([[1.0, 2.0, 3.0]]), k)
+    assert idx[0, 0] == 0 and d2[0, 0] == 81 + 324 + 729
+    if k == 2:
+        assert idx[0, 1] == 1 and np.isinf(d2[0, 1])  # scipy: index n, distance inf

@@ -1,0 +1,229 @@
+"""Generate the golden vectors under tests/golden/ from the LIVE reference.
+
+    python tools/make_golden.py
+
+Runs only in the build container (needs /root/reference).  The reference ships no tests or
+fixtures of its own, so these files -- outputs of the unmodified reference
+on deterministic synthetic inputs -- are what pins both the oracle and the CUDA path.
+Library versions are recorded in tests/golden/VERSIONS.json because the results depend on them.
+"""
+from __future__ import annotations
+
+import json
+import os
+import random
+import sys
+
+import numpy as np
+from PIL import Image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tools.ref_loader import load  # noqa: E402
+from dither_pie_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def images():
+    return {
+        "frame": synth.frame(40, 56, 0),
+        "noise": synth.noise_frame(36, 48, 1),
+        "blocks": synth.blocks_frame(40, 56, 2, 8, 6),
+    }
+
+
+def palettes():
+    return {
+        "pico8": synth.hex_palette(synth.PICO8),
+        "c64": synth.hex_palette(synth.C64),
+        "gb4": synth.hex_palette(synth.GB_POCKET),
+        "r16": synth.random_palette(16),
+        "r64": synth.random_palette(64),
+        "r256": synth.random_palette(256),
+        "lat27": synth.lattice_palette(27, 1, 127),
+        "one": np.array([[12, 200, 77]]),
+    }
+
+
+MODES = [
+    ("none", {}),
+    ("bayer", {"size": "2x2"}), ("bayer", {"size": "4x4"}), ("bayer", {"size": "8x8"}),
+    ("bayer", {"size": "16x16"}), ("bayer", {"size": "psx4x4"}),
+    ("blue_noise", {"size": 32, "seed": 5}),
+    ("IGN", {}), ("IGN", {"scale": 2.5, "seed": 17}),
+    ("polka_dot", {}), ("polka_dot", {"tile_size": 5, "gamma": 0.7}),
+    ("halftone", {}), ("halftone", {"cell_size": 3, "angle": 90.0}),
+    ("halftone", {"shape": "diamond", "angle": 30.0, "cell_size": 6}),
+    ("halftone", {"shape": "square", "angle": 0.0, "dot_gain": 1.7, "sharpness": 1.0,
+                  "min_dot_size": 0.1, "max_dot_size": 0.9}),
+    ("error_diffusion", {}),
+    ("error_diffusion", {"variant": "floyd_steinberg"}),
+    ("error_diffusion", {"variant": "jjn"}),
+    ("error_diffusion", {"variant": "stucki"}),
+    ("error_diffusion", {"variant": "burkes"}),
+    ("error_diffusion", {"variant": "sierra"}),
+    ("error_diffusion", {"variant": "sierra_two_row"}),
+    ("error_diffusion", {"variant": "sierra_lite"}),
+    ("error_diffusion", {"variant": "jjn", "serpentine": "true"}),
+    ("error_diffusion", {"variant": "floyd_steinberg", "serpentine": "true"}),
+    ("ostromoukhov", {}),
+    ("ostromoukhov", {"serpentine": "true"}),
+]
+
+
+def case_list():
+    """(image, palette, mode, params, gamma) -- a spread that keeps the file small."""
+    cases = []
+    for iname in ("frame", "noise", "blocks"):
+        for pname in ("pico8", "c64", "gb4", "r16", "r64", "r256", "lat27", "one"):
+            for mi, (mode, params) in enumerate(MODES):
+                # thin the cross product: every mode on 'frame'; a rotating subset elsewhere
+                if iname != "frame" and (mi + len(pname)) % 3 != 0 and pname not in ("pico8", "lat27"):
+                    continue
+                if mode == "ostromoukhov" and pname not in ("pico8", "lat27", "r64", "one"):
+                    continue
+                cases.append((iname, pname, mode, params, False))
+                if pname in ("pico8", "r64") and iname == "frame" and \
+                        params.get("size", "8x8") == "8x8" and params.get("variant", "jjn") == "jjn":
+                    cases.append((iname, pname, mode, params, True))
+    return cases
+
+
+def main():
+    dl, vp = load()
+    os.makedirs(OUT, exist_ok=True)
+    import numba
+    import PIL
+    import scipy
+    import sklearn
+    versions = {"numpy": np.__version__, "scipy": scipy.__version__,
+                "scikit-learn": sklearn.__version__, "Pillow": PIL.__version__,
+                "numba": numba.__version__, "numba_path_used": bool(dl._NUMBA_AVAILABLE)}
+    json.dump(versions, open(os.path.join(OUT, "VERSIONS.json"), "w"), indent=1)
+
+    imgs, pals = images(), palettes()
+
+    # ---- 1. whole-image dithering through ImageDitherer.apply_dithering
+    store = {}
+    meta = []
+    for n, (iname, pname, mode, params, gamma) in enumerate(case_list()):
+        d = dl.ImageDitherer(num_colors=len(pals[pname]), dither_mode=dl.DitherMode(mode),
+                             palette=[tuple(int(v) for v in c) for c in pals[pname]],
+                             use_gamma=gamma, dither_params=dict(params))
+        out = np.array(d.apply_dithering(Image.fromarray(imgs[iname], "RGB")))
+        store[f"out_{n}"] = out
+        meta.append({"image": iname, "palette": pname, "mode": mode, "params": params,
+                     "gamma": gamma})
+    for k, v in imgs.items():
+        store[f"img_{k}"] = v
+    for k, v in pals.items():
+        store[f"pal_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "dither_cases.npz"), **store)
+    json.dump(meta, open(os.path.join(OUT, "dither_cases.json"), "w"))
+    print("dither cases:", len(meta))
+
+    # ---- 2. a larger error-diffusion / ostromoukhov image (long-range error propagation)
+    big = synth.frame(96, 160, 5)
+    store = {"img": big, "pal": pals["r64"], "pal16": pals["pico8"]}
+    for variant in ("floyd_steinberg", "atkinson", "jjn", "sierra"):
+        d = dl.ImageDitherer(dither_mode=dl.DitherMode.ERROR_DIFFUSION,
+                             palette=[tuple(int(v) for v in c) for c in pals["r64"]],
+                             dither_params={"variant": variant})
+        store[f"ed_{variant}"] = np.array(d.apply_dithering(Image.fromarray(big, "RGB")))
+    d = dl.ImageDitherer(dither_mode=dl.DitherMode.OSTROMOUKHOV,
+                         palette=[tuple(int(v) for v in c) for c in pals["pico8"]])
+    store["ostro"] = np.array(d.apply_dithering(Image.fromarray(big, "RGB")))
+    np.savez_compressed(os.path.join(OUT, "diffusion_big.npz"), **store)
+
+    # ---- 3. threshold sources
+    U = dl.DitherUtils
+    store = {"bayer_2x2": U.BAYER2x2, "bayer_4x4": U.BAYER4x4, "bayer_8x8": U.BAYER8x8,
+             "bayer_16x16": U.BAYER16x16, "bayer_psx4x4": U.PSX4x4,
+             "blue_64_42": dl.generate_blue_noise(64, 42),
+             "blue_32_5": dl.generate_blue_noise(32, 5),
+             "polka_8_1.5": dl.PolkaDotDitherStrategy(8, 1.5).threshold_matrix,
+             "polka_5_0.7": dl.PolkaDotDitherStrategy(5, 0.7).threshold_matrix,
+             "ign_1_0": dl.InterleavedGradientNoiseDitherStrategy(1.0, 0)._generate_thresholds((33, 47)),
+             "ign_2.5_17": dl.InterleavedGradientNoiseDitherStrategy(2.5, 17)._generate_thresholds((33, 47)),
+             "ostro_coeffs": np.asarray(dl.OstromoukhovDitherStrategy.COEFFS_TABLE, np.int32)}
+    h = dl.HalftoneDitherStrategy()
+    s, c = h._generate_halftone_screen_with_cells(40, 56)
+    store["halftone_default_screen"] = s
+    h = dl.HalftoneDitherStrategy(cell_size=6, angle=30.0, shape="diamond")
+    s, c = h._generate_halftone_screen_with_cells(40, 56)
+    store["halftone_diamond_screen"] = s
+    np.savez_compressed(os.path.join(OUT, "threshold_sources.npz"), **store)
+
+    # ---- 4. scipy KD-tree queries on tie-heavy lattices (k=1 and k=2)
+    from scipy.spatial import KDTree
+    store = {}
+    kd_meta = []
+    for t, (k_pal, step_pal, step_pts) in enumerate(
+            [(4, 85, 17), (8, 51, 51), (10, 51, 17), (11, 51, 17), (16, 51, 17), (20, 51, 51),
+             (27, 127, 1), (40, 17, 17), (64, 51, 17), (100, 17, 17), (256, 17, 17)]):
+        pal = synth.lattice_palette(k_pal, seed=t, step=step_pal).astype(np.float32)
+        rs = np.random.RandomState(100 + t)
+        pts = (rs.randint(0, 255 // step_pts + 1, (600, 3)) * step_pts).astype(np.float64)
+        tree = KDTree(pal)
+        d1, i1 = tree.query(pts, k=1)
+        d2, i2 = tree.query(pts, k=2)
+        store[f"pal_{t}"] = pal
+        store[f"pts_{t}"] = pts.astype(np.uint8)
+        store[f"i1_{t}"] = i1.astype(np.int32)
+        store[f"i2_{t}"] = i2.astype(np.int32)
+        store[f"d2_{t}"] = d2
+        kd_meta.append(t)
+    np.savez_compressed(os.path.join(OUT, "kdtree_queries.npz"), **store)
+
+    # ---- 5. Pillow NEAREST tables + pixelize sizes
+    store = {}
+    pix_meta = []
+    for (w, hh) in [(1920, 1080), (3840, 2160), (640, 480), (333, 517), (1000, 999), (57, 31),
+                    (720, 1280), (100, 100)]:
+        # an image whose red/green channels encode x mod 256 / y mod 256 and blue the high bits
+        xs = np.arange(w)[None, :].repeat(hh, 0)
+        ys = np.arange(hh)[:, None].repeat(w, 1)
+        img = np.stack([xs % 256, ys % 256, (xs // 256) * 16 + (ys // 256)], 2).astype(np.uint8)
+        for ms in (128, 270, 64, 33, 17, 7):
+            out = np.array(vp.pixelize_regular(Image.fromarray(img, "RGB"), ms))
+            xt = out[0, :, 0].astype(np.int32) + 256 * (out[0, :, 2].astype(np.int32) // 16)
+            yt = out[:, 0, 1].astype(np.int32) + 256 * (out[:, 0, 2].astype(np.int32) % 16)
+            key = f"{w}x{hh}_{ms}"
+            store["xt_" + key] = xt
+            store["yt_" + key] = yt
+            pix_meta.append({"w": w, "h": hh, "max_size": ms, "tw": int(out.shape[1]),
+                             "th": int(out.shape[0])})
+    small = synth.noise_frame(31, 45, 9)
+    store["small"] = small
+    for m in (2, 3, 5):
+        store[f"small_x{m}_even"] = np.array(
+            vp._apply_final_resize_to_frame(Image.fromarray(small, "RGB"), m))
+        store[f"small_x{m}_cli"] = np.array(
+            Image.fromarray(small, "RGB").resize((45 * m, 31 * m), Image.Resampling.NEAREST))
+    np.savez_compressed(os.path.join(OUT, "pixelize.npz"), **store)
+    json.dump(pix_meta, open(os.path.join(OUT, "pixelize.json"), "w"))
+
+    # ---- 6. k-means (sklearn) on fixed sub-samples
+    from sklearn.cluster import KMeans
+    store = {}
+    for t, (hh, w, k) in enumerate([(1080, 1920, 16), (300, 400, 8), (90, 100, 5)]):
+        img = synth.frame(hh, w, 2 + t)
+        pix = img.reshape(-1, 3)
+        if len(pix) > 10000:
+            random.seed(7)
+            pix = pix[random.sample(range(len(pix)), 10000)]
+        km = KMeans(n_clusters=k, random_state=42).fit(pix)
+        random.seed(7)
+        pal = dl.ColorReducer.generate_kmeans_palette(Image.fromarray(img, "RGB"), k, 42)
+        store[f"sample_{t}"] = pix
+        store[f"centers_{t}"] = km.cluster_centers_
+        store[f"palette_{t}"] = np.asarray(pal, np.int64)
+        store[f"niter_{t}"] = np.asarray(km.n_iter_)
+    np.savez_compressed(os.path.join(OUT, "kmeans.npz"), **store)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
