@@ -1,0 +1,360 @@
+// dp_api.cu -- library plumbing and the palette handle of libditherpie_b200.
+#include <stdarg.h>
+
+#include <vector>
+
+#include "dp_common.cuh"
+
+// ---------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void dp_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *dp_last_error(void) { return g_err; }
+extern "C" int dp_version(void) { return 100; }
+
+int dp_num_sms()
+{
+    static thread_local int cached_dev = -1, cached = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+extern "C" int dp_device_count(int *count)
+{
+    DP_REQUIRE(count, "null argument");
+    DP_CUDA(cudaGetDeviceCount(count));
+    return 0;
+}
+
+extern "C" int dp_set_device(int device)
+{
+    DP_CUDA(cudaSetDevice(device));
+    int major = 0;
+    DP_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    DP_REQUIRE(major >= 10, "libditherpie_b200 needs an sm_100a (B200) device");
+    return 0;
+}
+
+extern "C" int dp_malloc(void **dptr, size_t bytes)
+{
+    DP_REQUIRE(dptr, "null argument");
+    DP_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    return 0;
+}
+extern "C" int dp_free(void *dptr)
+{
+    DP_CUDA(cudaFree(dptr));
+    return 0;
+}
+extern "C" int dp_host_alloc(void **hptr, size_t bytes)
+{
+    DP_REQUIRE(hptr, "null argument");
+    DP_CUDA(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return 0;
+}
+extern "C" int dp_host_free(void *hptr)
+{
+    DP_CUDA(cudaFreeHost(hptr));
+    return 0;
+}
+extern "C" int dp_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream)
+{
+    DP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, dp_stream(stream)));
+    return 0;
+}
+extern "C" int dp_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream)
+{
+    DP_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, dp_stream(stream)));
+    return 0;
+}
+extern "C" int dp_memset(void *dst, int value, size_t bytes, void *stream)
+{
+    DP_CUDA(cudaMemsetAsync(dst, value, bytes, dp_stream(stream)));
+    return 0;
+}
+extern "C" int dp_stream_create(void **stream)
+{
+    DP_REQUIRE(stream, "null argument");
+    cudaStream_t s;
+    DP_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *stream = s;
+    return 0;
+}
+extern "C" int dp_stream_destroy(void *stream)
+{
+    DP_CUDA(cudaStreamDestroy(dp_stream(stream)));
+    return 0;
+}
+extern "C" int dp_stream_sync(void *stream)
+{
+    DP_CUDA(cudaStreamSynchronize(dp_stream(stream)));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// 32^3 candidate grid: for every 8x8x8 box of colour space the palette rows that can be the
+// nearest row of SOME point of the box (closed box, conservative slack), ascending.
+// Used by the diffusion kernels, whose pixel values are arbitrary f32 in [0,255].
+// ---------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ void cell_bounds(int cell, double lo[3], double hi[3])
+{
+    int c[3] = {cell >> 10, (cell >> 5) & 31, cell & 31};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        lo[i] = 8.0 * c[i];
+        hi[i] = 8.0 * c[i] + 8.0;
+    }
+}
+
+__device__ __forceinline__ void box_dists(const double *pp, const double lo[3],
+                                          const double hi[3], double &mn, double &mx)
+{
+    mn = 0.0;
+    mx = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        double a = lo[i] - pp[i], b = pp[i] - hi[i];
+        double g = fmax(0.0, fmax(a, b));
+        double f = fmax(fabs(a), fabs(b));
+        mn += g * g;
+        mx += f * f;
+    }
+}
+
+__global__ void k_cell_count(const double *pal, int K, uint32_t *count, uint8_t *list,
+                             const uint32_t *off)
+{
+    int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= 32768) return;
+    double lo[3], hi[3];
+    cell_bounds(cell, lo, hi);
+    double bound = 1e300;
+    for (int i = 0; i < K; ++i) {
+        double mn, mx;
+        box_dists(pal + 3 * i, lo, hi, mn, mx);
+        bound = fmin(bound, mx);
+    }
+    bound = bound * (1.0 + 1e-9) + 1e-6;
+    uint32_t n = 0;
+    uint32_t o = off ? off[cell] : 0;
+    for (int i = 0; i < K; ++i) {
+        double mn, mx;
+        box_dists(pal + 3 * i, lo, hi, mn, mx);
+        if (mn <= bound) {
+            if (list) list[o + n] = (uint8_t)i;
+            ++n;
+        }
+    }
+    if (count) count[cell] = n;
+}
+
+__global__ void k_scan_32768(const uint32_t *count, uint32_t *off)
+{
+    __shared__ uint32_t part[1024];
+    int t = threadIdx.x;
+    uint32_t loc[32];
+    uint32_t s = 0;
+    for (int i = 0; i < 32; ++i) {
+        loc[i] = s;
+        s += count[t * 32 + i];
+    }
+    part[t] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        uint32_t v = (t >= d) ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint32_t base = (t == 0) ? 0 : part[t - 1];
+    for (int i = 0; i < 32; ++i) off[t * 32 + i] = base + loc[i];
+    if (t == 1023) off[32768] = part[1023];
+}
+
+template <typename T>
+size_t put(std::vector<uint8_t> &buf, const T *src, size_t n, size_t align = 16)
+{
+    size_t o = (buf.size() + align - 1) / align * align;
+    buf.resize(o + n * sizeof(T));
+    if (src) memcpy(buf.data() + o, src, n * sizeof(T));
+    return o;
+}
+
+}  // namespace
+
+extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out_rgb,
+                                 const uint8_t *in_lut, int kd_nodes,
+                                 const int32_t *kd_split_dim, const double *kd_split,
+                                 const int32_t *kd_start_idx, const int32_t *kd_end_idx,
+                                 const int32_t *kd_lesser, const int32_t *kd_greater,
+                                 const int32_t *kd_indices, const double *kd_mins,
+                                 const double *kd_maxes, dp_palette **out)
+{
+    DP_REQUIRE(palette && out_rgb && out, "null argument");
+    DP_REQUIRE(K >= 1 && K <= DP_MAX_COLORS, "palette size must be 1..256");
+    DP_REQUIRE(kd_nodes >= 1 && kd_split_dim && kd_split && kd_start_idx && kd_end_idx &&
+                   kd_lesser && kd_greater && kd_indices && kd_mins && kd_maxes,
+               "KD-tree arrays missing");
+    int inner = 0;
+    for (int i = 0; i < kd_nodes; ++i) {
+        if (kd_split_dim[i] != -1) {
+            ++inner;
+            DP_REQUIRE(kd_split_dim[i] >= 0 && kd_split_dim[i] < 3, "bad split_dim");
+            DP_REQUIRE(kd_lesser[i] > 0 && kd_lesser[i] < kd_nodes && kd_greater[i] > 0 &&
+                           kd_greater[i] < kd_nodes, "bad child index");
+        } else {
+            DP_REQUIRE(kd_start_idx[i] >= 0 && kd_end_idx[i] <= K &&
+                           kd_start_idx[i] <= kd_end_idx[i], "bad leaf range");
+        }
+    }
+    DP_REQUIRE(inner + 1 <= 72, "KD-tree has too many inner nodes for the device traversal");
+    for (int i = 0; i < K; ++i)
+        DP_REQUIRE(kd_indices[i] >= 0 && kd_indices[i] < K, "bad kd index");
+
+    dp_palette *h = new dp_palette();
+    memset(h, 0, sizeof(*h));
+    DP_CUDA(cudaGetDevice(&h->device));
+
+    bool integral = true;
+    std::vector<double> p64(K * 3);
+    std::vector<int4> coef(K);
+    for (int i = 0; i < K * 3; ++i) {
+        float v = palette[i];
+        h->host_pal[i] = v;
+        p64[i] = (double)v;
+        if (!(v >= 0.0f && v <= 255.0f && v == (float)(int)v)) integral = false;
+    }
+    if (integral) {
+        for (int i = 0; i < K; ++i) {
+            int r = (int)palette[3 * i], g = (int)palette[3 * i + 1], b = (int)palette[3 * i + 2];
+            coef[i].x = (-2 * r) * 256;
+            coef[i].y = (-2 * g) * 256;
+            coef[i].z = (-2 * b) * 256;
+            coef[i].w = (r * r + g * g + b * b) * 256 + i;
+        }
+    }
+    std::vector<uint8_t> orgb(K * 4, 0);
+    for (int i = 0; i < K; ++i)
+        for (int c = 0; c < 3; ++c) orgb[4 * i + c] = out_rgb[3 * i + c];
+    uint8_t lut[256];
+    h->has_lut = 0;
+    for (int i = 0; i < 256; ++i) {
+        lut[i] = in_lut ? in_lut[i] : (uint8_t)i;
+        if (lut[i] != i) h->has_lut = 1;
+    }
+
+    std::vector<uint8_t> buf;
+    PalDev d;
+    memset(&d, 0, sizeof(d));
+    size_t o_self = put<PalDev>(buf, nullptr, 1, 256);
+    size_t o_f32 = put(buf, palette, (size_t)K * 3);
+    size_t o_f64 = put(buf, p64.data(), (size_t)K * 3);
+    size_t o_coef = put(buf, coef.data(), (size_t)K);
+    size_t o_orgb = put(buf, orgb.data(), (size_t)K * 4);
+    size_t o_lut = put(buf, lut, 256);
+    size_t o_sd = put(buf, kd_split_dim, (size_t)kd_nodes);
+    size_t o_sp = put(buf, kd_split, (size_t)kd_nodes);
+    size_t o_st = put(buf, kd_start_idx, (size_t)kd_nodes);
+    size_t o_en = put(buf, kd_end_idx, (size_t)kd_nodes);
+    size_t o_le = put(buf, kd_lesser, (size_t)kd_nodes);
+    size_t o_gr = put(buf, kd_greater, (size_t)kd_nodes);
+    size_t o_ix = put(buf, kd_indices, (size_t)K);
+    (void)o_self;
+
+    uint8_t *blob = nullptr;
+    if (cudaMalloc(&blob, buf.size()) != cudaSuccess) {
+        delete h;
+        dp_set_error("cudaMalloc(%zu) failed for the palette blob", buf.size());
+        return 1;
+    }
+    d.K = K;
+    d.integral = integral ? 1 : 0;
+    d.kd_nodes = kd_nodes;
+    d.pal_f32 = reinterpret_cast<const float *>(blob + o_f32);
+    d.pal_f64 = reinterpret_cast<const double *>(blob + o_f64);
+    d.coef = reinterpret_cast<const int4 *>(blob + o_coef);
+    d.out_rgb = blob + o_orgb;
+    d.in_lut = blob + o_lut;
+    d.kd_split_dim = reinterpret_cast<const int *>(blob + o_sd);
+    d.kd_split = reinterpret_cast<const double *>(blob + o_sp);
+    d.kd_start = reinterpret_cast<const int *>(blob + o_st);
+    d.kd_end = reinterpret_cast<const int *>(blob + o_en);
+    d.kd_lesser = reinterpret_cast<const int *>(blob + o_le);
+    d.kd_greater = reinterpret_cast<const int *>(blob + o_gr);
+    d.kd_indices = reinterpret_cast<const int *>(blob + o_ix);
+    for (int i = 0; i < 3; ++i) {
+        d.kd_mins[i] = kd_mins[i];
+        d.kd_maxes[i] = kd_maxes[i];
+    }
+    h->blob = blob;
+
+    // candidate grid (count -> scan -> fill), synchronous: palette creation is set-up
+    uint32_t *count = nullptr, *off = nullptr;
+    uint8_t *list = nullptr;
+    bool ok = cudaMemcpy(blob, buf.data(), buf.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaMalloc(&count, 32768 * 4) == cudaSuccess;
+    ok = ok && cudaMalloc(&off, 32769 * 4) == cudaSuccess;
+    uint32_t total = 0;
+    if (ok) {
+        k_cell_count<<<128, 256>>>(d.pal_f64, K, count, nullptr, nullptr);
+        k_scan_32768<<<1, 1024>>>(count, off);
+        ok = cudaMemcpy(&total, off + 32768, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    ok = ok && cudaMalloc(&list, total ? total : 1) == cudaSuccess;
+    if (ok) {
+        k_cell_count<<<128, 256>>>(d.pal_f64, K, nullptr, list, off);
+        ok = cudaDeviceSynchronize() == cudaSuccess && cudaGetLastError() == cudaSuccess;
+    }
+    if (count) cudaFree(count);
+    if (!ok) {
+        dp_set_error("palette candidate-grid build failed: %s",
+                     cudaGetErrorString(cudaGetLastError()));
+        if (off) cudaFree(off);
+        if (list) cudaFree(list);
+        cudaFree(blob);
+        delete h;
+        return 1;
+    }
+    d.cell_off = off;
+    d.cell_list = list;
+    h->cell_off = off;
+    h->cell_list = list;
+    h->dev = d;
+    if (cudaMemcpy(blob, &d, sizeof(d), cudaMemcpyHostToDevice) != cudaSuccess) {
+        dp_set_error("palette upload failed");
+        dp_palette_destroy(h);
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+extern "C" int dp_palette_destroy(dp_palette *pal)
+{
+    if (!pal) return 0;
+    if (pal->cell_off) cudaFree(pal->cell_off);
+    if (pal->cell_list) cudaFree(pal->cell_list);
+    if (pal->blob) cudaFree(pal->blob);
+    delete pal;
+    return 0;
+}
+
+extern "C" int dp_palette_num_colors(const dp_palette *pal) { return pal ? pal->dev.K : 0; }

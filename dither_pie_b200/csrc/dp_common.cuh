@@ -1,0 +1,74 @@
+// dp_common.cuh -- shared host/device definitions of libditherpie_b200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ditherpie_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libditherpie_b200 targets sm_100a (B200) only"
+#endif
+
+// ---------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------
+void dp_set_error(const char *fmt, ...);
+
+#define DP_CUDA(call)                                                                     \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            dp_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return 1;                                                                     \
+        }                                                                                 \
+    } while (0)
+
+#define DP_REQUIRE(cond, msg)                                      \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            dp_set_error("%s:%d %s", __FILE__, __LINE__, msg);     \
+            return 2;                                              \
+        }                                                          \
+    } while (0)
+
+#define DP_LAUNCH_CHECK() DP_CUDA(cudaGetLastError())
+
+static inline cudaStream_t dp_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---------------------------------------------------------------------------------------
+// Palette as the kernels see it (plain device pointers, passed by value)
+// ---------------------------------------------------------------------------------------
+struct PalDev {
+    int K;
+    int integral;          // every palette value is an integer in [0,255] -> exact int path
+    int kd_nodes;
+    const float *pal_f32;  // [K,3]
+    const double *pal_f64; // [K,3]
+    const int4 *coef;      // [K] integer path: (-2r<<8, -2g<<8, -2b<<8, (|p|^2<<8)|i)
+    const uint8_t *out_rgb;  // [K,4] (r,g,b,0) bytes written for each palette row
+    const uint8_t *in_lut;   // [256]
+    // scipy KD-tree, flattened pre-order
+    const int *kd_split_dim;
+    const double *kd_split;
+    const int *kd_start, *kd_end, *kd_lesser, *kd_greater, *kd_indices;
+    double kd_mins[3], kd_maxes[3];
+    // 32^3 candidate grid for nearest-colour search on arbitrary f32 values (diffusion modes)
+    const uint32_t *cell_off;  // [32768+1]
+    const uint8_t *cell_list;  // concatenated candidate lists, ascending index
+};
+
+struct dp_palette {
+    PalDev dev;
+    int has_lut;   // in_lut is not the identity
+    int device;
+    void *blob;    // single device allocation backing every pointer above (except cell_*)
+    void *cell_off;
+    void *cell_list;
+    float host_pal[DP_MAX_COLORS * 3];
+};
+
+// number of SMs of the current device (cached)
+int dp_num_sms();

@@ -1,0 +1,465 @@
+// dp_threshold.cu -- ordered / threshold family and nearest-colour quantisation.
+//
+// Replaces NoDitherStrategy.dither (dithering_lib.py:333-341), MatrixDitherStrategy.dither
+// (:355-378; Bayer :402-448, blue noise :451-499), InterleavedGradientNoiseDitherStrategy.dither
+// (:539-568) and PolkaDotDitherStrategy.dither (:745-766), optionally fused with
+// pixelize_regular (video_processor.py:563-577) in front and the integer up-scale
+// (video_processor.py:393-420) behind.
+//
+// Data layout: interleaved u8 RGB, frames contiguous.  The identity-geometry kernel streams
+// 4096-pixel tiles (12 KB in, 12 KB out) through shared memory with 128-bit global accesses;
+// the palette coefficients, threshold matrix, gamma LUT and output colours live in shared
+// memory for the lifetime of the (persistent) block.
+// Algorithmic bytes: 3 read + 3 written per pixel; HBM-bound by design.
+#include "dp_search.cuh"
+
+namespace {
+
+struct FastDiv {
+    uint32_t mul, shr, d;
+};
+
+FastDiv make_fastdiv(uint32_t d)
+{
+    FastDiv f;
+    f.d = d;
+    if (d <= 1) {
+        f.mul = 0;
+        f.shr = 0;
+        f.d = 1;
+        return f;
+    }
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) ++lg;
+    uint32_t p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+    f.shr = p - 32;
+    return f;
+}
+
+__device__ __forceinline__ uint32_t fd_div(const FastDiv f, uint32_t n)
+{
+    return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shr);  // n < 2^31
+}
+
+constexpr int TILE_PX = 4096;
+constexpr int THREADS = 256;
+constexpr int TILE_BYTES = TILE_PX * 3;        // 12288, a multiple of 16
+constexpr int TILE_BUF = TILE_BYTES + 32;      // room for the 16-byte misalignment shift
+
+struct ThreshParams {
+    const PalDev *P;
+    const uint8_t *src;
+    uint8_t *dst;
+    uint8_t *dst_idx;
+    int frames, h, w, npix;
+    const float *matrix;
+    int mh, mw;
+    FastDiv dw, dmh, dmw;
+    float ign_xoff, ign_yoff, ign_scale;
+    int tiles_per_frame;
+    int total_tiles;
+    int K, integral, has_lut;
+    // geometry kernel only
+    int src_h, src_w, upscale;
+    const int *ytab, *xtab;
+};
+
+// IGN threshold (:541-549): f32, one rounding per numpy ufunc, no contraction.
+__device__ __forceinline__ float ign_threshold(const ThreshParams &p, int x, int y)
+{
+    float xv = __fmul_rn(__fadd_rn((float)x, p.ign_xoff), p.ign_scale);
+    float yv = __fmul_rn(__fadd_rn((float)y, p.ign_yoff), p.ign_scale);
+    float t = __fadd_rn(__fmul_rn(xv, 0.06711056f), __fmul_rn(yv, 0.00583715f));
+    t = __fsub_rn(t, floorf(t));
+    float u = __fmul_rn(t, 52.9829189f);
+    return __fsub_rn(u, floorf(u));
+}
+
+template <int KIND>
+__device__ __forceinline__ float threshold_at(const ThreshParams &p, const float *s_mat,
+                                              bool mat_in_smem, int x, int y)
+{
+    if (KIND == DP_THRESH_MATRIX) {
+        uint32_t ym = (uint32_t)y - fd_div(p.dmh, (uint32_t)y) * p.mh;
+        uint32_t xm = (uint32_t)x - fd_div(p.dmw, (uint32_t)x) * p.mw;
+        uint32_t o = ym * p.mw + xm;
+        return mat_in_smem ? s_mat[o] : __ldg(p.matrix + o);
+    } else if (KIND == DP_THRESH_IGN) {
+        return ign_threshold(p, x, y);
+    }
+    return 0.0f;
+}
+
+// ---- integer palette: exact search + decision ------------------------------------------
+template <int KIND>
+__device__ __forceinline__ int pick_int(const PalDev *P, const int4 *s_coef, int K, int r,
+                                        int g, int b, float thr)
+{
+    if (K == 1) return 0;
+    Top3 t;
+    top3_init(t);
+#pragma unroll 4
+    for (int i = 0; i < K; ++i) top3_push(t, key_of(s_coef[i], r, g, b));
+    int i1 = t.m1 & 255, i2 = t.m2 & 255;
+    int s1 = t.m1 >> 8, s2 = t.m2 >> 8, s3 = t.m3 >> 8;
+    bool amb = (s1 == s2);
+    if (KIND != DP_THRESH_NONE) amb = amb || (K >= 3 && s2 == s3);
+    if (amb) {
+        int oi[2];
+        double os[2];
+        if (KIND == DP_THRESH_NONE)
+            kd_emulate<1>(P, (double)r, (double)g, (double)b, oi, os);
+        else
+            kd_emulate<2>(P, (double)r, (double)g, (double)b, oi, os);
+        i1 = oi[0];
+        if (KIND != DP_THRESH_NONE) i2 = oi[1];
+        // the multiset of distances is unchanged: (s1, s2) stay valid
+    }
+    if (KIND == DP_THRESH_NONE) return i1;
+    int vv = r * r + g * g + b * b;
+    return factor_le_int(s1 + vv, s2 + vv, thr) ? i1 : i2;
+}
+
+// ---- general palette (gamma: non-integral f32 rows): f64 search + f64 decision -----------
+template <int KIND>
+__device__ __noinline__ int pick_f64(const PalDev *P, int K, int r, int g, int b, float thr)
+{
+    double x0 = (double)r, x1 = (double)g, x2 = (double)b;
+    double s1 = DP_INF_F64, s2 = DP_INF_F64, s3 = DP_INF_F64;
+    int i1 = K, i2 = K;
+    for (int i = 0; i < K; ++i) {
+        const double *pp = P->pal_f64 + 3 * i;
+        double d0 = __dsub_rn(pp[0], x0), d1 = __dsub_rn(pp[1], x1), d2 = __dsub_rn(pp[2], x2);
+        double s = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(d0, d0)), __dmul_rn(d1, d1)),
+                             __dmul_rn(d2, d2));
+        if (s < s1) {
+            s3 = s2;
+            s2 = s1;
+            i2 = i1;
+            s1 = s;
+            i1 = i;
+        } else if (s < s2) {
+            s3 = s2;
+            s2 = s;
+            i2 = i;
+        } else if (s < s3) {
+            s3 = s;
+        }
+    }
+    bool amb = (K >= 2 && s1 == s2);
+    if (KIND != DP_THRESH_NONE) amb = amb || (K >= 3 && s2 == s3);
+    if (amb) {
+        int oi[2];
+        double os[2];
+        if (KIND == DP_THRESH_NONE)
+            kd_emulate<1>(P, x0, x1, x2, oi, os);
+        else
+            kd_emulate<2>(P, x0, x1, x2, oi, os);
+        i1 = oi[0];
+        if (KIND != DP_THRESH_NONE) i2 = oi[1];
+    }
+    if (KIND == DP_THRESH_NONE || K == 1) return i1;
+    return factor_le_f64(s1, s2, thr) ? i1 : min(i2, K - 1);
+}
+
+// ---------------------------------------------------------------------------------------
+// Identity geometry: persistent blocks, 4096-pixel tiles staged through shared memory.
+// ---------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(THREADS) k_thresh_tile(const ThreshParams p)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *s_in = smem;                       // TILE_BUF
+    uint8_t *s_out = s_in + TILE_BUF;           // TILE_BUF
+    uint8_t *s_idx = s_out + TILE_BUF;          // TILE_PX
+    uint8_t *s_lut = s_idx + TILE_PX;           // 256
+    uint8_t *s_orgb = s_lut + 256;              // 1024
+    int4 *s_coef = reinterpret_cast<int4 *>(s_orgb + 1024);  // K
+    float *s_mat = reinterpret_cast<float *>(s_coef + p.K);  // <= 1024 floats
+
+    const PalDev *P = p.P;
+    const int tid = threadIdx.x;
+    const int K = p.K;
+    const bool mat_in_smem = (KIND == DP_THRESH_MATRIX) && (p.mh * p.mw <= 1024);
+
+    s_lut[tid] = P->in_lut[tid];
+    for (int i = tid; i < K * 4; i += THREADS) s_orgb[i] = P->out_rgb[i];
+    if (p.integral)
+        for (int i = tid; i < K; i += THREADS) s_coef[i] = P->coef[i];
+    if (mat_in_smem)
+        for (int i = tid; i < p.mh * p.mw; i += THREADS) s_mat[i] = p.matrix[i];
+    __syncthreads();
+
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int f = tile / p.tiles_per_frame;
+        const int tin = tile - f * p.tiles_per_frame;
+        const int px0 = tin * TILE_PX;
+        const int npx = min(TILE_PX, p.npix - px0);
+        const int nbytes = npx * 3;
+        const size_t goff = ((size_t)f * p.npix + px0) * 3;
+
+        // ---- load: aligned 128-bit reads; byte b of the tile lands at s_in[mis_in + b]
+        const uint8_t *gsrc = p.src + goff;
+        const int mis_in = (int)(reinterpret_cast<uintptr_t>(gsrc) & 15);
+        {
+            const uint4 *g4 = reinterpret_cast<const uint4 *>(gsrc - mis_in);
+            const int n16 = (mis_in + nbytes + 15) >> 4;
+            uint4 *s4 = reinterpret_cast<uint4 *>(s_in);
+            for (int i = tid; i < n16; i += THREADS) s4[i] = __ldcs(g4 + i);
+        }
+        uint8_t *gdst = p.dst + goff;
+        const int mis_out = (int)(reinterpret_cast<uintptr_t>(gdst) & 15);
+        __syncthreads();
+
+        // ---- compute: thread t owns pixels t, t+256, ... (conflict-free byte accesses)
+#pragma unroll 1
+        for (int j = tid; j < npx; j += THREADS) {
+            const uint8_t *q = s_in + mis_in + 3 * j;
+            int r = q[0], g = q[1], b = q[2];
+            if (p.has_lut) {
+                r = s_lut[r];
+                g = s_lut[g];
+                b = s_lut[b];
+            }
+            float thr = 0.0f;
+            if (KIND != DP_THRESH_NONE) {
+                uint32_t pi = (uint32_t)(px0 + j);
+                uint32_t y = fd_div(p.dw, pi);
+                uint32_t x = pi - y * p.w;
+                thr = threshold_at<KIND>(p, s_mat, mat_in_smem, (int)x, (int)y);
+            }
+            int idx = p.integral ? pick_int<KIND>(P, s_coef, K, r, g, b, thr)
+                                 : pick_f64<KIND>(P, K, r, g, b, thr);
+            uint8_t *o = s_out + mis_out + 3 * j;
+            o[0] = s_orgb[4 * idx];
+            o[1] = s_orgb[4 * idx + 1];
+            o[2] = s_orgb[4 * idx + 2];
+            s_idx[j] = (uint8_t)idx;
+        }
+        __syncthreads();
+
+        // ---- store: 128-bit writes for the aligned interior, bytes for the fringes
+        {
+            const int head = (16 - mis_out) & 15;           // bytes before the first aligned word
+            const int hb = min(head, nbytes);
+            if (tid < hb) gdst[tid] = s_out[mis_out + tid];
+            const int nmid = (nbytes - hb) >> 4;
+            uint4 *g4 = reinterpret_cast<uint4 *>(gdst + hb);
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(s_out + mis_out + hb);
+            for (int i = tid; i < nmid; i += THREADS) __stcs(g4 + i, s4[i]);
+            const int tail0 = hb + (nmid << 4);
+            if (tid < nbytes - tail0) gdst[tail0 + tid] = s_out[mis_out + tail0 + tid];
+            if (p.dst_idx) {
+                uint8_t *gi = p.dst_idx + (size_t)f * p.npix + px0;
+                for (int i = tid; i < npx; i += THREADS) gi[i] = s_idx[i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Fused geometry: gather (pixelize) -> dither -> m x m block store (up-scale).
+// One thread per dithered pixel.
+// ---------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(THREADS) k_thresh_geom(const ThreshParams p)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *s_lut = smem;
+    uint8_t *s_orgb = s_lut + 256;
+    int4 *s_coef = reinterpret_cast<int4 *>(s_orgb + 1024);
+    float *s_mat = reinterpret_cast<float *>(s_coef + p.K);
+
+    const PalDev *P = p.P;
+    const int tid = threadIdx.x;
+    const int K = p.K;
+    const bool mat_in_smem = (KIND == DP_THRESH_MATRIX) && (p.mh * p.mw <= 1024);
+    s_lut[tid] = P->in_lut[tid];
+    for (int i = tid; i < K * 4; i += THREADS) s_orgb[i] = P->out_rgb[i];
+    if (p.integral)
+        for (int i = tid; i < K; i += THREADS) s_coef[i] = P->coef[i];
+    if (mat_in_smem)
+        for (int i = tid; i < p.mh * p.mw; i += THREADS) s_mat[i] = p.matrix[i];
+    __syncthreads();
+
+    const int m = p.upscale;
+    const size_t src_frame = (size_t)p.src_h * p.src_w * 3;
+    const size_t out_w = (size_t)p.w * m;
+    const size_t dst_frame = (size_t)p.h * m * out_w * 3;
+    const long long total = (long long)p.frames * p.npix;
+    for (long long gi = (long long)blockIdx.x * THREADS + tid; gi < total;
+         gi += (long long)gridDim.x * THREADS) {
+        const int f = (int)(gi / p.npix);
+        const uint32_t pi = (uint32_t)(gi - (long long)f * p.npix);
+        const uint32_t y = fd_div(p.dw, pi);
+        const uint32_t x = pi - y * p.w;
+        const int sy = p.ytab ? __ldg(p.ytab + y) : (int)y;
+        const int sx = p.xtab ? __ldg(p.xtab + x) : (int)x;
+        const uint8_t *q = p.src + (size_t)f * src_frame + ((size_t)sy * p.src_w + sx) * 3;
+        int r = q[0], g = q[1], b = q[2];
+        if (p.has_lut) {
+            r = s_lut[r];
+            g = s_lut[g];
+            b = s_lut[b];
+        }
+        float thr = threshold_at<KIND>(p, s_mat, mat_in_smem, (int)x, (int)y);
+        int idx = p.integral ? pick_int<KIND>(P, s_coef, K, r, g, b, thr)
+                             : pick_f64<KIND>(P, K, r, g, b, thr);
+        const uint8_t o0 = s_orgb[4 * idx], o1 = s_orgb[4 * idx + 1], o2 = s_orgb[4 * idx + 2];
+        uint8_t *d = p.dst + (size_t)f * dst_frame + ((size_t)y * m * out_w + (size_t)x * m) * 3;
+        for (int yy = 0; yy < m; ++yy) {
+            uint8_t *row = d + (size_t)yy * out_w * 3;
+            for (int xx = 0; xx < m; ++xx) {
+                row[3 * xx] = o0;
+                row[3 * xx + 1] = o1;
+                row[3 * xx + 2] = o2;
+            }
+        }
+        if (p.dst_idx) p.dst_idx[gi] = (uint8_t)idx;
+    }
+}
+
+template <int KIND>
+int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
+{
+    int sms = dp_num_sms();
+    size_t mat_bytes = (KIND == DP_THRESH_MATRIX && p.mh * p.mw <= 1024) ? (size_t)p.mh * p.mw * 4 : 0;
+    if (!geom) {
+        size_t smem = 2 * TILE_BUF + TILE_PX + 256 + 1024 + (size_t)p.K * 16 + mat_bytes;
+        DP_CUDA(cudaFuncSetAttribute(k_thresh_tile<KIND>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_thresh_tile<KIND>,
+                                                              THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        int grid = sms * per_sm;
+        if (grid > p.total_tiles) grid = p.total_tiles;
+        k_thresh_tile<KIND><<<grid, THREADS, smem, st>>>(p);
+    } else {
+        size_t smem = 256 + 1024 + (size_t)p.K * 16 + mat_bytes;
+        long long total = (long long)p.frames * p.npix;
+        long long want = (total + THREADS - 1) / THREADS;
+        int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+        k_thresh_geom<KIND><<<grid, THREADS, smem, st>>>(p);
+    }
+    DP_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb, int frames,
+                                   const dp_geometry *geo, int kind, const float *matrix,
+                                   int mat_h, int mat_w, float ign_xoff, float ign_yoff,
+                                   float ign_scale, uint8_t *dst_rgb, uint8_t *dst_idx,
+                                   void *stream)
+{
+    DP_REQUIRE(pal && src_rgb && dst_rgb && geo, "null argument");
+    DP_REQUIRE(frames >= 0 && geo->h >= 0 && geo->w >= 0, "negative size");
+    DP_REQUIRE(kind >= DP_THRESH_NONE && kind <= DP_THRESH_IGN, "unknown threshold kind");
+    if (frames == 0 || geo->h == 0 || geo->w == 0) return 0;
+    DP_REQUIRE((long long)geo->h * geo->w < (1ll << 31), "frame too large");
+    if (kind == DP_THRESH_MATRIX)
+        DP_REQUIRE(matrix && mat_h > 0 && mat_w > 0, "threshold matrix missing");
+    const int m = geo->upscale < 1 ? 1 : geo->upscale;
+    const bool geom = geo->ytab || geo->xtab || m != 1;
+    if (!geom)
+        DP_REQUIRE(geo->src_h == geo->h && geo->src_w == geo->w, "identity geometry size mismatch");
+
+    ThreshParams p;
+    memset(&p, 0, sizeof(p));
+    p.P = reinterpret_cast<const PalDev *>(pal->blob);
+    p.src = src_rgb;
+    p.dst = dst_rgb;
+    p.dst_idx = dst_idx;
+    p.frames = frames;
+    p.h = geo->h;
+    p.w = geo->w;
+    p.npix = geo->h * geo->w;
+    p.matrix = matrix;
+    p.mh = mat_h > 0 ? mat_h : 1;
+    p.mw = mat_w > 0 ? mat_w : 1;
+    p.dw = make_fastdiv((uint32_t)geo->w);
+    p.dmh = make_fastdiv((uint32_t)p.mh);
+    p.dmw = make_fastdiv((uint32_t)p.mw);
+    p.ign_xoff = ign_xoff;
+    p.ign_yoff = ign_yoff;
+    p.ign_scale = ign_scale;
+    p.tiles_per_frame = (p.npix + TILE_PX - 1) / TILE_PX;
+    long long tt = (long long)p.tiles_per_frame * frames;
+    DP_REQUIRE(tt < (1ll << 31), "too many tiles in one call");
+    p.total_tiles = (int)tt;
+    p.K = pal->dev.K;
+    p.integral = pal->dev.integral;
+    p.has_lut = pal->has_lut;
+    p.src_h = geo->src_h;
+    p.src_w = geo->src_w;
+    p.upscale = m;
+    p.ytab = geo->ytab;
+    p.xtab = geo->xtab;
+    cudaStream_t st = dp_stream(stream);
+    switch (kind) {
+        case DP_THRESH_NONE: return launch_kind<DP_THRESH_NONE>(p, geom, st);
+        case DP_THRESH_MATRIX: return launch_kind<DP_THRESH_MATRIX>(p, geom, st);
+        default: return launch_kind<DP_THRESH_IGN>(p, geom, st);
+    }
+}
+
+// Host-buffer convenience: H2D, kernel, D2H and a stream synchronise inside the call.
+extern "C" int dp_threshold_dither_host(const dp_palette *pal, const uint8_t *src_rgb_host,
+                                        int frames, int h, int w, int kind,
+                                        const float *matrix_host, int mat_h, int mat_w,
+                                        float ign_xoff, float ign_yoff, float ign_scale,
+                                        uint8_t *dst_rgb_host)
+{
+    DP_REQUIRE(pal && src_rgb_host && dst_rgb_host, "null argument");
+    DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
+    const size_t bytes = (size_t)frames * h * w * 3;
+    if (bytes == 0) return 0;
+    cudaStream_t st = nullptr;
+    uint8_t *dsrc = nullptr, *ddst = nullptr;
+    float *dmat = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() {
+        if (dsrc) cudaFree(dsrc);
+        if (ddst) cudaFree(ddst);
+        if (dmat) cudaFree(dmat);
+    };
+    if (cudaMalloc(&dsrc, bytes) != cudaSuccess || cudaMalloc(&ddst, bytes) != cudaSuccess) {
+        dp_set_error("cudaMalloc failed in dp_threshold_dither_host");
+        cleanup();
+        return 1;
+    }
+    if (kind == DP_THRESH_MATRIX) {
+        if (!matrix_host || mat_h <= 0 || mat_w <= 0 ||
+            cudaMalloc(&dmat, (size_t)mat_h * mat_w * 4) != cudaSuccess ||
+            cudaMemcpyAsync(dmat, matrix_host, (size_t)mat_h * mat_w * 4, cudaMemcpyHostToDevice,
+                            st) != cudaSuccess) {
+            dp_set_error("threshold matrix upload failed");
+            cleanup();
+            return 1;
+        }
+    }
+    if (cudaMemcpyAsync(dsrc, src_rgb_host, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+        dp_set_error("H2D copy failed");
+        cleanup();
+        return 1;
+    }
+    dp_geometry geo;
+    memset(&geo, 0, sizeof(geo));
+    geo.src_h = geo.h = h;
+    geo.src_w = geo.w = w;
+    geo.upscale = 1;
+    rc = dp_threshold_dither(pal, dsrc, frames, &geo, kind, dmat, mat_h, mat_w, ign_xoff, ign_yoff,
+                             ign_scale, ddst, nullptr, st);
+    if (rc == 0 && (cudaMemcpyAsync(dst_rgb_host, ddst, bytes, cudaMemcpyDeviceToHost, st) !=
+                        cudaSuccess ||
+                    cudaStreamSynchronize(st) != cudaSuccess)) {
+        dp_set_error("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = 1;
+    }
+    cleanup();
+    return rc;
+}

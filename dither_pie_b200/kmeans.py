@@ -1,0 +1,126 @@
+"""K-means palette extraction: ColorReducer.generate_kmeans_palette (dithering_lib.py:1845-1857).
+
+The reference calls ``sklearn.cluster.KMeans(n_clusters, random_state).fit`` on at most 10 000
+sampled pixels.  Here the seeding (k-means++, a K-step sequential sampling procedure that must
+consume numpy's RandomState exactly like sklearn does) is host set-up, and the Lloyd iterations
+-- the per-pixel work -- run on the GPU with exact integer centroid sums:
+
+    dp_kmeans_accumulate   assignment + per-cluster (sum r, sum g, sum b, count) as u64
+    [all-reduce of the K x 4 integers across ranks when pixels are sharded over GPUs]
+    dp_kmeans_update       centres = sums / count, squared centre shift (sklearn's stop value)
+
+Because the sums are integers the centres are identical for any number of shards.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+from . import _capi
+from ._capi import DeviceBuffer, check, lib
+
+MAX_ITER = 300      # sklearn default
+TOL = 1e-4          # sklearn default (relative to the mean per-feature variance)
+SAMPLE = 10000      # dithering_lib.py:1850
+
+
+def kmeans_plusplus(Xc: np.ndarray, k: int, seed) -> np.ndarray:
+    """sklearn's greedy k-means++ (``_kmeans_plusplus``, n_local_trials = 2 + int(log k)) on the
+    centred f64 data, drawing from RandomState(seed) in the same order."""
+    rs = seed if isinstance(seed, np.random.RandomState) else np.random.RandomState(seed)
+    n = Xc.shape[0]
+    sq = np.einsum("ij,ij->i", Xc, Xc)
+    trials = 2 + int(np.log(k))
+    centers = np.empty((k, Xc.shape[1]), Xc.dtype)
+
+    def dist_to(c):
+        d = sq - 2.0 * (Xc @ c.T).T + np.einsum("ij,ij->i", c, c)[:, None]
+        np.maximum(d, 0, out=d)
+        return d
+
+    first = rs.choice(n, p=np.full(n, 1.0 / n))
+    centers[0] = Xc[first]
+    closest = dist_to(centers[0:1])[0]
+    pot = closest.sum()
+    for c in range(1, k):
+        draws = rs.uniform(size=trials) * pot
+        cand = np.searchsorted(np.cumsum(closest, dtype=np.float64), draws)
+        np.clip(cand, None, n - 1, out=cand)
+        dc = dist_to(Xc[cand])
+        np.minimum(closest, dc, out=dc)
+        pots = dc.sum(axis=1)
+        b = int(np.argmin(pots))
+        pot, closest = pots[b], dc[b]
+        centers[c] = Xc[cand[b]]
+    return centers
+
+
+def lloyd_device(pixels_ptr: int, n: int, centers: np.ndarray, tol: float,
+                 max_iter: int = MAX_ITER, sums_ptr: Optional[int] = None,
+                 allreduce: Optional[Callable[[], None]] = None, stream=None
+                 ) -> Tuple[np.ndarray, int]:
+    """Lloyd iterations on device-resident u8 pixels [n,3].  ``centers`` f64 [K,3] (uncentred).
+    When the pixels are one shard of a multi-GPU job pass ``sums_ptr`` (device u64 [K,4] the
+    caller can all-reduce) and ``allreduce`` (called after each accumulate, same stream)."""
+    K = centers.shape[0]
+    L = lib()
+    c_host = np.ascontiguousarray(centers, np.float64).copy()
+    c_dev = DeviceBuffer(K * 3 * 8).upload(c_host, stream)
+    own_sums = None
+    if sums_ptr is None:
+        own_sums = DeviceBuffer(K * 4 * 8)
+        sums_ptr = own_sums.ptr
+    shift_dev = DeviceBuffer(8)
+    shift = np.zeros(1, np.float64)
+    it = 0
+    try:
+        for it in range(1, max_iter + 1):
+            check(L.dp_memset(sums_ptr, 0, K * 4 * 8, stream), "dp_memset")
+            check(L.dp_kmeans_accumulate(pixels_ptr, n, c_dev.ptr, K, sums_ptr, stream),
+                  "dp_kmeans_accumulate")
+            if allreduce is not None:
+                allreduce()
+            check(L.dp_kmeans_update(sums_ptr, K, c_dev.ptr, shift_dev.ptr, stream),
+                  "dp_kmeans_update")
+            shift_dev.download(shift, stream)
+            _capi.sync(stream)
+            if shift[0] <= tol:
+                break
+        c_dev.download(c_host, stream)
+        _capi.sync(stream)
+    finally:
+        c_dev.free()
+        shift_dev.free()
+        if own_sums is not None:
+            own_sums.free()
+    return c_host, it
+
+
+def kmeans_fit(sample_u8: np.ndarray, k: int, random_state=42) -> Tuple[np.ndarray, int]:
+    """Pre-truncation centres (f64 [k,3]) and iteration count for the given pixels."""
+    _capi.ensure_device()
+    pix = np.ascontiguousarray(sample_u8, np.uint8).reshape(-1, 3)
+    X = pix.astype(np.float64)
+    mean = X.mean(axis=0)
+    Xc = X - mean
+    tol = float(np.mean(np.var(Xc, axis=0)) * TOL)
+    init = kmeans_plusplus(Xc, k, random_state) + mean
+    buf = DeviceBuffer(max(pix.nbytes, 4)).upload(pix)
+    try:
+        return lloyd_device(buf.ptr, pix.shape[0], init, tol)
+    finally:
+        buf.free()
+
+
+def kmeans_palette(arr_u8: np.ndarray, num_colors: int, random_state=42) -> List[tuple]:
+    """generate_kmeans_palette on a uint8 image: the 10 000-pixel sub-sample uses the global
+    ``random`` module exactly like the reference (:1850-1853; seed it to reproduce), centres are
+    truncated with ``astype(int)`` (:1856)."""
+    pix = np.asarray(arr_u8, np.uint8).reshape(-1, 3)
+    if len(pix) > SAMPLE:
+        pix = pix[random.sample(range(len(pix)), SAMPLE)]
+    centers, _ = kmeans_fit(pix, num_colors, random_state)
+    return [tuple(c) for c in centers.astype(int)]

@@ -1,0 +1,201 @@
+/*
+ * ditherpie_b200.h -- C ABI of the B200-native per-pixel hot path of dither_pie.
+ *
+ * One shared library (dither_pie_b200/libditherpie_b200.so, hand-written CUDA for sm_100a).
+ * Plain C types only: pointers, sizes, an opaque palette handle and a raw cudaStream_t passed
+ * as void*.  Every image pointer is a DEVICE pointer to interleaved 8-bit RGB, row-major
+ * [frames][h][w][3], frames contiguous; the *_host helpers at the end take HOST buffers and
+ * run the copies inside the call.  All calls are asynchronous on `stream` unless stated.
+ *
+ * Each entry point names the reference interface it replaces (file:line into
+ * dobrosketchkun/dither_pie).  The Python binding a maintainer would add is shown in
+ * INTEGRATION.md; dither_pie_b200/_capi.py is that binding.
+ *
+ * Return value: 0 on success, non-zero on error; dp_last_error() returns the message of the
+ * last failing call on the calling thread.  There is no CPU fallback anywhere.
+ */
+#ifndef DITHERPIE_B200_H
+#define DITHERPIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DP_MAX_COLORS 256
+
+/* ---------------------------------------------------------------------------------------
+ * Library / device / memory plumbing (no reference counterpart: the reference is CPU-only)
+ * ------------------------------------------------------------------------------------- */
+const char *dp_last_error(void);
+int dp_version(void);
+int dp_device_count(int *count);
+int dp_set_device(int device);
+int dp_malloc(void **dptr, size_t bytes);
+int dp_free(void *dptr);
+int dp_host_alloc(void **hptr, size_t bytes); /* pinned */
+int dp_host_free(void *hptr);
+int dp_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int dp_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int dp_memset(void *dst, int value, size_t bytes, void *stream);
+int dp_stream_create(void **stream);
+int dp_stream_destroy(void *stream);
+int dp_stream_sync(void *stream); /* NULL = default stream */
+
+/* ---------------------------------------------------------------------------------------
+ * Palette handle.
+ * Replaces the per-call palette set-up of every strategy: `palette_arr` (f32 [K,3]) plus
+ * `scipy.spatial.KDTree(palette_arr)` (dithering_lib.py:339, 358, 554, 748, 1229, 1612) and
+ * the gamma handling of ImageDitherer.apply_dithering (dithering_lib.py:1956-1974, 1986-1990).
+ *
+ *   palette      f32 [K,3], the palette in the space the search runs in (linear if gamma)
+ *   out_rgb      u8  [K,3], the bytes written for each palette row (reference:
+ *                `palette_arr[idx].astype(uint8)` then optional linear->sRGB, :1984-1990)
+ *   in_lut       u8  [256] applied to every input byte (sRGB->linear, :1956-1959) or NULL
+ *   kd_*         scipy's tree flattened in pre-order (built by the caller with scipy itself,
+ *                so the in-leaf order is the installed scipy's by construction):
+ *                split_dim (-1 = leaf), split, start_idx, end_idx, lesser, greater per node;
+ *                indices [K]; mins/maxes [3].
+ * All pointers are HOST pointers; the call copies them and may be followed by frees.
+ * ------------------------------------------------------------------------------------- */
+typedef struct dp_palette dp_palette;
+
+int dp_palette_create(const float *palette, int K, const uint8_t *out_rgb, const uint8_t *in_lut,
+                      int kd_nodes, const int32_t *kd_split_dim, const double *kd_split,
+                      const int32_t *kd_start_idx, const int32_t *kd_end_idx,
+                      const int32_t *kd_lesser, const int32_t *kd_greater,
+                      const int32_t *kd_indices, const double *kd_mins, const double *kd_maxes,
+                      dp_palette **out);
+int dp_palette_destroy(dp_palette *pal);
+int dp_palette_num_colors(const dp_palette *pal);
+
+/* ---------------------------------------------------------------------------------------
+ * Geometry shared by the per-pixel kernels: optional fused pixelization in front of the
+ * dither (video_processor.py:563-577 `pixelize_regular`) and optional integer up-scale
+ * behind it (video_processor.py:393-420, dither_cli.py:559-566).
+ *
+ *   src_h, src_w   size of each input frame
+ *   ytab, xtab     DEVICE int32 tables [h], [w]: source row/column of each dithered pixel
+ *                  (Pillow NEAREST mapping computed by the caller), or NULL for identity
+ *                  (then h == src_h, w == src_w)
+ *   h, w           size of the dithered image
+ *   upscale        integer m >= 1: every dithered pixel is written as an m x m block, i.e.
+ *                  output frames are [h*m, w*m] (what NEAREST resize to an exact multiple
+ *                  does).  Other output sizes: dither first, then dp_resample_nearest.
+ * ------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t src_h, src_w;
+    int32_t h, w;
+    int32_t upscale;
+    const int32_t *ytab, *xtab;
+} dp_geometry;
+
+/* Threshold source of the ordered family. */
+enum {
+    DP_THRESH_NONE = 0,   /* NoDitherStrategy.dither                dithering_lib.py:333-341 */
+    DP_THRESH_MATRIX = 1, /* MatrixDitherStrategy.dither (Bayer, blue noise) :355-378 and
+                             PolkaDotDitherStrategy.dither                   :745-766 */
+    DP_THRESH_IGN = 2     /* InterleavedGradientNoiseDitherStrategy.dither   :539-568 */
+};
+
+/*
+ * dp_threshold_dither -- nearest / second-nearest palette colour chosen by a threshold.
+ *   matrix      DEVICE f32 [mat_h, mat_w] (DP_THRESH_MATRIX), tiled over the dithered image
+ *   ign_*       f32 constants of :546-549 already rounded to f32 by the caller:
+ *               x' = (x + ign_xoff) * ign_scale,  y' = (y + ign_yoff) * ign_scale
+ *   dst_rgb     DEVICE u8 [frames, h*upscale, w*upscale, 3]
+ *   dst_idx     DEVICE u8 [frames, h, w] palette row per dithered pixel, or NULL
+ */
+int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb, int frames,
+                        const dp_geometry *geo, int kind, const float *matrix, int mat_h,
+                        int mat_w, float ign_xoff, float ign_yoff, float ign_scale,
+                        uint8_t *dst_rgb, uint8_t *dst_idx, void *stream);
+
+/*
+ * dp_halftone -- HalftoneDitherStrategy.dither, dithering_lib.py:1597-1644, with the screen and
+ * cell map of _generate_halftone_screen_with_cells (:1646-1695).
+ *   screen      DEVICE f32 [h,w] or NULL to have the library compute it (only when
+ *               dot_gain == 1.0, where no transcendental is needed)
+ *   shape       0 circle, 1 square, 2 diamond
+ *   cos_a,sin_a cos/sin(radians(angle)) as computed by the caller's libm (f64)
+ * Geometry: identity only in this version (no fused pixelize / up-scale).
+ */
+int dp_halftone(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h, int w,
+                int cell_size, double cos_a, double sin_a, double dot_gain, double min_dot,
+                double max_dot, int shape, double sharpness, const float *screen,
+                uint8_t *dst_rgb, uint8_t *dst_idx, void *stream);
+
+/* Error-diffusion kernels of ErrorDiffusionKernel, dithering_lib.py:107-188. */
+enum {
+    DP_ED_FLOYD_STEINBERG = 0,
+    DP_ED_JJN = 1,
+    DP_ED_STUCKI = 2,
+    DP_ED_BURKES = 3,
+    DP_ED_ATKINSON = 4,
+    DP_ED_SIERRA = 5,
+    DP_ED_SIERRA_TWO_ROW = 6,
+    DP_ED_SIERRA_LITE = 7
+};
+
+/*
+ * dp_error_diffusion -- ErrorDiffusionDitherStrategy.dither (:631-651) with the semantics of
+ * its numba core _error_diffusion_numba (:212-308): f32 state, f64 arithmetic, one f32
+ * rounding per accumulation, strict '<' first-index nearest colour.
+ * Frames are independent; each frame is a skewed-row wavefront (serpentine: serial rows).
+ */
+int dp_error_diffusion(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h, int w,
+                       int variant, int serpentine, uint8_t *dst_rgb, uint8_t *dst_idx,
+                       void *stream);
+
+/*
+ * dp_ostromoukhov -- OstromoukhovDitherStrategy.dither, the live path :1225-1269 (f32
+ * arithmetic, f32-rounded weights, KD-tree nearest).  coeffs: HOST int32 [256,3] (:1170-1203).
+ */
+int dp_ostromoukhov(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h, int w,
+                    const int32_t *coeffs, int serpentine, uint8_t *dst_rgb, uint8_t *dst_idx,
+                    void *stream);
+
+/*
+ * dp_resample_nearest -- Image.resize(NEAREST) as used by pixelize_regular
+ * (video_processor.py:576) and the final up-scale (:419, dither_cli.py:565):
+ * dst[f,y,x] = src[f, ytab[y], xtab[x]].  Tables are DEVICE int32.
+ */
+int dp_resample_nearest(const uint8_t *src_rgb, int frames, int src_h, int src_w,
+                        const int32_t *ytab, const int32_t *xtab, int dst_h, int dst_w,
+                        uint8_t *dst_rgb, void *stream);
+
+/*
+ * K-means palette extraction -- the Lloyd iterations inside
+ * ColorReducer.generate_kmeans_palette (dithering_lib.py:1854-1855 -> sklearn KMeans).
+ *
+ * dp_kmeans_accumulate: one assignment pass.  For every pixel find the nearest centre (f64,
+ *   first index on ties) and add it to that centre's exact integer sums.
+ *     pixels   DEVICE u8 [n,3]
+ *     centers  DEVICE f64 [K,3]
+ *     sums     DEVICE u64 [K,4] = (sum r, sum g, sum b, count); ACCUMULATED into (zero it
+ *              first); integer sums make the result independent of shard count and order,
+ *              so a multi-GPU run all-reduces `sums` (NCCL, done by the caller) and gets
+ *              bit-identical centres for any number of ranks.
+ * dp_kmeans_update: centres <- sums/count (empty clusters keep their centre), writes the
+ *   squared centre shift (sklearn's stopping quantity) to shift2 (DEVICE f64 [1]).
+ */
+int dp_kmeans_accumulate(const uint8_t *pixels, int64_t n, const double *centers, int K,
+                         unsigned long long *sums, void *stream);
+int dp_kmeans_update(const unsigned long long *sums, int K, double *centers, double *shift2,
+                     void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Host-buffer convenience (the end-to-end path a Python caller with numpy arrays uses):
+ * copies src to the device, runs the kernel, copies the result back, synchronises.
+ * ------------------------------------------------------------------------------------- */
+int dp_threshold_dither_host(const dp_palette *pal, const uint8_t *src_rgb_host, int frames,
+                             int h, int w, int kind, const float *matrix_host, int mat_h,
+                             int mat_w, float ign_xoff, float ign_yoff, float ign_scale,
+                             uint8_t *dst_rgb_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DITHERPIE_B200_H */

@@ -1,0 +1,102 @@
+"""CPU: host-side logic of the package (tables, geometry, sharding, API surface)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden
+import dither_pie_b200 as dp
+from dither_pie_b200 import engine, kmeans, synth
+from dither_pie_b200.video_processor import shard_frames
+
+
+def test_threshold_tables_match_reference_golden():
+    g = load_golden("threshold_sources.npz")
+    for s in ("2x2", "4x4", "8x8", "16x16", "psx4x4"):
+        assert np.array_equal(engine.bayer_matrix(s), g["bayer_" + s])
+    assert np.array_equal(engine.blue_noise_matrix(64, 42), g["blue_64_42"])
+    assert np.array_equal(dp.generate_blue_noise(32, 5), g["blue_32_5"])
+    assert np.array_equal(engine.polka_dot_matrix(8, 1.5), g["polka_8_1.5"])
+    assert np.array_equal(engine.ostromoukhov_coeffs(), g["ostro_coeffs"])
+    assert np.array_equal(dp.DitherUtils.BAYER8x8, g["bayer_8x8"])
+
+
+def test_pixelize_geometry_matches_pillow_golden():
+    g = load_golden("pixelize.npz")
+    meta = json.load(open(os.path.join(GOLDEN, "pixelize.json")))
+    for m in meta:
+        tw, th = engine.even_dimensions(m["w"], m["h"], m["max_size"])
+        assert (tw, th) == (m["tw"], m["th"])
+        key = f"{m['w']}x{m['h']}_{m['max_size']}"
+        assert np.array_equal(engine.nearest_table(m["w"], tw), g["xt_" + key])
+        assert np.array_equal(engine.nearest_table(m["h"], th), g["yt_" + key])
+
+
+def test_gamma_luts_are_the_elementwise_chain():
+    lut = engine.gamma_in_lut()
+    v = np.arange(256, dtype=np.uint8)
+    ref = np.clip(engine.srgb_to_linear(v.astype(np.float32) / 255.0) * 255.0, 0, 255).astype(np.uint8)
+    assert np.array_equal(lut, ref) and lut[0] == 0 and lut[255] == 255
+
+
+def test_kmeans_plusplus_matches_sklearn_public_function():
+    from sklearn.cluster import kmeans_plusplus
+    g = load_golden("kmeans.npz")
+    X = g["sample_1"].astype(np.float64)
+    Xc = X - X.mean(axis=0)
+    mine = kmeans.kmeans_plusplus(Xc, 8, 42)
+    ref, _ = kmeans_plusplus(Xc, 8, random_state=np.random.RandomState(42))
+    assert np.allclose(mine, ref, atol=1e-9)
+
+
+def test_shard_frames_partitions_contiguously():
+    for n in (0, 1, 7, 600, 301):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_frames(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_api_surface_matches_reference_names():
+    ref_all = ['DitherMode', 'PixelizeMethod', 'PaletteSource', 'ImageDitherer', 'ColorReducer',
+               'DitherUtils', 'BaseDitherStrategy', 'ErrorDiffusionKernel', 'NoDitherStrategy',
+               'MatrixDitherStrategy', 'BayerDitherStrategy', 'BlueNoiseDitherStrategy',
+               'InterleavedGradientNoiseDitherStrategy', 'ErrorDiffusionDitherStrategy',
+               'OstromoukhovDitherStrategy', 'RiemersmaDitherStrategy', 'PolkaDotDitherStrategy',
+               'WaveletDitherStrategy', 'AdaptiveVarianceDitherStrategy',
+               'PerceptualDitherStrategy', 'HybridDitherStrategy', 'HalftoneDitherStrategy',
+               'generate_blue_noise']
+    from dither_pie_b200 import dithering_lib as dl
+    assert sorted(dl.__all__) == sorted(ref_all)
+    for name in ref_all:
+        assert hasattr(dl, name)
+    assert [m.value for m in dl.DitherMode] == [
+        "none", "bayer", "error_diffusion", "riemersma", "blue_noise", "IGN", "polka_dot",
+        "wavelet", "adaptive_variance", "perceptual", "hybrid", "halftone", "ostromoukhov"]
+    assert dl.ErrorDiffusionDitherStrategy.get_parameter_info()["variant"]["default"] == "atkinson"
+    assert dl.ErrorDiffusionDitherStrategy().get_current_parameters() == {
+        "variant": "atkinson", "serpentine": "false"}
+    assert dl.ErrorDiffusionKernel.get_kernel("nope") is dl.ErrorDiffusionKernel.FLOYD_STEINBERG
+    assert dl.ErrorDiffusionKernel.JJN["divisor"] == 48 and len(dl.ErrorDiffusionKernel.SIERRA["weights"]) == 10
+    with pytest.raises(NotImplementedError):
+        dl.HybridDitherStrategy()
+    with pytest.raises(TypeError):
+        dl.ImageDitherer(palette=[(0, 0, 0)], dither_params={"bogus": 1})._get_dither_strategy(
+            dl.DitherMode.BAYER)
+    import pickle
+    d = dl.ImageDitherer(8, dl.DitherMode.HALFTONE, [(1, 2, 3)], True, {"cell_size": 4})
+    d2 = pickle.loads(pickle.dumps(d))
+    assert d2.palette == [(1, 2, 3)] and d2.dither_params == {"cell_size": 4}
+
+
+def test_median_cut_and_uniform_palettes_match_reference_semantics():
+    from PIL import Image
+    img = Image.fromarray(synth.frame(24, 32, 3), "RGB")
+    pal = dp.ColorReducer.reduce_colors(img, 12)   # depth = int(log2(12)) = 3 -> 8 colours
+    assert len(pal) == 8 and all(len(c) == 3 for c in pal)
+    assert dp.ColorReducer.generate_uniform_palette(8)[-1] == (255, 255, 255)
+    assert dp.ColorReducer.generate_uniform_palette(1) == [(128, 128, 128)]
