@@ -344,11 +344,14 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
                 need = min(need, W + SP::AMAX);
                 if (need > avail) {
                     int v = 0;
-                    for (;;) {
+                    for (unsigned spins = 0;; ++spins) {
                         if (lane == 0) v = ld_acquire(prog_in);
                         v = __shfl_sync(FULL, v, 0);
                         if (v >= need) break;
                         __nanosleep(64);
+                        // a band's predecessor always holds an earlier ticket, so this cannot
+                        // spin forever; the trap turns a protocol bug into an error, not a hang
+                        if (spins > (1u << 26)) __trap();
                     }
                     avail = v;
                 }
