@@ -189,6 +189,104 @@ __global__ void k_scan_32768(const uint32_t *count, uint32_t *off)
     if (t == 1023) off[32768] = part[1023];
 }
 
+// Exhaustive top-2 candidate masks: one block per cell of (1<<shift)^3 byte colours.  A palette
+// row is a candidate of the cell if, for SOME colour of the cell, its distance is <= the
+// second-smallest distance (so every row that can be nearest or second nearest, ties included).
+__global__ void __launch_bounds__(256) k_thr_masks(const int4 *__restrict__ coef, int K, int shift,
+                                                   uint32_t *__restrict__ masks)
+{
+    __shared__ int4 s_coef[DP_MAX_COLORS];
+    __shared__ uint32_t s_mask[8];
+    for (int i = threadIdx.x; i < K; i += 256) s_coef[i] = coef[i];
+    if (threadIdx.x < 8) s_mask[threadIdx.x] = 0;
+    __syncthreads();
+    const int n = 256 >> shift;            // cells per axis
+    const int side = 1 << shift;           // colours per axis in a cell
+    const int cell = blockIdx.x;
+    const int cr = cell / (n * n), cg = (cell / n) % n, cb = cell % n;
+    uint32_t local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int total = side * side * side;
+    for (int t = threadIdx.x; t < total; t += 256) {
+        const int r = (cr << shift) + t / (side * side);
+        const int g = (cg << shift) + (t / side) % side;
+        const int b = (cb << shift) + t % side;
+        int m1 = 0x7fffffff, m2 = 0x7fffffff;
+        for (int i = 0; i < K; ++i) {
+            const int4 c = s_coef[i];
+            const int s = (r * c.x + g * c.y + b * c.z + c.w) >> 8;  // score (idx stripped)
+            const int a = max(m1, s);
+            m1 = min(m1, s);
+            m2 = min(m2, a);
+        }
+        for (int i = 0; i < K; ++i) {
+            const int4 c = s_coef[i];
+            const int s = (r * c.x + g * c.y + b * c.z + c.w) >> 8;
+            if (s <= m2) local[i >> 5] |= 1u << (i & 31);
+        }
+    }
+    for (int wd = 0; wd < 8; ++wd)
+        if (local[wd]) atomicOr(&s_mask[wd], local[wd]);
+    __syncthreads();
+    if (threadIdx.x < 8) masks[(size_t)cell * 8 + threadIdx.x] = s_mask[threadIdx.x];
+}
+
+// Nearest-row candidates per 16^3 box by pairwise dominance: row j dominates row i on the box
+// iff  max_{x in box} (|x-p_j|^2 - |x-p_i|^2) < 0; the expression is linear in x, so the maximum
+// sits at the corner picked coordinate-wise by the sign of (p_j - p_i).
+__global__ void __launch_bounds__(256) k_ed_table(const double *__restrict__ pal, int K,
+                                                  uint2 *__restrict__ table,
+                                                  uint8_t *__restrict__ ovf)
+{
+    __shared__ double s_p[DP_MAX_COLORS * 3];
+    __shared__ double s_n[DP_MAX_COLORS];
+    __shared__ uint32_t s_mask[8];
+    const int cell = blockIdx.x;
+    for (int i = threadIdx.x; i < K; i += 256) {
+        const double a = pal[3 * i], b = pal[3 * i + 1], c = pal[3 * i + 2];
+        s_p[3 * i] = a;
+        s_p[3 * i + 1] = b;
+        s_p[3 * i + 2] = c;
+        s_n[i] = a * a + b * b + c * c;
+    }
+    if (threadIdx.x < 8) s_mask[threadIdx.x] = 0;
+    __syncthreads();
+    const double lo[3] = {16.0 * (cell >> 8), 16.0 * ((cell >> 4) & 15), 16.0 * (cell & 15)};
+    const int i = threadIdx.x;
+    if (i < K) {
+        bool dominated = false;
+        for (int j = 0; j < K && !dominated; ++j) {
+            if (j == i) continue;
+            double mx = s_n[j] - s_n[i];
+            for (int c = 0; c < 3; ++c) {
+                const double dlt = s_p[3 * j + c] - s_p[3 * i + c];
+                const double x = dlt > 0.0 ? lo[c] : lo[c] + 16.0;
+                mx += -2.0 * x * dlt;
+            }
+            dominated = mx < -1e-6;
+        }
+        if (!dominated) atomicOr(&s_mask[i >> 5], 1u << (i & 31));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint8_t cand[DP_MAX_COLORS];
+        int cnt = 0;
+        for (int k = 0; k < K; ++k)
+            if (s_mask[k >> 5] >> (k & 31) & 1u) cand[cnt++] = (uint8_t)k;
+        uint2 e;
+        if (cnt <= 7) {
+            unsigned long long v = (unsigned long long)cnt;
+            for (int k = 0; k < cnt; ++k) v |= (unsigned long long)cand[k] << (8 * (k + 1));
+            e.x = (uint32_t)v;
+            e.y = (uint32_t)(v >> 32);
+        } else {
+            e.x = 0xffu | ((uint32_t)cnt << 8);
+            e.y = (uint32_t)cell * 256u;
+            for (int k = 0; k < cnt; ++k) ovf[(size_t)cell * 256 + k] = cand[k];
+        }
+        table[cell] = e;
+    }
+}
+
 template <typename T>
 size_t put(std::vector<uint8_t> &buf, const T *src, size_t n, size_t align = 16)
 {
@@ -337,6 +435,90 @@ extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out
     d.cell_list = list;
     h->cell_off = off;
     h->cell_list = list;
+    {
+        void *et = nullptr, *eo = nullptr;
+        bool ok3 = cudaMalloc(&et, 4096 * 8) == cudaSuccess &&
+                   cudaMalloc(&eo, 4096 * 256) == cudaSuccess;
+        if (ok3) {
+            k_ed_table<<<4096, 256>>>(d.pal_f64, K, static_cast<uint2 *>(et),
+                                      static_cast<uint8_t *>(eo));
+            ok3 = cudaDeviceSynchronize() == cudaSuccess;
+        }
+        if (!ok3) {
+            dp_set_error("palette nearest-row table build failed: %s",
+                         cudaGetErrorString(cudaGetLastError()));
+            if (et) cudaFree(et);
+            if (eo) cudaFree(eo);
+            cudaFree(off);
+            cudaFree(list);
+            cudaFree(blob);
+            delete h;
+            return 1;
+        }
+        d.ed_table = static_cast<const uint2 *>(et);
+        d.ed_ovf = static_cast<const uint8_t *>(eo);
+        h->ed_table = et;
+        h->ed_ovf = eo;
+    }
+    if (integral && K >= 2) {
+        // top-2 candidate table for the threshold kernels
+        const int shift = (K <= 64) ? 4 : 3;
+        const int n = 256 >> shift, cells = n * n * n;
+        uint32_t *dmask = nullptr;
+        std::vector<uint32_t> hmask((size_t)cells * 8);
+        bool ok2 = cudaMalloc(&dmask, (size_t)cells * 32) == cudaSuccess;
+        if (ok2) {
+            k_thr_masks<<<cells, 256>>>(d.coef, K, shift, dmask);
+            ok2 = cudaMemcpy(hmask.data(), dmask, (size_t)cells * 32, cudaMemcpyDeviceToHost) ==
+                  cudaSuccess;
+        }
+        if (dmask) cudaFree(dmask);
+        std::vector<uint2> table(cells);
+        std::vector<uint8_t> ovf;
+        for (int c = 0; ok2 && c < cells; ++c) {
+            uint8_t cand[DP_MAX_COLORS];
+            int cnt = 0;
+            for (int i = 0; i < K; ++i)
+                if (hmask[(size_t)c * 8 + (i >> 5)] >> (i & 31) & 1u) cand[cnt++] = (uint8_t)i;
+            uint2 e;
+            if (cnt <= 7) {
+                uint64_t v = (uint64_t)cnt;
+                for (int j = 0; j < cnt; ++j) v |= (uint64_t)cand[j] << (8 * (j + 1));
+                e.x = (uint32_t)v;
+                e.y = (uint32_t)(v >> 32);
+            } else {
+                e.x = 0xffu | ((uint32_t)cnt << 8);
+                e.y = (uint32_t)ovf.size();
+                ovf.insert(ovf.end(), cand, cand + cnt);
+            }
+            table[c] = e;
+        }
+        void *dt = nullptr, *dovf = nullptr;
+        ok2 = ok2 && cudaMalloc(&dt, (size_t)cells * 8) == cudaSuccess &&
+              cudaMalloc(&dovf, ovf.size() + 16) == cudaSuccess &&
+              cudaMemcpy(dt, table.data(), (size_t)cells * 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+              (ovf.empty() ||
+               cudaMemcpy(dovf, ovf.data(), ovf.size(), cudaMemcpyHostToDevice) == cudaSuccess);
+        if (!ok2) {
+            dp_set_error("palette top-2 table build failed: %s",
+                         cudaGetErrorString(cudaGetLastError()));
+            if (dt) cudaFree(dt);
+            if (dovf) cudaFree(dovf);
+            cudaFree(h->ed_table);
+            cudaFree(h->ed_ovf);
+            cudaFree(off);
+            cudaFree(list);
+            cudaFree(blob);
+            delete h;
+            return 1;
+        }
+        d.thr_table = static_cast<const uint2 *>(dt);
+        d.thr_ovf = static_cast<const uint8_t *>(dovf);
+        d.thr_shift = shift;
+        d.thr_cells = cells;
+        h->thr_table = dt;
+        h->thr_ovf = dovf;
+    }
     h->dev = d;
     if (cudaMemcpy(blob, &d, sizeof(d), cudaMemcpyHostToDevice) != cudaSuccess) {
         dp_set_error("palette upload failed");
@@ -352,6 +534,10 @@ extern "C" int dp_palette_destroy(dp_palette *pal)
     if (!pal) return 0;
     if (pal->cell_off) cudaFree(pal->cell_off);
     if (pal->cell_list) cudaFree(pal->cell_list);
+    if (pal->ed_table) cudaFree(pal->ed_table);
+    if (pal->ed_ovf) cudaFree(pal->ed_ovf);
+    if (pal->thr_table) cudaFree(pal->thr_table);
+    if (pal->thr_ovf) cudaFree(pal->thr_ovf);
     if (pal->blob) cudaFree(pal->blob);
     delete pal;
     return 0;

@@ -58,6 +58,20 @@ struct PalDev {
     // 32^3 candidate grid for nearest-colour search on arbitrary f32 values (diffusion modes)
     const uint32_t *cell_off;  // [32768+1]
     const uint8_t *cell_list;  // concatenated candidate lists, ascending index
+    // top-2 candidate table for byte-valued pixels (integral palettes only): one 8-byte entry
+    // per (256>>thr_shift)^3 cell, built by exhaustive enumeration of the 2^24 colours.
+    //   x & 0xff = n (<= 7): candidates in bytes 1..7 of the entry, ascending
+    //   x & 0xff = 0xff    : n = x >> 8, candidates at thr_ovf[y .. y+n)
+    const uint2 *thr_table;
+    const uint8_t *thr_ovf;
+    int thr_shift;   // 4 -> 16^3 cells, 3 -> 32^3 cells
+    int thr_cells;
+    // nearest-row candidate table for arbitrary real values in [0,255]^3 (diffusion modes):
+    // 16^3 cells, same 8-byte entry format; a row is dropped from a cell only if another row
+    // is strictly nearer at EVERY point of the cell's closed box (exact linear test).
+    // Overflow lists live at ed_ovf[cell*256 ..).
+    const uint2 *ed_table;   // [4096]
+    const uint8_t *ed_ovf;   // [4096*256]
 };
 
 struct dp_palette {
@@ -67,6 +81,10 @@ struct dp_palette {
     void *blob;    // single device allocation backing every pointer above (except cell_*)
     void *cell_off;
     void *cell_list;
+    void *thr_table;
+    void *thr_ovf;
+    void *ed_table;
+    void *ed_ovf;
     float host_pal[DP_MAX_COLORS * 3];
 };
 

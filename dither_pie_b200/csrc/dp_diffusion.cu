@@ -139,10 +139,13 @@ struct WaveParams {
     const float *ostro_w;  // [256][4] f32 weights (c0,c1,c2)/sum, DEVICE (ostromoukhov only)
 };
 
-__device__ __forceinline__ int ld_acquire(const int *p)
+// Progress poll.  Relaxed (no L1 invalidation): everything the consumer reads after the poll is
+// fetched with ld.global.cg (L2 only) and the producer's st.release orders its data before the
+// flag in L2; loads issue in program order behind the branch on the polled value.
+__device__ __forceinline__ int ld_poll(const int *p)
 {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release(int *p, int v)
@@ -157,59 +160,81 @@ __device__ __forceinline__ float acc_f64(float acc, double prod)
 }
 
 struct Search {
-    const uint32_t *cell_off;
-    const uint8_t *cell_list;
-    const double *s_pal;  // shared, [K,3]
+    const uint2 *table;      // shared, [4096] 16^3 cells
+    const uint8_t *ovf;      // global overflow lists
+    const double *s_pal;     // shared, [K,3]
 };
 
 __device__ __forceinline__ int cell_of(double r, double g, double b)
 {
-    int ir = min(__double2int_rz(r), 255) >> 3;
-    int ig = min(__double2int_rz(g), 255) >> 3;
-    int ib = min(__double2int_rz(b), 255) >> 3;
-    return (ir << 10) | (ig << 5) | ib;
+    const int ir = min(__double2int_rz(r), 255) >> 4;
+    const int ig = min(__double2int_rz(g), 255) >> 4;
+    const int ib = min(__double2int_rz(b), 255) >> 4;
+    return (ir << 8) | (ig << 4) | ib;
+}
+
+__device__ __forceinline__ double dist_numba(const double *pp, double r, double g, double b)
+{
+    const double dr = __dsub_rn(r, pp[0]), dg = __dsub_rn(g, pp[1]), db = __dsub_rn(b, pp[2]);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dg, dg)), __dmul_rn(db, db));
 }
 
 // numba path (:254-263): strict '<' over f64 distances, first index wins.  The candidate list
-// of the pixel's 8^3 cell holds every row that can be nearest, in ascending order.
+// of the pixel's 16^3 cell holds every row that can be nearest there, in ascending order.
 __device__ __forceinline__ int nearest_first(const Search &s, double r, double g, double b)
 {
-    const int cell = cell_of(r, g, b);
-    uint32_t o = __ldg(s.cell_off + cell);
-    const uint32_t o1 = __ldg(s.cell_off + cell + 1);
+    const uint2 e = s.table[cell_of(r, g, b)];
+    const unsigned n = e.x & 255u;
     double best = 1e20;
     int bi = 0;
-    for (; o < o1; ++o) {
-        const int i = __ldg(s.cell_list + o);
-        const double dr = __dsub_rn(r, s.s_pal[3 * i]);
-        const double dg = __dsub_rn(g, s.s_pal[3 * i + 1]);
-        const double db = __dsub_rn(b, s.s_pal[3 * i + 2]);
-        const double d = __dadd_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dg, dg)), __dmul_rn(db, db));
-        if (d < best) {
-            best = d;
-            bi = i;
+    if (n != 255u) {
+        unsigned long long ev = ((unsigned long long)e.y << 32 | e.x) >> 8;
+        for (unsigned j = 0; j < n; ++j, ev >>= 8) {
+            const int i = (int)(ev & 255u);
+            const double d = dist_numba(s.s_pal + 3 * i, r, g, b);
+            if (d < best) {
+                best = d;
+                bi = i;
+            }
+        }
+    } else {
+        const unsigned cnt = e.x >> 8;
+        const uint8_t *lst = s.ovf + e.y;
+        for (unsigned j = 0; j < cnt; ++j) {
+            const int i = __ldg(lst + j);
+            const double d = dist_numba(s.s_pal + 3 * i, r, g, b);
+            if (d < best) {
+                best = d;
+                bi = i;
+            }
         }
     }
     return bi;
+}
+
+__device__ __forceinline__ double dist_scipy(const double *pp, double r, double g, double b)
+{
+    const double d0 = __dsub_rn(pp[0], r), d1 = __dsub_rn(pp[1], g), d2 = __dsub_rn(pp[2], b);
+    return __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(d0, d0)), __dmul_rn(d1, d1)),
+                     __dmul_rn(d2, d2));
 }
 
 // KD-tree nearest (:1243): unique minimum among the candidates, else replay scipy.
 __device__ __forceinline__ int nearest_kd(const PalDev *P, const Search &s, double r, double g,
                                           double b)
 {
-    const int cell = cell_of(r, g, b);
-    uint32_t o = __ldg(s.cell_off + cell);
-    const uint32_t o1 = __ldg(s.cell_off + cell + 1);
+    const uint2 e = s.table[cell_of(r, g, b)];
+    const unsigned n = e.x & 255u;
     double best = DP_INF_F64;
     int bi = 0;
     bool tie = false;
-    for (; o < o1; ++o) {
-        const int i = __ldg(s.cell_list + o);
-        const double d0 = __dsub_rn(s.s_pal[3 * i], r);
-        const double d1 = __dsub_rn(s.s_pal[3 * i + 1], g);
-        const double d2 = __dsub_rn(s.s_pal[3 * i + 2], b);
-        const double d = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(d0, d0)), __dmul_rn(d1, d1)),
-                                   __dmul_rn(d2, d2));
+    const bool inl = n != 255u;
+    const unsigned cnt = inl ? n : (e.x >> 8);
+    unsigned long long ev = ((unsigned long long)e.y << 32 | e.x) >> 8;
+    const uint8_t *lst = s.ovf + e.y;
+    for (unsigned j = 0; j < cnt; ++j, ev >>= 8) {
+        const int i = inl ? (int)(ev & 255u) : (int)__ldg(lst + j);
+        const double d = dist_scipy(s.s_pal + 3 * i, r, g, b);
         if (d < best) {
             best = d;
             bi = i;
@@ -274,8 +299,10 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
     __shared__ uint8_t s_orgb[DP_MAX_COLORS * 4];
     __shared__ float s_lutf[256];
     __shared__ float s_ow[SP::OSTRO ? 256 * 4 : 4];
+    __shared__ uint2 s_tab[4096];
 
     const PalDev *P = p.P;
+    for (int i = threadIdx.x; i < 4096; i += WAVE_THREADS) s_tab[i] = P->ed_table[i];
     for (int i = threadIdx.x; i < p.K * 3; i += WAVE_THREADS) {
         s_pal[i] = P->pal_f64[i];
         s_palf[i] = P->pal_f32[i];
@@ -287,8 +314,8 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
     __syncthreads();
 
     Search srch;
-    srch.cell_off = P->cell_off;
-    srch.cell_list = P->cell_list;
+    srch.table = s_tab;
+    srch.ovf = P->ed_ovf;
     srch.s_pal = s_pal;
 
     const unsigned FULL = 0xffffffffu;
@@ -345,10 +372,10 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
                 if (need > avail) {
                     int v = 0;
                     for (unsigned spins = 0;; ++spins) {
-                        if (lane == 0) v = ld_acquire(prog_in);
+                        if (lane == 0) v = ld_poll(prog_in);
                         v = __shfl_sync(FULL, v, 0);
                         if (v >= need) break;
-                        __nanosleep(64);
+                        __nanosleep(256);
                         // a band's predecessor always holds an earlier ticket, so this cannot
                         // spin forever; the trap turns a protocol bug into an error, not a hang
                         if (spins > (1u << 26)) __trap();
@@ -577,8 +604,8 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
     }
     __syncthreads();
     Search srch;
-    srch.cell_off = P->cell_off;
-    srch.cell_list = P->cell_list;
+    srch.table = P->ed_table;
+    srch.ovf = P->ed_ovf;
     srch.s_pal = s_pal;
 
     const int W = p.w, H = p.h;

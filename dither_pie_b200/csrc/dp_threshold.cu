@@ -63,6 +63,8 @@ struct ThreshParams {
     // geometry kernel only
     int src_h, src_w, upscale;
     const int *ytab, *xtab;
+    int fast;        // 0 generic kernel, 1 fast kernel with the candidate table in shared, 2 in global
+    int thr_cells;
 };
 
 // IGN threshold (:541-549): f32, one rounding per numpy ufunc, no contraction.
@@ -260,6 +262,213 @@ __global__ void __launch_bounds__(THREADS) k_thresh_tile(const ThreshParams p)
 }
 
 // ---------------------------------------------------------------------------------------
+// Fast identity-geometry kernel for integral palettes (the common case: no gamma).
+//
+// Per pixel the exact top-3 is taken over the CANDIDATES of the pixel's colour cell only -- the
+// palette rows that are nearest or second nearest (ties included) for at least one colour of
+// the cell, found by exhaustive enumeration at palette creation (k_thr_masks).  For 16 colours
+// the lists hold 2.3-2.7 rows on average, so the O(K) scan becomes ~3 distance evaluations:
+//   key_i = (|p_i|^2 << 8 | i) - 512 * dp4a(v, p_i)      (one LDS.64, one IDP4A, one IMAD)
+// Four pixels (12 bytes = three aligned words) per thread and iteration.
+// ---------------------------------------------------------------------------------------
+struct FastCtx {
+    const uint2 *table;   // shared or global
+    const uint8_t *ovf;   // global
+    const int2 *ent;      // shared: (packed rgb, |p|^2<<8 | i)
+    int shift, ncell;     // cell = ((r>>shift)*ncell + (g>>shift))*ncell + (b>>shift)
+};
+
+__device__ __forceinline__ int fast_key(const FastCtx &c, unsigned v, unsigned i)
+{
+    const int2 e = c.ent[i];
+    return e.y - 512 * (int)__dp4a(v, (unsigned)e.x, 0u);
+}
+
+template <int KIND>
+__device__ __forceinline__ int pick_fast(const PalDev *P, const FastCtx &c, int K, unsigned v,
+                                         float thr)
+{
+    const unsigned r = v & 255u, g = (v >> 8) & 255u, b = (v >> 16) & 255u;
+    const unsigned cell = ((r >> c.shift) * c.ncell + (g >> c.shift)) * c.ncell + (b >> c.shift);
+    const uint2 e = c.table[cell];
+    const unsigned n = e.x & 255u;
+    int m1, m2, m3 = 0x7fffffff;
+    if (n != 255u) {
+        const int k0 = fast_key(c, v, (e.x >> 8) & 255u);
+        const int k1 = fast_key(c, v, (e.x >> 16) & 255u);
+        m1 = min(k0, k1);
+        m2 = max(k0, k1);
+        if (n > 2) {
+            const int k2 = fast_key(c, v, e.x >> 24);
+            const int a = max(m1, k2);
+            m1 = min(m1, k2);
+            m3 = max(m2, a);
+            m2 = min(m2, a);
+            unsigned rest = e.y;
+            for (unsigned j = 3; j < n; ++j, rest >>= 8) {
+                const int k = fast_key(c, v, rest & 255u);
+                const int a2 = max(m1, k);
+                m1 = min(m1, k);
+                const int b2 = max(m2, a2);
+                m2 = min(m2, a2);
+                m3 = min(m3, b2);
+            }
+        }
+    } else {
+        const unsigned cnt = e.x >> 8;
+        const uint8_t *lst = c.ovf + e.y;
+        m1 = m2 = 0x7fffffff;
+        for (unsigned j = 0; j < cnt; ++j) {
+            const int k = fast_key(c, v, __ldg(lst + j));
+            const int a2 = max(m1, k);
+            m1 = min(m1, k);
+            const int b2 = max(m2, a2);
+            m2 = min(m2, a2);
+            m3 = min(m3, b2);
+        }
+    }
+    int i1 = m1 & 255, i2 = m2 & 255;
+    const int s1 = m1 >> 8, s2 = m2 >> 8, s3 = m3 >> 8;
+    bool amb = (s1 == s2);
+    if (KIND != DP_THRESH_NONE) amb = amb || (s2 == s3 && K >= 3);
+    if (amb) {
+        int oi[2];
+        double os[2];
+        if (KIND == DP_THRESH_NONE)
+            kd_emulate<1>(P, (double)r, (double)g, (double)b, oi, os);
+        else
+            kd_emulate<2>(P, (double)r, (double)g, (double)b, oi, os);
+        i1 = oi[0];
+        if (KIND != DP_THRESH_NONE) i2 = oi[1];
+    }
+    if (KIND == DP_THRESH_NONE) return i1;
+    const int vv = (int)__dp4a(v & 0xffffffu, v & 0xffffffu, 0u);
+    return factor_le_int(s1 + vv, s2 + vv, thr) ? i1 : i2;
+}
+
+template <int KIND, bool TABLE_SMEM>
+__global__ void __launch_bounds__(THREADS) k_thresh_fast(const ThreshParams p)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *s_in = smem;                                   // TILE_BUF
+    uint8_t *s_out = s_in + TILE_BUF;                       // TILE_BUF
+    uint8_t *s_idx = s_out + TILE_BUF;                      // TILE_PX
+    uint8_t *s_lut = s_idx + TILE_PX;                       // 256
+    unsigned *s_orgb = reinterpret_cast<unsigned *>(s_lut + 256);   // K words
+    int2 *s_ent = reinterpret_cast<int2 *>(s_orgb + DP_MAX_COLORS); // K
+    uint2 *s_table = reinterpret_cast<uint2 *>(s_ent + p.K);        // thr_cells or 0
+    const bool mat_in_smem = (KIND == DP_THRESH_MATRIX) && (p.mh * p.mw <= 1024);
+    float *s_mat = reinterpret_cast<float *>(s_table + (TABLE_SMEM ? p.thr_cells : 0));
+
+    const PalDev *P = p.P;
+    const int tid = threadIdx.x;
+    const int K = p.K;
+    s_lut[tid] = P->in_lut[tid];
+    for (int i = tid; i < K; i += THREADS) {
+        const uint8_t *o = P->out_rgb + 4 * i;
+        s_orgb[i] = (unsigned)o[0] | ((unsigned)o[1] << 8) | ((unsigned)o[2] << 16);
+        const int4 cf = P->coef[i];
+        const int pr = -cf.x >> 9, pg = -cf.y >> 9, pb = -cf.z >> 9;   // coef = -2p << 8
+        s_ent[i] = make_int2(pr | (pg << 8) | (pb << 16), cf.w);
+    }
+    if (mat_in_smem)
+        for (int i = tid; i < p.mh * p.mw; i += THREADS) s_mat[i] = p.matrix[i];
+    FastCtx ctx;
+    ctx.shift = P->thr_shift;
+    ctx.ncell = 256 >> ctx.shift;
+    ctx.ovf = P->thr_ovf;
+    ctx.ent = s_ent;
+    if (TABLE_SMEM) {
+        const int cells = P->thr_cells;
+        for (int i = tid; i < cells; i += THREADS) s_table[i] = P->thr_table[i];
+        ctx.table = s_table;
+    } else {
+        ctx.table = P->thr_table;
+    }
+    __syncthreads();
+
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int f = tile / p.tiles_per_frame;
+        const int tin = tile - f * p.tiles_per_frame;
+        const int px0 = tin * TILE_PX;
+        const int npx = min(TILE_PX, p.npix - px0);
+        const int nbytes = npx * 3;
+        const size_t goff = ((size_t)f * p.npix + px0) * 3;
+        const uint8_t *gsrc = p.src + goff;
+        const int mis_in = (int)(reinterpret_cast<uintptr_t>(gsrc) & 15);   // multiple of 4 here
+        {
+            const uint4 *g4 = reinterpret_cast<const uint4 *>(gsrc - mis_in);
+            const int n16 = (mis_in + nbytes + 15) >> 4;
+            uint4 *s4 = reinterpret_cast<uint4 *>(s_in);
+            for (int i = tid; i < n16; i += THREADS) s4[i] = __ldcs(g4 + i);
+        }
+        uint8_t *gdst = p.dst + goff;
+        const int mis_out = (int)(reinterpret_cast<uintptr_t>(gdst) & 15);
+        __syncthreads();
+
+        const unsigned *win = reinterpret_cast<const unsigned *>(s_in + mis_in);
+        unsigned *wout = reinterpret_cast<unsigned *>(s_out + mis_out);
+        const int ngroups = (npx + 3) >> 2;
+#pragma unroll 1
+        for (int gi = tid; gi < ngroups; gi += THREADS) {
+            const unsigned a = win[3 * gi], bw = win[3 * gi + 1], cw = win[3 * gi + 2];
+            unsigned px[4];
+            px[0] = a & 0xffffffu;
+            px[1] = __byte_perm(a, bw, 0x4543) & 0xffffffu;
+            px[2] = __byte_perm(bw, cw, 0x4432) & 0xffffffu;
+            px[3] = cw >> 8;
+            uint32_t pi = (uint32_t)(px0 + 4 * gi);
+            uint32_t y = 0, x = 0;
+            if (KIND != DP_THRESH_NONE) {
+                y = fd_div(p.dw, pi);
+                x = pi - y * p.w;
+            }
+            unsigned oc[4];
+            unsigned idx4 = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                unsigned v = px[q];
+                if (p.has_lut)
+                    v = (unsigned)s_lut[v & 255u] | ((unsigned)s_lut[(v >> 8) & 255u] << 8) |
+                        ((unsigned)s_lut[v >> 16] << 16);
+                float thr = 0.0f;
+                if (KIND != DP_THRESH_NONE) {
+                    thr = threshold_at<KIND>(p, s_mat, mat_in_smem, (int)x, (int)y);
+                    if (++x == (uint32_t)p.w) {
+                        x = 0;
+                        ++y;
+                    }
+                }
+                const int idx = pick_fast<KIND>(P, ctx, K, v, thr);
+                oc[q] = s_orgb[idx];
+                idx4 |= (unsigned)idx << (8 * q);
+            }
+            wout[3 * gi] = oc[0] | (oc[1] << 24);
+            wout[3 * gi + 1] = (oc[1] >> 8) | (oc[2] << 16);
+            wout[3 * gi + 2] = (oc[2] >> 16) | (oc[3] << 8);
+            reinterpret_cast<unsigned *>(s_idx)[gi] = idx4;
+        }
+        __syncthreads();
+        {
+            const int head = (16 - mis_out) & 15;
+            const int hb = min(head, nbytes);
+            if (tid < hb) gdst[tid] = s_out[mis_out + tid];
+            const int nmid = (nbytes - hb) >> 4;
+            uint4 *g4 = reinterpret_cast<uint4 *>(gdst + hb);
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(s_out + mis_out + hb);
+            for (int i = tid; i < nmid; i += THREADS) __stcs(g4 + i, s4[i]);
+            const int tail0 = hb + (nmid << 4);
+            if (tid < nbytes - tail0) gdst[tail0 + tid] = s_out[mis_out + tail0 + tid];
+            if (p.dst_idx) {
+                uint8_t *gi8 = p.dst_idx + (size_t)f * p.npix + px0;
+                for (int i = tid; i < npx; i += THREADS) gi8[i] = s_idx[i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Fused geometry: gather (pixelize) -> dither -> m x m block store (up-scale).
 // One thread per dithered pixel.
 // ---------------------------------------------------------------------------------------
@@ -326,7 +535,19 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
 {
     int sms = dp_num_sms();
     size_t mat_bytes = (KIND == DP_THRESH_MATRIX && p.mh * p.mw <= 1024) ? (size_t)p.mh * p.mw * 4 : 0;
-    if (!geom) {
+    if (!geom && p.fast) {
+        const bool tsm = p.fast == 1;
+        size_t smem = 2 * TILE_BUF + TILE_PX + 256 + DP_MAX_COLORS * 4 + (size_t)p.K * 8 + mat_bytes +
+                      (tsm ? (size_t)p.thr_cells * 8 : 0);
+        auto kern = tsm ? k_thresh_fast<KIND, true> : k_thresh_fast<KIND, false>;
+        DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        int grid = sms * per_sm;
+        if (grid > p.total_tiles) grid = p.total_tiles;
+        kern<<<grid, THREADS, smem, st>>>(p);
+    } else if (!geom) {
         size_t smem = 2 * TILE_BUF + TILE_PX + 256 + 1024 + (size_t)p.K * 16 + mat_bytes;
         DP_CUDA(cudaFuncSetAttribute(k_thresh_tile<KIND>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -399,6 +620,12 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
     p.upscale = m;
     p.ytab = geo->ytab;
     p.xtab = geo->xtab;
+    p.thr_cells = pal->dev.thr_cells;
+    p.fast = 0;
+    if (!geom && pal->dev.integral && pal->dev.K >= 2 && pal->dev.thr_table &&
+        ((reinterpret_cast<uintptr_t>(src_rgb) | reinterpret_cast<uintptr_t>(dst_rgb)) & 3) == 0 &&
+        ((size_t)p.npix * 3) % 4 == 0)
+        p.fast = (pal->dev.thr_cells <= 4096) ? 1 : 2;
     cudaStream_t st = dp_stream(stream);
     switch (kind) {
         case DP_THRESH_NONE: return launch_kind<DP_THRESH_NONE>(p, geom, st);
