@@ -124,8 +124,7 @@ struct Spec {
     static constexpr int BMAX = cmax(B1, ROWS3 ? B2 : 0);
 };
 
-constexpr int WAVE_THREADS = 128;
-constexpr int PUB = 16;  // progress is published every PUB pixels
+constexpr int WAVE_THREADS = 256;
 
 struct WaveParams {
     const PalDev *P;
@@ -290,27 +289,51 @@ __device__ __forceinline__ void apply_taps(std::integer_sequence<int, Ks...>, co
     (apply_tap<V, Ks, W1, W2>(e, q10, q20a, q20b, d1, d2), ...);
 }
 
+// Per-warp staging buffers (shared memory), refilled every 32 steps ("chunk"):
+//   inw  [32 rows][27] u32   the raw source bytes (aligned words) holding the 32 pixels each lane
+//                            seeds its deepest window with during the chunk -- one coalesced
+//                            word load per row
+//   hin  [32 steps][6] f32   lane 0's two incoming streams for the chunk (from the band above,
+//                            or raw rows 0/1 for the first band)
+//   out  [32 rows][36] u8    the palette rows chosen during the chunk -> written back coalesced
+//   hout [32 steps][6] f32   lane 31's two outgoing streams
+struct WarpStage {
+    unsigned inw[32][27];   // 108 raw source bytes per row: 96 wanted + alignment slack
+    float hin[32][6];
+    float hout[32][6];
+    unsigned char out[32][36];
+};
+
+constexpr int WAVE_WARPS = WAVE_THREADS / 32;
+
 template <int V>
 __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams p)
 {
     using SP = Spec<V>;
-    __shared__ double s_pal[DP_MAX_COLORS * 3];
-    __shared__ float s_palf[DP_MAX_COLORS * 3];
-    __shared__ uint8_t s_orgb[DP_MAX_COLORS * 4];
-    __shared__ float s_lutf[256];
-    __shared__ float s_ow[SP::OSTRO ? 256 * 4 : 4];
-    __shared__ uint2 s_tab[4096];
+    extern __shared__ __align__(16) unsigned char wave_smem[];
+    double *s_pal = reinterpret_cast<double *>(wave_smem);                   // [256*3]
+    uint2 *s_tab = reinterpret_cast<uint2 *>(s_pal + DP_MAX_COLORS * 3);      // [4096]
+    float *s_palf = reinterpret_cast<float *>(s_tab + 4096);                  // [256*3]
+    float *s_ow = s_palf + DP_MAX_COLORS * 3;                                 // [256*4]
+    unsigned *s_orgb = reinterpret_cast<unsigned *>(s_ow + 256 * 4);          // [256]
+    unsigned char *s_lut = reinterpret_cast<unsigned char *>(s_orgb + 256);   // [256]
+    WarpStage *stages = reinterpret_cast<WarpStage *>(s_lut + 256);
+    WarpStage &st = stages[threadIdx.x >> 5];
+    const int NT = blockDim.x;
 
     const PalDev *P = p.P;
-    for (int i = threadIdx.x; i < 4096; i += WAVE_THREADS) s_tab[i] = P->ed_table[i];
-    for (int i = threadIdx.x; i < p.K * 3; i += WAVE_THREADS) {
+    for (int i = threadIdx.x; i < 4096; i += NT) s_tab[i] = P->ed_table[i];
+    for (int i = threadIdx.x; i < p.K * 3; i += NT) {
         s_pal[i] = P->pal_f64[i];
         s_palf[i] = P->pal_f32[i];
     }
-    for (int i = threadIdx.x; i < p.K * 4; i += WAVE_THREADS) s_orgb[i] = P->out_rgb[i];
-    for (int i = threadIdx.x; i < 256; i += WAVE_THREADS) s_lutf[i] = (float)P->in_lut[i];
+    for (int i = threadIdx.x; i < p.K; i += NT) {
+        const uint8_t *o = P->out_rgb + 4 * i;
+        s_orgb[i] = (unsigned)o[0] | ((unsigned)o[1] << 8) | ((unsigned)o[2] << 16);
+    }
+    for (int i = threadIdx.x; i < 256; i += NT) s_lut[i] = P->in_lut[i];
     if (SP::OSTRO)
-        for (int i = threadIdx.x; i < 256 * 4; i += WAVE_THREADS) s_ow[i] = p.ostro_w[i];
+        for (int i = threadIdx.x; i < 256 * 4; i += NT) s_ow[i] = p.ostro_w[i];
     __syncthreads();
 
     Search srch;
@@ -323,25 +346,29 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
     const int W = p.w, H = p.h;
     const size_t frame_px = (size_t)W * H;
     const int T = W + SP::AMAX + SP::BMAX + SP::S * 31;
+    const int NCH = (T + 31) >> 5;
+    constexpr int DYF = SP::ROWS3 ? 2 : 1;             // row offset of the raw-pixel feed
+    constexpr int BF = SP::ROWS3 ? SP::B2 : SP::B1;    // its column offset
 
     for (;;) {
         int unit = 0;
         if (lane == 0) unit = atomicAdd(p.ticket, 1);
         unit = __shfl_sync(FULL, unit, 0);
         if (unit >= p.total_units) break;
-        const int f = unit / p.nbands;
-        const int band = unit - f * p.nbands;
-        const int y = band * 32 + lane;
+        // tickets run band-major over the frames (band 0 of every frame, then band 1, ...): the
+        // band above always holds an earlier ticket, and with many frames resident warps are
+        // busy instead of waiting for their turn in one frame's wavefront
+        const int band = unit / p.frames;
+        const int f = unit - band * p.frames;
+        unit = f * p.nbands + band;    // storage index of the hand-off streams
+        const int y0 = band * 32;
+        const int y = y0 + lane;
         const bool rowok = y < H;
         const bool has_next = (band + 1) < p.nbands;
         const uint8_t *src_f = p.src + frame_px * 3 * f;
         uint8_t *dst_f = p.dst + frame_px * 3 * f;
         uint8_t *idx_f = p.dst_idx ? p.dst_idx + frame_px * f : nullptr;
-        const uint8_t *srow0 = src_f + (size_t)min(y, H - 1) * W * 3;
-        const uint8_t *srow1 = src_f + (size_t)min(y + 1, H - 1) * W * 3;
-        const uint8_t *srow2 = src_f + (size_t)min(y + 2, H - 1) * W * 3;
-        const bool r1ok = (y + 1) < H, r2ok = (y + 2) < H;
-        const float *hin = p.hand + (size_t)(band > 0 ? unit - 1 : unit) * 2 * W * 3;  // band above
+        const float *hin = p.hand + (size_t)(band > 0 ? unit - 1 : unit) * 2 * W * 3;
         float *hout = p.hand + (size_t)unit * 2 * W * 3;
         const int *prog_in = p.progress + (band > 0 ? unit - 1 : unit);
         int *prog_out = p.progress + unit;
@@ -351,7 +378,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
         float fifoA[SP::DA > 1 ? SP::DA - 1 : 1][3], fifoB[SP::DB > 1 ? SP::DB - 1 : 1][3];
         float emitA[3] = {0.f, 0.f, 0.f}, emitB[3] = {0.f, 0.f, 0.f};
         double q10[3] = {0., 0., 0.}, q20a[3] = {0., 0., 0.}, q20b[3] = {0., 0., 0.};
-        float oq10[3] = {0.f, 0.f, 0.f};  // ostromoukhov: pending f32 product
+        float oq10[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int j = 0; j < SP::W1; ++j) d1[j][0] = d1[j][1] = d1[j][2] = 0.f;
 #pragma unroll
@@ -361,200 +388,257 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
 #pragma unroll
         for (int j = 0; j < (SP::DB > 1 ? SP::DB - 1 : 1); ++j) fifoB[j][0] = fifoB[j][1] = fifoB[j][2] = 0.f;
 
-#pragma unroll 1
-        for (int t = 0; t < T; ++t) {
-            const int x = t - SP::S * lane - SP::BMAX;
+        // byte offsets are relative to p.src; reads are whole aligned words inside the batch
+        const long long src_mis = (long long)(reinterpret_cast<uintptr_t>(p.src) & 3);
+        const long long src_hi = ((long long)(frame_px * 3) * p.frames + src_mis + 3) & ~3ll;
+        int my_o = 0;
 
-            // ---- wait for the band above (warp-uniform) -------------------------------
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+            const int t0 = ch << 5;
+            const int x00 = t0 - SP::BMAX;        // lane 0's x at the first step of the chunk
+            // this lane's row: byte offset (from p.src) of its first wanted column
+            const long long gb0_lane = (long long)(frame_px * 3 * f) +
+                                       ((long long)(y0 + lane + DYF) * W +
+                                        (x00 - SP::S * lane + BF)) * 3 + src_mis;
+
+            // ---- wait until the band above has published everything this chunk reads ------
             if (band > 0) {
-                int need = t - SP::BMAX + SP::S;
-                need = min(need, W + SP::AMAX);
+                const int need = min(x00 + 31 + SP::S, W + SP::AMAX);
                 if (need > avail) {
                     int v = 0;
                     for (unsigned spins = 0;; ++spins) {
                         if (lane == 0) v = ld_poll(prog_in);
                         v = __shfl_sync(FULL, v, 0);
                         if (v >= need) break;
-                        __nanosleep(256);
-                        // a band's predecessor always holds an earlier ticket, so this cannot
-                        // spin forever; the trap turns a protocol bug into an error, not a hang
-                        if (spins > (1u << 26)) __trap();
+                        __nanosleep(200);
+                        if (spins > (1u << 24)) __trap();  // protocol bug -> error, not a hang
                     }
                     avail = v;
                 }
             }
 
-            // ---- incoming streams ---------------------------------------------------
-            float fa[3], fb[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float ra = __shfl_up_sync(FULL, emitA[c], 1);
-                float rb = __shfl_up_sync(FULL, emitB[c], 1);
-                if (SP::DA > 1) {
-                    fa[c] = fifoA[0][c];
-#pragma unroll
-                    for (int j = 0; j + 1 < SP::DA - 1; ++j) fifoA[j][c] = fifoA[j + 1][c];
-                    fifoA[SP::DA - 2][c] = ra;
-                } else {
-                    fa[c] = ra;
-                }
-                if (SP::DB > 1) {
-                    fb[c] = fifoB[0][c];
-#pragma unroll
-                    for (int j = 0; j + 1 < SP::DB - 1; ++j) fifoB[j][c] = fifoB[j + 1][c];
-                    fifoB[SP::DB - 2][c] = rb;
-                } else {
-                    fb[c] = rb;
-                }
-            }
-            if (lane == 0) {
-                const int xb = x + SP::B1;
+            // ---- stage the chunk's inputs ---------------------------------------------
+            {
+                // lane 0's streams: column of step j is x00 + j
+                const int ca = x00 + lane, cb = ca + SP::B1;
+                float ha[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (band == 0) {
-                    if (x >= 0 && x < W) {
-                        const uint8_t *q = srow0 + 3 * x;
+                    if (ca >= 0 && ca < W) {
+                        const uint8_t *q = src_f + ((size_t)y0 * W + ca) * 3;
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) fa[c] = s_lutf[q[c]];
+                        for (int c = 0; c < 3; ++c) ha[c] = (float)s_lut[q[c]];
                     }
-                    if (SP::ROWS3 && r1ok && xb >= 0 && xb < W) {
-                        const uint8_t *q = srow1 + 3 * xb;
+                    if (SP::ROWS3 && y0 + 1 < H && cb >= 0 && cb < W) {
+                        const uint8_t *q = src_f + ((size_t)(y0 + 1) * W + cb) * 3;
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) fb[c] = s_lutf[q[c]];
+                        for (int c = 0; c < 3; ++c) ha[3 + c] = (float)s_lut[q[c]];
                     }
                 } else {
-                    if (x >= 0 && x < W) {
+                    if (ca >= 0 && ca < W) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) fa[c] = __ldcg(hin + 3 * x + c);
+                        for (int c = 0; c < 3; ++c) ha[c] = __ldcg(hin + 3 * ca + c);
                     }
-                    if (SP::ROWS3 && xb >= 0 && xb < W) {
+                    if (SP::ROWS3 && cb >= 0 && cb < W) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) fb[c] = __ldcg(hin + 3 * (W + xb) + c);
+                        for (int c = 0; c < 3; ++c) ha[3 + c] = __ldcg(hin + 3 * (W + cb) + c);
                     }
+                }
+#pragma unroll
+                for (int c = 0; c < 6; ++c) st.hin[lane][c] = ha[c];
+                // raw-pixel feed: for row r the 96 bytes of columns col0_r .. col0_r+31, fetched
+                // as the (up to 25) aligned words that contain them; bytes of columns outside the
+                // image belong to targets that do not exist and are never used
+                {
+                    const long long row_step = (long long)W * 3 - 3 * SP::S;
+                    long long gb = (long long)(frame_px * 3 * f) +
+                                   ((long long)(y0 + DYF) * W + (x00 + BF)) * 3 + src_mis;
+#pragma unroll 4
+                    for (int r = 0; r < 32; ++r, gb += row_step) {
+                        const long long wa = (gb & ~3ll) + 4 * lane;
+                        unsigned v = 0;
+                        if (lane < 25 && wa >= 0 && wa + 4 <= src_hi)
+                            v = __ldg(reinterpret_cast<const unsigned *>(p.src - src_mis + wa));
+                        if (lane < 27) st.inw[r][lane] = v;
+                    }
+                    my_o = (int)((gb0_lane) & 3);
                 }
             }
-            // ---- new top entries of the windows -------------------------------------
-            if (SP::ROWS3) {
-#pragma unroll
-                for (int c = 0; c < 3; ++c) d1[SP::W1 - 1][c] = fb[c];
-                const int x2 = x + SP::B2;
-                if (r2ok && x2 >= 0 && x2 < W) {
-                    const uint8_t *q = srow2 + 3 * x2;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) d2[SP::W2 - 1][c] = s_lutf[q[c]];
-                }
-            } else {
-                const int x1 = x + SP::B1;
-                if (r1ok && x1 >= 0 && x1 < W) {
-                    const uint8_t *q = srow1 + 3 * x1;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) d1[SP::W1 - 1][c] = s_lutf[q[c]];
-                }
-            }
+            __syncwarp();
 
-            // ---- this lane's pixel --------------------------------------------------
-            const bool active = rowok && x >= 0 && x < W;
-            if (active) {
-                if (!SP::OSTRO) {
-                    double v[3], e[3];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float a = fa[c];
-                        if (SP::H20) a = acc_f64(a, q20a[c]);   // from x-2 (older source first)
-                        if (SP::H10) a = acc_f64(a, q10[c]);    // from x-1
-                        double tv = (double)a;
-                        tv = tv < 0.0 ? 0.0 : (tv > 255.0 ? 255.0 : tv);
-                        v[c] = tv;
-                    }
-                    const int bi = nearest_first(srch, v[0], v[1], v[2]);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) e[c] = __dsub_rn(v[c], (double)s_palf[3 * bi + c]);
-                    uint8_t *o = dst_f + ((size_t)y * W + x) * 3;
-                    o[0] = s_orgb[4 * bi];
-                    o[1] = s_orgb[4 * bi + 1];
-                    o[2] = s_orgb[4 * bi + 2];
-                    if (idx_f) idx_f[(size_t)y * W + x] = (uint8_t)bi;
-                    apply_taps<V>(std::make_integer_sequence<int, SP::N>{}, e, q10, q20a, q20b,
-                                  d1, d2);
-                } else {
-                    // Ostromoukhov: f32 arithmetic (:1241-1266)
-                    float ov[3], er[3];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        float a = __fadd_rn(fa[c], oq10[c]);
-                        a = a < 0.f ? 0.f : (a > 255.f ? 255.f : a);
-                        ov[c] = a;
-                    }
-                    const int bi = nearest_kd(P, srch, (double)ov[0], (double)ov[1], (double)ov[2]);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], s_palf[3 * bi + c]);
-                    uint8_t *o = dst_f + ((size_t)y * W + x) * 3;
-                    o[0] = s_orgb[4 * bi];
-                    o[1] = s_orgb[4 * bi + 1];
-                    o[2] = s_orgb[4 * bi + 2];
-                    if (idx_f) idx_f[(size_t)y * W + x] = (uint8_t)bi;
-                    float lum = __fmul_rn(0.299f, ov[0]);
-                    lum = __fadd_rn(lum, __fmul_rn(0.587f, ov[1]));
-                    lum = __fadd_rn(lum, __fmul_rn(0.114f, ov[2]));
-                    lum = lum < 0.f ? 0.f : (lum > 255.f ? 255.f : lum);
-                    const int li = (int)lum;
-                    const float w0 = s_ow[4 * li], w1 = s_ow[4 * li + 1], w2 = s_ow[4 * li + 2];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        oq10[c] = __fmul_rn(er[c], w0);                                   // (x+1, y)
-                        d1[1][c] = __fadd_rn(d1[1][c], __fmul_rn(er[c], w2));             // (x, y+1)
-                        d1[0][c] = __fadd_rn(d1[0][c], __fmul_rn(er[c], w1));             // (x-1, y+1)
-                    }
-                }
-            } else {
+            // ---- 32 pixel steps --------------------------------------------------------
+#pragma unroll 1
+            for (int sidx = 0; sidx < 32; ++sidx) {
+                const int x = x00 + sidx - SP::S * lane;
+                float fa[3], fb[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    q10[c] = 0.0;
-                    q20a[c] = q20b[c];
-                    q20b[c] = 0.0;
-                    oq10[c] = 0.f;
-                }
-            }
-
-            // ---- finished entries leave the windows ---------------------------------
+                    const float ra = __shfl_up_sync(FULL, emitA[c], 1);
+                    const float rb = __shfl_up_sync(FULL, emitB[c], 1);
+                    if (SP::DA > 1) {
+                        fa[c] = fifoA[0][c];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                emitA[c] = d1[0][c];
-                emitB[c] = SP::ROWS3 ? d2[0][c] : 0.f;
-            }
-            if (lane == 31 && has_next) {
-                const int xa = x - SP::A1;
-                if (xa >= 0 && xa < W) {
+                        for (int j = 0; j + 1 < SP::DA - 1; ++j) fifoA[j][c] = fifoA[j + 1][c];
+                        fifoA[SP::DA - 2][c] = ra;
+                    } else {
+                        fa[c] = ra;
+                    }
+                    if (SP::DB > 1) {
+                        fb[c] = fifoB[0][c];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) __stcg(hout + 3 * xa + c, emitA[c]);
-                }
-                if (SP::ROWS3) {
-                    const int xb = x - SP::A2;
-                    if (xb >= 0 && xb < W) {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) __stcg(hout + 3 * (W + xb) + c, emitB[c]);
+                        for (int j = 0; j + 1 < SP::DB - 1; ++j) fifoB[j][c] = fifoB[j + 1][c];
+                        fifoB[SP::DB - 2][c] = rb;
+                    } else {
+                        fb[c] = rb;
                     }
                 }
-                const int prog = x + 1;
-                if (t == T - 1)
-                    st_release(prog_out, W + SP::AMAX);
-                else if (prog > 0 && (prog % PUB) == 0)
-                    st_release(prog_out, prog);
-            }
+                if (lane == 0) {
 #pragma unroll
-            for (int j = 0; j + 1 < SP::W1; ++j) {
+                    for (int c = 0; c < 3; ++c) {
+                        fa[c] = st.hin[sidx][c];
+                        fb[c] = st.hin[sidx][3 + c];
+                    }
+                }
+                {
+                    const unsigned char *pb =
+                        reinterpret_cast<const unsigned char *>(st.inw[lane]) + my_o + 3 * sidx;
+                    unsigned b0 = pb[0], b1 = pb[1], b2 = pb[2];
+                    if (p.has_lut) {
+                        b0 = s_lut[b0];
+                        b1 = s_lut[b1];
+                        b2 = s_lut[b2];
+                    }
+                    float *top = SP::ROWS3 ? d2[SP::W2 - 1] : d1[SP::W1 - 1];
+                    if (SP::ROWS3) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) d1[j][c] = d1[j + 1][c];
-            }
+                        for (int c = 0; c < 3; ++c) d1[SP::W1 - 1][c] = fb[c];
+                    }
+                    top[0] = (float)b0;
+                    top[1] = (float)b1;
+                    top[2] = (float)b2;
+                }
+
+                const bool active = rowok && x >= 0 && x < W;
+                if (active) {
+                    int bi;
+                    if (!SP::OSTRO) {
+                        double v[3], e[3];
 #pragma unroll
-            for (int c = 0; c < 3; ++c) d1[SP::W1 - 1][c] = 0.f;
-            if (SP::ROWS3) {
+                        for (int c = 0; c < 3; ++c) {
+                            float a = fa[c];
+                            if (SP::H20) a = acc_f64(a, q20a[c]);
+                            if (SP::H10) a = acc_f64(a, q10[c]);
+                            a = fminf(fmaxf(a, 0.f), 255.f);
+                            v[c] = (double)a;
+                        }
+                        bi = nearest_first(srch, v[0], v[1], v[2]);
 #pragma unroll
-                for (int j = 0; j + 1 < SP::W2; ++j) {
+                        for (int c = 0; c < 3; ++c) e[c] = __dsub_rn(v[c], (double)s_palf[3 * bi + c]);
+                        apply_taps<V>(std::make_integer_sequence<int, SP::N>{}, e, q10, q20a, q20b,
+                                      d1, d2);
+                    } else {
+                        float ov[3], er[3];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) d2[j][c] = d2[j + 1][c];
+                        for (int c = 0; c < 3; ++c) {
+                            float a = __fadd_rn(fa[c], oq10[c]);
+                            ov[c] = fminf(fmaxf(a, 0.f), 255.f);
+                        }
+                        bi = nearest_kd(P, srch, (double)ov[0], (double)ov[1], (double)ov[2]);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], s_palf[3 * bi + c]);
+                        float lum = __fmul_rn(0.299f, ov[0]);
+                        lum = __fadd_rn(lum, __fmul_rn(0.587f, ov[1]));
+                        lum = __fadd_rn(lum, __fmul_rn(0.114f, ov[2]));
+                        lum = fminf(fmaxf(lum, 0.f), 255.f);
+                        const int li = (int)lum;
+                        const float w0 = s_ow[4 * li], w1 = s_ow[4 * li + 1], w2 = s_ow[4 * li + 2];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            oq10[c] = __fmul_rn(er[c], w0);
+                            d1[1][c] = __fadd_rn(d1[1][c], __fmul_rn(er[c], w2));
+                            d1[0][c] = __fadd_rn(d1[0][c], __fmul_rn(er[c], w1));
+                        }
+                    }
+                    st.out[lane][sidx] = (unsigned char)bi;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        q10[c] = 0.0;
+                        q20a[c] = q20b[c];
+                        q20b[c] = 0.0;
+                        oq10[c] = 0.f;
+                    }
+                }
+
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    emitA[c] = d1[0][c];
+                    emitB[c] = SP::ROWS3 ? d2[0][c] : 0.f;
+                }
+                if (lane == 31) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        st.hout[sidx][c] = emitA[c];
+                        st.hout[sidx][3 + c] = emitB[c];
+                    }
                 }
 #pragma unroll
-                for (int c = 0; c < 3; ++c) d2[SP::W2 - 1][c] = 0.f;
+                for (int j = 0; j + 1 < SP::W1; ++j) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) d1[j][c] = d1[j + 1][c];
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) d1[SP::W1 - 1][c] = 0.f;
+                if (SP::ROWS3) {
+#pragma unroll
+                    for (int j = 0; j + 1 < SP::W2; ++j) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) d2[j][c] = d2[j + 1][c];
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) d2[SP::W2 - 1][c] = 0.f;
+                }
             }
+            __syncwarp();
+
+            // ---- write the chunk back ----------------------------------------------------
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                const int yr = y0 + r;
+                const int col = x00 + lane - SP::S * r;
+                if (yr < H && col >= 0 && col < W) {
+                    const unsigned bi = st.out[r][lane];
+                    const unsigned oc = s_orgb[bi];
+                    uint8_t *o = dst_f + ((size_t)yr * W + col) * 3;
+                    o[0] = (uint8_t)oc;
+                    o[1] = (uint8_t)(oc >> 8);
+                    o[2] = (uint8_t)(oc >> 16);
+                    if (idx_f) idx_f[(size_t)yr * W + col] = (uint8_t)bi;
+                }
+            }
+            if (has_next) {
+                // lane 31's x at step j of this chunk
+                const int x31 = x00 + lane - SP::S * 31;
+                const int xa = x31 - SP::A1;
+                if (xa >= 0 && xa < W) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) __stcg(hout + 3 * xa + c, st.hout[lane][c]);
+                }
+                if (SP::ROWS3) {
+                    const int xb = x31 - SP::A2;
+                    if (xb >= 0 && xb < W) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) __stcg(hout + 3 * (W + xb) + c, st.hout[lane][3 + c]);
+                    }
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) {
+                    const int prog = (ch == NCH - 1) ? 0x3fffffff : (x00 + 32 - SP::S * 31);
+                    st_release(prog_out, prog);
+                }
+            }
+            __syncwarp();
         }
     }
 }
@@ -708,15 +792,23 @@ struct Workspace {
 template <int V>
 int launch_wave(const WaveParams &p, cudaStream_t st)
 {
+    // Few bands (a single image, a small batch): 4-warp blocks so that the bands spread over
+    // the SM sub-partitions (the kernel is latency-bound per warp).  Many bands: 8-warp blocks,
+    // which share the tables and reach the occupancy limit set by registers.
+    const int sms = dp_num_sms();
+    const int warps = (p.total_units <= sms * 12) ? 4 : WAVE_WARPS;
+    const size_t smem = DP_MAX_COLORS * 3 * 8 + 4096 * 8 + DP_MAX_COLORS * 3 * 4 + 256 * 4 * 4 +
+                        256 * 4 + 256 + sizeof(WarpStage) * warps;
+    DP_CUDA(cudaFuncSetAttribute(k_diffuse_wave<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
     int per_sm = 0;
-    DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_diffuse_wave<V>,
-                                                          WAVE_THREADS, 0));
+    DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_diffuse_wave<V>, warps * 32,
+                                                          smem));
     if (per_sm < 1) per_sm = 1;
-    long long warps_needed = p.total_units;
-    long long blocks = (warps_needed + (WAVE_THREADS / 32) - 1) / (WAVE_THREADS / 32);
-    long long cap = (long long)dp_num_sms() * per_sm;
+    long long blocks = ((long long)p.total_units + warps - 1) / warps;
+    long long cap = (long long)sms * per_sm;
     int grid = (int)(blocks < cap ? blocks : cap);
-    k_diffuse_wave<V><<<grid, WAVE_THREADS, 0, st>>>(p);
+    k_diffuse_wave<V><<<grid, warps * 32, smem, st>>>(p);
     DP_LAUNCH_CHECK();
     return 0;
 }

@@ -269,7 +269,11 @@ __global__ void __launch_bounds__(THREADS) k_thresh_tile(const ThreshParams p)
 // the cell, found by exhaustive enumeration at palette creation (k_thr_masks).  For 16 colours
 // the lists hold 2.3-2.7 rows on average, so the O(K) scan becomes ~3 distance evaluations:
 //   key_i = (|p_i|^2 << 8 | i) - 512 * dp4a(v, p_i)      (one LDS.64, one IDP4A, one IMAD)
-// Four pixels (12 bytes = three aligned words) per thread and iteration.
+// Work is organised per WARP: a warp streams 512-pixel tiles (1536 B) through its private
+// shared-memory buffer with 128-bit coalesced loads/stores; lanes then own groups of four
+// pixels (three aligned words, conflict-free stride-3 access) and write the result in place.
+// No block-wide barrier in the loop.  Rare cases (exact distance ties, threshold equality) go
+// to out-of-line slow paths.
 // ---------------------------------------------------------------------------------------
 struct FastCtx {
     const uint2 *table;   // shared or global
@@ -278,17 +282,53 @@ struct FastCtx {
     int shift, ncell;     // cell = ((r>>shift)*ncell + (g>>shift))*ncell + (b>>shift)
 };
 
+constexpr int WTILE_PX = 512;
+constexpr int WTILE_BYTES = WTILE_PX * 3;   // 1536 = 96 x 16
+
 __device__ __forceinline__ int fast_key(const FastCtx &c, unsigned v, unsigned i)
 {
     const int2 e = c.ent[i];
     return e.y - 512 * (int)__dp4a(v, (unsigned)e.x, 0u);
 }
 
+// exact ties between candidate distances: replay scipy, then decide (out of line, rare)
+template <int KIND>
+__device__ __noinline__ int pick_tie(const PalDev *P, unsigned v, float thr)
+{
+    const int r = v & 255u, g = (v >> 8) & 255u, b = (v >> 16) & 255u;
+    int oi[2];
+    double os[2];
+    if (KIND == DP_THRESH_NONE) {
+        kd_emulate<1>(P, (double)r, (double)g, (double)b, oi, os);
+        return oi[0];
+    }
+    kd_emulate<2>(P, (double)r, (double)g, (double)b, oi, os);
+    // integer distances are exact in f64
+    return factor_le_int((int)os[0], (int)os[1], thr) ? oi[0] : oi[1];
+}
+
+__device__ __noinline__ bool factor_le_f64_slow(int n1, int n2, float thr)
+{
+    return factor_le_f64((double)n1, (double)n2, thr);
+}
+
+// same decision as factor_le_int, with the (very rare) f64 sequence kept out of line
+__device__ __forceinline__ bool factor_le_fast(int n1, int n2, float thr)
+{
+    const float N = (float)(n1 + n2);
+    const float p = __fmul_rn(thr, N);
+    const float e = __fmaf_rn(thr, N, -p);
+    const float d = __fsub_rn((float)n1, p);
+    if (n1 == 0) return true;
+    if (thr >= 1e-6f && d != e) return d < e;
+    return factor_le_f64_slow(n1, n2, thr);
+}
+
 template <int KIND>
 __device__ __forceinline__ int pick_fast(const PalDev *P, const FastCtx &c, int K, unsigned v,
                                          float thr)
 {
-    const unsigned r = v & 255u, g = (v >> 8) & 255u, b = (v >> 16) & 255u;
+    const unsigned r = v & 255u, g = (v >> 8) & 255u, b = v >> 16;
     const unsigned cell = ((r >> c.shift) * c.ncell + (g >> c.shift)) * c.ncell + (b >> c.shift);
     const uint2 e = c.table[cell];
     const unsigned n = e.x & 255u;
@@ -327,38 +367,26 @@ __device__ __forceinline__ int pick_fast(const PalDev *P, const FastCtx &c, int 
             m3 = min(m3, b2);
         }
     }
-    int i1 = m1 & 255, i2 = m2 & 255;
     const int s1 = m1 >> 8, s2 = m2 >> 8, s3 = m3 >> 8;
     bool amb = (s1 == s2);
     if (KIND != DP_THRESH_NONE) amb = amb || (s2 == s3 && K >= 3);
-    if (amb) {
-        int oi[2];
-        double os[2];
-        if (KIND == DP_THRESH_NONE)
-            kd_emulate<1>(P, (double)r, (double)g, (double)b, oi, os);
-        else
-            kd_emulate<2>(P, (double)r, (double)g, (double)b, oi, os);
-        i1 = oi[0];
-        if (KIND != DP_THRESH_NONE) i2 = oi[1];
-    }
-    if (KIND == DP_THRESH_NONE) return i1;
-    const int vv = (int)__dp4a(v & 0xffffffu, v & 0xffffffu, 0u);
-    return factor_le_int(s1 + vv, s2 + vv, thr) ? i1 : i2;
+    if (amb) return pick_tie<KIND>(P, v, thr);
+    if (KIND == DP_THRESH_NONE) return m1 & 255;
+    const int vv = (int)__dp4a(v, v, 0u);
+    return factor_le_fast(s1 + vv, s2 + vv, thr) ? (m1 & 255) : (m2 & 255);
 }
 
-template <int KIND, bool TABLE_SMEM>
+template <int KIND, bool TABLE_SMEM, bool MAT_POW2>
 __global__ void __launch_bounds__(THREADS) k_thresh_fast(const ThreshParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *s_in = smem;                                   // TILE_BUF
-    uint8_t *s_out = s_in + TILE_BUF;                       // TILE_BUF
-    uint8_t *s_idx = s_out + TILE_BUF;                      // TILE_PX
-    uint8_t *s_lut = s_idx + TILE_PX;                       // 256
-    unsigned *s_orgb = reinterpret_cast<unsigned *>(s_lut + 256);   // K words
-    int2 *s_ent = reinterpret_cast<int2 *>(s_orgb + DP_MAX_COLORS); // K
-    uint2 *s_table = reinterpret_cast<uint2 *>(s_ent + p.K);        // thr_cells or 0
-    const bool mat_in_smem = (KIND == DP_THRESH_MATRIX) && (p.mh * p.mw <= 1024);
+    uint4 *s_io = reinterpret_cast<uint4 *>(smem);                           // [warps][96]
+    unsigned *s_orgb = reinterpret_cast<unsigned *>(smem + (THREADS / 32) * WTILE_BYTES);
+    int2 *s_ent = reinterpret_cast<int2 *>(s_orgb + DP_MAX_COLORS);          // K
+    uint2 *s_table = reinterpret_cast<uint2 *>(s_ent + p.K);                 // thr_cells or 0
+    const bool mat_in_smem = (KIND == DP_THRESH_MATRIX) && (p.mh * p.mw <= 4096);
     float *s_mat = reinterpret_cast<float *>(s_table + (TABLE_SMEM ? p.thr_cells : 0));
+    uint8_t *s_lut = reinterpret_cast<uint8_t *>(s_mat + (mat_in_smem ? p.mh * p.mw : 0));
 
     const PalDev *P = p.P;
     const int tid = threadIdx.x;
@@ -387,84 +415,93 @@ __global__ void __launch_bounds__(THREADS) k_thresh_fast(const ThreshParams p)
     }
     __syncthreads();
 
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int f = tile / p.tiles_per_frame;
-        const int tin = tile - f * p.tiles_per_frame;
-        const int px0 = tin * TILE_PX;
-        const int npx = min(TILE_PX, p.npix - px0);
-        const int nbytes = npx * 3;
-        const size_t goff = ((size_t)f * p.npix + px0) * 3;
-        const uint8_t *gsrc = p.src + goff;
-        const int mis_in = (int)(reinterpret_cast<uintptr_t>(gsrc) & 15);   // multiple of 4 here
-        {
-            const uint4 *g4 = reinterpret_cast<const uint4 *>(gsrc - mis_in);
-            const int n16 = (mis_in + nbytes + 15) >> 4;
-            uint4 *s4 = reinterpret_cast<uint4 *>(s_in);
-            for (int i = tid; i < n16; i += THREADS) s4[i] = __ldcs(g4 + i);
-        }
-        uint8_t *gdst = p.dst + goff;
-        const int mis_out = (int)(reinterpret_cast<uintptr_t>(gdst) & 15);
-        __syncthreads();
+    const int lane = tid & 31;
+    const int wib = tid >> 5;
+    uint4 *io4 = s_io + wib * (WTILE_BYTES / 16);
+    unsigned *iow = reinterpret_cast<unsigned *>(io4);
+    const int wpf = p.tiles_per_frame;              // warp tiles per frame
+    const int nwarps = gridDim.x * (THREADS / 32);
+    const unsigned mwm = (unsigned)p.mw - 1u, mhm = (unsigned)p.mh - 1u;
 
-        const unsigned *win = reinterpret_cast<const unsigned *>(s_in + mis_in);
-        unsigned *wout = reinterpret_cast<unsigned *>(s_out + mis_out);
-        const int ngroups = (npx + 3) >> 2;
+    for (int wt = blockIdx.x * (THREADS / 32) + wib; wt < p.total_tiles; wt += nwarps) {
+        const int f = wt / wpf;
+        const int tin = wt - f * wpf;
+        const int px0 = tin * WTILE_PX;
+        const int npx = min(WTILE_PX, p.npix - px0);
+        const int n16 = (npx * 3) >> 4;                 // npix % 16 == 0 on this path
+        const size_t goff = ((size_t)f * p.npix + px0) * 3;
+        const uint4 *g4 = reinterpret_cast<const uint4 *>(p.src + goff);
+        uint4 *d4 = reinterpret_cast<uint4 *>(p.dst + goff);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int i = j * 32 + lane;
+            if (i < n16) io4[i] = __ldcs(g4 + i);
+        }
+        __syncwarp();
+        const int ngroups = npx >> 2;
 #pragma unroll 1
-        for (int gi = tid; gi < ngroups; gi += THREADS) {
-            const unsigned a = win[3 * gi], bw = win[3 * gi + 1], cw = win[3 * gi + 2];
-            unsigned px[4];
-            px[0] = a & 0xffffffu;
-            px[1] = __byte_perm(a, bw, 0x4543) & 0xffffffu;
-            px[2] = __byte_perm(bw, cw, 0x4432) & 0xffffffu;
-            px[3] = cw >> 8;
-            uint32_t pi = (uint32_t)(px0 + 4 * gi);
+        for (int gi = lane; gi < ngroups; gi += 32) {
+            // 12 bytes = 4 pixels, walked as a 96-bit shift register (keeps the loop rolled: the
+            // body is the whole per-pixel path and has to stay resident in the instruction cache)
+            unsigned a = iow[3 * gi], bw = iow[3 * gi + 1], cw = iow[3 * gi + 2];
+            unsigned oa = 0, ob = 0, oc = 0, idx4 = 0;
             uint32_t y = 0, x = 0;
+            const float *mrow = s_mat;
             if (KIND != DP_THRESH_NONE) {
+                const uint32_t pi = (uint32_t)(px0 + 4 * gi);
                 y = fd_div(p.dw, pi);
                 x = pi - y * p.w;
+                if (KIND == DP_THRESH_MATRIX) {
+                    const uint32_t ym = MAT_POW2 ? (y & mhm) : (y - fd_div(p.dmh, y) * p.mh);
+                    mrow = (mat_in_smem ? s_mat : p.matrix) + ym * p.mw;
+                }
             }
-            unsigned oc[4];
-            unsigned idx4 = 0;
-#pragma unroll
+#pragma unroll 1
             for (int q = 0; q < 4; ++q) {
-                unsigned v = px[q];
+                unsigned v = a & 0xffffffu;
+                a = __funnelshift_r(a, bw, 24);
+                bw = __funnelshift_r(bw, cw, 24);
+                cw >>= 24;
                 if (p.has_lut)
                     v = (unsigned)s_lut[v & 255u] | ((unsigned)s_lut[(v >> 8) & 255u] << 8) |
                         ((unsigned)s_lut[v >> 16] << 16);
                 float thr = 0.0f;
+                if (KIND == DP_THRESH_MATRIX) {
+                    const uint32_t xm = MAT_POW2 ? (x & mwm) : (x - fd_div(p.dmw, x) * p.mw);
+                    thr = mat_in_smem ? mrow[xm] : __ldg(mrow + xm);
+                } else if (KIND == DP_THRESH_IGN) {
+                    thr = ign_threshold(p, (int)x, (int)y);
+                }
                 if (KIND != DP_THRESH_NONE) {
-                    thr = threshold_at<KIND>(p, s_mat, mat_in_smem, (int)x, (int)y);
-                    if (++x == (uint32_t)p.w) {
+                    if (++x == (uint32_t)p.w) {   // row wrap inside the group (w % 4 != 0)
                         x = 0;
                         ++y;
+                        if (KIND == DP_THRESH_MATRIX) {
+                            const uint32_t ym = MAT_POW2 ? (y & mhm) : (y - fd_div(p.dmh, y) * p.mh);
+                            mrow = (mat_in_smem ? s_mat : p.matrix) + ym * p.mw;
+                        }
                     }
                 }
-                const int idx = pick_fast<KIND>(P, ctx, K, v, thr);
-                oc[q] = s_orgb[idx];
-                idx4 |= (unsigned)idx << (8 * q);
+                const unsigned idx = (unsigned)pick_fast<KIND>(P, ctx, K, v, thr);
+                const unsigned col = s_orgb[idx];
+                oa = __funnelshift_r(oa, ob, 24);
+                ob = __funnelshift_r(ob, oc, 24);
+                oc = (oc >> 24) | (col << 8);
+                idx4 = (idx4 >> 8) | (idx << 24);
             }
-            wout[3 * gi] = oc[0] | (oc[1] << 24);
-            wout[3 * gi + 1] = (oc[1] >> 8) | (oc[2] << 16);
-            wout[3 * gi + 2] = (oc[2] >> 16) | (oc[3] << 8);
-            reinterpret_cast<unsigned *>(s_idx)[gi] = idx4;
+            iow[3 * gi] = oa;
+            iow[3 * gi + 1] = ob;
+            iow[3 * gi + 2] = oc;
+            if (p.dst_idx)
+                reinterpret_cast<unsigned *>(p.dst_idx + (size_t)f * p.npix + px0)[gi] = idx4;
         }
-        __syncthreads();
-        {
-            const int head = (16 - mis_out) & 15;
-            const int hb = min(head, nbytes);
-            if (tid < hb) gdst[tid] = s_out[mis_out + tid];
-            const int nmid = (nbytes - hb) >> 4;
-            uint4 *g4 = reinterpret_cast<uint4 *>(gdst + hb);
-            const uint4 *s4 = reinterpret_cast<const uint4 *>(s_out + mis_out + hb);
-            for (int i = tid; i < nmid; i += THREADS) __stcs(g4 + i, s4[i]);
-            const int tail0 = hb + (nmid << 4);
-            if (tid < nbytes - tail0) gdst[tail0 + tid] = s_out[mis_out + tail0 + tid];
-            if (p.dst_idx) {
-                uint8_t *gi8 = p.dst_idx + (size_t)f * p.npix + px0;
-                for (int i = tid; i < npx; i += THREADS) gi8[i] = s_idx[i];
-            }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int i = j * 32 + lane;
+            if (i < n16) __stcs(d4 + i, io4[i]);
         }
-        __syncthreads();
+        __syncwarp();
     }
 }
 
@@ -537,16 +574,26 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
     size_t mat_bytes = (KIND == DP_THRESH_MATRIX && p.mh * p.mw <= 1024) ? (size_t)p.mh * p.mw * 4 : 0;
     if (!geom && p.fast) {
         const bool tsm = p.fast == 1;
-        size_t smem = 2 * TILE_BUF + TILE_PX + 256 + DP_MAX_COLORS * 4 + (size_t)p.K * 8 + mat_bytes +
-                      (tsm ? (size_t)p.thr_cells * 8 : 0);
-        auto kern = tsm ? k_thresh_fast<KIND, true> : k_thresh_fast<KIND, false>;
+        const bool pow2 = ((p.mw & (p.mw - 1)) == 0) && ((p.mh & (p.mh - 1)) == 0);
+        const size_t mat_sm = (KIND == DP_THRESH_MATRIX && p.mh * p.mw <= 4096) ? (size_t)p.mh * p.mw * 4 : 0;
+        size_t smem = (THREADS / 32) * WTILE_BYTES + DP_MAX_COLORS * 4 + (size_t)p.K * 8 +
+                      (tsm ? (size_t)p.thr_cells * 8 : 0) + mat_sm + 256;
+        void (*kern)(ThreshParams) =
+            tsm ? (pow2 ? k_thresh_fast<KIND, true, true> : k_thresh_fast<KIND, true, false>)
+                : (pow2 ? k_thresh_fast<KIND, false, true> : k_thresh_fast<KIND, false, false>);
         DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
         if (per_sm < 1) per_sm = 1;
-        int grid = sms * per_sm;
-        if (grid > p.total_tiles) grid = p.total_tiles;
-        kern<<<grid, THREADS, smem, st>>>(p);
+        ThreshParams q = p;
+        q.tiles_per_frame = (p.npix + WTILE_PX - 1) / WTILE_PX;
+        long long tt = (long long)q.tiles_per_frame * p.frames;
+        DP_REQUIRE(tt < (1ll << 31), "too many tiles in one call");
+        q.total_tiles = (int)tt;
+        long long want = (tt + (THREADS / 32) - 1) / (THREADS / 32);
+        long long cap = (long long)sms * per_sm;
+        int grid = (int)(want < cap ? want : cap);
+        kern<<<grid, THREADS, smem, st>>>(q);
     } else if (!geom) {
         size_t smem = 2 * TILE_BUF + TILE_PX + 256 + 1024 + (size_t)p.K * 16 + mat_bytes;
         DP_CUDA(cudaFuncSetAttribute(k_thresh_tile<KIND>,
@@ -623,8 +670,8 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
     p.thr_cells = pal->dev.thr_cells;
     p.fast = 0;
     if (!geom && pal->dev.integral && pal->dev.K >= 2 && pal->dev.thr_table &&
-        ((reinterpret_cast<uintptr_t>(src_rgb) | reinterpret_cast<uintptr_t>(dst_rgb)) & 3) == 0 &&
-        ((size_t)p.npix * 3) % 4 == 0)
+        ((reinterpret_cast<uintptr_t>(src_rgb) | reinterpret_cast<uintptr_t>(dst_rgb)) & 15) == 0 &&
+        p.npix % 16 == 0 && (!dst_idx || (reinterpret_cast<uintptr_t>(dst_idx) & 3) == 0))
         p.fast = (pal->dev.thr_cells <= 4096) ? 1 : 2;
     cudaStream_t st = dp_stream(stream);
     switch (kind) {
