@@ -35,6 +35,21 @@ int dp_num_sms()
     return cached;
 }
 
+// The per-call workspaces (hand-off streams, halftone maps) come from the stream-ordered pool.
+// Its default release threshold is 0, i.e. every synchronise hands the memory back to the OS and
+// the next call pays for a fresh several-hundred-MB allocation; keep it instead.
+int dp_retain_pool(int device)
+{
+    static thread_local unsigned long long done_mask = 0;
+    if (device >= 0 && device < 64 && (done_mask >> device & 1ull)) return 0;
+    cudaMemPool_t pool;
+    DP_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    DP_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    if (device >= 0 && device < 64) done_mask |= 1ull << device;
+    return 0;
+}
+
 extern "C" int dp_device_count(int *count)
 {
     DP_REQUIRE(count, "null argument");
@@ -48,7 +63,7 @@ extern "C" int dp_set_device(int device)
     int major = 0;
     DP_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
     DP_REQUIRE(major >= 10, "libditherpie_b200 needs an sm_100a (B200) device");
-    return 0;
+    return dp_retain_pool(device);
 }
 
 extern "C" int dp_malloc(void **dptr, size_t bytes)
@@ -230,12 +245,13 @@ __global__ void __launch_bounds__(256) k_thr_masks(const int4 *__restrict__ coef
     if (threadIdx.x < 8) masks[(size_t)cell * 8 + threadIdx.x] = s_mask[threadIdx.x];
 }
 
-// Nearest-row candidates per 16^3 box by pairwise dominance: row j dominates row i on the box
-// iff  max_{x in box} (|x-p_j|^2 - |x-p_i|^2) < 0; the expression is linear in x, so the maximum
-// sits at the corner picked coordinate-wise by the sign of (p_j - p_i).
-__global__ void __launch_bounds__(256) k_ed_table(const double *__restrict__ pal, int K,
-                                                  uint2 *__restrict__ table,
-                                                  uint8_t *__restrict__ ovf)
+// Nearest-row candidates per 8x8x8 box of colour space (table format: dp_common.cuh) by
+// pairwise dominance: row j dominates row i on the box iff
+//   max_{x in box} (|x-p_j|^2 - |x-p_i|^2) < 0;
+// the expression is linear in x, so the maximum sits at the corner picked coordinate-wise by
+// the sign of (p_j - p_i).  One block per cell; the result is a 256-bit mask of survivors.
+__global__ void __launch_bounds__(256) k_ed_masks(const double *__restrict__ pal, int K,
+                                                  uint32_t *__restrict__ masks)
 {
     __shared__ double s_p[DP_MAX_COLORS * 3];
     __shared__ double s_n[DP_MAX_COLORS];
@@ -250,7 +266,7 @@ __global__ void __launch_bounds__(256) k_ed_table(const double *__restrict__ pal
     }
     if (threadIdx.x < 8) s_mask[threadIdx.x] = 0;
     __syncthreads();
-    const double lo[3] = {16.0 * (cell >> 8), 16.0 * ((cell >> 4) & 15), 16.0 * (cell & 15)};
+    const double lo[3] = {8.0 * (cell >> 10), 8.0 * ((cell >> 5) & 31), 8.0 * (cell & 31)};
     const int i = threadIdx.x;
     if (i < K) {
         bool dominated = false;
@@ -259,7 +275,7 @@ __global__ void __launch_bounds__(256) k_ed_table(const double *__restrict__ pal
             double mx = s_n[j] - s_n[i];
             for (int c = 0; c < 3; ++c) {
                 const double dlt = s_p[3 * j + c] - s_p[3 * i + c];
-                const double x = dlt > 0.0 ? lo[c] : lo[c] + 16.0;
+                const double x = dlt > 0.0 ? lo[c] : lo[c] + 8.0;
                 mx += -2.0 * x * dlt;
             }
             dominated = mx < -1e-6;
@@ -267,24 +283,70 @@ __global__ void __launch_bounds__(256) k_ed_table(const double *__restrict__ pal
         if (!dominated) atomicOr(&s_mask[i >> 5], 1u << (i & 31));
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 8) masks[(size_t)cell * 8 + threadIdx.x] = s_mask[threadIdx.x];
+}
+
+// masks -> device tables (host side; palette creation is set-up)
+int build_ed_table(const double *d_pal64, int K, PalDev &d, dp_palette *h)
+{
+    const int cells = 32768;
+    uint32_t *dmask = nullptr;
+    std::vector<uint32_t> hmask((size_t)cells * 8);
+    if (cudaMalloc(&dmask, (size_t)cells * 32) != cudaSuccess) return 1;
+    k_ed_masks<<<cells, 256>>>(d_pal64, K, dmask);
+    bool ok = cudaMemcpy(hmask.data(), dmask, (size_t)cells * 32, cudaMemcpyDeviceToHost) ==
+              cudaSuccess;
+    cudaFree(dmask);
+    if (!ok) return 1;
+    std::vector<uint4> table(cells);
+    std::vector<int> ocells;
+    std::vector<uint32_t> ooff;
+    std::vector<uint8_t> olist;
+    for (int c = 0; c < cells; ++c) {
         uint8_t cand[DP_MAX_COLORS];
         int cnt = 0;
-        for (int k = 0; k < K; ++k)
-            if (s_mask[k >> 5] >> (k & 31) & 1u) cand[cnt++] = (uint8_t)k;
-        uint2 e;
-        if (cnt <= 7) {
-            unsigned long long v = (unsigned long long)cnt;
-            for (int k = 0; k < cnt; ++k) v |= (unsigned long long)cand[k] << (8 * (k + 1));
-            e.x = (uint32_t)v;
-            e.y = (uint32_t)(v >> 32);
-        } else {
-            e.x = 0xffu | ((uint32_t)cnt << 8);
-            e.y = (uint32_t)cell * 256u;
-            for (int k = 0; k < cnt; ++k) ovf[(size_t)cell * 256 + k] = cand[k];
+        for (int i = 0; i < K; ++i)
+            if (hmask[(size_t)c * 8 + (i >> 5)] >> (i & 31) & 1u) cand[cnt++] = (uint8_t)i;
+        unsigned slot[8];
+        for (int k = 0; k < 8; ++k) slot[k] = (k < cnt) ? (unsigned)cand[k] * 16u : DP_ED_PAD;
+        if (cnt > 7) {
+            slot[7] = DP_ED_OVERFLOW;
+            ocells.push_back(c);
+            ooff.push_back((uint32_t)olist.size());
+            olist.insert(olist.end(), cand, cand + cnt);
         }
-        table[cell] = e;
+        uint4 e;
+        e.x = slot[0] | (slot[1] << 16);
+        e.y = slot[2] | (slot[3] << 16);
+        e.z = slot[4] | (slot[5] << 16);
+        e.w = slot[6] | (slot[7] << 16);
+        table[c] = e;
     }
+    ooff.push_back((uint32_t)olist.size());
+    const size_t n = ocells.size();
+    const size_t o_cells = 0, o_off = (n * 4 + 15) / 16 * 16, o_list = o_off + ((n + 1) * 4 + 15) / 16 * 16;
+    std::vector<uint8_t> blob(o_list + olist.size() + 16, 0);
+    if (n) memcpy(blob.data() + o_cells, ocells.data(), n * 4);
+    memcpy(blob.data() + o_off, ooff.data(), (n + 1) * 4);
+    if (!olist.empty()) memcpy(blob.data() + o_list, olist.data(), olist.size());
+    void *dt = nullptr, *dov = nullptr;
+    ok = cudaMalloc(&dt, (size_t)cells * 16) == cudaSuccess &&
+         cudaMalloc(&dov, blob.size()) == cudaSuccess &&
+         cudaMemcpy(dt, table.data(), (size_t)cells * 16, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(dov, blob.data(), blob.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+        if (dt) cudaFree(dt);
+        if (dov) cudaFree(dov);
+        return 1;
+    }
+    d.ed_table = static_cast<const uint4 *>(dt);
+    d.ed_ovf_cells = reinterpret_cast<const int *>(static_cast<uint8_t *>(dov) + o_cells);
+    d.ed_ovf_off = reinterpret_cast<const uint32_t *>(static_cast<uint8_t *>(dov) + o_off);
+    d.ed_ovf = static_cast<uint8_t *>(dov) + o_list;
+    d.ed_novf = (int)n;
+    h->ed_table = dt;
+    h->ed_ovf = dov;
+    return 0;
 }
 
 template <typename T>
@@ -435,30 +497,14 @@ extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out
     d.cell_list = list;
     h->cell_off = off;
     h->cell_list = list;
-    {
-        void *et = nullptr, *eo = nullptr;
-        bool ok3 = cudaMalloc(&et, 4096 * 8) == cudaSuccess &&
-                   cudaMalloc(&eo, 4096 * 256) == cudaSuccess;
-        if (ok3) {
-            k_ed_table<<<4096, 256>>>(d.pal_f64, K, static_cast<uint2 *>(et),
-                                      static_cast<uint8_t *>(eo));
-            ok3 = cudaDeviceSynchronize() == cudaSuccess;
-        }
-        if (!ok3) {
-            dp_set_error("palette nearest-row table build failed: %s",
-                         cudaGetErrorString(cudaGetLastError()));
-            if (et) cudaFree(et);
-            if (eo) cudaFree(eo);
-            cudaFree(off);
-            cudaFree(list);
-            cudaFree(blob);
-            delete h;
-            return 1;
-        }
-        d.ed_table = static_cast<const uint2 *>(et);
-        d.ed_ovf = static_cast<const uint8_t *>(eo);
-        h->ed_table = et;
-        h->ed_ovf = eo;
+    if (build_ed_table(d.pal_f64, K, d, h)) {
+        dp_set_error("palette nearest-row table build failed: %s",
+                     cudaGetErrorString(cudaGetLastError()));
+        cudaFree(off);
+        cudaFree(list);
+        cudaFree(blob);
+        delete h;
+        return 1;
     }
     if (integral && K >= 2) {
         // top-2 candidate table for the threshold kernels

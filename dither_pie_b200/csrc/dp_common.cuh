@@ -36,6 +36,9 @@ void dp_set_error(const char *fmt, ...);
 
 #define DP_LAUNCH_CHECK() DP_CUDA(cudaGetLastError())
 
+#define DP_ED_PAD 4096u        /* row 256 of the float4 row array: the pad row */
+#define DP_ED_OVERFLOW 0xffffu
+
 static inline cudaStream_t dp_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // ---------------------------------------------------------------------------------------
@@ -67,11 +70,18 @@ struct PalDev {
     int thr_shift;   // 4 -> 16^3 cells, 3 -> 32^3 cells
     int thr_cells;
     // nearest-row candidate table for arbitrary real values in [0,255]^3 (diffusion modes):
-    // 16^3 cells, same 8-byte entry format; a row is dropped from a cell only if another row
-    // is strictly nearer at EVERY point of the cell's closed box (exact linear test).
-    // Overflow lists live at ed_ovf[cell*256 ..).
-    const uint2 *ed_table;   // [4096]
-    const uint8_t *ed_ovf;   // [4096*256]
+    // 32^3 cells of 8x8x8; a row is dropped from a cell only if another row is strictly nearer
+    // at EVERY point of the cell's closed box (exact linear test).  One 16-byte entry per cell =
+    // eight u16 slots holding row*16 (the byte offset of the row in the kernels' float4 row
+    // array), ascending; free slots hold DP_ED_PAD (the offset of a far-away pad row).  More
+    // than seven candidates (rare): slot 7 = DP_ED_OVERFLOW, slots 0..6 the first seven, and the
+    // full list is found through ed_ovf_cells (sorted cell numbers) -> ed_ovf_off -> ed_ovf.
+    // 512 KB, read through L1 (__ldg): a warp's pixels touch a few dozen neighbouring cells.
+    const uint4 *ed_table;        // [32768]
+    const int *ed_ovf_cells;      // [ed_novf] ascending
+    const uint32_t *ed_ovf_off;   // [ed_novf + 1] offsets into ed_ovf
+    const uint8_t *ed_ovf;        // concatenated candidate lists
+    int ed_novf;
 };
 
 struct dp_palette {
@@ -84,9 +94,11 @@ struct dp_palette {
     void *thr_table;
     void *thr_ovf;
     void *ed_table;
-    void *ed_ovf;
+    void *ed_ovf;   // one allocation: cells | offsets | lists
     float host_pal[DP_MAX_COLORS * 3];
 };
 
 // number of SMs of the current device (cached)
 int dp_num_sms();
+// make the device's default stream-ordered memory pool keep its memory between calls
+int dp_retain_pool(int device);

@@ -21,8 +21,11 @@
 // No atomics, no work buffer: the diffusion state lives in registers.  Between bands the last
 // lane writes the two outgoing streams to global memory and publishes a progress counter
 // (st.release); lane 0 of the next band polls it (ld.acquire) -- the flag-based hand-off.
-// Bands are handed out through an atomic ticket so that a band's predecessor is always
-// already running (no deadlock whatever the grid size).
+// Bands are handed out through a READY QUEUE in global memory: band 0 of every frame is seeded,
+// and a band enqueues its successor once it is far enough ahead for the successor to start.  A
+// resident warp therefore always holds runnable work (with many frames in flight every warp
+// slot of the GPU is busy), and a band's predecessor is always already running -- no deadlock
+// whatever the grid size.
 //
 // Arithmetic is the reference's: numba path = f32 state, f64 math, strict '<' first-index
 // nearest colour; Ostromoukhov = f32 math, f32-rounded weights, KD-tree nearest.
@@ -31,6 +34,8 @@
 //
 // Algorithmic bytes: 3 read + 3 written per pixel; the bound is the dependency chain
 // (W + S*(H-1) pixel steps per frame) and fp64 issue, not HBM.
+#include <stdlib.h>
+
 #include <utility>
 
 #include "dp_search.cuh"
@@ -126,15 +131,39 @@ struct Spec {
 
 constexpr int WAVE_THREADS = 256;
 
+#ifdef DP_WAVE_TIMING
+__device__ unsigned long long g_wave_timing[128 * 4 + 4];   // + counters: slow pixels, slow warp-steps
+#define DP_TICK(k)                                                     \
+    do {                                                               \
+        const long long _now = clock64();                              \
+        if (lane == 0 && f == 0 && band < 128)                         \
+            g_wave_timing[band * 4 + (k)] += (unsigned long long)(_now - _tick); \
+        _tick = _now;                                                  \
+    } while (0)
+__device__ unsigned long long g_step_timing[16];
+#define DP_STICK(k)                                                    \
+    do {                                                               \
+        const long long _snow = clock64();                             \
+        if (lane == 5 && f == 0 && band == 10)                         \
+            g_step_timing[(k)] += (unsigned long long)(_snow - _stick); \
+        _stick = _snow;                                                \
+    } while (0)
+#else
+#define DP_TICK(k) do { } while (0)
+#define DP_STICK(k) do { } while (0)
+#endif
+
 struct WaveParams {
     const PalDev *P;
     const uint8_t *src;
     uint8_t *dst;
     uint8_t *dst_idx;
     int frames, h, w, nbands, total_units, has_lut, K;
-    float *hand;        // [units][2][w][3] f32 hand-off streams
+    float *hand;        // [units][6 planes][TPAD] f32 hand-off streams (index = consumer step)
     int *progress;      // [units]
-    int *ticket;
+    int *qctrl;         // [0] queue head (consumers), [1] queue tail (producers)
+    int *queue;         // [units] unit + 1, 0 = not yet enqueued
+    int slack;          // extra chunks of lead before the successor band is enqueued
     const float *ostro_w;  // [256][4] f32 weights (c0,c1,c2)/sum, DEVICE (ostromoukhov only)
 };
 
@@ -158,18 +187,115 @@ __device__ __forceinline__ float acc_f64(float acc, double prod)
     return __double2float_rn(__dadd_rn((double)acc, prod));
 }
 
+// The wavefront kernel keeps the f32 work values of the numba path as DOUBLES that are exactly
+// representable in f32, because f32<->f64 conversions issue at 1/8 rate on sm_100 (measured:
+// 8.7 cycles per warp instruction, 18 cycles latency; tools/ubench/lat.cu) and the reference's
+// `+=` needs two of them per tap and channel.  Rounding an f64 to the nearest f32 (ties to even)
+// without a conversion: add and subtract 2^(e+29), e = exponent of x -- the sum's last mantissa
+// bit is then the f32 ulp of x's binade and the f64 adder does the round-to-nearest-even.
+// Identical to (double)(float)x for every x whose magnitude is 0 or in the normal f32 range
+// (work values are bounded by a few hundred; |x| < 2^-126 would need three consecutive exact
+// cancellations).  The sign of a zero result may differ (+0 for -0), which no comparison,
+// clamp or product downstream can observe in the chosen palette rows.
+__device__ __forceinline__ double round_to_f32(double x)
+{
+    const int hi = __double2hiint(x);
+    const double m = __hiloint2double((hi & (int)0xfff00000) + 0x01d00000, 0);
+    return __dsub_rn(__dadd_rn(x, m), m);
+}
+__device__ __forceinline__ double acc_r(double acc, double prod)
+{
+    return round_to_f32(__dadd_rn(acc, prod));
+}
+// clamp to [0,255] (the numba loop's `if r < 0 ... elif r > 255`, :247-252)
+__device__ __forceinline__ double clamp255(double a)
+{
+    a = (__double2hiint(a) < 0) ? 0.0 : a;
+    return (a > 255.0) ? 255.0 : a;
+}
+// f32 bit pattern of a double in [0,255] that is exactly representable in f32 (integer ops only)
+__device__ __forceinline__ float narrow_nonneg(double v)
+{
+    const int hi = __double2hiint(v);
+    const unsigned b = __funnelshift_l((unsigned)__double2loint(v), (unsigned)(hi - 0x38000000), 3);
+    return __int_as_float(hi < 0x38100000 ? 0 : (int)b);
+}
+
+// Loads from the read-only shared tables through 32-bit shared-space addresses: with generic
+// pointers the compiler re-derives the shared window base (S2R SR_CgaCtaId) inside the pixel
+// loop, on the critical path of every step.
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ float4 lds_f32x4(unsigned a)
+{
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned a)
+{
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(unsigned a)
+{
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned a)
+{
+    unsigned v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
 struct Search {
-    const uint2 *table;      // shared, [4096] 16^3 cells
-    const uint8_t *ovf;      // global overflow lists
+    const uint4 *table;      // global (L1-cached), [32768] 8x8x8 cells (format: dp_common.cuh)
+    const PalDev *P;         // overflow lists (rare)
     const double *s_pal;     // shared, [K,3]
+    unsigned rows_a;         // shared address of float4 [257]: (r, g, b, row index bits); 256 = pad
 };
 
-__device__ __forceinline__ int cell_of(double r, double g, double b)
+__device__ __forceinline__ int cell_of(float r, float g, float b)
 {
-    const int ir = min(__double2int_rz(r), 255) >> 4;
-    const int ig = min(__double2int_rz(g), 255) >> 4;
-    const int ib = min(__double2int_rz(b), 255) >> 4;
-    return (ir << 8) | (ig << 4) | ib;
+    // values are clamped to [0,255] by the caller; x + 2^23 rounded toward zero leaves trunc(x)
+    // in the low mantissa bits (F2I is a quarter-rate op)
+    const int ir = __float_as_int(__fadd_rz(r, 8388608.0f));
+    const int ig = __float_as_int(__fadd_rz(g, 8388608.0f));
+    const int ib = __float_as_int(__fadd_rz(b, 8388608.0f));
+    return ((ir & 0xf8) << 7) | ((ig & 0xf8) << 2) | ((ib >> 3) & 0x1f);
+}
+
+// Screening pass of the nearest-row search, all in f32: the (up to seven) candidate rows of the
+// cell are evaluated side by side, each distance is truncated to 16 mantissa bits and the row
+// index put in the freed byte, and the two smallest keys are kept.  The f32 distance is within
+// 5 * 2^-24 (relative) of the exact one and the truncation takes at most 2^-15 off, so a row
+// whose key is more than 2048 units (>= 1.2e-4 relative) above the smallest cannot be the
+// exact minimum: if the runner-up is that far away the smallest key's row IS the answer of the
+// reference's f64 comparison loop.  Otherwise (near-tie, exact tie, or a cell with more than
+// seven candidates) the caller takes the exact path below.
+__device__ __forceinline__ int nearest_screen(const Search &s, const uint4 e, float r, float g,
+                                              float b, bool &sure)
+{
+    const unsigned off[7] = {e.x & 0xffffu, e.x >> 16, e.y & 0xffffu, e.y >> 16,
+                             e.z & 0xffffu, e.z >> 16, e.w & 0xffffu};
+    int k1 = 0x7fffffff, k2 = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        const float4 p = lds_f32x4(s.rows_a + off[j]);
+        const float dr = __fsub_rn(r, p.x), dg = __fsub_rn(g, p.y), db = __fsub_rn(b, p.z);
+        const float d = __fmaf_rn(db, db, __fmaf_rn(dg, dg, __fmul_rn(dr, dr)));
+        const int key = (__float_as_int(d) & (int)0xffffff00) | __float_as_int(p.w);
+        const int hi = max(k1, key);
+        k1 = min(k1, key);
+        k2 = min(k2, hi);
+    }
+    sure = ((e.w >> 16) != DP_ED_OVERFLOW) && (k2 - k1 > 2048);
+    return k1 & 255;
 }
 
 __device__ __forceinline__ double dist_numba(const double *pp, double r, double g, double b)
@@ -178,34 +304,61 @@ __device__ __forceinline__ double dist_numba(const double *pp, double r, double 
     return __dadd_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dg, dg)), __dmul_rn(db, db));
 }
 
-// numba path (:254-263): strict '<' over f64 distances, first index wins.  The candidate list
-// of the pixel's 16^3 cell holds every row that can be nearest there, in ascending order.
-__device__ __forceinline__ int nearest_first(const Search &s, double r, double g, double b)
+// Candidate list of a cell for the exact paths: `n` rows, ascending; row j via cand_at().
+struct CandList {
+    uint4 e;
+    const uint8_t *ovf;   // non-null: the cell has more than seven candidates
+    int n;
+};
+
+__device__ __forceinline__ CandList cand_list(const Search &s, int cell)
 {
-    const uint2 e = s.table[cell_of(r, g, b)];
-    const unsigned n = e.x & 255u;
+    CandList L;
+    L.e = __ldg(s.table + cell);
+    L.ovf = nullptr;
+    if ((L.e.w >> 16) == DP_ED_OVERFLOW) {
+        const PalDev *P = s.P;
+        int lo = 0, hi = P->ed_novf - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (P->ed_ovf_cells[mid] < cell) lo = mid + 1; else hi = mid;
+        }
+        L.ovf = P->ed_ovf + P->ed_ovf_off[lo];
+        L.n = (int)(P->ed_ovf_off[lo + 1] - P->ed_ovf_off[lo]);
+    } else {
+        const unsigned w[4] = {L.e.x, L.e.y, L.e.z, L.e.w};
+        int n = 0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const unsigned o = (j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu);
+            n += (o != DP_ED_PAD) ? 1 : 0;
+        }
+        L.n = n;
+    }
+    return L;
+}
+
+__device__ __forceinline__ int cand_at(const CandList &L, int j)
+{
+    if (L.ovf) return (int)L.ovf[j];
+    const unsigned w = j < 2 ? L.e.x : j < 4 ? L.e.y : j < 6 ? L.e.z : L.e.w;
+    return (int)(((j & 1) ? (w >> 16) : (w & 0xffffu)) >> 4);
+}
+
+// numba path (:254-263), exact: strict '<' over f64 distances, first index wins.  The candidate
+// list of the pixel's cell holds every row that can be nearest there, in ascending order.
+__device__ __noinline__ int nearest_first_exact(const Search &s, int cell, double r, double g,
+                                                double b)
+{
+    const CandList L = cand_list(s, cell);
     double best = 1e20;
     int bi = 0;
-    if (n != 255u) {
-        unsigned long long ev = ((unsigned long long)e.y << 32 | e.x) >> 8;
-        for (unsigned j = 0; j < n; ++j, ev >>= 8) {
-            const int i = (int)(ev & 255u);
-            const double d = dist_numba(s.s_pal + 3 * i, r, g, b);
-            if (d < best) {
-                best = d;
-                bi = i;
-            }
-        }
-    } else {
-        const unsigned cnt = e.x >> 8;
-        const uint8_t *lst = s.ovf + e.y;
-        for (unsigned j = 0; j < cnt; ++j) {
-            const int i = __ldg(lst + j);
-            const double d = dist_numba(s.s_pal + 3 * i, r, g, b);
-            if (d < best) {
-                best = d;
-                bi = i;
-            }
+    for (int j = 0; j < L.n; ++j) {
+        const int i = cand_at(L, j);
+        const double d = dist_numba(s.s_pal + 3 * i, r, g, b);
+        if (d < best) {
+            best = d;
+            bi = i;
         }
     }
     return bi;
@@ -218,21 +371,16 @@ __device__ __forceinline__ double dist_scipy(const double *pp, double r, double 
                      __dmul_rn(d2, d2));
 }
 
-// KD-tree nearest (:1243): unique minimum among the candidates, else replay scipy.
-__device__ __forceinline__ int nearest_kd(const PalDev *P, const Search &s, double r, double g,
-                                          double b)
+// KD-tree nearest (:1243), exact: unique minimum among the candidates, else replay scipy.
+__device__ __noinline__ int nearest_kd_exact(const PalDev *P, const Search &s, int cell, double r,
+                                             double g, double b)
 {
-    const uint2 e = s.table[cell_of(r, g, b)];
-    const unsigned n = e.x & 255u;
+    const CandList L = cand_list(s, cell);
     double best = DP_INF_F64;
     int bi = 0;
     bool tie = false;
-    const bool inl = n != 255u;
-    const unsigned cnt = inl ? n : (e.x >> 8);
-    unsigned long long ev = ((unsigned long long)e.y << 32 | e.x) >> 8;
-    const uint8_t *lst = s.ovf + e.y;
-    for (unsigned j = 0; j < cnt; ++j, ev >>= 8) {
-        const int i = inl ? (int)(ev & 255u) : (int)__ldg(lst + j);
+    for (int j = 0; j < L.n; ++j) {
+        const int i = cand_at(L, j);
         const double d = dist_scipy(s.s_pal + 3 * i, r, g, b);
         if (d < best) {
             best = d;
@@ -251,12 +399,31 @@ __device__ __forceinline__ int nearest_kd(const PalDev *P, const Search &s, doub
     return bi;
 }
 
+// work values (clamped to [0,255]) -> palette row, the reference's answer.  (r,g,b) are the f32
+// screening copies of the exact values (xr,xg,xb).
+template <bool KD>
+__device__ __forceinline__ int nearest_row(const PalDev *P, const Search &s, float r, float g,
+                                           float b, double xr, double xg, double xb)
+{
+    const int cell = cell_of(r, g, b);
+    bool sure;
+    int bi = nearest_screen(s, __ldg(s.table + cell), r, g, b, sure);
+#ifdef DP_WAVE_TIMING
+    if (!sure) atomicAdd(&g_wave_timing[128 * 4], 1ull);
+    if (__any_sync(__activemask(), !sure) && (threadIdx.x & 31) == (__ffs(__activemask()) - 1))
+        atomicAdd(&g_wave_timing[128 * 4 + 1], 1ull);
+#endif
+    if (!sure)
+        bi = KD ? nearest_kd_exact(P, s, cell, xr, xg, xb) : nearest_first_exact(s, cell, xr, xg, xb);
+    return bi;
+}
+
 // One tap, everything about it known at compile time (weight = f64(f32(w)) / divisor, the
 // reference's `weights[k] / divisor`, :280).
 template <int V, int K, int W1, int W2>
 __device__ __forceinline__ void apply_tap(const double (&e)[3], double (&q10)[3],
                                           double (&q20a)[3], double (&q20b)[3],
-                                          float (&d1)[W1][3], float (&d2)[W2][3])
+                                          double (&d1)[W1][3], double (&d2)[W2][3])
 {
     using SP = Spec<V>;
     constexpr Tap tp = ed_tap(V, K);
@@ -272,10 +439,10 @@ __device__ __forceinline__ void apply_tap(const double (&e)[3], double (&q10)[3]
                 q20b[c] = pr;
             }
         } else if (tp.dy == 1) {
-            d1[tp.dx + SP::A1][c] = acc_f64(d1[tp.dx + SP::A1][c], pr);
+            d1[tp.dx + SP::A1][c] = acc_r(d1[tp.dx + SP::A1][c], pr);
         } else {
             d2[(tp.dy == 2 ? tp.dx + SP::A2 : 0)][c] =
-                acc_f64(d2[(tp.dy == 2 ? tp.dx + SP::A2 : 0)][c], pr);
+                acc_r(d2[(tp.dy == 2 ? tp.dx + SP::A2 : 0)][c], pr);
         }
     }
 }
@@ -283,46 +450,79 @@ __device__ __forceinline__ void apply_tap(const double (&e)[3], double (&q10)[3]
 template <int V, int... Ks, int W1, int W2>
 __device__ __forceinline__ void apply_taps(std::integer_sequence<int, Ks...>, const double (&e)[3],
                                            double (&q10)[3], double (&q20a)[3],
-                                           double (&q20b)[3], float (&d1)[W1][3],
-                                           float (&d2)[W2][3])
+                                           double (&q20b)[3], double (&d1)[W1][3],
+                                           double (&d2)[W2][3])
 {
     (apply_tap<V, Ks, W1, W2>(e, q10, q20a, q20b, d1, d2), ...);
 }
 
-// Per-warp staging buffers (shared memory), refilled every 32 steps ("chunk"):
-//   inw  [32 rows][27] u32   the raw source bytes (aligned words) holding the 32 pixels each lane
-//                            seeds its deepest window with during the chunk -- one coalesced
-//                            word load per row
-//   hin  [32 steps][6] f32   lane 0's two incoming streams for the chunk (from the band above,
-//                            or raw rows 0/1 for the first band)
-//   out  [32 rows][36] u8    the palette rows chosen during the chunk -> written back coalesced
-//   hout [32 steps][6] f32   lane 31's two outgoing streams
-struct WarpStage {
-    unsigned inw[32][27];   // 108 raw source bytes per row: 96 wanted + alignment slack
-    float hin[32][6];
-    float hout[32][6];
-    unsigned char out[32][36];
+// State type of the wavefront: doubles holding f32 values for the numba variants (see
+// round_to_f32), plain f32 for Ostromoukhov (whose reference arithmetic is f32 throughout).
+template <int V> struct StateOf { using T = double; };
+template <> struct StateOf<V_OSTRO> { using T = float; };
+
+// Per-warp staging buffers (shared memory), one "chunk" = 32 pixel steps:
+//   inw  [2][32 rows][25] u32  raw source bytes (aligned words) holding the 32 pixels each lane
+//                              seeds its deepest window with during a chunk; double-buffered,
+//                              the next chunk's rows are in flight (cp.async) during this one
+//   hin  [32 steps][3|6]       lane 0's two incoming streams for the chunk (from the band above,
+//                              or raw rows 0/1 for the first band)
+//   hout [32 steps][3|6]       lane 31's two outgoing streams
+//   outb [32 rows][108] u8     the output bytes of the chunk, each row shifted by the (constant)
+//                              misalignment m of its global address so that whole aligned words
+//                              can be stored; word 24 (the trailing m bytes) is carried into
+//                              word 0 of the next chunk
+//   outi [32 rows][36]  u8     the palette rows chosen (only when an index image is wanted)
+template <typename T, int NS>
+struct WarpStageT {
+    unsigned inw[2][32][25];       // 99 bytes per row are read at most
+    T hin[32][NS];
+    T hout[32][NS];
+    unsigned char outb[32][108];
+    unsigned char outi[32][36];
 };
 
-constexpr int WAVE_WARPS = WAVE_THREADS / 32;
+// Warps per block: the numba variants with a 5x5 footprint (JJN, Stucki) keep ~55 doubles of
+// window state per lane (242 registers) -> 8 warps; everything else fits 12 warps per SM.
+template <int V>
+constexpr int wave_max_warps()
+{
+    return (V == DP_ED_JJN || V == DP_ED_STUCKI) ? 8 : 12;
+}
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, bool valid)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int n = valid ? 4 : 0;   // src-size 0: nothing is read, the word is zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(n)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ float to_f32(double v) { return __double2float_rn(v); }
+__device__ __forceinline__ float to_f32(float v) { return v; }
 
 template <int V>
-__global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams p)
+__global__ void __launch_bounds__(wave_max_warps<V>() * 32) k_diffuse_wave(const WaveParams p)
 {
     using SP = Spec<V>;
+    using T = typename StateOf<V>::T;
+    using Stage = WarpStageT<T, SP::ROWS3 ? 6 : 3>;
     extern __shared__ __align__(16) unsigned char wave_smem[];
-    double *s_pal = reinterpret_cast<double *>(wave_smem);                   // [256*3]
-    uint2 *s_tab = reinterpret_cast<uint2 *>(s_pal + DP_MAX_COLORS * 3);      // [4096]
-    float *s_palf = reinterpret_cast<float *>(s_tab + 4096);                  // [256*3]
+    double *s_pal = reinterpret_cast<double *>(wave_smem);                    // [256*3]
+    float4 *s_rows = reinterpret_cast<float4 *>(s_pal + DP_MAX_COLORS * 3);   // [257]
+    double *s_lutd = reinterpret_cast<double *>(s_rows + DP_MAX_COLORS + 1);  // [256] (as T)
+    float *s_palf = reinterpret_cast<float *>(s_lutd + 256);                  // [256*3]
     float *s_ow = s_palf + DP_MAX_COLORS * 3;                                 // [256*4]
     unsigned *s_orgb = reinterpret_cast<unsigned *>(s_ow + 256 * 4);          // [256]
-    unsigned char *s_lut = reinterpret_cast<unsigned char *>(s_orgb + 256);   // [256]
-    WarpStage *stages = reinterpret_cast<WarpStage *>(s_lut + 256);
-    WarpStage &st = stages[threadIdx.x >> 5];
+    Stage *stages = reinterpret_cast<Stage *>(s_orgb + 256);
+    Stage &st = stages[threadIdx.x >> 5];
+    T *s_lut = reinterpret_cast<T *>(s_lutd);   // source byte -> work value (gamma LUT folded in)
     const int NT = blockDim.x;
 
     const PalDev *P = p.P;
-    for (int i = threadIdx.x; i < 4096; i += NT) s_tab[i] = P->ed_table[i];
     for (int i = threadIdx.x; i < p.K * 3; i += NT) {
         s_pal[i] = P->pal_f64[i];
         s_palf[i] = P->pal_f32[i];
@@ -331,36 +531,59 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
         const uint8_t *o = P->out_rgb + 4 * i;
         s_orgb[i] = (unsigned)o[0] | ((unsigned)o[1] << 8) | ((unsigned)o[2] << 16);
     }
-    for (int i = threadIdx.x; i < 256; i += NT) s_lut[i] = P->in_lut[i];
+    for (int i = threadIdx.x; i <= DP_MAX_COLORS; i += NT) {
+        // rows past K (and the pad row 256) sit far outside the colour cube
+        float4 rw = make_float4(1e18f, 1e18f, 1e18f, __int_as_float(0));
+        if (i < p.K)
+            rw = make_float4(P->pal_f32[3 * i], P->pal_f32[3 * i + 1], P->pal_f32[3 * i + 2],
+                             __int_as_float(i));
+        s_rows[i] = rw;
+    }
+    for (int i = threadIdx.x; i < 256; i += NT) s_lut[i] = (T)P->in_lut[i];
     if (SP::OSTRO)
         for (int i = threadIdx.x; i < 256 * 4; i += NT) s_ow[i] = p.ostro_w[i];
     __syncthreads();
 
     Search srch;
-    srch.table = s_tab;
-    srch.ovf = P->ed_ovf;
+    srch.table = P->ed_table;
+    srch.P = P;
     srch.s_pal = s_pal;
+    srch.rows_a = smem_u32(s_rows);
+    const unsigned pal_a = smem_u32(s_pal), palf_a = smem_u32(s_palf), lut_a = smem_u32(s_lut),
+                   orgb_a = smem_u32(s_orgb), ow_a = smem_u32(s_ow);
 
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int W = p.w, H = p.h;
     const size_t frame_px = (size_t)W * H;
-    const int T = W + SP::AMAX + SP::BMAX + SP::S * 31;
-    const int NCH = (T + 31) >> 5;
+    const int T_STEPS = W + SP::AMAX + SP::BMAX + SP::S * 31;
+    const int NCH = (T_STEPS + 31) >> 5;
+    const int TPAD = NCH << 5;                         // stream length (consumer step index)
     constexpr int DYF = SP::ROWS3 ? 2 : 1;             // row offset of the raw-pixel feed
     constexpr int BF = SP::ROWS3 ? SP::B2 : SP::B1;    // its column offset
+    constexpr int NS = SP::ROWS3 ? 6 : 3;              // stream values per step
+    constexpr int NFA = SP::DA > 1 ? SP::DA - 1 : 1, NFB = SP::DB > 1 ? SP::DB - 1 : 1;
+    // byte offsets are relative to p.src; reads are whole aligned words inside the batch
+    const long long src_mis = (long long)(reinterpret_cast<uintptr_t>(p.src) & 3);
+    const long long src_hi = ((long long)(frame_px * 3) * p.frames + src_mis + 3) & ~3ll;
+    const long long row_step = (long long)W * 3 - 3 * SP::S;
 
     for (;;) {
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(p.qctrl, 1);
+        slot = __shfl_sync(FULL, slot, 0);
+        if (slot >= p.total_units) break;
         int unit = 0;
-        if (lane == 0) unit = atomicAdd(p.ticket, 1);
-        unit = __shfl_sync(FULL, unit, 0);
-        if (unit >= p.total_units) break;
-        // tickets run band-major over the frames (band 0 of every frame, then band 1, ...): the
-        // band above always holds an earlier ticket, and with many frames resident warps are
-        // busy instead of waiting for their turn in one frame's wavefront
-        const int band = unit / p.frames;
-        const int f = unit - band * p.frames;
-        unit = f * p.nbands + band;    // storage index of the hand-off streams
+        for (unsigned spins = 0;; ++spins) {
+            if (lane == 0) unit = ld_poll(p.queue + slot);
+            unit = __shfl_sync(FULL, unit, 0);
+            if (unit > 0) break;
+            __nanosleep(200);
+            if (spins > (1u << 26)) __trap();  // protocol bug -> error, not a hang
+        }
+        unit -= 1;                          // storage index of the hand-off streams: f * nbands + band
+        const int f = unit / p.nbands;
+        const int band = unit - f * p.nbands;
         const int y0 = band * 32;
         const int y = y0 + lane;
         const bool rowok = y < H;
@@ -368,174 +591,197 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
         const uint8_t *src_f = p.src + frame_px * 3 * f;
         uint8_t *dst_f = p.dst + frame_px * 3 * f;
         uint8_t *idx_f = p.dst_idx ? p.dst_idx + frame_px * f : nullptr;
-        const float *hin = p.hand + (size_t)(band > 0 ? unit - 1 : unit) * 2 * W * 3;
-        float *hout = p.hand + (size_t)unit * 2 * W * 3;
+        const float *hin = p.hand + (size_t)(band > 0 ? unit - 1 : unit) * 6 * TPAD;
+        float *hout = p.hand + (size_t)unit * 6 * TPAD;
         const int *prog_in = p.progress + (band > 0 ? unit - 1 : unit);
         int *prog_out = p.progress + unit;
         int avail = 0;
 
-        float d1[SP::W1][3], d2[SP::W2][3];
-        float fifoA[SP::DA > 1 ? SP::DA - 1 : 1][3], fifoB[SP::DB > 1 ? SP::DB - 1 : 1][3];
-        float emitA[3] = {0.f, 0.f, 0.f}, emitB[3] = {0.f, 0.f, 0.f};
+        T d1[SP::W1][3], d2[SP::W2][3];
+        T fifoA[NFA][3], fifoB[NFB][3];
+        T emitA[3] = {0, 0, 0}, emitB[3] = {0, 0, 0};
         double q10[3] = {0., 0., 0.}, q20a[3] = {0., 0., 0.}, q20b[3] = {0., 0., 0.};
         float oq10[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < SP::W1; ++j) d1[j][0] = d1[j][1] = d1[j][2] = 0.f;
+        for (int j = 0; j < SP::W1; ++j) d1[j][0] = d1[j][1] = d1[j][2] = 0;
 #pragma unroll
-        for (int j = 0; j < SP::W2; ++j) d2[j][0] = d2[j][1] = d2[j][2] = 0.f;
+        for (int j = 0; j < SP::W2; ++j) d2[j][0] = d2[j][1] = d2[j][2] = 0;
 #pragma unroll
-        for (int j = 0; j < (SP::DA > 1 ? SP::DA - 1 : 1); ++j) fifoA[j][0] = fifoA[j][1] = fifoA[j][2] = 0.f;
+        for (int j = 0; j < NFA; ++j) fifoA[j][0] = fifoA[j][1] = fifoA[j][2] = 0;
 #pragma unroll
-        for (int j = 0; j < (SP::DB > 1 ? SP::DB - 1 : 1); ++j) fifoB[j][0] = fifoB[j][1] = fifoB[j][2] = 0.f;
+        for (int j = 0; j < NFB; ++j) fifoB[j][0] = fifoB[j][1] = fifoB[j][2] = 0;
 
-        // byte offsets are relative to p.src; reads are whole aligned words inside the batch
-        const long long src_mis = (long long)(reinterpret_cast<uintptr_t>(p.src) & 3);
-        const long long src_hi = ((long long)(frame_px * 3) * p.frames + src_mis + 3) & ~3ll;
-        int my_o = 0;
+        // this lane's rows: (a) the feed row y+DYF, first wanted byte at chunk 0 (relative to
+        // p.src, advances 96 bytes per chunk); (b) the output row y, byte offset in the frame of
+        // the pixel processed at step 0 of chunk 0 (may be negative), also +96 per chunk
+        const long long feed0 = (long long)(frame_px * 3 * f) +
+                                ((long long)(y + DYF) * W + (-SP::BMAX - SP::S * lane + BF)) * 3 +
+                                src_mis;
+        const int my_o = (int)(feed0 & 3);
+        const long long out0 = ((long long)y * W + (-SP::BMAX - SP::S * lane)) * 3;
+        const int my_m = (int)((reinterpret_cast<uintptr_t>(dst_f) + (unsigned long long)out0) & 3);
+
+        // rows of chunk `c` -> st.inw[c & 1] (asynchronous; completion via cp_async_wait)
+        auto issue_rows = [&](int c) {
+            long long gb = (long long)(frame_px * 3 * f) +
+                           ((long long)(y0 + DYF) * W + ((c << 5) - SP::BMAX + BF)) * 3 + src_mis;
+            unsigned *dstw = &st.inw[c & 1][0][lane];
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r, gb += row_step, dstw += 25) {
+                const long long wa = (gb & ~3ll) + 4 * lane;
+                const bool ok = wa >= 0 && wa + 4 <= src_hi;
+                if (lane < 25) cp_async4(dstw, p.src - src_mis + (ok ? wa : 0), ok);
+            }
+            cp_async_commit();
+        };
+        issue_rows(0);
 
 #pragma unroll 1
         for (int ch = 0; ch < NCH; ++ch) {
+#ifdef DP_WAVE_TIMING
+            long long _tick = clock64();
+#endif
             const int t0 = ch << 5;
             const int x00 = t0 - SP::BMAX;        // lane 0's x at the first step of the chunk
-            // this lane's row: byte offset (from p.src) of its first wanted column
-            const long long gb0_lane = (long long)(frame_px * 3 * f) +
-                                       ((long long)(y0 + lane + DYF) * W +
-                                        (x00 - SP::S * lane + BF)) * 3 + src_mis;
+            if (ch + 1 < NCH)
+                issue_rows(ch + 1);
+            else
+                cp_async_commit();                // keep one group per chunk in flight
 
             // ---- wait until the band above has published everything this chunk reads ------
             if (band > 0) {
-                const int need = min(x00 + 31 + SP::S, W + SP::AMAX);
+                const int need = min(t0 + 32, W + SP::BMAX);
                 if (need > avail) {
                     int v = 0;
                     for (unsigned spins = 0;; ++spins) {
                         if (lane == 0) v = ld_poll(prog_in);
                         v = __shfl_sync(FULL, v, 0);
                         if (v >= need) break;
-                        __nanosleep(200);
+                        __nanosleep(100);
                         if (spins > (1u << 24)) __trap();  // protocol bug -> error, not a hang
                     }
                     avail = v;
                 }
             }
+            DP_TICK(0);
 
-            // ---- stage the chunk's inputs ---------------------------------------------
+            // ---- lane 0's streams for the chunk: step j of the chunk is handled by lane j ----
             {
-                // lane 0's streams: column of step j is x00 + j
                 const int ca = x00 + lane, cb = ca + SP::B1;
-                float ha[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                const bool oka = ca >= 0 && ca < W;
+                const bool okb = SP::ROWS3 && cb >= 0 && cb < W;
+                T ha[6] = {0, 0, 0, 0, 0, 0};
                 if (band == 0) {
-                    if (ca >= 0 && ca < W) {
+                    if (oka) {
                         const uint8_t *q = src_f + ((size_t)y0 * W + ca) * 3;
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) ha[c] = (float)s_lut[q[c]];
+                        for (int c = 0; c < 3; ++c) ha[c] = s_lut[q[c]];
                     }
-                    if (SP::ROWS3 && y0 + 1 < H && cb >= 0 && cb < W) {
+                    if (okb && y0 + 1 < H) {
                         const uint8_t *q = src_f + ((size_t)(y0 + 1) * W + cb) * 3;
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) ha[3 + c] = (float)s_lut[q[c]];
+                        for (int c = 0; c < 3; ++c) ha[3 + c] = s_lut[q[c]];
                     }
                 } else {
-                    if (ca >= 0 && ca < W) {
+                    float hv[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) ha[c] = __ldcg(hin + 3 * ca + c);
-                    }
-                    if (SP::ROWS3 && cb >= 0 && cb < W) {
+                    for (int c = 0; c < NS; ++c) hv[c] = __ldcg(hin + (size_t)c * TPAD + t0 + lane);
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) ha[3 + c] = __ldcg(hin + 3 * (W + cb) + c);
+                    for (int c = 0; c < 3; ++c) {
+                        ha[c] = oka ? (T)hv[c] : (T)0;
+                        if (SP::ROWS3) ha[3 + c] = okb ? (T)hv[3 + c] : (T)0;
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < 6; ++c) st.hin[lane][c] = ha[c];
-                // raw-pixel feed: for row r the 96 bytes of columns col0_r .. col0_r+31, fetched
-                // as the (up to 25) aligned words that contain them; bytes of columns outside the
-                // image belong to targets that do not exist and are never used
-                {
-                    const long long row_step = (long long)W * 3 - 3 * SP::S;
-                    long long gb = (long long)(frame_px * 3 * f) +
-                                   ((long long)(y0 + DYF) * W + (x00 + BF)) * 3 + src_mis;
-#pragma unroll 4
-                    for (int r = 0; r < 32; ++r, gb += row_step) {
-                        const long long wa = (gb & ~3ll) + 4 * lane;
-                        unsigned v = 0;
-                        if (lane < 25 && wa >= 0 && wa + 4 <= src_hi)
-                            v = __ldg(reinterpret_cast<const unsigned *>(p.src - src_mis + wa));
-                        if (lane < 27) st.inw[r][lane] = v;
-                    }
-                    my_o = (int)((gb0_lane) & 3);
-                }
+                for (int c = 0; c < NS; ++c) st.hin[lane][c] = ha[c];
             }
+            cp_async_wait<1>();   // this chunk's rows have landed (the next chunk's may still fly)
             __syncwarp();
+            DP_TICK(1);
 
             // ---- 32 pixel steps --------------------------------------------------------
+            const unsigned char *feed = reinterpret_cast<const unsigned char *>(st.inw[ch & 1][lane]) + my_o;
+            unsigned char *ob = st.outb[lane] + my_m;
 #pragma unroll 1
             for (int sidx = 0; sidx < 32; ++sidx) {
                 const int x = x00 + sidx - SP::S * lane;
-                float fa[3], fb[3];
+#ifdef DP_WAVE_TIMING
+                long long _stick = clock64();
+#endif
+                T fa[3], fb[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
-                    const float ra = __shfl_up_sync(FULL, emitA[c], 1);
-                    const float rb = __shfl_up_sync(FULL, emitB[c], 1);
+                    const T ra = __shfl_up_sync(FULL, emitA[c], 1);
                     if (SP::DA > 1) {
                         fa[c] = fifoA[0][c];
 #pragma unroll
                         for (int j = 0; j + 1 < SP::DA - 1; ++j) fifoA[j][c] = fifoA[j + 1][c];
-                        fifoA[SP::DA - 2][c] = ra;
+                        fifoA[NFA - 1][c] = ra;
                     } else {
                         fa[c] = ra;
                     }
-                    if (SP::DB > 1) {
-                        fb[c] = fifoB[0][c];
+                    if (SP::ROWS3) {
+                        const T rb = __shfl_up_sync(FULL, emitB[c], 1);
+                        if (SP::DB > 1) {
+                            fb[c] = fifoB[0][c];
 #pragma unroll
-                        for (int j = 0; j + 1 < SP::DB - 1; ++j) fifoB[j][c] = fifoB[j + 1][c];
-                        fifoB[SP::DB - 2][c] = rb;
+                            for (int j = 0; j + 1 < SP::DB - 1; ++j) fifoB[j][c] = fifoB[j + 1][c];
+                            fifoB[NFB - 1][c] = rb;
+                        } else {
+                            fb[c] = rb;
+                        }
                     } else {
-                        fb[c] = rb;
+                        fb[c] = 0;
                     }
                 }
                 if (lane == 0) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         fa[c] = st.hin[sidx][c];
-                        fb[c] = st.hin[sidx][3 + c];
+                        if (SP::ROWS3) fb[c] = st.hin[sidx][3 + c];
                     }
                 }
                 {
-                    const unsigned char *pb =
-                        reinterpret_cast<const unsigned char *>(st.inw[lane]) + my_o + 3 * sidx;
-                    unsigned b0 = pb[0], b1 = pb[1], b2 = pb[2];
-                    if (p.has_lut) {
-                        b0 = s_lut[b0];
-                        b1 = s_lut[b1];
-                        b2 = s_lut[b2];
-                    }
-                    float *top = SP::ROWS3 ? d2[SP::W2 - 1] : d1[SP::W1 - 1];
+                    const unsigned char *pb = feed + 3 * sidx;
+                    T *top = SP::ROWS3 ? d2[SP::W2 - 1] : d1[SP::W1 - 1];
                     if (SP::ROWS3) {
 #pragma unroll
                         for (int c = 0; c < 3; ++c) d1[SP::W1 - 1][c] = fb[c];
                     }
-                    top[0] = (float)b0;
-                    top[1] = (float)b1;
-                    top[2] = (float)b2;
+                    if constexpr (sizeof(T) == 8) {
+                        top[0] = lds_f64(lut_a + 8u * pb[0]);
+                        top[1] = lds_f64(lut_a + 8u * pb[1]);
+                        top[2] = lds_f64(lut_a + 8u * pb[2]);
+                    } else {
+                        top[0] = lds_f32(lut_a + 4u * pb[0]);
+                        top[1] = lds_f32(lut_a + 4u * pb[1]);
+                        top[2] = lds_f32(lut_a + 4u * pb[2]);
+                    }
                 }
 
+                DP_STICK(0);
                 const bool active = rowok && x >= 0 && x < W;
                 if (active) {
                     int bi;
-                    if (!SP::OSTRO) {
+                    if constexpr (!SP::OSTRO) {
                         double v[3], e[3];
+                        float vf[3];
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            float a = fa[c];
-                            if (SP::H20) a = acc_f64(a, q20a[c]);
-                            if (SP::H10) a = acc_f64(a, q10[c]);
-                            a = fminf(fmaxf(a, 0.f), 255.f);
-                            v[c] = (double)a;
+                            double a = fa[c];
+                            if (SP::H20) a = acc_r(a, q20a[c]);
+                            if (SP::H10) a = acc_r(a, q10[c]);
+                            v[c] = clamp255(a);
+                            vf[c] = narrow_nonneg(v[c]);
                         }
-                        bi = nearest_first(srch, v[0], v[1], v[2]);
+                        DP_STICK(1);
+                        bi = nearest_row<false>(P, srch, vf[0], vf[1], vf[2], v[0], v[1], v[2]);
+                        DP_STICK(2);
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) e[c] = __dsub_rn(v[c], (double)s_palf[3 * bi + c]);
+                        for (int c = 0; c < 3; ++c) e[c] = __dsub_rn(v[c], lds_f64(pal_a + 24u * bi + 8u * c));
                         apply_taps<V>(std::make_integer_sequence<int, SP::N>{}, e, q10, q20a, q20b,
                                       d1, d2);
+                        DP_STICK(3);
                     } else {
                         float ov[3], er[3];
 #pragma unroll
@@ -543,15 +789,17 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
                             float a = __fadd_rn(fa[c], oq10[c]);
                             ov[c] = fminf(fmaxf(a, 0.f), 255.f);
                         }
-                        bi = nearest_kd(P, srch, (double)ov[0], (double)ov[1], (double)ov[2]);
+                        bi = nearest_row<true>(P, srch, ov[0], ov[1], ov[2], (double)ov[0],
+                                               (double)ov[1], (double)ov[2]);
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], s_palf[3 * bi + c]);
+                        for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], lds_f32(palf_a + 12u * bi + 4u * c));
                         float lum = __fmul_rn(0.299f, ov[0]);
                         lum = __fadd_rn(lum, __fmul_rn(0.587f, ov[1]));
                         lum = __fadd_rn(lum, __fmul_rn(0.114f, ov[2]));
                         lum = fminf(fmaxf(lum, 0.f), 255.f);
-                        const int li = (int)lum;
-                        const float w0 = s_ow[4 * li], w1 = s_ow[4 * li + 1], w2 = s_ow[4 * li + 2];
+                        const int li = __float_as_int(__fadd_rz(lum, 8388608.0f)) & 255;  // int(lum)
+                        const float4 ow4 = lds_f32x4(ow_a + 16u * li);
+                        const float w0 = ow4.x, w1 = ow4.y, w2 = ow4.z;
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
                             oq10[c] = __fmul_rn(er[c], w0);
@@ -559,7 +807,12 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
                             d1[0][c] = __fadd_rn(d1[0][c], __fmul_rn(er[c], w1));
                         }
                     }
-                    st.out[lane][sidx] = (unsigned char)bi;
+                    const unsigned oc = lds_u32(orgb_a + 4u * bi);
+                    ob[3 * sidx] = (unsigned char)oc;
+                    ob[3 * sidx + 1] = (unsigned char)(oc >> 8);
+                    ob[3 * sidx + 2] = (unsigned char)(oc >> 16);
+                    if (idx_f) st.outi[lane][sidx] = (unsigned char)bi;
+                    DP_STICK(4);
                 } else {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
@@ -573,13 +826,13 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     emitA[c] = d1[0][c];
-                    emitB[c] = SP::ROWS3 ? d2[0][c] : 0.f;
+                    emitB[c] = SP::ROWS3 ? d2[0][c] : (T)0;
                 }
                 if (lane == 31) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         st.hout[sidx][c] = emitA[c];
-                        st.hout[sidx][3 + c] = emitB[c];
+                        if (SP::ROWS3) st.hout[sidx][3 + c] = emitB[c];
                     }
                 }
 #pragma unroll
@@ -588,7 +841,7 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
                     for (int c = 0; c < 3; ++c) d1[j][c] = d1[j + 1][c];
                 }
 #pragma unroll
-                for (int c = 0; c < 3; ++c) d1[SP::W1 - 1][c] = 0.f;
+                for (int c = 0; c < 3; ++c) d1[SP::W1 - 1][c] = 0;
                 if (SP::ROWS3) {
 #pragma unroll
                     for (int j = 0; j + 1 < SP::W2; ++j) {
@@ -596,50 +849,80 @@ __global__ void __launch_bounds__(WAVE_THREADS) k_diffuse_wave(const WaveParams 
                         for (int c = 0; c < 3; ++c) d2[j][c] = d2[j + 1][c];
                     }
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) d2[SP::W2 - 1][c] = 0.f;
+                    for (int c = 0; c < 3; ++c) d2[SP::W2 - 1][c] = 0;
                 }
+                DP_STICK(5);
             }
             __syncwarp();
+            DP_TICK(2);
 
-            // ---- write the chunk back ----------------------------------------------------
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-                const int yr = y0 + r;
-                const int col = x00 + lane - SP::S * r;
-                if (yr < H && col >= 0 && col < W) {
-                    const unsigned bi = st.out[r][lane];
-                    const unsigned oc = s_orgb[bi];
-                    uint8_t *o = dst_f + ((size_t)yr * W + col) * 3;
-                    o[0] = (uint8_t)oc;
-                    o[1] = (uint8_t)(oc >> 8);
-                    o[2] = (uint8_t)(oc >> 16);
-                    if (idx_f) idx_f[(size_t)yr * W + col] = (uint8_t)bi;
-                }
-            }
+            // ---- hand the outgoing streams to the band below first (it may be waiting) --------
             if (has_next) {
-                // lane 31's x at step j of this chunk
+                // lane j holds step j: lane 31 was at column x31; stream A carries column
+                // x31 - A1, stream B column x31 - A2; both are stored at the CONSUMER's step index
                 const int x31 = x00 + lane - SP::S * 31;
                 const int xa = x31 - SP::A1;
                 if (xa >= 0 && xa < W) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) __stcg(hout + 3 * xa + c, st.hout[lane][c]);
+                    for (int c = 0; c < 3; ++c)
+                        __stcg(hout + (size_t)c * TPAD + xa + SP::BMAX, to_f32(st.hout[lane][c]));
                 }
                 if (SP::ROWS3) {
                     const int xb = x31 - SP::A2;
                     if (xb >= 0 && xb < W) {
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) __stcg(hout + 3 * (W + xb) + c, st.hout[lane][3 + c]);
+                        for (int c = 0; c < 3; ++c)
+                            __stcg(hout + (size_t)(3 + c) * TPAD + xb + SP::BMAX - SP::B1,
+                                   to_f32(st.hout[lane][3 + c]));
                     }
                 }
                 __threadfence();
                 __syncwarp();
                 if (lane == 0) {
-                    const int prog = (ch == NCH - 1) ? 0x3fffffff : (x00 + 32 - SP::S * 31);
+                    // every consumer step index below this one is complete in both streams
+                    const int prog = (ch == NCH - 1) ? 0x3fffffff : (t0 + 32 - SP::S * 32 + 1);
                     st_release(prog_out, prog);
+                    // the band below can run its first chunk once chunk S of this band is out
+                    if (ch == min(SP::S + p.slack, NCH - 1)) {
+                        const int pos = atomicAdd(p.qctrl + 1, 1);
+                        st_release(p.queue + pos, unit + 2);   // (unit + 1) + 1
+                    }
                 }
             }
+
+            // ---- write the chunk's pixels: each lane stores its own row -------------------
+            {
+                const int xfirst = x00 - SP::S * lane;          // column of this lane's step 0
+                const long long obyte = out0 + 96ll * ch;       // its byte offset in the frame
+                unsigned *ow = reinterpret_cast<unsigned *>(st.outb[lane]);
+                if (rowok && xfirst + 31 >= 0 && xfirst - 1 < W) {
+                    const bool lead_ok = xfirst >= 1 || (xfirst == 0 && my_m == 0);
+                    if (lead_ok && xfirst + 32 < W) {
+                        unsigned *g = reinterpret_cast<unsigned *>(dst_f + (obyte - my_m));
+#pragma unroll
+                        for (int wd = 0; wd < 24; ++wd) g[wd] = ow[wd];
+                    } else {
+                        // row start / row end: byte by byte; k < my_m are the carried bytes of
+                        // pixel xfirst-1
+                        const unsigned char *sb = st.outb[lane];
+                        for (int k = 0; k < my_m + 96; ++k) {
+                            const int j = k - my_m;
+                            const int xp = xfirst + (j >= 0 ? j / 3 : -1);
+                            if (xp >= 0 && xp < W) dst_f[obyte + j] = sb[k];
+                        }
+                    }
+                    if (idx_f) {
+                        for (int j = 0; j < 32; ++j)
+                            if (xfirst + j >= 0 && xfirst + j < W)
+                                idx_f[(size_t)y * W + xfirst + j] = st.outi[lane][j];
+                    }
+                }
+                ow[0] = ow[24];   // trailing partial word -> leading bytes of the next chunk
+            }
             __syncwarp();
+            DP_TICK(3);
         }
+        cp_async_wait<0>();
     }
 }
 
@@ -689,8 +972,9 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
     __syncthreads();
     Search srch;
     srch.table = P->ed_table;
-    srch.ovf = P->ed_ovf;
+    srch.P = P;
     srch.s_pal = s_pal;
+    srch.rows_a = 0;   // exact search only
 
     const int W = p.w, H = p.h;
     const size_t frame_px = (size_t)W * H;
@@ -720,7 +1004,8 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
                             double tv = (double)px[c];
                             v[c] = tv < 0.0 ? 0.0 : (tv > 255.0 ? 255.0 : tv);
                         }
-                        bi = nearest_first(srch, v[0], v[1], v[2]);
+                        bi = nearest_first_exact(srch, cell_of((float)v[0], (float)v[1], (float)v[2]),
+                                                 v[0], v[1], v[2]);
                         for (int c = 0; c < 3; ++c) e[c] = __dsub_rn(v[c], (double)s_palf[3 * bi + c]);
                         for (int k = 0; k < ntaps; ++k) {
                             const int nx = x + s_tdx[k] * dir;
@@ -735,7 +1020,8 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
                             float a = px[c];
                             ov[c] = a < 0.f ? 0.f : (a > 255.f ? 255.f : a);
                         }
-                        bi = nearest_kd(P, srch, (double)ov[0], (double)ov[1], (double)ov[2]);
+                        bi = nearest_kd_exact(P, srch, cell_of(ov[0], ov[1], ov[2]), (double)ov[0],
+                                              (double)ov[1], (double)ov[2]);
                         for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], s_palf[3 * bi + c]);
                         float lum = __fmul_rn(0.299f, ov[0]);
                         lum = __fadd_rn(lum, __fmul_rn(0.587f, ov[1]));
@@ -780,6 +1066,9 @@ struct Workspace {
     int alloc(size_t bytes, cudaStream_t s)
     {
         st = s;
+        int dev = 0;
+        DP_CUDA(cudaGetDevice(&dev));
+        if (dp_retain_pool(dev)) return 1;
         DP_CUDA(cudaMallocAsync(&ptr, bytes ? bytes : 1, s));
         return 0;
     }
@@ -789,16 +1078,33 @@ struct Workspace {
     }
 };
 
+__global__ void k_wave_init(int *progress, int *qctrl, int *queue, int units, int frames, int nbands)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < units; i += gridDim.x * blockDim.x) {
+        progress[i] = 0;
+        queue[i] = i < frames ? i * nbands + 1 : 0;   // band 0 of frame i, stored as unit + 1
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        qctrl[0] = 0;
+        qctrl[1] = frames;
+    }
+}
+
 template <int V>
 int launch_wave(const WaveParams &p, cudaStream_t st)
 {
     // Few bands (a single image, a small batch): 4-warp blocks so that the bands spread over
-    // the SM sub-partitions (the kernel is latency-bound per warp).  Many bands: 8-warp blocks,
-    // which share the tables and reach the occupancy limit set by registers.
+    // the SM sub-partitions (a lone warp is latency-bound).  Many bands: one 8- or 12-warp block
+    // per SM, which shares the tables.
+    using Stage = WarpStageT<typename StateOf<V>::T, Spec<V>::ROWS3 ? 6 : 3>;
     const int sms = dp_num_sms();
-    const int warps = (p.total_units <= sms * 12) ? 4 : WAVE_WARPS;
-    const size_t smem = DP_MAX_COLORS * 3 * 8 + 4096 * 8 + DP_MAX_COLORS * 3 * 4 + 256 * 4 * 4 +
-                        256 * 4 + 256 + sizeof(WarpStage) * warps;
+    int warps = (p.total_units <= sms * 8) ? 4 : wave_max_warps<V>();
+    if (const char *ev = getenv("DP_WAVE_WARPS")) {   // tuning knob (tools/): 1..max warps per block
+        const int w = atoi(ev);
+        if (w >= 1 && w <= wave_max_warps<V>()) warps = w;
+    }
+    const size_t smem = DP_MAX_COLORS * 3 * 8 + (DP_MAX_COLORS + 1) * 16 + 256 * 8 +
+                        DP_MAX_COLORS * 3 * 4 + 256 * 4 * 4 + 256 * 4 + sizeof(Stage) * warps;
     DP_CUDA(cudaFuncSetAttribute(k_diffuse_wave<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     int per_sm = 0;
@@ -811,6 +1117,30 @@ int launch_wave(const WaveParams &p, cudaStream_t st)
     k_diffuse_wave<V><<<grid, warps * 32, smem, st>>>(p);
     DP_LAUNCH_CHECK();
     return 0;
+}
+
+template <int V>
+constexpr int wave_extra_steps()
+{
+    return Spec<V>::AMAX + Spec<V>::BMAX + Spec<V>::S * 31;
+}
+
+// stream length = the kernel's step count rounded up to whole chunks (see k_diffuse_wave)
+int wave_tpad(int variant, int w)
+{
+    int extra;
+    switch (variant) {
+        case DP_ED_FLOYD_STEINBERG: extra = wave_extra_steps<DP_ED_FLOYD_STEINBERG>(); break;
+        case DP_ED_JJN: extra = wave_extra_steps<DP_ED_JJN>(); break;
+        case DP_ED_STUCKI: extra = wave_extra_steps<DP_ED_STUCKI>(); break;
+        case DP_ED_BURKES: extra = wave_extra_steps<DP_ED_BURKES>(); break;
+        case DP_ED_ATKINSON: extra = wave_extra_steps<DP_ED_ATKINSON>(); break;
+        case DP_ED_SIERRA: extra = wave_extra_steps<DP_ED_SIERRA>(); break;
+        case DP_ED_SIERRA_TWO_ROW: extra = wave_extra_steps<DP_ED_SIERRA_TWO_ROW>(); break;
+        case DP_ED_SIERRA_LITE: extra = wave_extra_steps<DP_ED_SIERRA_LITE>(); break;
+        default: extra = wave_extra_steps<V_OSTRO>(); break;
+    }
+    return ((w + extra + 31) >> 5) << 5;
 }
 
 int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, int w, int variant,
@@ -870,12 +1200,17 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
     p.K = pal->dev.K;
     p.ostro_w = ostro_w;
     Workspace hand, flags;
-    if (hand.alloc((size_t)units * 2 * w * 3 * sizeof(float), st)) return 1;
-    if (flags.alloc((size_t)(units + 1) * sizeof(int), st)) return 1;
-    DP_CUDA(cudaMemsetAsync(flags.ptr, 0, (size_t)(units + 1) * sizeof(int), st));
+    if (hand.alloc((size_t)units * 6 * (size_t)wave_tpad(variant, w) * sizeof(float), st)) return 1;
+    if (flags.alloc((size_t)(2 * units + 2) * sizeof(int), st)) return 1;
     p.hand = static_cast<float *>(hand.ptr);
     p.progress = static_cast<int *>(flags.ptr);
-    p.ticket = p.progress + units;
+    p.qctrl = p.progress + units;
+    p.queue = p.qctrl + 2;
+    p.slack = 0;   // measured: extra lead only delays the successor (9.6 ms vs 11.0 ms at 32 frames)
+    if (const char *ev = getenv("DP_WAVE_SLACK")) p.slack = atoi(ev) > 0 ? atoi(ev) : 0;   // tuning knob
+    k_wave_init<<<(int)((units + 255) / 256 < 1024 ? (units + 255) / 256 : 1024), 256, 0, st>>>(
+        p.progress, p.qctrl, p.queue, (int)units, frames, p.nbands);
+    DP_LAUNCH_CHECK();
     switch (variant) {
         case DP_ED_FLOYD_STEINBERG: return launch_wave<DP_ED_FLOYD_STEINBERG>(p, st);
         case DP_ED_JJN: return launch_wave<DP_ED_JJN>(p, st);
@@ -890,6 +1225,20 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
 }
 
 }  // namespace
+
+#ifdef DP_WAVE_TIMING
+extern "C" int dp_debug_wave_timing(unsigned long long *out, int reset)
+{
+    DP_CUDA(cudaMemcpyFromSymbol(out, g_wave_timing, sizeof(unsigned long long) * (128 * 4 + 4)));
+    DP_CUDA(cudaMemcpyFromSymbol(out + 128 * 4 + 4, g_step_timing, sizeof(unsigned long long) * 16));
+    if (reset) {
+        static unsigned long long zeros[128 * 4 + 4];
+        DP_CUDA(cudaMemcpyToSymbol(g_wave_timing, zeros, sizeof(zeros)));
+        DP_CUDA(cudaMemcpyToSymbol(g_step_timing, zeros, sizeof(unsigned long long) * 16));
+    }
+    return 0;
+}
+#endif
 
 extern "C" int dp_error_diffusion(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h,
                                   int w, int variant, int serpentine, uint8_t *dst_rgb,

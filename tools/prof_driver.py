@@ -46,14 +46,18 @@ def main():
         plan = engine.Plan(a.mode, params, a.h, a.w)
     dst = _capi.DeviceBuffer(a.frames * plan.out_h * plan.out_w * 3)
     import time
+    ts = []
     for r in range(a.reps):
         _capi.sync()
         t0 = time.perf_counter()
         plan.run(pal, src.ptr, a.frames, dst.ptr, None, None)
         _capi.sync()
-        dt = time.perf_counter() - t0
-        px = a.frames * a.h * a.w
-        print(f"rep {r}: {dt*1e3:.3f} ms  {px/dt/1e9:.2f} Gpx/s  {6*px/dt/1e9:.1f} GB/s(alg)")
+        ts.append(time.perf_counter() - t0)
+    px = a.frames * a.h * a.w
+    ts = sorted(ts[1:] or ts)
+    dt = ts[len(ts) // 2]
+    print(f"{a.mode} {a.params} {a.h}x{a.w} x{a.frames} K={a.k}: median {dt*1e3:.3f} ms (min {ts[0]*1e3:.3f}, max "
+          f"{ts[-1]*1e3:.3f}, n={len(ts)})  {px/dt/1e9:.2f} Gpx/s  {6*px/dt/1e9:.1f} GB/s(alg)")
 
 
 if __name__ == "__main__":
