@@ -3,7 +3,9 @@
 
 #include <vector>
 
-#include "dp_common.cuh"
+#include <algorithm>
+
+#include "dp_search.cuh"
 
 // ---------------------------------------------------------------------------------------
 // errors
@@ -349,6 +351,73 @@ int build_ed_table(const double *d_pal64, int K, PalDev &d, dp_palette *h)
     return 0;
 }
 
+// Every byte colour with an exact distance tie among its three nearest rows -> scipy's answers
+// for query(k=1) and query(k=2) (format: dp_common.cuh, tie_table).  One block per (r, g), one
+// thread per b.  `count` may run past `cap`; the host then discards the table.
+__global__ void __launch_bounds__(256) k_tie_scan(const PalDev *__restrict__ P, int K, uint2 *out,
+                                                  unsigned cap, unsigned *count)
+{
+    __shared__ int4 s_coef[DP_MAX_COLORS];
+    for (int i = threadIdx.x; i < K; i += 256) s_coef[i] = P->coef[i];
+    __syncthreads();
+    const int r = blockIdx.x >> 8, g = blockIdx.x & 255, b = threadIdx.x;
+    Top3 t;
+    top3_init(t);
+    for (int i = 0; i < K; ++i) top3_push(t, key_of(s_coef[i], r, g, b));
+    const int s1 = t.m1 >> 8, s2 = t.m2 >> 8, s3 = t.m3 >> 8;
+    if (!(s1 == s2 || (K >= 3 && s2 == s3))) return;
+    int o1[1], o2[2];
+    double os[2];
+    kd_emulate<1>(P, (double)r, (double)g, (double)b, o1, os);
+    kd_emulate<2>(P, (double)r, (double)g, (double)b, o2, os);
+    const unsigned pos = atomicAdd(count, 1u);
+    if (pos < cap)
+        out[pos] = make_uint2((unsigned)r | ((unsigned)g << 8) | ((unsigned)b << 16) |
+                                  ((unsigned)o1[0] << 24),
+                              (unsigned)o2[0] | ((unsigned)o2[1] << 8));
+}
+
+int build_tie_table(PalDev &d, dp_palette *h, const void *dev_paldev, int K)
+{
+    d.tie_table = nullptr;
+    d.tie_n = -1;
+    const unsigned cap = 1u << 21;   // 2M tie colours (16 MB); beyond that replay in the kernels
+    uint2 *dout = nullptr;
+    unsigned *dcnt = nullptr;
+    if (cudaMalloc(&dout, (size_t)cap * 8) != cudaSuccess) return 0;
+    if (cudaMalloc(&dcnt, 4) != cudaSuccess) {
+        cudaFree(dout);
+        return 0;
+    }
+    cudaMemset(dcnt, 0, 4);
+    k_tie_scan<<<65536, 256>>>(static_cast<const PalDev *>(dev_paldev), K, dout, cap, dcnt);
+    unsigned n = 0;
+    bool ok = cudaMemcpy(&n, dcnt, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+    cudaFree(dcnt);
+    if (!ok || n > cap) {
+        cudaFree(dout);
+        return ok ? 0 : 1;
+    }
+    std::vector<uint2> host(n);
+    if (n && cudaMemcpy(host.data(), dout, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaFree(dout);
+        return 1;
+    }
+    cudaFree(dout);
+    std::sort(host.begin(), host.end(),
+              [](const uint2 &a, const uint2 &b) { return (a.x & 0xffffffu) < (b.x & 0xffffffu); });
+    void *dt = nullptr;
+    if (cudaMalloc(&dt, (size_t)(n ? n : 1) * 8) != cudaSuccess) return 0;
+    if (n && cudaMemcpy(dt, host.data(), (size_t)n * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(dt);
+        return 1;
+    }
+    d.tie_table = static_cast<const uint2 *>(dt);
+    d.tie_n = (int)n;
+    h->tie_table = dt;
+    return 0;
+}
+
 template <typename T>
 size_t put(std::vector<uint8_t> &buf, const T *src, size_t n, size_t align = 16)
 {
@@ -564,12 +633,65 @@ extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out
         d.thr_cells = cells;
         h->thr_table = dt;
         h->thr_ovf = dovf;
+        if (K <= 30) {
+            // compact 32^3 table for k_thresh_v4 (format: dp_common.cuh)
+            std::vector<uint32_t> m3;
+            const std::vector<uint32_t> *mk = &hmask;
+            if (shift != 3) {
+                uint32_t *dm = nullptr;
+                m3.resize((size_t)32768 * 8);
+                bool ok4 = cudaMalloc(&dm, (size_t)32768 * 32) == cudaSuccess;
+                if (ok4) {
+                    k_thr_masks<<<32768, 256>>>(d.coef, K, 3, dm);
+                    ok4 = cudaMemcpy(m3.data(), dm, (size_t)32768 * 32, cudaMemcpyDeviceToHost) ==
+                          cudaSuccess;
+                }
+                if (dm) cudaFree(dm);
+                mk = ok4 ? &m3 : nullptr;
+            }
+            void *d4 = nullptr;
+            if (mk) {
+                std::vector<uint32_t> t4(32768);
+                for (int c = 0; c < 32768; ++c) {
+                    unsigned slot[4] = {(unsigned)K * 8u, (unsigned)K * 8u, (unsigned)K * 8u,
+                                        (unsigned)K * 8u};
+                    int cnt = 0;
+                    const uint32_t w0 = (*mk)[(size_t)c * 8];
+                    for (int i = 0; i < K; ++i)
+                        if (w0 >> i & 1u) {
+                            if (cnt < 4) slot[cnt] = (unsigned)i * 8u;
+                            ++cnt;
+                        }
+                    if (cnt > 4) slot[3] = 0xf8u;   // row 31: a pad row, and the overflow mark
+                    t4[c] = slot[0] | (slot[1] << 8) | (slot[2] << 16) | (slot[3] << 24);
+                }
+                if (cudaMalloc(&d4, 32768 * 4) == cudaSuccess &&
+                    cudaMemcpy(d4, t4.data(), 32768 * 4, cudaMemcpyHostToDevice) == cudaSuccess) {
+                    d.thr4_table = static_cast<const uint32_t *>(d4);
+                    h->thr4_table = d4;
+                } else if (d4) {
+                    cudaFree(d4);   // the v3 kernels still work without it
+                }
+            }
+        }
     }
+    d.tie_table = nullptr;
+    d.tie_n = -1;
     h->dev = d;
     if (cudaMemcpy(blob, &d, sizeof(d), cudaMemcpyHostToDevice) != cudaSuccess) {
         dp_set_error("palette upload failed");
         dp_palette_destroy(h);
         return 1;
+    }
+    if (integral && K >= 2) {
+        // the scan reads the palette through the descriptor just uploaded
+        if (build_tie_table(d, h, blob, K) ||
+            cudaMemcpy(blob, &d, sizeof(d), cudaMemcpyHostToDevice) != cudaSuccess) {
+            dp_set_error("palette tie table build failed: %s", cudaGetErrorString(cudaGetLastError()));
+            dp_palette_destroy(h);
+            return 1;
+        }
+        h->dev = d;
     }
     *out = h;
     return 0;
@@ -584,6 +706,8 @@ extern "C" int dp_palette_destroy(dp_palette *pal)
     if (pal->ed_ovf) cudaFree(pal->ed_ovf);
     if (pal->thr_table) cudaFree(pal->thr_table);
     if (pal->thr_ovf) cudaFree(pal->thr_ovf);
+    if (pal->thr4_table) cudaFree(pal->thr4_table);
+    if (pal->tie_table) cudaFree(pal->tie_table);
     if (pal->blob) cudaFree(pal->blob);
     delete pal;
     return 0;

@@ -69,6 +69,18 @@ struct PalDev {
     const uint8_t *thr_ovf;
     int thr_shift;   // 4 -> 16^3 cells, 3 -> 32^3 cells
     int thr_cells;
+    // compact top-2 table for the v4 threshold kernel (integral palettes with K <= 30): one u32
+    // per 8x8x8 colour cell = four candidate slots, each the byte offset row*8 of the row in the
+    // kernel's int2 row array (free slots: K*8, a pad row that never wins).  A cell with more
+    // than four candidates has 0xf8 (row 31, also a pad row) in its last slot.
+    const uint32_t *thr4_table;   // [32768] or null
+    // Exception table of the byte colours with an exact distance tie among their three nearest
+    // rows (integral palettes): scipy's answers, replayed once at palette creation.
+    //   x = colour (r | g<<8 | b<<16) | nearest row of query(k=1) << 24
+    //   y = first | second << 8 row of query(k=2)
+    // sorted by colour; tie_n < 0: not built (the kernels replay the KD-tree themselves).
+    const uint2 *tie_table;
+    int tie_n;
     // nearest-row candidate table for arbitrary real values in [0,255]^3 (diffusion modes):
     // 32^3 cells of 8x8x8; a row is dropped from a cell only if another row is strictly nearer
     // at EVERY point of the cell's closed box (exact linear test).  One 16-byte entry per cell =
@@ -93,6 +105,8 @@ struct dp_palette {
     void *cell_list;
     void *thr_table;
     void *thr_ovf;
+    void *thr4_table;
+    void *tie_table;
     void *ed_table;
     void *ed_ovf;   // one allocation: cells | offsets | lists
     float host_pal[DP_MAX_COLORS * 3];

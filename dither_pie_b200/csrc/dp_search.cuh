@@ -166,6 +166,36 @@ __device__ __noinline__ void kd_emulate(const PalDev *__restrict__ P, double x0,
 }
 
 // ---------------------------------------------------------------------------------------
+// Exact-tie answers for byte colours and integral palettes: binary search in the palette's
+// exception table (built by k_tie_scan at palette creation), KD-tree replay if there is none.
+// ---------------------------------------------------------------------------------------
+template <int KQ>
+__device__ __forceinline__ void tie_answer(const PalDev *__restrict__ P, int r, int g, int b, int *oi)
+{
+    const int n = P->tie_n;
+    if (n > 0) {
+        const unsigned key = (unsigned)r | ((unsigned)g << 8) | ((unsigned)b << 16);
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((__ldg(&P->tie_table[mid].x) & 0xffffffu) < key) lo = mid + 1; else hi = mid;
+        }
+        const uint2 e = __ldg(P->tie_table + lo);
+        if ((e.x & 0xffffffu) == key) {
+            if (KQ == 1) {
+                oi[0] = (int)(e.x >> 24);
+            } else {
+                oi[0] = (int)(e.y & 255u);
+                oi[1] = (int)((e.y >> 8) & 255u);
+            }
+            return;
+        }
+    }
+    double os[2];
+    kd_emulate<KQ>(P, (double)r, (double)g, (double)b, oi, os);
+}
+
+// ---------------------------------------------------------------------------------------
 // Integer fast path: keys  key_i = (score_i << 8) | i  with
 //   score_i = |p_i|^2 - 2 v.p_i = dist_i - |v|^2   (exact, |score| <= 195075)
 // computed as three IMADs from the precomputed coefficients; top-3 kept by min/max.

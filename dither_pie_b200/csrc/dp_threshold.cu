@@ -11,6 +11,8 @@
 // the palette coefficients, threshold matrix, gamma LUT and output colours live in shared
 // memory for the lifetime of the (persistent) block.
 // Algorithmic bytes: 3 read + 3 written per pixel; HBM-bound by design.
+#include <stdlib.h>
+
 #include "dp_search.cuh"
 
 namespace {
@@ -65,6 +67,8 @@ struct ThreshParams {
     const int *ytab, *xtab;
     int fast;        // 0 generic kernel, 1 fast kernel with the candidate table in shared, 2 in global
     int thr_cells;
+    int wm;          // v4: width of the widened threshold matrix in shared memory (multiple of 16)
+    FastDiv dwm, dnpix;
 };
 
 // IGN threshold (:541-549): f32, one rounding per numpy ufunc, no contraction.
@@ -109,11 +113,10 @@ __device__ __forceinline__ int pick_int(const PalDev *P, const int4 *s_coef, int
     if (KIND != DP_THRESH_NONE) amb = amb || (K >= 3 && s2 == s3);
     if (amb) {
         int oi[2];
-        double os[2];
         if (KIND == DP_THRESH_NONE)
-            kd_emulate<1>(P, (double)r, (double)g, (double)b, oi, os);
+            tie_answer<1>(P, r, g, b, oi);
         else
-            kd_emulate<2>(P, (double)r, (double)g, (double)b, oi, os);
+            tie_answer<2>(P, r, g, b, oi);
         i1 = oi[0];
         if (KIND != DP_THRESH_NONE) i2 = oi[1];
         // the multiset of distances is unchanged: (s1, s2) stay valid
@@ -297,14 +300,16 @@ __device__ __noinline__ int pick_tie(const PalDev *P, unsigned v, float thr)
 {
     const int r = v & 255u, g = (v >> 8) & 255u, b = (v >> 16) & 255u;
     int oi[2];
-    double os[2];
     if (KIND == DP_THRESH_NONE) {
-        kd_emulate<1>(P, (double)r, (double)g, (double)b, oi, os);
+        tie_answer<1>(P, r, g, b, oi);
         return oi[0];
     }
-    kd_emulate<2>(P, (double)r, (double)g, (double)b, oi, os);
-    // integer distances are exact in f64
-    return factor_le_int((int)os[0], (int)os[1], thr) ? oi[0] : oi[1];
+    tie_answer<2>(P, r, g, b, oi);
+    // the two smallest distances as a multiset do not depend on the tie order
+    const int4 c0 = P->coef[oi[0]], c1 = P->coef[oi[1]];
+    const int vv = r * r + g * g + b * b;
+    const int n0 = (key_of(c0, r, g, b) >> 8) + vv, n1 = (key_of(c1, r, g, b) >> 8) + vv;
+    return factor_le_int(min(n0, n1), max(n0, n1), thr) ? oi[0] : oi[1];
 }
 
 __device__ __noinline__ bool factor_le_f64_slow(int n1, int n2, float thr)
@@ -506,6 +511,288 @@ __global__ void __launch_bounds__(THREADS) k_thresh_fast(const ThreshParams p)
 }
 
 // ---------------------------------------------------------------------------------------
+// v4: identity geometry, integral palette with K <= 30, image width a multiple of 16.
+//
+// Uniform cost per pixel, no data-dependent control flow outside the rare slow path:
+//   * the 32^3 top-2 candidate table (one u32 = four row offsets per 8x8x8 colour cell, 128 KB)
+//     is resident in shared memory: one random LDS.32 per pixel;
+//   * the four candidate rows are always evaluated:  key = (|p|^2 << 8 | row) - 512 * dp4a(v, p)
+//     (PRMT, LDS.64, IDP.4A, IMAD), pad rows lose every comparison;
+//   * a 10-op min/max network yields the three smallest keys; ties in the upper 24 bits (exact
+//     distance ties), cells with more than four candidates and exact threshold equality go to
+//     an out-of-line exact path;
+//   * the reference's f64 `factor <= T` test is the sign of ONE f32 fma: T*N - n1 with
+//     n1 < N < 2^19 exact in f32; the fma rounds the exact value once, so its sign is the sign of
+//     T*(n1+n2) - n1 unless that is exactly 0.  A non-zero difference is a multiple of
+//     ulp(T)/2^23-ish relative 2^-43 of N, far above the 2^-50 relative error of the reference's
+//     f64 sqrt/square/divide chain, so the decisions agree; exact equality replays that chain.
+// A warp streams 512-pixel tiles (3 x 128-bit coalesced accesses per lane each way) through a
+// private, double-buffered 1.5 KB shared buffer (the next tile is in flight as cp.async while
+// the current one is processed); a lane owns 16 consecutive pixels (48 bytes) in registers.
+// ---------------------------------------------------------------------------------------
+constexpr int V4_THREADS = 768;
+constexpr int V4_WARPS = V4_THREADS / 32;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned a)
+{
+    unsigned v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int2 lds_s32x2(unsigned a)
+{
+    int2 v;
+    asm("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(unsigned a)
+{
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+
+struct V4Ctx {
+    unsigned table_a, ent_a, orgb_a;   // shared-space addresses
+    const PalDev *P;
+    int K;
+};
+
+// one pixel: v = r | g<<8 | b<<16 (bits 24..31 arbitrary) -> palette row; `slow` is set when
+// the exact path has to decide (see above).  The byte extractions and the table address use
+// IDP.4A / IMAD so that the ALU pipe (64 lanes/clk, the bottleneck) and the IMAD pipe share
+// the work.
+template <int KIND>
+__device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float thr, bool &slow)
+{
+    // byte offset of the pixel's cell in the u32 table: (r>>3)*4096 + (g>>3)*128 + (b>>3)*4
+    const unsigned a5 = (v >> 3) & 0x1f1f1fu;
+    const unsigned ta = (a5 & 0x1fu) * 4096u + __dp4a(a5, 0x00048000u, c.table_a);
+    const unsigned e = lds_u32(ta);
+    const int2 q0 = lds_s32x2(__dp4a(e, 0x00000001u, c.ent_a));   // base + byte j of e
+    const int2 q1 = lds_s32x2(__dp4a(e, 0x00000100u, c.ent_a));
+    const int2 q2 = lds_s32x2(__dp4a(e, 0x00010000u, c.ent_a));
+    const int2 q3 = lds_s32x2(__dp4a(e, 0x01000000u, c.ent_a));
+    const int k0 = q0.y - 512 * (int)__dp4a(v, (unsigned)q0.x, 0u);
+    const int k1 = q1.y - 512 * (int)__dp4a(v, (unsigned)q1.x, 0u);
+    const int k2 = q2.y - 512 * (int)__dp4a(v, (unsigned)q2.x, 0u);
+    const int k3 = q3.y - 512 * (int)__dp4a(v, (unsigned)q3.x, 0u);
+    // the three smallest of the four keys (real keys are distinct; two pads may coincide)
+    const int lo01 = min(k0, k1), hi01 = max(k0, k1), lo23 = min(k2, k3), hi23 = max(k2, k3);
+    const int m1 = min(lo01, lo23);
+    const int x = max(lo01, lo23);
+    const int m2 = min(min(x, hi01), hi23);
+    slow = e >= 0xf8000000u;                                    // more than four candidates
+    if (KIND == DP_THRESH_NONE) {
+        slow = slow || ((unsigned)(m1 ^ m2) < 256u);            // nearest not unique
+        return (unsigned)m1 & 255u;
+    }
+    const int mx = max(max(x, hi01), hi23);
+    // the median of {x, hi01, hi23}; modular arithmetic, the pad key 0x7fffffff may wrap
+    const int m3 = (int)((unsigned)x + (unsigned)hi01 + (unsigned)hi23 - (unsigned)m2 - (unsigned)mx);
+    slow = slow || (min((unsigned)(m1 ^ m2), (unsigned)(m2 ^ m3)) < 256u);
+    const unsigned vm = v & 0xffffffu;
+    const int vv = (int)__dp4a(vm, vm, 0u);
+    const int n1 = (vv * 256 + m1) >> 8;                        // exact squared distances
+    const int nn = (vv * 512 + m1 + m2) >> 8;                   // n1 + n2 (row bits never carry: K <= 30)
+    const float s = __fmaf_rn(thr, __int2float_rn(nn), -__int2float_rn(n1));
+    slow = slow || (s == 0.0f);
+    return (unsigned)(s > 0.0f ? m1 : m2) & 255u;
+}
+
+// exact decision for the pixels v4_pick flagged (rare): re-reads the pixel from global memory,
+// patches its output bytes in the warp's staging buffer and its index byte in global memory
+template <int KIND, bool WM_POW2>
+__device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, long long gp, uint32_t x,
+                                    uint32_t y, unsigned ra, uint8_t *out_bytes, const unsigned *s_orgb)
+{
+    const PalDev *P = p.P;
+    while (slowmask) {
+        const int j = __ffs(slowmask) - 1;
+        slowmask &= slowmask - 1;
+        const uint8_t *q = p.src + (gp + j) * 3;
+        float thr = 0.0f;
+        if (KIND == DP_THRESH_MATRIX) {
+            float t;
+            asm("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(ra + 4u * j));
+            thr = t;
+        } else if (KIND == DP_THRESH_IGN) {
+            thr = ign_threshold(p, (int)x + j, (int)y);
+        }
+        const int idx = pick_int<KIND>(P, P->coef, p.K, q[0], q[1], q[2], thr);
+        const unsigned col = s_orgb[idx];
+        out_bytes[3 * j] = (uint8_t)col;
+        out_bytes[3 * j + 1] = (uint8_t)(col >> 8);
+        out_bytes[3 * j + 2] = (uint8_t)(col >> 16);
+        if (p.dst_idx) p.dst_idx[gp + j] = (uint8_t)idx;
+    }
+}
+
+template <int KIND, bool WM_POW2>
+__global__ void __launch_bounds__(V4_THREADS, 1) k_thresh_v4(const ThreshParams p)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *s_table = reinterpret_cast<uint32_t *>(smem);                    // [32768]
+    int2 *s_ent = reinterpret_cast<int2 *>(smem + 131072);                     // [34]
+    unsigned *s_orgb = reinterpret_cast<unsigned *>(smem + 131072 + 272);      // [32]
+    uint4 *s_io = reinterpret_cast<uint4 *>(smem + 131072 + 272 + 128);        // [warps][2][96]
+    float *s_mat = reinterpret_cast<float *>(s_io + V4_WARPS * 192);           // [mh][wm]
+
+    const PalDev *P = p.P;
+    const int tid = threadIdx.x;
+    const int K = p.K;
+    {
+        const uint4 *src4 = reinterpret_cast<const uint4 *>(P->thr4_table);
+        uint4 *dst4 = reinterpret_cast<uint4 *>(s_table);
+        for (int i = tid; i < 8192; i += V4_THREADS) dst4[i] = __ldg(src4 + i);
+    }
+    if (tid < 34) {
+        int2 en = make_int2(0, 0x7fffff00 | 255);       // pad rows never win
+        if (tid < K) {
+            const int4 cf = P->coef[tid];
+            const int pr = -cf.x >> 9, pg = -cf.y >> 9, pb = -cf.z >> 9;   // coef = -2p << 8
+            en = make_int2(pr | (pg << 8) | (pb << 16), cf.w);
+        }
+        s_ent[tid] = en;
+    }
+    if (tid < 32) {
+        unsigned col = 0;
+        if (tid < K) {
+            const uint8_t *o = P->out_rgb + 4 * tid;
+            col = (unsigned)o[0] | ((unsigned)o[1] << 8) | ((unsigned)o[2] << 16);
+        }
+        s_orgb[tid] = col;
+    }
+    if (KIND == DP_THRESH_MATRIX) {
+        // widened copy: row r holds the matrix row repeated up to a multiple of 16 columns
+        const int n = p.mh * p.wm;
+        for (int i = tid; i < n; i += V4_THREADS) {
+            const int r = i / p.wm, cc = i - r * p.wm;
+            s_mat[i] = p.matrix[r * p.mw + cc % p.mw];
+        }
+    }
+    __syncthreads();
+
+    V4Ctx ctx;
+    ctx.table_a = smem_u32(s_table);
+    ctx.ent_a = smem_u32(s_ent);
+    ctx.orgb_a = smem_u32(s_orgb);
+    ctx.P = P;
+    ctx.K = K;
+    const unsigned mat_a = smem_u32(s_mat);
+
+    const int lane = tid & 31;
+    const int wib = tid >> 5;
+    uint4 *io4 = s_io + wib * 192;
+    const long long total_px = (long long)p.frames * p.npix;         // frames are contiguous
+    const long long ntiles = (total_px + 511) >> 9;
+    const long long wstride = (long long)gridDim.x * V4_WARPS;
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(p.src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(p.dst);
+    const long long n16_total = total_px * 3 / 16;                   // 16-byte units in the batch
+
+    // tile `t` -> staging buffer `buf` of this warp, asynchronously (LDGSTS, L2 -> shared)
+    auto issue = [&](long long t, int buf) {
+        const long long b16 = t * 96;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const long long i = b16 + 32 * j + lane;
+            if (i < n16_total) {
+                const unsigned d = smem_u32(io4 + buf * 96 + 32 * j + lane);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g4 + i) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    long long wt = (long long)blockIdx.x * V4_WARPS + wib;
+    int buf = 0;
+    if (wt < ntiles) issue(wt, 0);
+    for (; wt < ntiles; wt += wstride, buf ^= 1) {
+        const long long b16 = wt * 96;
+        if (wt + wstride < ntiles)
+            issue(wt + wstride, buf ^ 1);
+        else
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        uint4 *cur = io4 + buf * 96;
+        // this lane's 16 pixels
+        unsigned w[12];
+        {
+            const uint4 a = cur[3 * lane], b = cur[3 * lane + 1], cq = cur[3 * lane + 2];
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+            w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+            w[8] = cq.x; w[9] = cq.y; w[10] = cq.z; w[11] = cq.w;
+        }
+        const long long gp = (wt << 9) + 16 * lane;                  // first pixel (batch index)
+        const bool live = gp < total_px;
+        uint32_t x = 0, y = 0;
+        if (KIND != DP_THRESH_NONE) {
+            uint32_t pin;
+            if (total_px < (1ll << 31)) {
+                pin = (uint32_t)gp - fd_div(p.dnpix, (uint32_t)gp) * (uint32_t)p.npix;
+            } else {
+                pin = (uint32_t)(gp % p.npix);
+            }
+            y = fd_div(p.dw, pin);
+            x = pin - y * p.w;                                       // multiple of 16
+        }
+        unsigned ra = 0;   // shared address of this lane's 16 thresholds
+        if (KIND == DP_THRESH_MATRIX) {
+            const uint32_t ym = y - fd_div(p.dmh, y) * p.mh;
+            const uint32_t xm = WM_POW2 ? (x & (uint32_t)(p.wm - 1)) : (x - fd_div(p.dwm, x) * p.wm);
+            ra = mat_a + 4u * (ym * p.wm + xm);
+        }
+        unsigned idxw[4] = {0, 0, 0, 0};
+        unsigned slowmask = 0;
+        if (live) {
+#pragma unroll
+            for (int gq = 0; gq < 4; ++gq) {
+                const unsigned a = w[3 * gq], b = w[3 * gq + 1], cq = w[3 * gq + 2];
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (KIND == DP_THRESH_MATRIX) {
+                    t = lds_f32x4(ra + 16u * gq);
+                } else if (KIND == DP_THRESH_IGN) {
+                    t.x = ign_threshold(p, (int)x + 4 * gq, (int)y);
+                    t.y = ign_threshold(p, (int)x + 4 * gq + 1, (int)y);
+                    t.z = ign_threshold(p, (int)x + 4 * gq + 2, (int)y);
+                    t.w = ign_threshold(p, (int)x + 4 * gq + 3, (int)y);
+                }
+                bool s0, s1, s2, s3;
+                const unsigned i0 = v4_pick<KIND>(ctx, a, t.x, s0);
+                const unsigned i1 = v4_pick<KIND>(ctx, __funnelshift_r(a, b, 24), t.y, s1);
+                const unsigned i2 = v4_pick<KIND>(ctx, __funnelshift_r(b, cq, 16), t.z, s2);
+                const unsigned i3 = v4_pick<KIND>(ctx, cq >> 8, t.w, s3);
+                slowmask |= ((s0 ? 1u : 0u) | (s1 ? 2u : 0u) | (s2 ? 4u : 0u) | (s3 ? 8u : 0u)) << (4 * gq);
+                const unsigned c0 = lds_u32(ctx.orgb_a + 4u * i0), c1 = lds_u32(ctx.orgb_a + 4u * i1),
+                               c2 = lds_u32(ctx.orgb_a + 4u * i2), c3 = lds_u32(ctx.orgb_a + 4u * i3);
+                w[3 * gq] = c0 | (c1 << 24);
+                w[3 * gq + 1] = (c1 >> 8) | (c2 << 16);
+                w[3 * gq + 2] = (c2 >> 16) | (c3 << 8);
+                idxw[gq] = i0 | (i1 << 8) | (i2 << 16) | (i3 << 24);
+            }
+            if (p.dst_idx)
+                *reinterpret_cast<uint4 *>(p.dst_idx + gp) = make_uint4(idxw[0], idxw[1], idxw[2], idxw[3]);
+        }
+        cur[3 * lane] = make_uint4(w[0], w[1], w[2], w[3]);      // own slots: no hazard with other lanes
+        cur[3 * lane + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+        cur[3 * lane + 2] = make_uint4(w[8], w[9], w[10], w[11]);
+        if (slowmask)
+            v4_fix<KIND, WM_POW2>(p, slowmask, gp, x, y, ra, reinterpret_cast<uint8_t *>(cur + 3 * lane),
+                                  s_orgb);
+        __syncwarp();
+        if (b16 + lane < n16_total) __stcs(d4 + b16 + lane, cur[lane]);
+        if (b16 + 32 + lane < n16_total) __stcs(d4 + b16 + 32 + lane, cur[32 + lane]);
+        if (b16 + 64 + lane < n16_total) __stcs(d4 + b16 + 64 + lane, cur[64 + lane]);
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Fused geometry: gather (pixelize) -> dither -> m x m block store (up-scale).
 // One thread per dithered pixel.
 // ---------------------------------------------------------------------------------------
@@ -572,7 +859,17 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
 {
     int sms = dp_num_sms();
     size_t mat_bytes = (KIND == DP_THRESH_MATRIX && p.mh * p.mw <= 1024) ? (size_t)p.mh * p.mw * 4 : 0;
-    if (!geom && p.fast) {
+    if (!geom && p.fast == 4) {
+        const bool pow2 = (p.wm & (p.wm - 1)) == 0;
+        const size_t smem = 131072 + 272 + 128 + (size_t)V4_WARPS * 3072 +
+                            (KIND == DP_THRESH_MATRIX ? (size_t)p.mh * p.wm * 4 : 0);
+        void (*kern)(ThreshParams) = pow2 ? k_thresh_v4<KIND, true> : k_thresh_v4<KIND, false>;
+        DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long ntiles = ((long long)p.frames * p.npix + 511) >> 9;
+        const long long want = (ntiles + V4_WARPS - 1) / V4_WARPS;
+        const int grid = (int)(want < sms ? want : sms);
+        kern<<<grid, V4_THREADS, smem, st>>>(p);
+    } else if (!geom && p.fast) {
         const bool tsm = p.fast == 1;
         const bool pow2 = ((p.mw & (p.mw - 1)) == 0) && ((p.mh & (p.mh - 1)) == 0);
         const size_t mat_sm = (KIND == DP_THRESH_MATRIX && p.mh * p.mw <= 4096) ? (size_t)p.mh * p.mw * 4 : 0;
@@ -673,6 +970,22 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
         ((reinterpret_cast<uintptr_t>(src_rgb) | reinterpret_cast<uintptr_t>(dst_rgb)) & 15) == 0 &&
         p.npix % 16 == 0 && (!dst_idx || (reinterpret_cast<uintptr_t>(dst_idx) & 3) == 0))
         p.fast = (pal->dev.thr_cells <= 4096) ? 1 : 2;
+    if (p.fast && pal->dev.thr4_table && pal->dev.K <= 30 && !pal->has_lut && geo->w % 16 == 0 &&
+        (!dst_idx || (reinterpret_cast<uintptr_t>(dst_idx) & 15) == 0) && !getenv("DP_THRESH_NO_V4")) {
+        // widened matrix width: the smallest common multiple of mat_w and 16
+        int wm = 16;
+        if (kind == DP_THRESH_MATRIX) {
+            int a = p.mw, b = 16;
+            while (b) { int t = a % b; a = b; b = t; }
+            wm = p.mw / a * 16;
+        }
+        if (kind != DP_THRESH_MATRIX || (long long)p.mh * wm <= 4096) {
+            p.fast = 4;
+            p.wm = wm;
+            p.dwm = make_fastdiv((uint32_t)wm);
+            p.dnpix = make_fastdiv((uint32_t)p.npix);
+        }
+    }
     cudaStream_t st = dp_stream(stream);
     switch (kind) {
         case DP_THRESH_NONE: return launch_kind<DP_THRESH_NONE>(p, geom, st);
