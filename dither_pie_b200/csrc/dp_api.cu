@@ -651,26 +651,68 @@ extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out
             }
             void *d4 = nullptr;
             if (mk) {
-                std::vector<uint32_t> t4(32768);
-                for (int c = 0; c < 32768; ++c) {
+                auto pack4 = [K](uint32_t w0, bool &over) {
                     unsigned slot[4] = {(unsigned)K * 8u, (unsigned)K * 8u, (unsigned)K * 8u,
                                         (unsigned)K * 8u};
                     int cnt = 0;
-                    const uint32_t w0 = (*mk)[(size_t)c * 8];
                     for (int i = 0; i < K; ++i)
                         if (w0 >> i & 1u) {
                             if (cnt < 4) slot[cnt] = (unsigned)i * 8u;
                             ++cnt;
                         }
-                    if (cnt > 4) slot[3] = 0xf8u;   // row 31: a pad row, and the overflow mark
-                    t4[c] = slot[0] | (slot[1] << 8) | (slot[2] << 16) | (slot[3] << 24);
+                    over = cnt > 4;
+                    if (over) slot[3] = 0xf8u;   // row 31: a pad row, and the overflow mark
+                    return slot[0] | (slot[1] << 8) | (slot[2] << 16) | (slot[3] << 24);
+                };
+                std::vector<uint32_t> t4(32768), sub;
+                std::vector<int> ocell;
+                for (int c = 0; c < 32768; ++c) {
+                    bool over;
+                    t4[c] = pack4((*mk)[(size_t)c * 8], over);
+                    if (over) {
+                        t4[c] = 0xf8000000u | (uint32_t)ocell.size();
+                        ocell.push_back(c);
+                    }
                 }
-                if (cudaMalloc(&d4, 32768 * 4) == cudaSuccess &&
-                    cudaMemcpy(d4, t4.data(), 32768 * 4, cudaMemcpyHostToDevice) == cudaSuccess) {
+                bool ok5 = true;
+                if (!ocell.empty()) {
+                    // masks of the 4x4x4 sub-cells (64^3 grid), only read for the overflow cells
+                    uint32_t *dm2 = nullptr;
+                    std::vector<uint32_t> m2((size_t)262144 * 8);
+                    ok5 = cudaMalloc(&dm2, (size_t)262144 * 32) == cudaSuccess;
+                    if (ok5) {
+                        k_thr_masks<<<262144, 64>>>(d.coef, K, 2, dm2);
+                        ok5 = cudaMemcpy(m2.data(), dm2, (size_t)262144 * 32,
+                                         cudaMemcpyDeviceToHost) == cudaSuccess;
+                    }
+                    if (dm2) cudaFree(dm2);
+                    sub.resize(ocell.size() * 8);
+                    for (size_t n = 0; ok5 && n < ocell.size(); ++n) {
+                        const int c = ocell[n], cr = c >> 10, cg = (c >> 5) & 31, cb = c & 31;
+                        for (int s8 = 0; s8 < 8; ++s8) {
+                            const int fr = cr * 2 + (s8 >> 2), fg = cg * 2 + ((s8 >> 1) & 1),
+                                      fb = cb * 2 + (s8 & 1);
+                            bool over;
+                            sub[n * 8 + s8] = pack4(m2[((size_t)(fr * 64 + fg) * 64 + fb) * 8], over);
+                        }
+                    }
+                }
+                void *dsub = nullptr;
+                ok5 = ok5 && ocell.size() <= 1024 &&
+                      cudaMalloc(&d4, 32768 * 4) == cudaSuccess &&
+                      cudaMemcpy(d4, t4.data(), 32768 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+                      cudaMalloc(&dsub, sub.size() * 4 + 16) == cudaSuccess &&
+                      (sub.empty() || cudaMemcpy(dsub, sub.data(), sub.size() * 4,
+                                                 cudaMemcpyHostToDevice) == cudaSuccess);
+                if (ok5) {
                     d.thr4_table = static_cast<const uint32_t *>(d4);
+                    d.thr4_sub = static_cast<const uint32_t *>(dsub);
+                    d.thr4_nsub = (int)ocell.size();
                     h->thr4_table = d4;
-                } else if (d4) {
-                    cudaFree(d4);   // the v3 kernels still work without it
+                    h->thr4_sub = dsub;
+                } else {   // the v3 kernels still work without it
+                    if (d4) cudaFree(d4);
+                    if (dsub) cudaFree(dsub);
                 }
             }
         }
@@ -707,6 +749,7 @@ extern "C" int dp_palette_destroy(dp_palette *pal)
     if (pal->thr_table) cudaFree(pal->thr_table);
     if (pal->thr_ovf) cudaFree(pal->thr_ovf);
     if (pal->thr4_table) cudaFree(pal->thr4_table);
+    if (pal->thr4_sub) cudaFree(pal->thr4_sub);
     if (pal->tie_table) cudaFree(pal->tie_table);
     if (pal->blob) cudaFree(pal->blob);
     delete pal;

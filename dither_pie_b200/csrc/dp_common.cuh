@@ -72,8 +72,12 @@ struct PalDev {
     // compact top-2 table for the v4 threshold kernel (integral palettes with K <= 30): one u32
     // per 8x8x8 colour cell = four candidate slots, each the byte offset row*8 of the row in the
     // kernel's int2 row array (free slots: K*8, a pad row that never wins).  A cell with more
-    // than four candidates has 0xf8 (row 31, also a pad row) in its last slot.
+    // than four candidates holds 0xf8000000 | n: its eight 4x4x4 sub-cells have entries of the
+    // same format at thr4_sub[8n + ((r>>2)&1)*4 + ((g>>2)&1)*2 + ((b>>2)&1)]; a sub-cell that
+    // still has more than four candidates has 0xf8 (row 31, also a pad row) in its last slot.
     const uint32_t *thr4_table;   // [32768] or null
+    const uint32_t *thr4_sub;     // [8 * thr4_nsub]
+    int thr4_nsub;
     // Exception table of the byte colours with an exact distance tie among their three nearest
     // rows (integral palettes): scipy's answers, replayed once at palette creation.
     //   x = colour (r | g<<8 | b<<16) | nearest row of query(k=1) << 24
@@ -106,6 +110,7 @@ struct dp_palette {
     void *thr_table;
     void *thr_ovf;
     void *thr4_table;
+    void *thr4_sub;
     void *tie_table;
     void *ed_table;
     void *ed_ovf;   // one allocation: cells | offsets | lists

@@ -68,6 +68,7 @@ struct ThreshParams {
     int fast;        // 0 generic kernel, 1 fast kernel with the candidate table in shared, 2 in global
     int thr_cells;
     int wm;          // v4: width of the widened threshold matrix in shared memory (multiple of 16)
+    int sub_bytes;   // v4: shared bytes of the sub-cell table (multiple of 16)
     FastDiv dwm, dnpix;
 };
 
@@ -557,7 +558,7 @@ __device__ __forceinline__ float4 lds_f32x4(unsigned a)
 }
 
 struct V4Ctx {
-    unsigned table_a, ent_a, orgb_a;   // shared-space addresses
+    unsigned table_a, ent_a, orgb_a, sub_a;   // shared-space addresses
     const PalDev *P;
     int K;
 };
@@ -572,7 +573,11 @@ __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float th
     // byte offset of the pixel's cell in the u32 table: (r>>3)*4096 + (g>>3)*128 + (b>>3)*4
     const unsigned a5 = (v >> 3) & 0x1f1f1fu;
     const unsigned ta = (a5 & 0x1fu) * 4096u + __dp4a(a5, 0x00048000u, c.table_a);
-    const unsigned e = lds_u32(ta);
+    unsigned e = lds_u32(ta);
+    if (e >= 0xf8000000u) {   // more than four candidates in the 8^3 cell: refine to the 4^3 sub-cell
+        const unsigned sc = ((v >> 2) & 1u) * 4u + ((v >> 10) & 1u) * 2u + ((v >> 18) & 1u);
+        e = lds_u32(c.sub_a + ((e & 0xffffu) * 8u + sc) * 4u);
+    }
     const int2 q0 = lds_s32x2(__dp4a(e, 0x00000001u, c.ent_a));   // base + byte j of e
     const int2 q1 = lds_s32x2(__dp4a(e, 0x00000100u, c.ent_a));
     const int2 q2 = lds_s32x2(__dp4a(e, 0x00010000u, c.ent_a));
@@ -586,7 +591,7 @@ __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float th
     const int m1 = min(lo01, lo23);
     const int x = max(lo01, lo23);
     const int m2 = min(min(x, hi01), hi23);
-    slow = e >= 0xf8000000u;                                    // more than four candidates
+    slow = e >= 0xf8000000u;                                    // still more than four candidates
     if (KIND == DP_THRESH_NONE) {
         slow = slow || ((unsigned)(m1 ^ m2) < 256u);            // nearest not unique
         return (unsigned)m1 & 255u;
@@ -636,11 +641,13 @@ template <int KIND, bool WM_POW2>
 __global__ void __launch_bounds__(V4_THREADS, 1) k_thresh_v4(const ThreshParams p)
 {
     extern __shared__ __align__(16) uint8_t smem[];
+    const int P_nsub = p.P->thr4_nsub;
     uint32_t *s_table = reinterpret_cast<uint32_t *>(smem);                    // [32768]
     int2 *s_ent = reinterpret_cast<int2 *>(smem + 131072);                     // [34]
     unsigned *s_orgb = reinterpret_cast<unsigned *>(smem + 131072 + 272);      // [32]
     uint4 *s_io = reinterpret_cast<uint4 *>(smem + 131072 + 272 + 128);        // [warps][2][96]
-    float *s_mat = reinterpret_cast<float *>(s_io + V4_WARPS * 192);           // [mh][wm]
+    uint32_t *s_sub = reinterpret_cast<uint32_t *>(s_io + V4_WARPS * 192);     // [8 * nsub]
+    float *s_mat = reinterpret_cast<float *>(s_sub + ((8 * P_nsub + 3) & ~3));   // [mh][wm]
 
     const PalDev *P = p.P;
     const int tid = threadIdx.x;
@@ -649,6 +656,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_thresh_v4(const ThreshParams 
         const uint4 *src4 = reinterpret_cast<const uint4 *>(P->thr4_table);
         uint4 *dst4 = reinterpret_cast<uint4 *>(s_table);
         for (int i = tid; i < 8192; i += V4_THREADS) dst4[i] = __ldg(src4 + i);
+        for (int i = tid; i < 8 * P_nsub; i += V4_THREADS) s_sub[i] = __ldg(P->thr4_sub + i);
     }
     if (tid < 34) {
         int2 en = make_int2(0, 0x7fffff00 | 255);       // pad rows never win
@@ -681,6 +689,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_thresh_v4(const ThreshParams 
     ctx.table_a = smem_u32(s_table);
     ctx.ent_a = smem_u32(s_ent);
     ctx.orgb_a = smem_u32(s_orgb);
+    ctx.sub_a = smem_u32(s_sub);
     ctx.P = P;
     ctx.K = K;
     const unsigned mat_a = smem_u32(s_mat);
@@ -861,7 +870,7 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
     size_t mat_bytes = (KIND == DP_THRESH_MATRIX && p.mh * p.mw <= 1024) ? (size_t)p.mh * p.mw * 4 : 0;
     if (!geom && p.fast == 4) {
         const bool pow2 = (p.wm & (p.wm - 1)) == 0;
-        const size_t smem = 131072 + 272 + 128 + (size_t)V4_WARPS * 3072 +
+        const size_t smem = 131072 + 272 + 128 + (size_t)V4_WARPS * 3072 + (size_t)p.sub_bytes +
                             (KIND == DP_THRESH_MATRIX ? (size_t)p.mh * p.wm * 4 : 0);
         void (*kern)(ThreshParams) = pow2 ? k_thresh_v4<KIND, true> : k_thresh_v4<KIND, false>;
         DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -979,8 +988,12 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
             while (b) { int t = a % b; a = b; b = t; }
             wm = p.mw / a * 16;
         }
-        if (kind != DP_THRESH_MATRIX || (long long)p.mh * wm <= 4096) {
+        const int sub_bytes = ((8 * pal->dev.thr4_nsub + 3) & ~3) * 4;
+        const long long need = 131072 + 272 + 128 + (long long)V4_WARPS * 3072 + sub_bytes +
+                               (kind == DP_THRESH_MATRIX ? (long long)p.mh * wm * 4 : 0);
+        if (need <= 227 * 1024 && (kind != DP_THRESH_MATRIX || (long long)p.mh * wm <= 4096)) {
             p.fast = 4;
+            p.sub_bytes = sub_bytes;
             p.wm = wm;
             p.dwm = make_fastdiv((uint32_t)wm);
             p.dnpix = make_fastdiv((uint32_t)p.npix);
