@@ -5,7 +5,7 @@
 
 Workload (BASELINE.json configs[1]): 3840x2160 RGB frames, error diffusion with the
 Floyd-Steinberg + Atkinson + JJN kernels, 256-colour palette.  One "step" is one pass of the
-three kernels over a batch of 64 synthetic 4K frames (1.6 GB, far larger than L2).
+three kernels over a batch of 128 synthetic 4K frames (3.2 GB, far larger than L2).
 Metric: Mpixels/s (input pixels x dither passes per second), whole job over all ranks.
 N > 1: one process per GPU (torchrun), every rank owns its own batch of frames (frames are
 independent -> weak scaling, no data-path collective); time = max over ranks.
@@ -116,7 +116,7 @@ def workload_config(n_gpus, batch):
             "frames_per_step_per_gpu": batch, "passes_per_frame": len(ED_VARIANTS),
             "palette": "first 256 unique rows of RandomState(2024).randint(0,256)",
             "frame": "synth.frame(2160,3840,seed) gradient + uniform noise [-16,16]",
-            "l2_policy": "inputs larger than L2 (a batch of 64 4K frames is 1.6 GB in, 3x that out)",
+            "l2_policy": "inputs larger than L2 (a batch of 128 4K frames is 3.2 GB in, 3x that out)",
             "parallelism": f"frame-sharded x{n_gpus}, no data-path collective"}
 
 
@@ -185,6 +185,8 @@ def run_gpu(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from dither_pie_b200 import _capi, engine, synth
@@ -199,15 +201,22 @@ def run_gpu(args):
     pal_rows = synth.random_palette(K_COLOURS)
     pal = engine.get_palette(pal_rows)
     # per-rank synthetic frames (seed depends on the rank so that ranks do different work)
-    base = np.stack([synth.frame(H4K, W4K, 1 + rank * 16 + t) for t in range(min(B, 4))])
-    host_in = _capi.PinnedArray((B, H4K, W4K, 3), np.uint8)
-    for t in range(B):
+    # The host side holds a block of HB frames in pinned memory; the device batch is that block
+    # repeated (frames rolled per repeat would only change the bytes, not the work).  Every e2e
+    # step still moves B frames in and 3 x B frames out over PCIe, block by block.
+    HB = min(B, 32)
+    assert B % HB == 0, "--batch must be a multiple of 32 (or smaller than 32)"
+    base = np.stack([synth.frame(H4K, W4K, 1 + rank * 16 + t) for t in range(min(HB, 4))])
+    host_in = _capi.PinnedArray((HB, H4K, W4K, 3), np.uint8)
+    for t in range(HB):
         host_in.array[t] = base[t % base.shape[0]]
         if t >= base.shape[0]:
             host_in.array[t] = np.roll(host_in.array[t], 7 * t, axis=1)
     src = torch.empty((B, H4K, W4K, 3), dtype=torch.uint8, device=dev)
     dst = [torch.empty_like(src) for _ in ED_VARIANTS]
-    src.copy_(torch.from_numpy(host_in.array), non_blocking=False)
+    blk = torch.from_numpy(host_in.array)
+    for q in range(B // HB):
+        src[q * HB:(q + 1) * HB].copy_(blk, non_blocking=False)
     plans = [engine.Plan("error_diffusion", {"variant": v}, H4K, W4K) for v in ED_VARIANTS]
     px_per_step = B * H4K * W4K * len(ED_VARIANTS)
     launches = 0
@@ -258,8 +267,9 @@ def run_gpu(args):
     # Three streams (copy-in, kernels, copy-out) and two device buffer sets: the H2D of step
     # n+1 and the D2H of kernel v overlap the kernels, which is how video_processor streams a
     # clip.  Every step still moves its whole input and all three results over PCIe.
-    host_out = [_capi.PinnedArray((B, H4K, W4K, 3), np.uint8) for _ in ED_VARIANTS]
+    host_out = [_capi.PinnedArray((HB, H4K, W4K, 3), np.uint8) for _ in ED_VARIANTS]
     nbytes = B * H4K * W4K * 3
+    blk_bytes = HB * H4K * W4K * 3
     s_in, s_k, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
     p_in, p_k, p_out = (C.c_void_p(x.cuda_stream) for x in (s_in, s_k, s_out))
     src2 = [src, torch.empty_like(src)]
@@ -274,7 +284,9 @@ def run_gpu(args):
             b = n & 1
             if n >= 2:
                 s_in.wait_event(ev_src_free[b])          # kernels of step n-2 are done with src2[b]
-            check(L.dp_memcpy_h2d(src2[b].data_ptr(), host_in.ptr, nbytes, p_in), "h2d")
+            for q in range(B // HB):
+                check(L.dp_memcpy_h2d(src2[b].data_ptr() + q * blk_bytes, host_in.ptr, blk_bytes, p_in),
+                      "h2d")
             ev_in[b].record(s_in)
             s_k.wait_event(ev_in[b])
             for v, (pl, ho) in enumerate(zip(plans, host_out)):
@@ -283,7 +295,9 @@ def run_gpu(args):
                 pl.run(pal, src2[b].data_ptr(), B, dst2[b][v].data_ptr(), None, p_k)
                 ev_k[b][v].record(s_k)
                 s_out.wait_event(ev_k[b][v])
-                check(L.dp_memcpy_d2h(ho.ptr, dst2[b][v].data_ptr(), nbytes, p_out), "d2h")
+                for q in range(B // HB):
+                    check(L.dp_memcpy_d2h(ho.ptr, dst2[b][v].data_ptr() + q * blk_bytes, blk_bytes, p_out),
+                          "d2h")
                 ev_out[b][v].record(s_out)
             ev_src_free[b].record(s_k)
         for x in (s_in, s_k, s_out):
@@ -335,7 +349,7 @@ def run_gpu(args):
     if world == 1:
         # cpu baseline: bounded sample of the same workload on the host cores
         cores = os.cpu_count() or 1
-        crops = [np.ascontiguousarray(host_in.array[t % B][:540, :960]) for t in range(cores)]
+        crops = [np.ascontiguousarray(host_in.array[t % HB][:540, :960]) for t in range(cores)]
         t0 = time.perf_counter()
         px = cpu_reference_step(crops, pal_rows.astype(np.float32), cores)
         dt = time.perf_counter() - t0
@@ -419,7 +433,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="4K frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=128, help="4K frames per step per GPU")
     ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -4,6 +4,8 @@
 #include <vector>
 
 #include <algorithm>
+#include <array>
+#include <map>
 
 #include "dp_search.cuh"
 
@@ -300,7 +302,9 @@ int build_ed_table(const double *d_pal64, int K, PalDev &d, dp_palette *h)
               cudaSuccess;
     cudaFree(dmask);
     if (!ok) return 1;
-    std::vector<uint4> table(cells);
+    std::vector<uint16_t> l1(cells);
+    std::vector<uint4> pats;
+    std::map<std::array<uint32_t, 4>, int> seen;
     std::vector<int> ocells;
     std::vector<uint32_t> ooff;
     std::vector<uint8_t> olist;
@@ -317,12 +321,14 @@ int build_ed_table(const double *d_pal64, int K, PalDev &d, dp_palette *h)
             ooff.push_back((uint32_t)olist.size());
             olist.insert(olist.end(), cand, cand + cnt);
         }
-        uint4 e;
-        e.x = slot[0] | (slot[1] << 16);
-        e.y = slot[2] | (slot[3] << 16);
-        e.z = slot[4] | (slot[5] << 16);
-        e.w = slot[6] | (slot[7] << 16);
-        table[c] = e;
+        const std::array<uint32_t, 4> key = {slot[0] | (slot[1] << 16), slot[2] | (slot[3] << 16),
+                                             slot[4] | (slot[5] << 16), slot[6] | (slot[7] << 16)};
+        auto it = seen.find(key);
+        if (it == seen.end()) {
+            it = seen.emplace(key, (int)pats.size()).first;
+            pats.push_back(make_uint4(key[0], key[1], key[2], key[3]));
+        }
+        l1[c] = (uint16_t)it->second;   // at most 32768 patterns
     }
     ooff.push_back((uint32_t)olist.size());
     const size_t n = ocells.size();
@@ -332,16 +338,27 @@ int build_ed_table(const double *d_pal64, int K, PalDev &d, dp_palette *h)
     memcpy(blob.data() + o_off, ooff.data(), (n + 1) * 4);
     if (!olist.empty()) memcpy(blob.data() + o_list, olist.data(), olist.size());
     void *dt = nullptr, *dov = nullptr;
-    ok = cudaMalloc(&dt, (size_t)cells * 16) == cudaSuccess &&
+    const size_t l1_bytes = (size_t)cells * 2;
+    const size_t pat_bytes = pats.size() * 16;
+    std::vector<uint4> flat(cells);
+    for (int c = 0; c < cells; ++c) flat[c] = pats[l1[c]];
+    ok = cudaMalloc(&dt, l1_bytes + pat_bytes + (size_t)cells * 16) == cudaSuccess &&
+         cudaMemcpy(static_cast<uint8_t *>(dt) + l1_bytes + pat_bytes, flat.data(), (size_t)cells * 16,
+                    cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMalloc(&dov, blob.size()) == cudaSuccess &&
-         cudaMemcpy(dt, table.data(), (size_t)cells * 16, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(dt, l1.data(), l1_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(static_cast<uint8_t *>(dt) + l1_bytes, pats.data(), pats.size() * 16,
+                    cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(dov, blob.data(), blob.size(), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
         if (dt) cudaFree(dt);
         if (dov) cudaFree(dov);
         return 1;
     }
-    d.ed_table = static_cast<const uint4 *>(dt);
+    d.ed_l1 = static_cast<const uint16_t *>(dt);
+    d.ed_pat = reinterpret_cast<const uint4 *>(static_cast<uint8_t *>(dt) + l1_bytes);
+    d.ed_npat = (int)pats.size();
+    d.ed_flat = reinterpret_cast<const uint4 *>(static_cast<uint8_t *>(dt) + l1_bytes + pat_bytes);
     d.ed_ovf_cells = reinterpret_cast<const int *>(static_cast<uint8_t *>(dov) + o_cells);
     d.ed_ovf_off = reinterpret_cast<const uint32_t *>(static_cast<uint8_t *>(dov) + o_off);
     d.ed_ovf = static_cast<uint8_t *>(dov) + o_list;

@@ -85,15 +85,23 @@ struct PalDev {
     // sorted by colour; tie_n < 0: not built (the kernels replay the KD-tree themselves).
     const uint2 *tie_table;
     int tie_n;
-    // nearest-row candidate table for arbitrary real values in [0,255]^3 (diffusion modes):
-    // 32^3 cells of 8x8x8; a row is dropped from a cell only if another row is strictly nearer
-    // at EVERY point of the cell's closed box (exact linear test).  One 16-byte entry per cell =
-    // eight u16 slots holding row*16 (the byte offset of the row in the kernels' float4 row
-    // array), ascending; free slots hold DP_ED_PAD (the offset of a far-away pad row).  More
-    // than seven candidates (rare): slot 7 = DP_ED_OVERFLOW, slots 0..6 the first seven, and the
-    // full list is found through ed_ovf_cells (sorted cell numbers) -> ed_ovf_off -> ed_ovf.
-    // 512 KB, read through L1 (__ldg): a warp's pixels touch a few dozen neighbouring cells.
-    const uint4 *ed_table;        // [32768]
+    // nearest-row candidates for arbitrary real values in [0,255]^3 (diffusion modes): 32^3 cells
+    // of 8x8x8; a row is dropped from a cell only if another row is strictly nearer at EVERY
+    // point of the cell's closed box (exact linear test).  Two levels, because few candidate
+    // sets are distinct (141 / 939 / 4 106 for the 16 / 64 / 256-colour test palettes):
+    //   ed_l1  [32768] u16   cell -> pattern number (the kernels keep this level in shared memory)
+    //   ed_pat [ed_npat]     one 16-byte pattern = eight u16 slots holding row*16 (the byte offset
+    //                        of the row in the kernels' float4 row array), ascending; free slots
+    //                        hold DP_ED_PAD (the offset of a far-away pad row).
+    // More than seven candidates (rare): the cell gets a pattern of its own with slot 7 =
+    // DP_ED_OVERFLOW and slots 0..6 the first seven; the full list is found through
+    // ed_ovf_cells (sorted cell numbers) -> ed_ovf_off -> ed_ovf.
+    const uint16_t *ed_l1;
+    const uint4 *ed_pat;
+    int ed_npat;
+    // the same information flattened, ed_flat[cell] = ed_pat[ed_l1[cell]] (512 KB): one L1-cached
+    // load per pixel for saturating batches, where shared memory is better spent on more warps
+    const uint4 *ed_flat;
     const int *ed_ovf_cells;      // [ed_novf] ascending
     const uint32_t *ed_ovf_off;   // [ed_novf + 1] offsets into ed_ovf
     const uint8_t *ed_ovf;        // concatenated candidate lists
@@ -112,8 +120,8 @@ struct dp_palette {
     void *thr4_table;
     void *thr4_sub;
     void *tie_table;
-    void *ed_table;
-    void *ed_ovf;   // one allocation: cells | offsets | lists
+    void *ed_table;   // one allocation: level 1 | patterns | flat
+    void *ed_ovf;     // one allocation: cells | offsets | lists
     float host_pal[DP_MAX_COLORS * 3];
 };
 

@@ -164,6 +164,8 @@ struct WaveParams {
     int *qctrl;         // [0] queue head (consumers), [1] queue tail (producers)
     int *queue;         // [units] unit + 1, 0 = not yet enqueued
     int slack;          // extra chunks of lead before the successor band is enqueued
+    int pat_smem;       // number of candidate patterns kept in shared memory (all or none)
+    int l1_smem;        // first table level in shared memory (else read through L1)
     const float *ostro_w;  // [256][4] f32 weights (c0,c1,c2)/sum, DEVICE (ostromoukhov only)
 };
 
@@ -253,8 +255,25 @@ __device__ __forceinline__ unsigned lds_u32(unsigned a)
     return v;
 }
 
+__device__ __forceinline__ unsigned lds_u16(unsigned a)
+{
+    unsigned short v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u32x4(unsigned a)
+{
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+
 struct Search {
-    const uint4 *table;      // global (L1-cached), [32768] 8x8x8 cells (format: dp_common.cuh)
+    const uint16_t *l1;      // global: cell -> pattern (format: dp_common.cuh)
+    const uint4 *pat;        // global: candidate patterns
+    const uint4 *flat;       // global: pattern of every cell (one load; saturating batches)
+    unsigned l1_a;           // shared copy of l1 (wavefront kernel)
+    unsigned pat_a;          // shared copy of the patterns, 0 if they stay in global memory (L1)
     const PalDev *P;         // overflow lists (rare)
     const double *s_pal;     // shared, [K,3]
     unsigned rows_a;         // shared address of float4 [257]: (r, g, b, row index bits); 256 = pad
@@ -314,7 +333,7 @@ struct CandList {
 __device__ __forceinline__ CandList cand_list(const Search &s, int cell)
 {
     CandList L;
-    L.e = __ldg(s.table + cell);
+    L.e = __ldg(s.pat + __ldg(s.l1 + cell));
     L.ovf = nullptr;
     if ((L.e.w >> 16) == DP_ED_OVERFLOW) {
         const PalDev *P = s.P;
@@ -407,7 +426,14 @@ __device__ __forceinline__ int nearest_row(const PalDev *P, const Search &s, flo
 {
     const int cell = cell_of(r, g, b);
     bool sure;
-    int bi = nearest_screen(s, __ldg(s.table + cell), r, g, b, sure);
+    uint4 e;
+    if (s.l1_a) {
+        const unsigned pi = lds_u16(s.l1_a + 2u * cell);
+        e = s.pat_a ? lds_u32x4(s.pat_a + 16u * pi) : __ldg(s.pat + pi);
+    } else {
+        e = __ldg(s.flat + cell);
+    }
+    int bi = nearest_screen(s, e, r, g, b, sure);
 #ifdef DP_WAVE_TIMING
     if (!sure) atomicAdd(&g_wave_timing[128 * 4], 1ull);
     if (__any_sync(__activemask(), !sure) && (threadIdx.x & 31) == (__ffs(__activemask()) - 1))
@@ -472,14 +498,12 @@ template <> struct StateOf<V_OSTRO> { using T = float; };
 //                              misalignment m of its global address so that whole aligned words
 //                              can be stored; word 24 (the trailing m bytes) is carried into
 //                              word 0 of the next chunk
-//   outi [32 rows][36]  u8     the palette rows chosen (only when an index image is wanted)
 template <typename T, int NS>
 struct WarpStageT {
     unsigned inw[2][32][25];       // 99 bytes per row are read at most
     T hin[32][NS];
     T hout[32][NS];
     unsigned char outb[32][108];
-    unsigned char outi[32][36];
 };
 
 // Warps per block: the numba variants with a 5x5 footprint (JJN, Stucki) keep ~55 doubles of
@@ -487,7 +511,8 @@ struct WarpStageT {
 template <int V>
 constexpr int wave_max_warps()
 {
-    return (V == DP_ED_JJN || V == DP_ED_STUCKI) ? 8 : 12;
+    return (V == DP_ED_JJN || V == DP_ED_STUCKI) ? 8
+         : (V == DP_ED_FLOYD_STEINBERG || V == DP_ED_ATKINSON || V == DP_ED_SIERRA_LITE) ? 16 : 12;
 }
 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, bool valid)
@@ -514,18 +539,27 @@ __global__ void __launch_bounds__(wave_max_warps<V>() * 32) k_diffuse_wave(const
     double *s_pal = reinterpret_cast<double *>(wave_smem);                    // [256*3]
     float4 *s_rows = reinterpret_cast<float4 *>(s_pal + DP_MAX_COLORS * 3);   // [257]
     double *s_lutd = reinterpret_cast<double *>(s_rows + DP_MAX_COLORS + 1);  // [256] (as T)
-    float *s_palf = reinterpret_cast<float *>(s_lutd + 256);                  // [256*3]
-    float *s_ow = s_palf + DP_MAX_COLORS * 3;                                 // [256*4]
-    unsigned *s_orgb = reinterpret_cast<unsigned *>(s_ow + 256 * 4);          // [256]
-    Stage *stages = reinterpret_cast<Stage *>(s_orgb + 256);
+    float *s_palf = reinterpret_cast<float *>(s_lutd + 256);                  // [256*3] (Ostromoukhov)
+    float *s_ow = s_palf + (SP::OSTRO ? DP_MAX_COLORS * 3 : 0);               // [256*4] (Ostromoukhov)
+    unsigned *s_orgb = reinterpret_cast<unsigned *>(s_ow + (SP::OSTRO ? 256 * 4 : 0));   // [256]
+    uint16_t *s_l1 = reinterpret_cast<uint16_t *>(s_orgb + 256);              // [32768] if l1_smem
+    uint4 *s_pat = reinterpret_cast<uint4 *>(s_l1 + (p.l1_smem ? 32768 : 0)); // [p.pat_smem]
+    Stage *stages = reinterpret_cast<Stage *>(s_pat + p.pat_smem);
     Stage &st = stages[threadIdx.x >> 5];
     T *s_lut = reinterpret_cast<T *>(s_lutd);   // source byte -> work value (gamma LUT folded in)
     const int NT = blockDim.x;
 
     const PalDev *P = p.P;
+    {
+        const uint4 *src4 = reinterpret_cast<const uint4 *>(P->ed_l1);
+        uint4 *dst4 = reinterpret_cast<uint4 *>(s_l1);
+        if (p.l1_smem)
+            for (int i = threadIdx.x; i < 4096; i += NT) dst4[i] = __ldg(src4 + i);
+        for (int i = threadIdx.x; i < p.pat_smem; i += NT) s_pat[i] = __ldg(P->ed_pat + i);
+    }
     for (int i = threadIdx.x; i < p.K * 3; i += NT) {
         s_pal[i] = P->pal_f64[i];
-        s_palf[i] = P->pal_f32[i];
+        if (SP::OSTRO) s_palf[i] = P->pal_f32[i];
     }
     for (int i = threadIdx.x; i < p.K; i += NT) {
         const uint8_t *o = P->out_rgb + 4 * i;
@@ -545,7 +579,11 @@ __global__ void __launch_bounds__(wave_max_warps<V>() * 32) k_diffuse_wave(const
     __syncthreads();
 
     Search srch;
-    srch.table = P->ed_table;
+    srch.l1 = P->ed_l1;
+    srch.pat = P->ed_pat;
+    srch.flat = P->ed_flat;
+    srch.l1_a = p.l1_smem ? smem_u32(s_l1) : 0u;
+    srch.pat_a = p.pat_smem ? smem_u32(s_pat) : 0u;
     srch.P = P;
     srch.s_pal = s_pal;
     srch.rows_a = smem_u32(s_rows);
@@ -811,7 +849,7 @@ __global__ void __launch_bounds__(wave_max_warps<V>() * 32) k_diffuse_wave(const
                     ob[3 * sidx] = (unsigned char)oc;
                     ob[3 * sidx + 1] = (unsigned char)(oc >> 8);
                     ob[3 * sidx + 2] = (unsigned char)(oc >> 16);
-                    if (idx_f) st.outi[lane][sidx] = (unsigned char)bi;
+                    if (idx_f) idx_f[(size_t)y * W + x] = (unsigned char)bi;   // optional index plane
                     DP_STICK(4);
                 } else {
 #pragma unroll
@@ -911,11 +949,6 @@ __global__ void __launch_bounds__(wave_max_warps<V>() * 32) k_diffuse_wave(const
                             if (xp >= 0 && xp < W) dst_f[obyte + j] = sb[k];
                         }
                     }
-                    if (idx_f) {
-                        for (int j = 0; j < 32; ++j)
-                            if (xfirst + j >= 0 && xfirst + j < W)
-                                idx_f[(size_t)y * W + xfirst + j] = st.outi[lane][j];
-                    }
                 }
                 ow[0] = ow[24];   // trailing partial word -> leading bytes of the next chunk
             }
@@ -971,7 +1004,11 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
     }
     __syncthreads();
     Search srch;
-    srch.table = P->ed_table;
+    srch.l1 = P->ed_l1;
+    srch.pat = P->ed_pat;
+    srch.flat = P->ed_flat;
+    srch.l1_a = 0;
+    srch.pat_a = 0;
     srch.P = P;
     srch.s_pal = s_pal;
     srch.rows_a = 0;   // exact search only
@@ -1091,20 +1128,32 @@ __global__ void k_wave_init(int *progress, int *qctrl, int *queue, int units, in
 }
 
 template <int V>
-int launch_wave(const WaveParams &p, cudaStream_t st)
+int launch_wave(const WaveParams &p0, cudaStream_t st, int npat)
 {
     // Few bands (a single image, a small batch): 4-warp blocks so that the bands spread over
-    // the SM sub-partitions (a lone warp is latency-bound).  Many bands: one 8- or 12-warp block
-    // per SM, which shares the tables.
+    // the SM sub-partitions (a lone warp is latency-bound).  Many bands: one block per SM with
+    // as many warps as registers (wave_max_warps) and shared memory allow.
     using Stage = WarpStageT<typename StateOf<V>::T, Spec<V>::ROWS3 ? 6 : 3>;
+    WaveParams p = p0;
     const int sms = dp_num_sms();
-    int warps = (p.total_units <= sms * 8) ? 4 : wave_max_warps<V>();
+    const size_t base = DP_MAX_COLORS * 3 * 8 + (DP_MAX_COLORS + 1) * 16 + 256 * 8 +
+                        (V == V_OSTRO ? DP_MAX_COLORS * 3 * 4 + 256 * 4 * 4 : 0) + 256 * 4;
+    const size_t limit = 227 * 1024;
+    const bool big = p.total_units > sms * 8;
+    int warps = big ? wave_max_warps<V>() : 4;
     if (const char *ev = getenv("DP_WAVE_WARPS")) {   // tuning knob (tools/): 1..max warps per block
         const int w = atoi(ev);
         if (w >= 1 && w <= wave_max_warps<V>()) warps = w;
     }
-    const size_t smem = DP_MAX_COLORS * 3 * 8 + (DP_MAX_COLORS + 1) * 16 + 256 * 8 +
-                        DP_MAX_COLORS * 3 * 4 + 256 * 4 * 4 + 256 * 4 + sizeof(Stage) * warps;
+    // First table level (64 KB) in shared memory: always for latency-bound launches; for
+    // saturating batches only if it does not cost warps (occupancy is worth more there).
+    p.l1_smem = (!big || base + 65536 + sizeof(Stage) * warps <= limit) ? 1 : 0;
+    if (const char *ev = getenv("DP_WAVE_L1SMEM")) p.l1_smem = atoi(ev) ? 1 : 0;   // tuning knob
+    const size_t fixed = base + (p.l1_smem ? 65536 : 0);
+    while (warps > 1 && fixed + sizeof(Stage) * warps > limit) --warps;
+    // the patterns join it when they fit beside the stages
+    p.pat_smem = (p.l1_smem && fixed + sizeof(Stage) * warps + (size_t)npat * 16 <= limit) ? npat : 0;
+    const size_t smem = fixed + sizeof(Stage) * warps + (size_t)p.pat_smem * 16;
     DP_CUDA(cudaFuncSetAttribute(k_diffuse_wave<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     int per_sm = 0;
@@ -1211,16 +1260,17 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
     k_wave_init<<<(int)((units + 255) / 256 < 1024 ? (units + 255) / 256 : 1024), 256, 0, st>>>(
         p.progress, p.qctrl, p.queue, (int)units, frames, p.nbands);
     DP_LAUNCH_CHECK();
+    const int npat = pal->dev.ed_npat;
     switch (variant) {
-        case DP_ED_FLOYD_STEINBERG: return launch_wave<DP_ED_FLOYD_STEINBERG>(p, st);
-        case DP_ED_JJN: return launch_wave<DP_ED_JJN>(p, st);
-        case DP_ED_STUCKI: return launch_wave<DP_ED_STUCKI>(p, st);
-        case DP_ED_BURKES: return launch_wave<DP_ED_BURKES>(p, st);
-        case DP_ED_ATKINSON: return launch_wave<DP_ED_ATKINSON>(p, st);
-        case DP_ED_SIERRA: return launch_wave<DP_ED_SIERRA>(p, st);
-        case DP_ED_SIERRA_TWO_ROW: return launch_wave<DP_ED_SIERRA_TWO_ROW>(p, st);
-        case DP_ED_SIERRA_LITE: return launch_wave<DP_ED_SIERRA_LITE>(p, st);
-        default: return launch_wave<V_OSTRO>(p, st);
+        case DP_ED_FLOYD_STEINBERG: return launch_wave<DP_ED_FLOYD_STEINBERG>(p, st, npat);
+        case DP_ED_JJN: return launch_wave<DP_ED_JJN>(p, st, npat);
+        case DP_ED_STUCKI: return launch_wave<DP_ED_STUCKI>(p, st, npat);
+        case DP_ED_BURKES: return launch_wave<DP_ED_BURKES>(p, st, npat);
+        case DP_ED_ATKINSON: return launch_wave<DP_ED_ATKINSON>(p, st, npat);
+        case DP_ED_SIERRA: return launch_wave<DP_ED_SIERRA>(p, st, npat);
+        case DP_ED_SIERRA_TWO_ROW: return launch_wave<DP_ED_SIERRA_TWO_ROW>(p, st, npat);
+        case DP_ED_SIERRA_LITE: return launch_wave<DP_ED_SIERRA_LITE>(p, st, npat);
+        default: return launch_wave<V_OSTRO>(p, st, npat);
     }
 }
 

@@ -113,6 +113,32 @@ def test_threshold_family_vs_oracle(pname):
             assert mismatch(gpu(img, pal, mode, params), ref) == 0, (pname, mode, params, img.shape)
 
 
+@pytest.mark.parametrize("k", [2, 3, 16, 27, 30, 31])
+def test_threshold_v4_kernel_vs_oracle(k):
+    """Widths that are multiples of 16 take k_thresh_v4 (K <= 30, shared-memory 32^3 table);
+    K = 31 and odd widths take the older kernels.  Tiles that straddle frames, ragged last
+    tiles, non-power-of-two widened matrices, cells with more than four candidates (noise and
+    lattice palettes), index output."""
+    pal = synth.random_palette(k, seed=100 + k) if k not in (16, 27) else (
+        PALS["pico8"] if k == 16 else PALS["lat27"])
+    modes = THRESH_MODES + [("bayer", {"size": "psx4x4"}), ("polka_dot", {"tile_size": 6}),
+                            ("blue_noise", {"size": 64, "seed": 42})]
+    for (h, w, kind) in [(16, 48, "noise"), (40, 64, "frame"), (33, 112, "blocks"), (96, 160, "noise")]:
+        if kind == "noise":
+            frames = np.stack([synth.noise_frame(h, w, 50 + t) for t in range(3)])
+        elif kind == "blocks":
+            frames = np.stack([synth.blocks_frame(h, w, 60 + t, 4, 5) for t in range(3)])
+        else:
+            frames = np.stack([synth.frame(h, w, 70 + t) for t in range(3)])
+        for mode, params in modes:
+            out, idx = engine.dither_frames(frames, pal, mode, params, return_indices=True)
+            for t in range(3):
+                ref = O.apply_dithering(frames[t], pal, mode, params)
+                assert mismatch(out[t], ref) == 0, (k, h, w, kind, mode, params, t)
+                # the index plane names a row with the output colour
+                assert np.array_equal(np.asarray(pal, np.uint8)[idx[t]], out[t]), (k, mode)
+
+
 @pytest.mark.parametrize("pname", ["pico8", "r64", "lat27"])
 def test_threshold_family_gamma_vs_oracle(pname):
     pal = PALS[pname]
