@@ -70,6 +70,7 @@ struct ThreshParams {
     int wm;          // v4: width of the widened threshold matrix in shared memory (multiple of 16)
     int sub_bytes;   // v4: shared bytes of the sub-cell table (multiple of 16)
     FastDiv dwm, dnpix;
+    FastDiv dspr, dh;   // geom2: strips per row, rows per frame
 };
 
 // IGN threshold (:541-549): f32, one rounding per numpy ufunc, no contraction.
@@ -863,6 +864,109 @@ __global__ void __launch_bounds__(THREADS) k_thresh_geom(const ThreshParams p)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Fused geometry, coalesced stores (config 4: pixelize -> dither -> x m up-scale).  The work is
+// dominated by the m*m-times larger output, so the kernel is organised around the stores: a warp
+// takes a strip of 32 consecutive dithered pixels of one row, every lane replicates its colour m
+// times into a shared row image (96*m bytes), and the warp writes that image to each of the m
+// output rows with 128-bit stores.  The lane's source pixel is fetched one strip ahead.
+// Needs 16-byte aligned output rows; otherwise k_thresh_geom.
+// ---------------------------------------------------------------------------------------
+constexpr int GEOM2_MAX_M = 8;
+
+template <int KIND>
+__global__ void __launch_bounds__(THREADS) k_thresh_geom2(const ThreshParams p)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *s_lut = smem;
+    uint8_t *s_orgb = s_lut + 256;
+    int4 *s_coef = reinterpret_cast<int4 *>(s_orgb + 1024);
+    float *s_mat = reinterpret_cast<float *>(s_coef + p.K);
+    const bool mat_in_smem = (KIND == DP_THRESH_MATRIX) && (p.mh * p.mw <= 1024);
+    uint8_t *s_row = reinterpret_cast<uint8_t *>(s_mat + (mat_in_smem ? p.mh * p.mw : 0));
+    s_row += (16 - (reinterpret_cast<uintptr_t>(s_row) & 15)) & 15;
+
+    const PalDev *P = p.P;
+    const int tid = threadIdx.x;
+    const int K = p.K;
+    s_lut[tid] = P->in_lut[tid];
+    for (int i = tid; i < K * 4; i += THREADS) s_orgb[i] = P->out_rgb[i];
+    if (p.integral)
+        for (int i = tid; i < K; i += THREADS) s_coef[i] = P->coef[i];
+    if (mat_in_smem)
+        for (int i = tid; i < p.mh * p.mw; i += THREADS) s_mat[i] = p.matrix[i];
+    __syncthreads();
+
+    const int lane = tid & 31, wib = tid >> 5;
+    const int m = p.upscale;
+    uint8_t *rowimg = s_row + wib * (96 * GEOM2_MAX_M);       // this warp's row image
+    const int strips_per_row = (p.w + 31) >> 5;
+    const uint32_t total = (uint32_t)p.frames * p.h * strips_per_row;     // < 2^31 (host check)
+    const size_t src_frame = (size_t)p.src_h * p.src_w * 3;
+    const size_t out_w3 = (size_t)p.w * m * 3;
+    const size_t dst_frame = (size_t)p.h * m * out_w3;
+    const uint32_t stride = gridDim.x * (THREADS / 32);
+
+    // strip id -> (frame, row, strip in the row)
+    auto locate = [&](uint32_t st, int &f, int &y, int &strip) {
+        const uint32_t rowid = fd_div(p.dspr, st);
+        strip = (int)(st - rowid * strips_per_row);
+        f = (int)fd_div(p.dh, rowid);
+        y = (int)(rowid - (uint32_t)f * p.h);
+    };
+    auto fetch = [&](uint32_t st) -> unsigned {
+        if (st >= total) return 0u;
+        int f, y, strip;
+        locate(st, f, y, strip);
+        const int x = strip * 32 + lane;
+        if (x >= p.w) return 0u;
+        const int sy = p.ytab ? __ldg(p.ytab + y) : y;
+        const int sx = p.xtab ? __ldg(p.xtab + x) : x;
+        const uint8_t *q = p.src + (size_t)f * src_frame + ((size_t)sy * p.src_w + sx) * 3;
+        return (unsigned)__ldg(q) | ((unsigned)__ldg(q + 1) << 8) | ((unsigned)__ldg(q + 2) << 16);
+    };
+    uint32_t st = blockIdx.x * (THREADS / 32) + wib;
+    unsigned nextv = fetch(st);
+    for (; st < total; st += stride) {
+        const unsigned v = nextv;
+        nextv = fetch(st + stride);
+        int f, y, strip;
+        locate(st, f, y, strip);
+        const int x = strip * 32 + lane;
+        const int nvalid = min(32, p.w - strip * 32);
+        if (x < p.w) {
+            int r = v & 255u, g = (v >> 8) & 255u, b = (v >> 16) & 255u;
+            if (p.has_lut) {
+                r = s_lut[r];
+                g = s_lut[g];
+                b = s_lut[b];
+            }
+            const float thr = threshold_at<KIND>(p, s_mat, mat_in_smem, x, y);
+            const int idx = p.integral ? pick_int<KIND>(P, s_coef, K, r, g, b, thr)
+                                       : pick_f64<KIND>(P, K, r, g, b, thr);
+            const uint8_t o0 = s_orgb[4 * idx], o1 = s_orgb[4 * idx + 1], o2 = s_orgb[4 * idx + 2];
+            uint8_t *d = rowimg + lane * m * 3;
+            for (int k = 0; k < m; ++k) {
+                d[3 * k] = o0;
+                d[3 * k + 1] = o1;
+                d[3 * k + 2] = o2;
+            }
+            if (p.dst_idx) p.dst_idx[((size_t)f * p.h + y) * p.w + x] = (uint8_t)idx;
+        }
+        __syncwarp();
+        const int nbytes = nvalid * m * 3;
+        const int n16 = nbytes >> 4;
+        uint8_t *drow = p.dst + (size_t)f * dst_frame + (size_t)y * m * out_w3 + (size_t)strip * 96 * m;
+        for (int rr = 0; rr < m; ++rr) {
+            uint8_t *o = drow + (size_t)rr * out_w3;
+            for (int j = lane; j < n16; j += 32)
+                __stcs(reinterpret_cast<uint4 *>(o) + j, reinterpret_cast<const uint4 *>(rowimg)[j]);
+            for (int j = (n16 << 4) + lane; j < nbytes; j += 32) o[j] = rowimg[j];
+        }
+        __syncwarp();
+    }
+}
+
 template <int KIND>
 int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
 {
@@ -911,6 +1015,20 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
         int grid = sms * per_sm;
         if (grid > p.total_tiles) grid = p.total_tiles;
         k_thresh_tile<KIND><<<grid, THREADS, smem, st>>>(p);
+    } else if (p.upscale <= GEOM2_MAX_M && ((size_t)p.w * p.upscale * 3) % 16 == 0 &&
+               (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0 &&
+               ((size_t)p.h * p.upscale * p.w * p.upscale * 3) % 16 == 0 &&
+               (long long)p.frames * p.h * ((p.w + 31) / 32) < (1ll << 31)) {
+        // output rows are 16-byte aligned: strip kernel with 128-bit stores
+        ThreshParams q = p;
+        q.dspr = make_fastdiv((uint32_t)((p.w + 31) / 32));
+        q.dh = make_fastdiv((uint32_t)p.h);
+        size_t smem = 256 + 1024 + (size_t)p.K * 16 + mat_bytes + 16 +
+                      (size_t)(THREADS / 32) * 96 * GEOM2_MAX_M;
+        long long strips = (long long)p.frames * p.h * ((p.w + 31) / 32);
+        long long want = (strips + THREADS / 32 - 1) / (THREADS / 32);
+        int grid = (int)(want < (long long)sms * 8 ? want : (long long)sms * 8);
+        k_thresh_geom2<KIND><<<grid, THREADS, smem, st>>>(q);
     } else {
         size_t smem = 256 + 1024 + (size_t)p.K * 16 + mat_bytes;
         long long total = (long long)p.frames * p.npix;
