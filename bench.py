@@ -225,7 +225,7 @@ def run_gpu(args):
         nonlocal launches
         for pl, d in zip(plans, dst):
             pl.run(pal, src.data_ptr(), B, d.data_ptr(), None, sp)
-            launches += 1  # one k_diffuse_wave launch per call
+            launches += 2  # k_wave_init + k_diffuse_wave per call
 
     def barrier():
         if world > 1:
@@ -250,7 +250,7 @@ def run_gpu(args):
             ev[k][0].record(stream)
             pl.run(pal, src.data_ptr(), B, d.data_ptr(), None, sp)
             ev[k][1].record(stream)
-            launches += 1
+            launches += 2
             k += 1
     e1.record(stream)
     barrier()

@@ -126,87 +126,7 @@ extern "C" int dp_stream_sync(void *stream)
     return 0;
 }
 
-// ---------------------------------------------------------------------------------------
-// 32^3 candidate grid: for every 8x8x8 box of colour space the palette rows that can be the
-// nearest row of SOME point of the box (closed box, conservative slack), ascending.
-// Used by the diffusion kernels, whose pixel values are arbitrary f32 in [0,255].
-// ---------------------------------------------------------------------------------------
 namespace {
-
-__device__ __forceinline__ void cell_bounds(int cell, double lo[3], double hi[3])
-{
-    int c[3] = {cell >> 10, (cell >> 5) & 31, cell & 31};
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        lo[i] = 8.0 * c[i];
-        hi[i] = 8.0 * c[i] + 8.0;
-    }
-}
-
-__device__ __forceinline__ void box_dists(const double *pp, const double lo[3],
-                                          const double hi[3], double &mn, double &mx)
-{
-    mn = 0.0;
-    mx = 0.0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        double a = lo[i] - pp[i], b = pp[i] - hi[i];
-        double g = fmax(0.0, fmax(a, b));
-        double f = fmax(fabs(a), fabs(b));
-        mn += g * g;
-        mx += f * f;
-    }
-}
-
-__global__ void k_cell_count(const double *pal, int K, uint32_t *count, uint8_t *list,
-                             const uint32_t *off)
-{
-    int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= 32768) return;
-    double lo[3], hi[3];
-    cell_bounds(cell, lo, hi);
-    double bound = 1e300;
-    for (int i = 0; i < K; ++i) {
-        double mn, mx;
-        box_dists(pal + 3 * i, lo, hi, mn, mx);
-        bound = fmin(bound, mx);
-    }
-    bound = bound * (1.0 + 1e-9) + 1e-6;
-    uint32_t n = 0;
-    uint32_t o = off ? off[cell] : 0;
-    for (int i = 0; i < K; ++i) {
-        double mn, mx;
-        box_dists(pal + 3 * i, lo, hi, mn, mx);
-        if (mn <= bound) {
-            if (list) list[o + n] = (uint8_t)i;
-            ++n;
-        }
-    }
-    if (count) count[cell] = n;
-}
-
-__global__ void k_scan_32768(const uint32_t *count, uint32_t *off)
-{
-    __shared__ uint32_t part[1024];
-    int t = threadIdx.x;
-    uint32_t loc[32];
-    uint32_t s = 0;
-    for (int i = 0; i < 32; ++i) {
-        loc[i] = s;
-        s += count[t * 32 + i];
-    }
-    part[t] = s;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {
-        uint32_t v = (t >= d) ? part[t - d] : 0;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
-    }
-    uint32_t base = (t == 0) ? 0 : part[t - 1];
-    for (int i = 0; i < 32; ++i) off[t * 32 + i] = base + loc[i];
-    if (t == 1023) off[32768] = part[1023];
-}
 
 // Exhaustive top-2 candidate masks: one block per cell of (1<<shift)^3 byte colours.  A palette
 // row is a candidate of the cell if, for SOME colour of the cell, its distance is <= the
@@ -552,42 +472,15 @@ extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out
     }
     h->blob = blob;
 
-    // candidate grid (count -> scan -> fill), synchronous: palette creation is set-up
-    uint32_t *count = nullptr, *off = nullptr;
-    uint8_t *list = nullptr;
-    bool ok = cudaMemcpy(blob, buf.data(), buf.size(), cudaMemcpyHostToDevice) == cudaSuccess;
-    ok = ok && cudaMalloc(&count, 32768 * 4) == cudaSuccess;
-    ok = ok && cudaMalloc(&off, 32769 * 4) == cudaSuccess;
-    uint32_t total = 0;
-    if (ok) {
-        k_cell_count<<<128, 256>>>(d.pal_f64, K, count, nullptr, nullptr);
-        k_scan_32768<<<1, 1024>>>(count, off);
-        ok = cudaMemcpy(&total, off + 32768, 4, cudaMemcpyDeviceToHost) == cudaSuccess;
-    }
-    ok = ok && cudaMalloc(&list, total ? total : 1) == cudaSuccess;
-    if (ok) {
-        k_cell_count<<<128, 256>>>(d.pal_f64, K, nullptr, list, off);
-        ok = cudaDeviceSynchronize() == cudaSuccess && cudaGetLastError() == cudaSuccess;
-    }
-    if (count) cudaFree(count);
-    if (!ok) {
-        dp_set_error("palette candidate-grid build failed: %s",
-                     cudaGetErrorString(cudaGetLastError()));
-        if (off) cudaFree(off);
-        if (list) cudaFree(list);
+    if (cudaMemcpy(blob, buf.data(), buf.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        dp_set_error("palette upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         cudaFree(blob);
         delete h;
         return 1;
     }
-    d.cell_off = off;
-    d.cell_list = list;
-    h->cell_off = off;
-    h->cell_list = list;
     if (build_ed_table(d.pal_f64, K, d, h)) {
         dp_set_error("palette nearest-row table build failed: %s",
                      cudaGetErrorString(cudaGetLastError()));
-        cudaFree(off);
-        cudaFree(list);
         cudaFree(blob);
         delete h;
         return 1;
@@ -638,8 +531,6 @@ extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out
             if (dovf) cudaFree(dovf);
             cudaFree(h->ed_table);
             cudaFree(h->ed_ovf);
-            cudaFree(off);
-            cudaFree(list);
             cudaFree(blob);
             delete h;
             return 1;
@@ -759,8 +650,6 @@ extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out
 extern "C" int dp_palette_destroy(dp_palette *pal)
 {
     if (!pal) return 0;
-    if (pal->cell_off) cudaFree(pal->cell_off);
-    if (pal->cell_list) cudaFree(pal->cell_list);
     if (pal->ed_table) cudaFree(pal->ed_table);
     if (pal->ed_ovf) cudaFree(pal->ed_ovf);
     if (pal->thr_table) cudaFree(pal->thr_table);

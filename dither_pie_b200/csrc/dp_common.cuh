@@ -58,9 +58,6 @@ struct PalDev {
     const double *kd_split;
     const int *kd_start, *kd_end, *kd_lesser, *kd_greater, *kd_indices;
     double kd_mins[3], kd_maxes[3];
-    // 32^3 candidate grid for nearest-colour search on arbitrary f32 values (diffusion modes)
-    const uint32_t *cell_off;  // [32768+1]
-    const uint8_t *cell_list;  // concatenated candidate lists, ascending index
     // top-2 candidate table for byte-valued pixels (integral palettes only): one 8-byte entry
     // per (256>>thr_shift)^3 cell, built by exhaustive enumeration of the 2^24 colours.
     //   x & 0xff = n (<= 7): candidates in bytes 1..7 of the entry, ascending
@@ -112,9 +109,7 @@ struct dp_palette {
     PalDev dev;
     int has_lut;   // in_lut is not the identity
     int device;
-    void *blob;    // single device allocation backing every pointer above (except cell_*)
-    void *cell_off;
-    void *cell_list;
+    void *blob;    // single device allocation backing the palette arrays and the KD-tree
     void *thr_table;
     void *thr_ovf;
     void *thr4_table;

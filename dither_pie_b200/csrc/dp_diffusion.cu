@@ -129,8 +129,6 @@ struct Spec {
     static constexpr int BMAX = cmax(B1, ROWS3 ? B2 : 0);
 };
 
-constexpr int WAVE_THREADS = 256;
-
 #ifdef DP_WAVE_TIMING
 __device__ unsigned long long g_wave_timing[128 * 4 + 4];   // + counters: slow pixels, slow warp-steps
 #define DP_TICK(k)                                                     \

@@ -53,6 +53,98 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate(
     }
 }
 
+// K <= 32: no atomics in the pixel loop.  A warp labels 32 pixels at a time; the labels are
+// screened in f32 against all centres (two smallest distances kept) and only pixels whose two
+// best distances are closer than the f32 error bound repeat the exact f64 comparison (strict
+// '<', first index).  The per-cluster sums of the 32 pixels are formed with warp reductions
+// (REDUX) cluster by cluster -- neighbouring pixels fall into a handful of clusters -- and lane
+// k keeps the running 64-bit totals of cluster k in registers; one flush per warp at the end.
+__global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate_warp(
+    const uint8_t *__restrict__ px, long long n, const double *__restrict__ centers, int K,
+    unsigned long long *__restrict__ sums)
+{
+    __shared__ double s_c[32 * 3];
+    __shared__ float4 s_cf[32];
+    if (threadIdx.x < K * 3) s_c[threadIdx.x] = centers[threadIdx.x];
+    if (threadIdx.x < K)
+        s_cf[threadIdx.x] = make_float4((float)centers[3 * threadIdx.x], (float)centers[3 * threadIdx.x + 1],
+                                        (float)centers[3 * threadIdx.x + 2], 0.f);
+    __syncthreads();
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const long long nchunk = (n + 31) >> 5;
+    const long long wstride = (long long)gridDim.x * (KM_THREADS / 32);
+    unsigned long long ar = 0, ag = 0, ab = 0, an = 0;     // totals of cluster `lane`
+    for (long long ch = (long long)blockIdx.x * (KM_THREADS / 32) + (threadIdx.x >> 5); ch < nchunk;
+         ch += wstride) {
+        const long long i = ch * 32 + lane;
+        const bool ok = i < n;
+        int r = 0, g = 0, b = 0, label = -1;
+        if (ok) {
+            const uint8_t *q = px + (size_t)i * 3;
+            r = q[0];
+            g = q[1];
+            b = q[2];
+            const float fr = (float)r, fg = (float)g, fb = (float)b;
+            float d1 = 3.0e38f, d2 = 3.0e38f;
+            int bi = 0;
+            for (int k = 0; k < K; ++k) {
+                const float4 c = s_cf[k];
+                const float e0 = fr - c.x, e1 = fg - c.y, e2 = fb - c.z;
+                const float d = fmaf(e2, e2, fmaf(e1, e1, e0 * e0));
+                if (d < d1) {
+                    d2 = d1;
+                    d1 = d;
+                    bi = k;
+                } else if (d < d2) {
+                    d2 = d;
+                }
+            }
+            // centre rounded to f32 (<= 255 * 2^-24) and the rounded difference give |e32 - e| <= 3.1e-5
+            // per channel, so |d32 - D| <= 1.07e-4 sqrt(D) + 1.8e-7 D; twice that (both distances)
+            // is below the margin used here for every D in [0, 195075]
+            if (d2 - d1 <= 3.0e-4f * sqrtf(d2) + 5.0e-7f * d2 + 3.0e-4f) {
+                const double x0 = r, x1 = g, x2 = b;
+                double best = 1e300;
+                for (int k = 0; k < K; ++k) {
+                    const double f0 = x0 - s_c[3 * k], f1 = x1 - s_c[3 * k + 1], f2 = x2 - s_c[3 * k + 2];
+                    const double d = __dadd_rn(__dadd_rn(__dmul_rn(f0, f0), __dmul_rn(f1, f1)),
+                                               __dmul_rn(f2, f2));
+                    if (d < best) {
+                        best = d;
+                        bi = k;
+                    }
+                }
+            }
+            label = bi;
+        }
+        // clusters present among the 32 pixels, one after the other (warp-uniform loop)
+        unsigned todo = __ballot_sync(FULL, ok);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            const int k = __shfl_sync(FULL, label, src);
+            const bool mine = ok && label == k;
+            const unsigned m = __ballot_sync(FULL, mine);
+            const unsigned sr = __reduce_add_sync(FULL, mine ? (unsigned)r : 0u);
+            const unsigned sg = __reduce_add_sync(FULL, mine ? (unsigned)g : 0u);
+            const unsigned sb = __reduce_add_sync(FULL, mine ? (unsigned)b : 0u);
+            if (lane == k) {
+                ar += sr;
+                ag += sg;
+                ab += sb;
+                an += __popc(m);
+            }
+            todo &= ~m;
+        }
+    }
+    if (lane < K && an) {
+        atomicAdd(&sums[4 * lane], ar);
+        atomicAdd(&sums[4 * lane + 1], ag);
+        atomicAdd(&sums[4 * lane + 2], ab);
+        atomicAdd(&sums[4 * lane + 3], an);
+    }
+}
+
 __global__ void k_kmeans_update(const unsigned long long *__restrict__ sums, int K,
                                 double *__restrict__ centers, double *__restrict__ shift2)
 {
@@ -80,8 +172,16 @@ extern "C" int dp_kmeans_accumulate(const uint8_t *pixels, int64_t n, const doub
     DP_REQUIRE(pixels && centers && sums, "null argument");
     DP_REQUIRE(K >= 1 && K <= DP_MAX_COLORS && n >= 0, "bad size");
     if (n == 0) return 0;
-    long long chunks = (n + KM_PIX_PER_BLOCK - 1) / KM_PIX_PER_BLOCK;
     long long cap = (long long)dp_num_sms() * 8;
+    if (K <= 32) {
+        long long blocks = ((n + 31) / 32 + KM_THREADS / 32 - 1) / (KM_THREADS / 32);
+        int grid = (int)(blocks < cap ? blocks : cap);
+        k_kmeans_accumulate_warp<<<grid, KM_THREADS, 0, dp_stream(stream)>>>(pixels, n, centers, K,
+                                                                             sums);
+        DP_LAUNCH_CHECK();
+        return 0;
+    }
+    long long chunks = (n + KM_PIX_PER_BLOCK - 1) / KM_PIX_PER_BLOCK;
     int grid = (int)(chunks < cap ? chunks : cap);
     k_kmeans_accumulate<<<grid, KM_THREADS, 0, dp_stream(stream)>>>(pixels, n, centers, K, sums);
     DP_LAUNCH_CHECK();
