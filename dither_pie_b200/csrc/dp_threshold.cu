@@ -698,31 +698,44 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_thresh_v4(const ThreshParams 
     const int lane = tid & 31;
     const int wib = tid >> 5;
     uint4 *io4 = s_io + wib * 192;
-    const long long total_px = (long long)p.frames * p.npix;         // frames are contiguous
-    const long long ntiles = (total_px + 511) >> 9;
-    const long long wstride = (long long)gridDim.x * V4_WARPS;
+    // 32-bit indexing: the host splits batches so that frames * npix < 2^31
+    const uint32_t total_px = (uint32_t)p.frames * (uint32_t)p.npix;  // frames are contiguous
+    const uint32_t ntiles = (total_px + 511u) >> 9;
+    const uint32_t wstride = gridDim.x * V4_WARPS;
     const uint4 *g4 = reinterpret_cast<const uint4 *>(p.src);
     uint4 *d4 = reinterpret_cast<uint4 *>(p.dst);
-    const long long n16_total = total_px * 3 / 16;                   // 16-byte units in the batch
+    const uint32_t n16_total = (total_px >> 4) * 3u;                  // 16-byte units in the batch
 
     // tile `t` -> staging buffer `buf` of this warp, asynchronously (LDGSTS, L2 -> shared)
-    auto issue = [&](long long t, int buf) {
-        const long long b16 = t * 96;
+    auto issue = [&](uint32_t t, int buf) {
+        const uint32_t b16 = t * 96u;
+        const uint4 *g = g4 + b16 + lane;
+        const unsigned d = smem_u32(io4 + buf * 96 + lane);
+        if (b16 + 96u <= n16_total) {     // whole tile (warp-uniform)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u), "l"(g + 32) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 1024u), "l"(g + 64) : "memory");
+        } else {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const long long i = b16 + 32 * j + lane;
-            if (i < n16_total) {
-                const unsigned d = smem_u32(io4 + buf * 96 + 32 * j + lane);
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g4 + i) : "memory");
-            }
+            for (int j = 0; j < 3; ++j)
+                if (b16 + 32u * j + lane < n16_total)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u * j), "l"(g + 32 * j)
+                                 : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    long long wt = (long long)blockIdx.x * V4_WARPS + wib;
+    uint32_t wt = blockIdx.x * V4_WARPS + wib;
     int buf = 0;
     if (wt < ntiles) issue(wt, 0);
+    // position of this lane's first pixel inside its frame, advanced incrementally
+    uint32_t pin = 0, pstep = 0;
+    if (KIND != DP_THRESH_NONE) {
+        const uint32_t gp0 = (wt << 9) + 16u * lane, adv = wstride << 9;
+        pin = gp0 - fd_div(p.dnpix, gp0) * (uint32_t)p.npix;
+        pstep = adv - fd_div(p.dnpix, adv) * (uint32_t)p.npix;
+    }
     for (; wt < ntiles; wt += wstride, buf ^= 1) {
-        const long long b16 = wt * 96;
+        const uint32_t b16 = wt * 96u;
         if (wt + wstride < ntiles)
             issue(wt + wstride, buf ^ 1);
         else
@@ -738,18 +751,14 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_thresh_v4(const ThreshParams 
             w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
             w[8] = cq.x; w[9] = cq.y; w[10] = cq.z; w[11] = cq.w;
         }
-        const long long gp = (wt << 9) + 16 * lane;                  // first pixel (batch index)
+        const uint32_t gp = (wt << 9) + 16u * lane;                  // first pixel (batch index)
         const bool live = gp < total_px;
         uint32_t x = 0, y = 0;
         if (KIND != DP_THRESH_NONE) {
-            uint32_t pin;
-            if (total_px < (1ll << 31)) {
-                pin = (uint32_t)gp - fd_div(p.dnpix, (uint32_t)gp) * (uint32_t)p.npix;
-            } else {
-                pin = (uint32_t)(gp % p.npix);
-            }
             y = fd_div(p.dw, pin);
             x = pin - y * p.w;                                       // multiple of 16
+            pin += pstep;
+            if (pin >= (uint32_t)p.npix) pin -= (uint32_t)p.npix;
         }
         unsigned ra = 0;   // shared address of this lane's 16 thresholds
         if (KIND == DP_THRESH_MATRIX) {
@@ -795,9 +804,18 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_thresh_v4(const ThreshParams 
             v4_fix<KIND, WM_POW2>(p, slowmask, gp, x, y, ra, reinterpret_cast<uint8_t *>(cur + 3 * lane),
                                   s_orgb);
         __syncwarp();
-        if (b16 + lane < n16_total) __stcs(d4 + b16 + lane, cur[lane]);
-        if (b16 + 32 + lane < n16_total) __stcs(d4 + b16 + 32 + lane, cur[32 + lane]);
-        if (b16 + 64 + lane < n16_total) __stcs(d4 + b16 + 64 + lane, cur[64 + lane]);
+        {
+            uint4 *o = d4 + b16 + lane;
+            if (b16 + 96u <= n16_total) {     // whole tile (warp-uniform)
+                __stcs(o, cur[lane]);
+                __stcs(o + 32, cur[32 + lane]);
+                __stcs(o + 64, cur[64 + lane]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if (b16 + 32u * j + lane < n16_total) __stcs(o + 32 * j, cur[32 * j + lane]);
+            }
+        }
         __syncwarp();
     }
 }
@@ -979,7 +997,7 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
         void (*kern)(ThreshParams) = pow2 ? k_thresh_v4<KIND, true> : k_thresh_v4<KIND, false>;
         DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const long long ntiles = ((long long)p.frames * p.npix + 511) >> 9;
-        const long long want = (ntiles + V4_WARPS - 1) / V4_WARPS;
+        const long long want = (ntiles + V4_WARPS - 1) / V4_WARPS;   // frames * npix < 2^31 here
         const int grid = (int)(want < sms ? want : sms);
         kern<<<grid, V4_THREADS, smem, st>>>(p);
     } else if (!geom && p.fast) {
@@ -1109,7 +1127,8 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
         const int sub_bytes = ((8 * pal->dev.thr4_nsub + 3) & ~3) * 4;
         const long long need = 131072 + 272 + 128 + (long long)V4_WARPS * 3072 + sub_bytes +
                                (kind == DP_THRESH_MATRIX ? (long long)p.mh * wm * 4 : 0);
-        if (need <= 227 * 1024 && (kind != DP_THRESH_MATRIX || (long long)p.mh * wm <= 4096)) {
+        if (need <= 227 * 1024 && (long long)frames * p.npix < (1ll << 31) &&
+            (kind != DP_THRESH_MATRIX || (long long)p.mh * wm <= 4096)) {
             p.fast = 4;
             p.sub_bytes = sub_bytes;
             p.wm = wm;
