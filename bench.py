@@ -328,8 +328,15 @@ def run_gpu(args):
     avg_kernel_ms = sum(kernel_ms) / len(kernel_ms)
     alg_bytes = BYTES_PER_PX * B * H4K * W4K
     achieved = alg_bytes / (avg_kernel_ms * 1e-3) / 1e9
+    # DRAM traffic per launch: 7.85 GB for 128 4K frames in the ncu --set full capture of
+    # k_diffuse_wave<floyd_steinberg> (profiles/r1f_diffuse_wave_fs_K256_4k_x128.txt), i.e.
+    # 7.39 B/pixel against 6 algorithmic -- the hand-off streams and the candidate table
+    traffic = 7.849621e9 / (128 * H4K * W4K) * (B * H4K * W4K)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "kernel": "k_diffuse_wave",
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
+                                  "profiles/r1f_diffuse_wave_fs_K256_4k_x128.txt (scaled by frames)",
+                "kernel": "k_diffuse_wave",
                 "peak_source": peak_src, "avg_launch_ms": avg_kernel_ms,
                 "note": "error diffusion is bounded by its per-pixel dependency chain (~1100 cycles "
                         "per wavefront step, 314 instructions) and by instruction issue, not by HBM; "
