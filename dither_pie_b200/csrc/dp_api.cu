@@ -130,9 +130,11 @@ namespace {
 
 // Exhaustive top-2 candidate masks: one block per cell of (1<<shift)^3 byte colours.  A palette
 // row is a candidate of the cell if, for SOME colour of the cell, its distance is <= the
-// second-smallest distance (so every row that can be nearest or second nearest, ties included).
+// second-smallest distance (so every row that can be nearest or second nearest, ties included);
+// with nearest_only: <= the smallest distance (every row that can be nearest, ties included).
 __global__ void __launch_bounds__(256) k_thr_masks(const int4 *__restrict__ coef, int K, int shift,
-                                                   uint32_t *__restrict__ masks)
+                                                   uint32_t *__restrict__ masks,
+                                                   int nearest_only = 0)
 {
     __shared__ int4 s_coef[DP_MAX_COLORS];
     __shared__ uint32_t s_mask[8];
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(256) k_thr_masks(const int4 *__restrict__ coef
         for (int i = 0; i < K; ++i) {
             const int4 c = s_coef[i];
             const int s = (r * c.x + g * c.y + b * c.z + c.w) >> 8;
-            if (s <= m2) local[i >> 5] |= 1u << (i & 31);
+            if (s <= (nearest_only ? m1 : m2)) local[i >> 5] |= 1u << (i & 31);
         }
     }
     for (int wd = 0; wd < 8; ++wd)
@@ -355,6 +357,83 @@ int build_tie_table(PalDev &d, dp_palette *h, const void *dev_paldev, int K)
     return 0;
 }
 
+// Compact 32^3 candidate table for k_thresh_v4 (format: dp_common.cuh): `slots` candidates per
+// u32 entry, cells with more get eight 4x4x4 sub-cell entries.  K <= 30.  Returns false if the
+// table cannot be built (the older kernels then do the work).
+bool build_compact_table(const int4 *d_coef, int K, int nearest_only, int slots, void **out_table,
+                         void **out_sub, int *out_nsub)
+{
+    std::vector<uint32_t> m3((size_t)32768 * 8);
+    uint32_t *dm = nullptr;
+    bool ok = cudaMalloc(&dm, (size_t)32768 * 32) == cudaSuccess;
+    if (ok) {
+        k_thr_masks<<<32768, 256>>>(d_coef, K, 3, dm, nearest_only);
+        ok = cudaMemcpy(m3.data(), dm, (size_t)32768 * 32, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    if (dm) cudaFree(dm);
+    if (!ok) return false;
+    auto pack = [K, slots](uint32_t w0, bool &over) {
+        unsigned slot[4] = {(unsigned)K * 8u, (unsigned)K * 8u, (unsigned)K * 8u, 0u};
+        if (slots == 4) slot[3] = (unsigned)K * 8u;
+        int cnt = 0;
+        for (int i = 0; i < K; ++i)
+            if (w0 >> i & 1u) {
+                if (cnt < slots) slot[cnt] = (unsigned)i * 8u;
+                ++cnt;
+            }
+        over = cnt > slots;
+        if (over) slot[3] = 0xf8u;   // row 31: a pad row, and the overflow mark
+        return slot[0] | (slot[1] << 8) | (slot[2] << 16) | (slot[3] << 24);
+    };
+    std::vector<uint32_t> t4(32768), sub;
+    std::vector<int> ocell;
+    for (int c = 0; c < 32768; ++c) {
+        bool over;
+        t4[c] = pack(m3[(size_t)c * 8], over);
+        if (over) {
+            t4[c] = 0xf8000000u | (uint32_t)ocell.size();
+            ocell.push_back(c);
+        }
+    }
+    if (ocell.size() > 8192) return false;
+    if (!ocell.empty()) {
+        // masks of the 4x4x4 sub-cells (64^3 grid), only read for the crowded cells
+        uint32_t *dm2 = nullptr;
+        std::vector<uint32_t> m2((size_t)262144 * 8);
+        ok = cudaMalloc(&dm2, (size_t)262144 * 32) == cudaSuccess;
+        if (ok) {
+            k_thr_masks<<<262144, 64>>>(d_coef, K, 2, dm2, nearest_only);
+            ok = cudaMemcpy(m2.data(), dm2, (size_t)262144 * 32, cudaMemcpyDeviceToHost) == cudaSuccess;
+        }
+        if (dm2) cudaFree(dm2);
+        if (!ok) return false;
+        sub.resize(ocell.size() * 8);
+        for (size_t n = 0; n < ocell.size(); ++n) {
+            const int c = ocell[n], cr = c >> 10, cg = (c >> 5) & 31, cb = c & 31;
+            for (int s8 = 0; s8 < 8; ++s8) {
+                const int fr = cr * 2 + (s8 >> 2), fg = cg * 2 + ((s8 >> 1) & 1), fb = cb * 2 + (s8 & 1);
+                bool over;
+                sub[n * 8 + s8] = pack(m2[((size_t)(fr * 64 + fg) * 64 + fb) * 8], over);
+            }
+        }
+    }
+    void *d4 = nullptr, *dsub = nullptr;
+    ok = cudaMalloc(&d4, 32768 * 4) == cudaSuccess &&
+         cudaMemcpy(d4, t4.data(), 32768 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMalloc(&dsub, sub.size() * 4 + 16) == cudaSuccess &&
+         (sub.empty() ||
+          cudaMemcpy(dsub, sub.data(), sub.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess);
+    if (!ok) {
+        if (d4) cudaFree(d4);
+        if (dsub) cudaFree(dsub);
+        return false;
+    }
+    *out_table = d4;
+    *out_sub = dsub;
+    *out_nsub = (int)ocell.size();
+    return true;
+}
+
 template <typename T>
 size_t put(std::vector<uint8_t> &buf, const T *src, size_t n, size_t align = 16)
 {
@@ -542,86 +621,27 @@ extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out
         h->thr_table = dt;
         h->thr_ovf = dovf;
         if (K <= 30) {
-            // compact 32^3 table for k_thresh_v4 (format: dp_common.cuh)
-            std::vector<uint32_t> m3;
-            const std::vector<uint32_t> *mk = &hmask;
-            if (shift != 3) {
-                uint32_t *dm = nullptr;
-                m3.resize((size_t)32768 * 8);
-                bool ok4 = cudaMalloc(&dm, (size_t)32768 * 32) == cudaSuccess;
-                if (ok4) {
-                    k_thr_masks<<<32768, 256>>>(d.coef, K, 3, dm);
-                    ok4 = cudaMemcpy(m3.data(), dm, (size_t)32768 * 32, cudaMemcpyDeviceToHost) ==
-                          cudaSuccess;
-                }
-                if (dm) cudaFree(dm);
-                mk = ok4 ? &m3 : nullptr;
+            // compact 32^3 tables for k_thresh_v4: top-2 candidates (4 slots) for the threshold
+            // modes, nearest candidates (3 slots) for plain quantisation
+            void *t = nullptr, *sb = nullptr;
+            int ns = 0;
+            if (build_compact_table(d.coef, K, 0, 4, &t, &sb, &ns) && ns <= 1024) {
+                d.thr4_table = static_cast<const uint32_t *>(t);
+                d.thr4_sub = static_cast<const uint32_t *>(sb);
+                d.thr4_nsub = ns;
+                h->thr4_table = t;
+                h->thr4_sub = sb;
+            } else {
+                if (t) cudaFree(t);
+                if (sb) cudaFree(sb);
             }
-            void *d4 = nullptr;
-            if (mk) {
-                auto pack4 = [K](uint32_t w0, bool &over) {
-                    unsigned slot[4] = {(unsigned)K * 8u, (unsigned)K * 8u, (unsigned)K * 8u,
-                                        (unsigned)K * 8u};
-                    int cnt = 0;
-                    for (int i = 0; i < K; ++i)
-                        if (w0 >> i & 1u) {
-                            if (cnt < 4) slot[cnt] = (unsigned)i * 8u;
-                            ++cnt;
-                        }
-                    over = cnt > 4;
-                    if (over) slot[3] = 0xf8u;   // row 31: a pad row, and the overflow mark
-                    return slot[0] | (slot[1] << 8) | (slot[2] << 16) | (slot[3] << 24);
-                };
-                std::vector<uint32_t> t4(32768), sub;
-                std::vector<int> ocell;
-                for (int c = 0; c < 32768; ++c) {
-                    bool over;
-                    t4[c] = pack4((*mk)[(size_t)c * 8], over);
-                    if (over) {
-                        t4[c] = 0xf8000000u | (uint32_t)ocell.size();
-                        ocell.push_back(c);
-                    }
-                }
-                bool ok5 = true;
-                if (!ocell.empty()) {
-                    // masks of the 4x4x4 sub-cells (64^3 grid), only read for the overflow cells
-                    uint32_t *dm2 = nullptr;
-                    std::vector<uint32_t> m2((size_t)262144 * 8);
-                    ok5 = cudaMalloc(&dm2, (size_t)262144 * 32) == cudaSuccess;
-                    if (ok5) {
-                        k_thr_masks<<<262144, 64>>>(d.coef, K, 2, dm2);
-                        ok5 = cudaMemcpy(m2.data(), dm2, (size_t)262144 * 32,
-                                         cudaMemcpyDeviceToHost) == cudaSuccess;
-                    }
-                    if (dm2) cudaFree(dm2);
-                    sub.resize(ocell.size() * 8);
-                    for (size_t n = 0; ok5 && n < ocell.size(); ++n) {
-                        const int c = ocell[n], cr = c >> 10, cg = (c >> 5) & 31, cb = c & 31;
-                        for (int s8 = 0; s8 < 8; ++s8) {
-                            const int fr = cr * 2 + (s8 >> 2), fg = cg * 2 + ((s8 >> 1) & 1),
-                                      fb = cb * 2 + (s8 & 1);
-                            bool over;
-                            sub[n * 8 + s8] = pack4(m2[((size_t)(fr * 64 + fg) * 64 + fb) * 8], over);
-                        }
-                    }
-                }
-                void *dsub = nullptr;
-                ok5 = ok5 && ocell.size() <= 1024 &&
-                      cudaMalloc(&d4, 32768 * 4) == cudaSuccess &&
-                      cudaMemcpy(d4, t4.data(), 32768 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
-                      cudaMalloc(&dsub, sub.size() * 4 + 16) == cudaSuccess &&
-                      (sub.empty() || cudaMemcpy(dsub, sub.data(), sub.size() * 4,
-                                                 cudaMemcpyHostToDevice) == cudaSuccess);
-                if (ok5) {
-                    d.thr4_table = static_cast<const uint32_t *>(d4);
-                    d.thr4_sub = static_cast<const uint32_t *>(dsub);
-                    d.thr4_nsub = (int)ocell.size();
-                    h->thr4_table = d4;
-                    h->thr4_sub = dsub;
-                } else {   // the v3 kernels still work without it
-                    if (d4) cudaFree(d4);
-                    if (dsub) cudaFree(dsub);
-                }
+            t = sb = nullptr;
+            if (build_compact_table(d.coef, K, 1, 3, &t, &sb, &ns)) {
+                d.near3_table = static_cast<const uint32_t *>(t);
+                d.near3_sub = static_cast<const uint32_t *>(sb);
+                d.near3_nsub = ns;
+                h->near3_table = t;
+                h->near3_sub = sb;
             }
         }
     }
@@ -656,6 +676,8 @@ extern "C" int dp_palette_destroy(dp_palette *pal)
     if (pal->thr_ovf) cudaFree(pal->thr_ovf);
     if (pal->thr4_table) cudaFree(pal->thr4_table);
     if (pal->thr4_sub) cudaFree(pal->thr4_sub);
+    if (pal->near3_table) cudaFree(pal->near3_table);
+    if (pal->near3_sub) cudaFree(pal->near3_sub);
     if (pal->tie_table) cudaFree(pal->tie_table);
     if (pal->blob) cudaFree(pal->blob);
     delete pal;

@@ -75,6 +75,11 @@ struct PalDev {
     const uint32_t *thr4_table;   // [32768] or null
     const uint32_t *thr4_sub;     // [8 * thr4_nsub]
     int thr4_nsub;
+    // the same for plain nearest-colour quantisation: rows that can be NEAREST (ties included),
+    // three slots per entry; sub-cell entries are read from global memory (L1)
+    const uint32_t *near3_table;  // [32768] or null
+    const uint32_t *near3_sub;    // [8 * near3_nsub]
+    int near3_nsub;
     // Exception table of the byte colours with an exact distance tie among their three nearest
     // rows (integral palettes): scipy's answers, replayed once at palette creation.
     //   x = colour (r | g<<8 | b<<16) | nearest row of query(k=1) << 24
@@ -114,6 +119,8 @@ struct dp_palette {
     void *thr_ovf;
     void *thr4_table;
     void *thr4_sub;
+    void *near3_table;
+    void *near3_sub;
     void *tie_table;
     void *ed_table;   // one allocation: level 1 | patterns | flat
     void *ed_ovf;     // one allocation: cells | offsets | lists

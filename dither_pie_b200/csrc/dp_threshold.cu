@@ -560,6 +560,7 @@ __device__ __forceinline__ float4 lds_f32x4(unsigned a)
 
 struct V4Ctx {
     unsigned table_a, ent_a, orgb_a, sub_a;   // shared-space addresses
+    const uint32_t *sub_g;                    // nearest-only table: sub-cell entries (global, L1)
     const PalDev *P;
     int K;
 };
@@ -575,6 +576,25 @@ __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float th
     const unsigned a5 = (v >> 3) & 0x1f1f1fu;
     const unsigned ta = (a5 & 0x1fu) * 4096u + __dp4a(a5, 0x00048000u, c.table_a);
     unsigned e = lds_u32(ta);
+    if (KIND == DP_THRESH_NONE) {
+        // plain quantisation: the table holds the rows that can be NEAREST in the cell, three
+        // slots; the answer is the smallest key unless the two smallest tie
+        if (e >= 0xf8000000u) {
+            const unsigned sc = ((v >> 2) & 1u) * 4u + ((v >> 10) & 1u) * 2u + ((v >> 18) & 1u);
+            e = __ldg(c.sub_g + (e & 0xffffu) * 8u + sc);
+        }
+        const int2 q0 = lds_s32x2(__dp4a(e, 0x00000001u, c.ent_a));
+        const int2 q1 = lds_s32x2(__dp4a(e, 0x00000100u, c.ent_a));
+        const int2 q2 = lds_s32x2(__dp4a(e, 0x00010000u, c.ent_a));
+        const int k0 = q0.y - 512 * (int)__dp4a(v, (unsigned)q0.x, 0u);
+        const int k1 = q1.y - 512 * (int)__dp4a(v, (unsigned)q1.x, 0u);
+        const int k2 = q2.y - 512 * (int)__dp4a(v, (unsigned)q2.x, 0u);
+        const int m1 = min(min(k0, k1), k2);
+        const int m3 = max(max(k0, k1), k2);
+        const int m2 = (int)((unsigned)k0 + (unsigned)k1 + (unsigned)k2 - (unsigned)m1 - (unsigned)m3);
+        slow = (e >= 0xf8000000u) || ((unsigned)(m1 ^ m2) < 256u);
+        return (unsigned)m1 & 255u;
+    }
     if (e >= 0xf8000000u) {   // more than four candidates in the 8^3 cell: refine to the 4^3 sub-cell
         const unsigned sc = ((v >> 2) & 1u) * 4u + ((v >> 10) & 1u) * 2u + ((v >> 18) & 1u);
         e = lds_u32(c.sub_a + ((e & 0xffffu) * 8u + sc) * 4u);
@@ -593,10 +613,6 @@ __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float th
     const int x = max(lo01, lo23);
     const int m2 = min(min(x, hi01), hi23);
     slow = e >= 0xf8000000u;                                    // still more than four candidates
-    if (KIND == DP_THRESH_NONE) {
-        slow = slow || ((unsigned)(m1 ^ m2) < 256u);            // nearest not unique
-        return (unsigned)m1 & 255u;
-    }
     const int mx = max(max(x, hi01), hi23);
     // the median of {x, hi01, hi23}; modular arithmetic, the pad key 0x7fffffff may wrap
     const int m3 = (int)((unsigned)x + (unsigned)hi01 + (unsigned)hi23 - (unsigned)m2 - (unsigned)mx);
@@ -654,10 +670,12 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_thresh_v4(const ThreshParams 
     const int tid = threadIdx.x;
     const int K = p.K;
     {
-        const uint4 *src4 = reinterpret_cast<const uint4 *>(P->thr4_table);
+        const uint4 *src4 = reinterpret_cast<const uint4 *>(KIND == DP_THRESH_NONE ? P->near3_table
+                                                                                   : P->thr4_table);
         uint4 *dst4 = reinterpret_cast<uint4 *>(s_table);
         for (int i = tid; i < 8192; i += V4_THREADS) dst4[i] = __ldg(src4 + i);
-        for (int i = tid; i < 8 * P_nsub; i += V4_THREADS) s_sub[i] = __ldg(P->thr4_sub + i);
+        if (KIND != DP_THRESH_NONE)
+            for (int i = tid; i < 8 * P_nsub; i += V4_THREADS) s_sub[i] = __ldg(P->thr4_sub + i);
     }
     if (tid < 34) {
         int2 en = make_int2(0, 0x7fffff00 | 255);       // pad rows never win
@@ -691,6 +709,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_thresh_v4(const ThreshParams 
     ctx.ent_a = smem_u32(s_ent);
     ctx.orgb_a = smem_u32(s_orgb);
     ctx.sub_a = smem_u32(s_sub);
+    ctx.sub_g = P->near3_sub;
     ctx.P = P;
     ctx.K = K;
     const unsigned mat_a = smem_u32(s_mat);
@@ -1115,7 +1134,7 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
         ((reinterpret_cast<uintptr_t>(src_rgb) | reinterpret_cast<uintptr_t>(dst_rgb)) & 15) == 0 &&
         p.npix % 16 == 0 && (!dst_idx || (reinterpret_cast<uintptr_t>(dst_idx) & 3) == 0))
         p.fast = (pal->dev.thr_cells <= 4096) ? 1 : 2;
-    if (p.fast && pal->dev.thr4_table && pal->dev.K <= 30 && !pal->has_lut && geo->w % 16 == 0 &&
+    if (p.fast && (kind == DP_THRESH_NONE ? pal->dev.near3_table : pal->dev.thr4_table) && pal->dev.K <= 30 && !pal->has_lut && geo->w % 16 == 0 &&
         (!dst_idx || (reinterpret_cast<uintptr_t>(dst_idx) & 15) == 0) && !getenv("DP_THRESH_NO_V4")) {
         // widened matrix width: the smallest common multiple of mat_w and 16
         int wm = 16;
