@@ -532,8 +532,13 @@ __global__ void __launch_bounds__(THREADS) k_thresh_fast(const ThreshParams p)
 // private, double-buffered 1.5 KB shared buffer (the next tile is in flight as cp.async while
 // the current one is processed); a lane owns 16 consecutive pixels (48 bytes) in registers.
 // ---------------------------------------------------------------------------------------
-constexpr int V4_THREADS = 768;
-constexpr int V4_WARPS = V4_THREADS / 32;
+// 24 warps per SM for the threshold kinds (80 registers); plain quantisation needs fewer
+// registers and no matrix, so 32 warps fit beside the table
+template <int KIND>
+__host__ __device__ constexpr int v4_threads()
+{
+    return KIND == DP_THRESH_NONE ? 1024 : 768;
+}
 
 __device__ __forceinline__ unsigned smem_u32(const void *p)
 {
@@ -655,8 +660,10 @@ __device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, lo
 }
 
 template <int KIND, bool WM_POW2>
-__global__ void __launch_bounds__(V4_THREADS, 1) k_thresh_v4(const ThreshParams p)
+__global__ void __launch_bounds__(v4_threads<KIND>(), 1) k_thresh_v4(const ThreshParams p)
 {
+    constexpr int V4_THREADS = v4_threads<KIND>();
+    constexpr int V4_WARPS = V4_THREADS / 32;
     extern __shared__ __align__(16) uint8_t smem[];
     const int P_nsub = p.P->thr4_nsub;
     uint32_t *s_table = reinterpret_cast<uint32_t *>(smem);                    // [32768]
@@ -664,7 +671,7 @@ __global__ void __launch_bounds__(V4_THREADS, 1) k_thresh_v4(const ThreshParams 
     unsigned *s_orgb = reinterpret_cast<unsigned *>(smem + 131072 + 272);      // [32]
     uint4 *s_io = reinterpret_cast<uint4 *>(smem + 131072 + 272 + 128);        // [warps][2][96]
     uint32_t *s_sub = reinterpret_cast<uint32_t *>(s_io + V4_WARPS * 192);     // [8 * nsub]
-    float *s_mat = reinterpret_cast<float *>(s_sub + ((8 * P_nsub + 3) & ~3));   // [mh][wm]
+    float *s_mat = reinterpret_cast<float *>(s_sub + (KIND == DP_THRESH_NONE ? 0 : ((8 * P_nsub + 3) & ~3)));   // [mh][wm]
 
     const PalDev *P = p.P;
     const int tid = threadIdx.x;
@@ -1011,7 +1018,10 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
     size_t mat_bytes = (KIND == DP_THRESH_MATRIX && p.mh * p.mw <= 1024) ? (size_t)p.mh * p.mw * 4 : 0;
     if (!geom && p.fast == 4) {
         const bool pow2 = (p.wm & (p.wm - 1)) == 0;
-        const size_t smem = 131072 + 272 + 128 + (size_t)V4_WARPS * 3072 + (size_t)p.sub_bytes +
+        constexpr int V4_THREADS = v4_threads<KIND>();
+        constexpr int V4_WARPS = V4_THREADS / 32;
+        const size_t smem = 131072 + 272 + 128 + (size_t)V4_WARPS * 3072 +
+                            (KIND == DP_THRESH_NONE ? 0 : (size_t)p.sub_bytes) +
                             (KIND == DP_THRESH_MATRIX ? (size_t)p.mh * p.wm * 4 : 0);
         void (*kern)(ThreshParams) = pow2 ? k_thresh_v4<KIND, true> : k_thresh_v4<KIND, false>;
         DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1144,7 +1154,8 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
             wm = p.mw / a * 16;
         }
         const int sub_bytes = ((8 * pal->dev.thr4_nsub + 3) & ~3) * 4;
-        const long long need = 131072 + 272 + 128 + (long long)V4_WARPS * 3072 + sub_bytes +
+        const long long need = 131072 + 272 + 128 +
+                               (kind == DP_THRESH_NONE ? 32ll * 3072 : 24ll * 3072 + sub_bytes) +
                                (kind == DP_THRESH_MATRIX ? (long long)p.mh * wm * 4 : 0);
         if (need <= 227 * 1024 && (long long)frames * p.npix < (1ll << 31) &&
             (kind != DP_THRESH_MATRIX || (long long)p.mh * wm <= 4096)) {
