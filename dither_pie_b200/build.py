@@ -67,5 +67,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_timing() -> str:
+    """Debug variant for tools/wave_timing.py: the wavefront kernel with per-phase clock64()
+    counters (-DDP_WAVE_TIMING).  Written next to the objects, never loaded by the product."""
+    build()
+    out = os.path.join(OBJ_DIR, "libditherpie_b200_timing.so")
+    tobj = os.path.join(OBJ_DIR, "dp_diffusion_timing.o")
+    subprocess.check_call(["nvcc", *NVCC_FLAGS, "-DDP_WAVE_TIMING", "-c",
+                           os.path.join(CSRC, "dp_diffusion.cu"), "-o", tobj])
+    others = [os.path.join(OBJ_DIR, s[:-3] + ".o") for s in sources() if s != "dp_diffusion.cu"]
+    subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-o", out, tobj, *others, "-lcudart"])
+    return out
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--timing" in sys.argv:
+        print(build_timing())
+    else:
+        print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

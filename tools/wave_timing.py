@@ -1,4 +1,6 @@
-"""Debug: per-phase cycle counts of k_diffuse_wave (library built with -DDP_WAVE_TIMING)."""
+"""Debug: per-phase cycle counts of k_diffuse_wave.  Needs the instrumented library:
+    python -m dither_pie_b200.build --timing
+    gpurun -- 'python tools/wave_timing.py floyd_steinberg 1'"""
 import ctypes as C, json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
