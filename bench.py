@@ -176,7 +176,17 @@ class ClockSampler:
 # GPU arm
 # ------------------------------------------------------------------------------------------
 
+def _emit(line: dict, fd: int):
+    """The one JSON line, written to the REAL stdout (fd saved before anything else could print)."""
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def run_gpu(args):
+    # Libraries print to stdout (NCCL's version banner at the first collective): keep the process's
+    # stdout for the one JSON line and send everything else to stderr.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -368,7 +378,7 @@ def run_gpu(args):
                 line["modes"] = extra_modes(torch, engine, synth, sp, stream, peak)
             except Exception as e:  # never lose the headline line to an extra
                 line["modes"] = {"error": str(e)[:200]}
-    print(json.dumps(line))
+    _emit(line, real_stdout)
     if world > 1:
         dist.destroy_process_group()
 
