@@ -528,7 +528,7 @@ __device__ __forceinline__ float to_f32(double v) { return __double2float_rn(v);
 __device__ __forceinline__ float to_f32(float v) { return v; }
 
 template <int V>
-__global__ void __launch_bounds__(wave_max_warps<V>() * 32) k_diffuse_wave(const WaveParams p)
+__global__ void __launch_bounds__(wave_max_warps<V>() * 32, 1) k_diffuse_wave(const WaveParams p)
 {
     using SP = Spec<V>;
     using T = typename StateOf<V>::T;
