@@ -504,13 +504,14 @@ struct WarpStageT {
     unsigned char outb[32][108];
 };
 
-// Warps per block: the numba variants with a 5x5 footprint (JJN, Stucki) keep ~55 doubles of
-// window state per lane (242 registers) -> 8 warps; everything else fits 12 warps per SM.
+// Warps per block, from the registers ptxas needs without spilling the window state: 8 for the
+// 5x5 footprints (JJN, Stucki: 221 registers; capping them at 168 for 12 warps gains 4 % on
+// saturating batches but costs 9 % on a single image), 12 for Sierra and Ostromoukhov (168), 16
+// (128 registers) for the rest.
 template <int V>
 constexpr int wave_max_warps()
 {
-    return (V == DP_ED_JJN || V == DP_ED_STUCKI) ? 8
-         : (V == DP_ED_FLOYD_STEINBERG || V == DP_ED_ATKINSON || V == DP_ED_SIERRA_LITE) ? 16 : 12;
+    return (V == DP_ED_JJN || V == DP_ED_STUCKI) ? 8 : (V == DP_ED_SIERRA || V == V_OSTRO) ? 12 : 16;
 }
 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, bool valid)
