@@ -384,7 +384,11 @@ def run_gpu(args):
 
 
 def extra_modes(torch, engine, synth, sp, stream, peak):
-    """The other BASELINE.json configs, device-resident, batched (>= L2), 5 timed repetitions."""
+    """The other BASELINE.json configs, device-resident, batched (>= L2), 5 timed repetitions.
+    Each entry also carries ``cpu_mpx_s``: the oracle (the reference's algorithm: numpy + scipy
+    KD-tree with all host threads, C port of the numba loop) on a bounded sample of the same
+    mode -- a baseline, not a target."""
+    from oracle import dither_oracle as O
     dev = torch.device("cuda", torch.cuda.current_device())
     out = {}
 
@@ -400,9 +404,20 @@ def extra_modes(torch, engine, synth, sp, stream, peak):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
 
-    def entry(name, px, ms, alg_bytes=None):
+    def cpu_rate(img, pal_rows, mode, params):
+        """Mpx/s of the oracle on one (cropped) frame; the first call warms caches."""
+        try:
+            O.apply_dithering(img[:64, :64], pal_rows, mode, params)
+            t0 = time.perf_counter()
+            O.apply_dithering(img, pal_rows, mode, params)
+            return img.shape[0] * img.shape[1] / (time.perf_counter() - t0) / 1e6
+        except Exception:
+            return None
+
+    def entry(name, px, ms, alg_bytes=None, cpu=None):
         gbs = (alg_bytes if alg_bytes is not None else BYTES_PER_PX * px) / (ms * 1e-3) / 1e9
-        out[name] = {"mpx_s": px / (ms * 1e-3) / 1e6, "ms": ms, "gb_s": gbs, "hbm_frac": gbs / peak}
+        out[name] = {"mpx_s": px / (ms * 1e-3) / 1e6, "ms": ms, "gb_s": gbs, "hbm_frac": gbs / peak,
+                     "cpu_mpx_s": cpu}
 
     pico = synth.hex_palette(synth.PICO8)
     for (label, h, w, nf) in (("1080p", 1080, 1920, 64), ("4k", 2160, 3840, 16)):
@@ -414,16 +429,21 @@ def extra_modes(torch, engine, synth, sp, stream, peak):
                                   ("bayer", {"size": "8x8"}, 256), ("halftone", {}, 16)):
             if label == "4k" and mode in ("IGN", "blue_noise"):
                 continue
-            pal = engine.get_palette(pico if K == 16 else synth.random_palette(K))
+            rows = pico if K == 16 else synth.random_palette(K)
+            pal = engine.get_palette(rows)
             plan = engine.Plan(mode, params, h, w)
             ms = timed(lambda: plan.run(pal, src.data_ptr(), nf, dst.data_ptr(), None, sp))
-            entry(f"{label}_{mode}_K{K}", nf * h * w, ms)
+            cpu = None
+            if label == "1080p" and mode != "blue_noise":   # (its matrix takes seconds to generate)
+                cpu = cpu_rate(frames[0], rows, mode, params)
+            entry(f"{label}_{mode}_K{K}", nf * h * w, ms, cpu=cpu)
+        pal64_rows = synth.random_palette(64)
+        pal64 = engine.get_palette(pal64_rows)
         if label == "1080p":
-            pal64 = engine.get_palette(synth.random_palette(64))
-            for v in ("sierra",):
-                plan = engine.Plan("error_diffusion", {"variant": v}, h, w)
-                ms = timed(lambda: plan.run(pal64, src.data_ptr(), nf, dst.data_ptr(), None, sp), 3)
-                entry(f"{label}_ed_{v}_K64", nf * h * w, ms)
+            plan = engine.Plan("error_diffusion", {"variant": "sierra"}, h, w)
+            ms = timed(lambda: plan.run(pal64, src.data_ptr(), nf, dst.data_ptr(), None, sp), 3)
+            entry(f"{label}_ed_sierra_K64", nf * h * w, ms,
+                  cpu=cpu_rate(frames[0][:540, :960], pal64_rows, "error_diffusion", {"variant": "sierra"}))
             # config 4: pixelize 1080p -> 480x270, dither, x4 up-scale, fused
             pal16 = engine.get_palette(pico)
             for mode in ("blue_noise", "IGN"):
@@ -431,6 +451,14 @@ def extra_modes(torch, engine, synth, sp, stream, peak):
                 ms = timed(lambda: plan.run(pal16, src.data_ptr(), nf, dst.data_ptr(), None, sp))
                 entry(f"video1080p_pixelize270_{mode}_x4", nf * h * w, ms,
                       nf * (3 * 480 * 270 + 3 * 1920 * 1080))
+        else:
+            # config 5: 4K, 64 colours, Ostromoukhov and Sierra (per GPU; frames shard over GPUs)
+            for (mode, params, tag) in (("ostromoukhov", {}, "ostromoukhov"),
+                                        ("error_diffusion", {"variant": "sierra"}, "ed_sierra")):
+                plan = engine.Plan(mode, params, h, w)
+                ms = timed(lambda: plan.run(pal64, src.data_ptr(), nf, dst.data_ptr(), None, sp), 3)
+                crop = frames[0][:540, :960]
+                entry(f"{label}_{tag}_K64_x{nf}", nf * h * w, ms, cpu=cpu_rate(crop, pal64_rows, mode, params))
         del src, dst
     # config 3: k-means Lloyd iteration over a full 4K frame, K=16 (3 B/pixel/iteration)
     from dither_pie_b200._capi import check, lib
