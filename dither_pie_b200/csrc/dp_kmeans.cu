@@ -88,17 +88,14 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate_warp(
             const float fr = (float)r, fg = (float)g, fb = (float)b;
             float d1 = 3.0e38f, d2 = 3.0e38f;
             int bi = 0;
-            for (int k = 0; k < K; ++k) {
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {     // branch-free: lanes of a warp disagree on every test
                 const float4 c = s_cf[k];
                 const float e0 = fr - c.x, e1 = fg - c.y, e2 = fb - c.z;
                 const float d = fmaf(e2, e2, fmaf(e1, e1, e0 * e0));
-                if (d < d1) {
-                    d2 = d1;
-                    d1 = d;
-                    bi = k;
-                } else if (d < d2) {
-                    d2 = d;
-                }
+                d2 = fminf(d2, fmaxf(d1, d));
+                bi = d < d1 ? k : bi;
+                d1 = fminf(d1, d);
             }
             // centre rounded to f32 (<= 255 * 2^-24) and the rounded difference give |e32 - e| <= 3.1e-5
             // per channel, so |d32 - D| <= 1.07e-4 sqrt(D) + 1.8e-7 D; twice that (both distances)
@@ -137,12 +134,19 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate_warp(
             todo &= ~m;
         }
     }
+    // block totals first (the global accumulators are 4K addresses shared by every block: one
+    // flush per block instead of one per warp keeps the L2 atomic unit out of the critical path)
+    __shared__ unsigned long long s_tot[32 * 4];
+    if (threadIdx.x < 32 * 4) s_tot[threadIdx.x] = 0;
+    __syncthreads();
     if (lane < K && an) {
-        atomicAdd(&sums[4 * lane], ar);
-        atomicAdd(&sums[4 * lane + 1], ag);
-        atomicAdd(&sums[4 * lane + 2], ab);
-        atomicAdd(&sums[4 * lane + 3], an);
+        atomicAdd(&s_tot[4 * lane], ar);
+        atomicAdd(&s_tot[4 * lane + 1], ag);
+        atomicAdd(&s_tot[4 * lane + 2], ab);
+        atomicAdd(&s_tot[4 * lane + 3], an);
     }
+    __syncthreads();
+    if (threadIdx.x < K * 4 && s_tot[threadIdx.x]) atomicAdd(&sums[threadIdx.x], s_tot[threadIdx.x]);
 }
 
 __global__ void k_kmeans_update(const unsigned long long *__restrict__ sums, int K,
@@ -175,7 +179,7 @@ extern "C" int dp_kmeans_accumulate(const uint8_t *pixels, int64_t n, const doub
     long long cap = (long long)dp_num_sms() * 8;
     if (K <= 32) {
         long long blocks = ((n + 31) / 32 + KM_THREADS / 32 - 1) / (KM_THREADS / 32);
-        int grid = (int)(blocks < cap ? blocks : cap);
+        int grid = (int)(blocks < cap ? blocks : cap);   // 8 resident blocks of 8 warps per SM
         k_kmeans_accumulate_warp<<<grid, KM_THREADS, 0, dp_stream(stream)>>>(pixels, n, centers, K,
                                                                              sums);
         DP_LAUNCH_CHECK();
