@@ -324,3 +324,26 @@ def test_kmeans_full_image_sharding_invariance():
     assert np.array_equal(results[0], results[1]) and np.array_equal(results[0], results[2])
     ref, _ = O.lloyd(img.astype(np.float64), init, -1.0, 5)
     assert np.abs(ref - results[0]).max() < 1e-9
+
+
+# ------------------------------------------------------------------ randomised sweep vs the oracle
+def test_random_sweep_vs_oracle():
+    """Seeded random palettes / sizes / modes (both kernel families, every code path that depends
+    on K, on the width and on the palette being integral)."""
+    rs = np.random.RandomState(20260118)
+    modes = THRESH_MODES + [("error_diffusion", {"variant": v}) for v in O.ED_KERNELS] + \
+        [("error_diffusion", {"variant": "floyd_steinberg", "serpentine": "true"}),
+         ("ostromoukhov", {}), ("halftone", {}), ("halftone", {"cell_size": 5, "angle": 30.0, "shape": "diamond"})]
+    for trial in range(40):
+        k = int(rs.choice([2, 3, 4, 7, 16, 29, 30, 31, 40, 100]))
+        pal = synth.random_palette(k, seed=int(rs.randint(1, 10 ** 6)))
+        w = int(rs.choice([16, 32, 48, 80, 37, 53]))
+        h = int(rs.choice([8, 17, 33, 40]))
+        kind = int(rs.randint(3))
+        img = (synth.frame(h, w, trial) if kind == 0 else synth.noise_frame(h, w, trial) if kind == 1
+               else synth.blocks_frame(h, w, trial, 4, 5))
+        mode, params = modes[int(rs.randint(len(modes)))]
+        gamma = bool(rs.randint(4) == 0)
+        ref = O.apply_dithering(img, pal, mode, params, gamma)
+        got = gpu(img, pal, mode, params, gamma)
+        assert mismatch(got, ref) == 0, (trial, k, h, w, kind, mode, params, gamma)
