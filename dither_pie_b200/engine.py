@@ -427,6 +427,40 @@ def resample(src_ptr: int, frames: int, src_h: int, src_w: int, dst_h: int, dst_
 
 
 # ----------------------------------------------------------------------------------------
+# device buffer cache for the numpy-level entry point: cudaMalloc/cudaFree cost about as much
+# as dithering a 1080p frame, and callers (GUI preview, per-frame video loop) come back with
+# the same sizes.  Buffers return to the cache only after the call's final synchronise.
+# ----------------------------------------------------------------------------------------
+_buf_cache: Dict[tuple, list] = {}
+_buf_lock = threading.Lock()
+_buf_cached_bytes = 0
+_BUF_CACHE_MAX = 1 << 30
+
+
+def _acquire(nbytes: int) -> DeviceBuffer:
+    size = max(1 << 20, (int(nbytes) + (1 << 20) - 1) >> 20 << 20)
+    key = (_capi.ensure_device(), size)
+    global _buf_cached_bytes
+    with _buf_lock:
+        lst = _buf_cache.get(key)
+        if lst:
+            _buf_cached_bytes -= size
+            return lst.pop()
+    return DeviceBuffer(size)
+
+
+def _release(buf: DeviceBuffer):
+    global _buf_cached_bytes
+    key = (_capi.ensure_device(), buf.nbytes)
+    with _buf_lock:
+        if _buf_cached_bytes + buf.nbytes <= _BUF_CACHE_MAX:
+            _buf_cache.setdefault(key, []).append(buf)
+            _buf_cached_bytes += buf.nbytes
+            return
+    buf.free()
+
+
+# ----------------------------------------------------------------------------------------
 # numpy-level entry point (H2D + kernels + D2H): what the drop-in classes call
 # ----------------------------------------------------------------------------------------
 
@@ -459,35 +493,35 @@ def dither_frames(frames_u8: np.ndarray, palette, mode: str, params: Optional[di
 
     bufs = []
     try:
-        src = DeviceBuffer(max(arr.nbytes, 4)).upload(arr)
+        src = _acquire(max(arr.nbytes, 4)).upload(arr)
         bufs.append(src)
         probe = Plan(mode, params, h, w)
         fused = probe.fused_geometry
         idx_buf = None
         if fused and exact_multiple:
             plan = Plan(mode, params, h, w, (H, W), m)
-            dst = DeviceBuffer(max(F * oh * ow * 3, 4))
+            dst = _acquire(max(F * oh * ow * 3, 4))
             bufs.append(dst)
             if return_indices:
-                idx_buf = DeviceBuffer(max(F * h * w, 4))
+                idx_buf = _acquire(max(F * h * w, 4))
                 bufs.append(idx_buf)
             plan.run(pal, src.ptr, F, dst.ptr, idx_buf.ptr if idx_buf else None)
         else:
             cur, ch, cw = src, H, W
             if (h, w) != (H, W):
-                small = DeviceBuffer(max(F * h * w * 3, 4))
+                small = _acquire(max(F * h * w * 3, 4))
                 bufs.append(small)
                 resample(src.ptr, F, H, W, h, w, small.ptr)
                 cur, ch, cw = small, h, w
-            dith = DeviceBuffer(max(F * h * w * 3, 4))
+            dith = _acquire(max(F * h * w * 3, 4))
             bufs.append(dith)
             if return_indices:
-                idx_buf = DeviceBuffer(max(F * h * w, 4))
+                idx_buf = _acquire(max(F * h * w, 4))
                 bufs.append(idx_buf)
             probe.run(pal, cur.ptr, F, dith.ptr, idx_buf.ptr if idx_buf else None)
             dst = dith
             if (oh, ow) != (h, w):
-                dst = DeviceBuffer(max(F * oh * ow * 3, 4))
+                dst = _acquire(max(F * oh * ow * 3, 4))
                 bufs.append(dst)
                 resample(dith.ptr, F, h, w, oh, ow, dst.ptr)
         out = np.empty((F, oh, ow, 3), np.uint8)
@@ -497,9 +531,12 @@ def dither_frames(frames_u8: np.ndarray, palette, mode: str, params: Optional[di
             idx = np.empty((F, h, w), np.uint8)
             idx_buf.download(idx)
         _capi.sync()
-    finally:
-        for b in bufs:
+    except BaseException:
+        for b in bufs:      # state unknown (a kernel may still run): do not recycle
             b.free()
+        raise
+    for b in bufs:
+        _release(b)
     if single:
         out = out[0]
         idx = idx[0] if idx is not None else None
