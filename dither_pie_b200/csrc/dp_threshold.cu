@@ -528,9 +528,10 @@ __global__ void __launch_bounds__(THREADS) k_thresh_fast(const ThreshParams p)
 //     T*(n1+n2) - n1 unless that is exactly 0.  A non-zero difference is a multiple of
 //     ulp(T)/2^23-ish relative 2^-43 of N, far above the 2^-50 relative error of the reference's
 //     f64 sqrt/square/divide chain, so the decisions agree; exact equality replays that chain.
-// A warp streams 512-pixel tiles (3 x 128-bit coalesced accesses per lane each way) through a
-// private, double-buffered 1.5 KB shared buffer (the next tile is in flight as cp.async while
-// the current one is processed); a lane owns 16 consecutive pixels (48 bytes) in registers.
+// A warp streams 512-pixel tiles through a private, double-buffered 1.5 KB shared buffer: TMA
+// bulk copies (cp.async.bulk, one instruction per tile and direction, issued by lane 0) bring
+// the next tile in while the current one is processed and take the finished tile out; a lane
+// owns 16 consecutive pixels (48 bytes) in registers.
 // ---------------------------------------------------------------------------------------
 // 24 warps per SM for the threshold kinds (80 registers); plain quantisation needs fewer
 // registers and no matrix, so 32 warps fit beside the table
@@ -561,6 +562,39 @@ __device__ __forceinline__ float4 lds_f32x4(unsigned a)
     float4 v;
     asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
+}
+
+// ---- TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) with mbarrier completion ---------------
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned dst_smem, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst, unsigned src_smem, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
 struct V4Ctx {
@@ -669,7 +703,8 @@ __global__ void __launch_bounds__(v4_threads<KIND>(), 1) k_thresh_v4(const Thres
     uint32_t *s_table = reinterpret_cast<uint32_t *>(smem);                    // [32768]
     int2 *s_ent = reinterpret_cast<int2 *>(smem + 131072);                     // [34]
     unsigned *s_orgb = reinterpret_cast<unsigned *>(smem + 131072 + 272);      // [32]
-    uint4 *s_io = reinterpret_cast<uint4 *>(smem + 131072 + 272 + 128);        // [warps][2][96]
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem + 131072 + 272 + 128);   // [warps][2]
+    uint4 *s_io = reinterpret_cast<uint4 *>(smem + 131072 + 272 + 128 + 512);  // [warps][2][96]
     uint32_t *s_sub = reinterpret_cast<uint32_t *>(s_io + V4_WARPS * 192);     // [8 * nsub]
     float *s_mat = reinterpret_cast<float *>(s_sub + (KIND == DP_THRESH_NONE ? 0 : ((8 * P_nsub + 3) & ~3)));   // [mh][wm]
 
@@ -732,26 +767,29 @@ __global__ void __launch_bounds__(v4_threads<KIND>(), 1) k_thresh_v4(const Thres
     uint4 *d4 = reinterpret_cast<uint4 *>(p.dst);
     const uint32_t n16_total = (total_px >> 4) * 3u;                  // 16-byte units in the batch
 
-    // tile `t` -> staging buffer `buf` of this warp, asynchronously (LDGSTS, L2 -> shared)
+    // tile `t` -> staging buffer `buf` of this warp: ONE TMA bulk copy issued by lane 0, completion
+    // on the buffer's mbarrier.  The buffer was the source of a bulk store two tiles ago; lane 0
+    // (which committed that store) first waits until the store has finished reading it.
+    const unsigned bar_a = smem_u32(s_bar + 2 * wib);
+    const unsigned io_a = smem_u32(io4);
+    if (lane == 0) {
+        mbar_init(bar_a, 1);
+        mbar_init(bar_a + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     auto issue = [&](uint32_t t, int buf) {
-        const uint32_t b16 = t * 96u;
-        const uint4 *g = g4 + b16 + lane;
-        const unsigned d = smem_u32(io4 + buf * 96 + lane);
-        if (b16 + 96u <= n16_total) {     // whole tile (warp-uniform)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(g) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u), "l"(g + 32) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 1024u), "l"(g + 64) : "memory");
-        } else {
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                if (b16 + 32u * j + lane < n16_total)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 512u * j), "l"(g + 32 * j)
-                                 : "memory");
+        if (lane == 0) {
+            const uint32_t b16 = t * 96u;
+            const uint32_t n16 = min(96u, n16_total - b16);
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            mbar_expect_tx(bar_a + 8 * buf, n16 * 16u);
+            bulk_load(io_a + buf * 1536, g4 + b16, n16 * 16u, bar_a + 8 * buf);
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
     };
     uint32_t wt = blockIdx.x * V4_WARPS + wib;
     int buf = 0;
+    unsigned it = 0;    // tiles done by this warp: buffer it & 1, barrier parity (it >> 1) & 1
     if (wt < ntiles) issue(wt, 0);
     // position of this lane's first pixel inside its frame, advanced incrementally
     uint32_t pin = 0, pstep = 0;
@@ -760,14 +798,10 @@ __global__ void __launch_bounds__(v4_threads<KIND>(), 1) k_thresh_v4(const Thres
         pin = gp0 - fd_div(p.dnpix, gp0) * (uint32_t)p.npix;
         pstep = adv - fd_div(p.dnpix, adv) * (uint32_t)p.npix;
     }
-    for (; wt < ntiles; wt += wstride, buf ^= 1) {
+    for (; wt < ntiles; wt += wstride, buf ^= 1, ++it) {
         const uint32_t b16 = wt * 96u;
-        if (wt + wstride < ntiles)
-            issue(wt + wstride, buf ^ 1);
-        else
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        __syncwarp();
+        if (wt + wstride < ntiles) issue(wt + wstride, buf ^ 1);
+        mbar_wait(bar_a + 8 * buf, (it >> 1) & 1u);
         uint4 *cur = io4 + buf * 96;
         // this lane's 16 pixels
         unsigned w[12];
@@ -829,21 +863,15 @@ __global__ void __launch_bounds__(v4_threads<KIND>(), 1) k_thresh_v4(const Thres
         if (slowmask)
             v4_fix<KIND, WM_POW2>(p, slowmask, gp, x, y, ra, reinterpret_cast<uint8_t *>(cur + 3 * lane),
                                   s_orgb);
+        // generic-proxy writes -> visible to the async proxy, then one bulk store by lane 0
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        {
-            uint4 *o = d4 + b16 + lane;
-            if (b16 + 96u <= n16_total) {     // whole tile (warp-uniform)
-                __stcs(o, cur[lane]);
-                __stcs(o + 32, cur[32 + lane]);
-                __stcs(o + 64, cur[64 + lane]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    if (b16 + 32u * j + lane < n16_total) __stcs(o + 32 * j, cur[32 * j + lane]);
-            }
+        if (lane == 0) {
+            const uint32_t n16 = min(96u, n16_total - b16);
+            bulk_store(d4 + b16, io_a + buf * 1536, n16 * 16u);
         }
-        __syncwarp();
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1020,7 +1048,7 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
         const bool pow2 = (p.wm & (p.wm - 1)) == 0;
         constexpr int V4_THREADS = v4_threads<KIND>();
         constexpr int V4_WARPS = V4_THREADS / 32;
-        const size_t smem = 131072 + 272 + 128 + (size_t)V4_WARPS * 3072 +
+        const size_t smem = 131072 + 272 + 128 + 512 + (size_t)V4_WARPS * 3072 +
                             (KIND == DP_THRESH_NONE ? 0 : (size_t)p.sub_bytes) +
                             (KIND == DP_THRESH_MATRIX ? (size_t)p.mh * p.wm * 4 : 0);
         void (*kern)(ThreshParams) = pow2 ? k_thresh_v4<KIND, true> : k_thresh_v4<KIND, false>;
@@ -1154,7 +1182,7 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
             wm = p.mw / a * 16;
         }
         const int sub_bytes = ((8 * pal->dev.thr4_nsub + 3) & ~3) * 4;
-        const long long need = 131072 + 272 + 128 +
+        const long long need = 131072 + 272 + 128 + 512 +
                                (kind == DP_THRESH_NONE ? 32ll * 3072 : 24ll * 3072 + sub_bytes) +
                                (kind == DP_THRESH_MATRIX ? (long long)p.mh * wm * 4 : 0);
         if (need <= 227 * 1024 && (long long)frames * p.npix < (1ll << 31) &&
