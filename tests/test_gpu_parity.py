@@ -347,3 +347,32 @@ def test_random_sweep_vs_oracle():
         ref = O.apply_dithering(img, pal, mode, params, gamma)
         got = gpu(img, pal, mode, params, gamma)
         assert mismatch(got, ref) == 0, (trial, k, h, w, kind, mode, params, gamma)
+
+
+def test_concurrent_callers_get_the_sequential_results():
+    """The GUI calls apply_dithering from several daemon threads (dither_pie_gui.py:989-1010):
+    the library, the palette/table caches and the buffer cache must be re-entrant."""
+    import threading
+    pal = PALS["pico8"]
+    jobs = [("bayer", {"size": "8x8"}), ("none", {}), ("error_diffusion", {"variant": "atkinson"}),
+            ("halftone", {}), ("IGN", {}), ("ostromoukhov", {})]
+    imgs = [synth.frame(96, 160, 200 + i) for i in range(len(jobs))]
+    want = [gpu(img, pal, m, p) for img, (m, p) in zip(imgs, jobs)]
+    got = [None] * len(jobs)
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(5):
+                got[i] = gpu(imgs[i], pal, *jobs[i])
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for i in range(len(jobs)):
+        assert np.array_equal(got[i], want[i]), jobs[i]
