@@ -194,6 +194,23 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # Keep this rank (and the pinned host buffers it first-touches) on the NUMA node of its GPU:
+    # with 8 ranks the e2e leg is bound by host memory and PCIe, not by the kernels.
+    numa = "unpinned"
+    orig_affinity = os.sched_getaffinity(0)
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(local)
+            hnd = pynvml.nvmlDeviceGetHandleByPciBusId(
+                f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        except Exception:
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+        pynvml.nvmlDeviceSetCpuAffinity(hnd)
+        numa = f"cpu affinity of GPU {local}: {len(os.sched_getaffinity(0))} cores"
+    except Exception as e:   # best effort
+        numa = f"unpinned ({type(e).__name__})"
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout
@@ -360,12 +377,15 @@ def run_gpu(args):
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_val, "unit": "Mpx/s", "h2d_bytes_per_step": nbytes,
                 "d2h_bytes_per_step": nbytes * len(ED_VARIANTS), "steps": e2e_steps,
-                "pipeline": "3 streams, double-buffered device batches; PCIe D2H-bound"},
+                "pipeline": "3 streams, double-buffered device batches; PCIe D2H-bound",
+                "host_affinity": numa},
         "roofline": roofline,
     }
     if world == 1:
-        # cpu baseline: bounded sample of the same workload on the host cores
-        cores = os.cpu_count() or 1
+        # cpu baseline: bounded sample of the same workload on ALL host cores (undo the GPU-local
+        # affinity first; worker threads inherit the mask when they are created)
+        os.sched_setaffinity(0, orig_affinity)
+        cores = len(orig_affinity) or 1
         crops = [np.ascontiguousarray(host_in.array[t % HB][:540, :960]) for t in range(cores)]
         t0 = time.perf_counter()
         px = cpu_reference_step(crops, pal_rows.astype(np.float32), cores)
