@@ -986,28 +986,33 @@ __global__ void __launch_bounds__(THREADS) k_thresh_geom2(const ThreshParams p)
         f = (int)fd_div(p.dh, rowid);
         y = (int)(rowid - (uint32_t)f * p.h);
     };
-    auto fetch = [&](uint32_t st) -> unsigned {
-        if (st >= total) return 0u;
+    // the three source bytes of this lane's pixel of strip `st`, as raw loads: nothing is done
+    // with them until the next iteration, so the loads stay in flight behind this strip's work
+    auto fetch = [&](uint32_t st, unsigned &b0, unsigned &b1, unsigned &b2) {
+        b0 = b1 = b2 = 0u;
+        if (st >= total) return;
         int f, y, strip;
         locate(st, f, y, strip);
         const int x = strip * 32 + lane;
-        if (x >= p.w) return 0u;
+        if (x >= p.w) return;
         const int sy = p.ytab ? __ldg(p.ytab + y) : y;
         const int sx = p.xtab ? __ldg(p.xtab + x) : x;
         const uint8_t *q = p.src + (size_t)f * src_frame + ((size_t)sy * p.src_w + sx) * 3;
-        return (unsigned)__ldg(q) | ((unsigned)__ldg(q + 1) << 8) | ((unsigned)__ldg(q + 2) << 16);
+        b0 = __ldg(q);
+        b1 = __ldg(q + 1);
+        b2 = __ldg(q + 2);
     };
     uint32_t st = blockIdx.x * (THREADS / 32) + wib;
-    unsigned nextv = fetch(st);
+    unsigned n0, n1, n2;
+    fetch(st, n0, n1, n2);
     for (; st < total; st += stride) {
-        const unsigned v = nextv;
-        nextv = fetch(st + stride);
+        int r = (int)n0, g = (int)n1, b = (int)n2;
+        fetch(st + stride, n0, n1, n2);
         int f, y, strip;
         locate(st, f, y, strip);
         const int x = strip * 32 + lane;
         const int nvalid = min(32, p.w - strip * 32);
         if (x < p.w) {
-            int r = v & 255u, g = (v >> 8) & 255u, b = (v >> 16) & 255u;
             if (p.has_lut) {
                 r = s_lut[r];
                 g = s_lut[g];
@@ -1016,24 +1021,36 @@ __global__ void __launch_bounds__(THREADS) k_thresh_geom2(const ThreshParams p)
             const float thr = threshold_at<KIND>(p, s_mat, mat_in_smem, x, y);
             const int idx = p.integral ? pick_int<KIND>(P, s_coef, K, r, g, b, thr)
                                        : pick_f64<KIND>(P, K, r, g, b, thr);
-            const uint8_t o0 = s_orgb[4 * idx], o1 = s_orgb[4 * idx + 1], o2 = s_orgb[4 * idx + 2];
-            uint8_t *d = rowimg + lane * m * 3;
-            for (int k = 0; k < m; ++k) {
-                d[3 * k] = o0;
-                d[3 * k + 1] = o1;
-                d[3 * k + 2] = o2;
+            const unsigned c = (unsigned)s_orgb[4 * idx] | ((unsigned)s_orgb[4 * idx + 1] << 8) |
+                               ((unsigned)s_orgb[4 * idx + 2] << 16);
+            if (m == 4) {   // 12 bytes = three aligned words (lane * 12 bytes into the row image)
+                unsigned *dw = reinterpret_cast<unsigned *>(rowimg) + lane * 3;
+                dw[0] = c | (c << 24);
+                dw[1] = (c >> 8) | (c << 16);
+                dw[2] = (c >> 16) | (c << 8);
+            } else {
+                uint8_t *d = rowimg + lane * m * 3;
+                for (int k = 0; k < m; ++k) {
+                    d[3 * k] = (uint8_t)c;
+                    d[3 * k + 1] = (uint8_t)(c >> 8);
+                    d[3 * k + 2] = (uint8_t)(c >> 16);
+                }
             }
             if (p.dst_idx) p.dst_idx[((size_t)f * p.h + y) * p.w + x] = (uint8_t)idx;
         }
         __syncwarp();
         const int nbytes = nvalid * m * 3;
-        const int n16 = nbytes >> 4;
+        const int n16 = nbytes >> 4;          // <= 6 * GEOM2_MAX_M = 48 sixteen-byte pieces
         uint8_t *drow = p.dst + (size_t)f * dst_frame + (size_t)y * m * out_w3 + (size_t)strip * 96 * m;
+        const uint4 *img4 = reinterpret_cast<const uint4 *>(rowimg);
+        const uint4 v0 = lane < n16 ? img4[lane] : make_uint4(0, 0, 0, 0);
+        const uint4 v1 = lane + 32 < n16 ? img4[lane + 32] : make_uint4(0, 0, 0, 0);
         for (int rr = 0; rr < m; ++rr) {
-            uint8_t *o = drow + (size_t)rr * out_w3;
-            for (int j = lane; j < n16; j += 32)
-                __stcs(reinterpret_cast<uint4 *>(o) + j, reinterpret_cast<const uint4 *>(rowimg)[j]);
-            for (int j = (n16 << 4) + lane; j < nbytes; j += 32) o[j] = rowimg[j];
+            uint4 *o = reinterpret_cast<uint4 *>(drow + (size_t)rr * out_w3);
+            if (lane < n16) __stcs(o + lane, v0);
+            if (lane + 32 < n16) __stcs(o + lane + 32, v1);
+            if ((n16 << 4) != nbytes)     // ragged last strip of a row: the few bytes left over
+                for (int j = (n16 << 4) + lane; j < nbytes; j += 32) (drow + (size_t)rr * out_w3)[j] = rowimg[j];
         }
         __syncwarp();
     }
