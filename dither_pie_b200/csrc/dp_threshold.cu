@@ -71,6 +71,7 @@ struct ThreshParams {
     int sub_bytes;   // v4: shared bytes of the sub-cell table (multiple of 16)
     FastDiv dwm, dnpix;
     FastDiv dspr, dh;   // geom2: strips per row, rows per frame
+    int geom_table;     // geom2: the compact candidate tables exist (K <= 30, integral, no LUT)
 };
 
 // IGN threshold (:541-549): f32, one rounding per numpy ufunc, no contraction.
@@ -600,6 +601,7 @@ __device__ __forceinline__ void bulk_store(void *dst, unsigned src_smem, unsigne
 struct V4Ctx {
     unsigned table_a, ent_a, orgb_a, sub_a;   // shared-space addresses
     const uint32_t *sub_g;                    // nearest-only table: sub-cell entries (global, L1)
+    const uint32_t *table_g, *subt_g;         // TG variant: both table levels in global memory (L1)
     const PalDev *P;
     int K;
 };
@@ -608,13 +610,16 @@ struct V4Ctx {
 // the exact path has to decide (see above).  The byte extractions and the table address use
 // IDP.4A / IMAD so that the ALU pipe (64 lanes/clk, the bottleneck) and the IMAD pipe share
 // the work.
-template <int KIND>
+// TG = the table is read from global memory through L1 (kernels that cannot afford 128 KB of
+// shared memory for it, e.g. the fused geometry kernel) instead of from shared memory.
+template <int KIND, bool TG = false>
 __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float thr, bool &slow)
 {
     // byte offset of the pixel's cell in the u32 table: (r>>3)*4096 + (g>>3)*128 + (b>>3)*4
     const unsigned a5 = (v >> 3) & 0x1f1f1fu;
-    const unsigned ta = (a5 & 0x1fu) * 4096u + __dp4a(a5, 0x00048000u, c.table_a);
-    unsigned e = lds_u32(ta);
+    const unsigned ta = (a5 & 0x1fu) * 4096u + __dp4a(a5, 0x00048000u, TG ? 0u : c.table_a);
+    unsigned e = TG ? __ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(c.table_g) + ta))
+                    : lds_u32(ta);
     if (KIND == DP_THRESH_NONE) {
         // plain quantisation: the table holds the rows that can be NEAREST in the cell, three
         // slots; the answer is the smallest key unless the two smallest tie
@@ -636,7 +641,7 @@ __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float th
     }
     if (e >= 0xf8000000u) {   // more than four candidates in the 8^3 cell: refine to the 4^3 sub-cell
         const unsigned sc = ((v >> 2) & 1u) * 4u + ((v >> 10) & 1u) * 2u + ((v >> 18) & 1u);
-        e = lds_u32(c.sub_a + ((e & 0xffffu) * 8u + sc) * 4u);
+        e = TG ? __ldg(c.subt_g + (e & 0xffffu) * 8u + sc) : lds_u32(c.sub_a + ((e & 0xffffu) * 8u + sc) * 4u);
     }
     const int2 q0 = lds_s32x2(__dp4a(e, 0x00000001u, c.ent_a));   // base + byte j of e
     const int2 q1 = lds_s32x2(__dp4a(e, 0x00000100u, c.ent_a));
@@ -972,6 +977,29 @@ __global__ void __launch_bounds__(THREADS) k_thresh_geom2(const ThreshParams p)
     const int lane = tid & 31, wib = tid >> 5;
     const int m = p.upscale;
     uint8_t *rowimg = s_row + wib * (96 * GEOM2_MAX_M);       // this warp's row image
+    // candidate-table pick (K <= 30, integral palette): the 32^3 table through L1, rows in shared
+    __shared__ int2 s_ent[34];
+    V4Ctx ctx;
+    const bool use_table = p.geom_table != 0;
+    if (use_table) {
+        if (tid < 34) {
+            int2 en = make_int2(0, 0x7fffff00 | 255);
+            if (tid < K) {
+                const int4 cf = P->coef[tid];
+                const int pr = -cf.x >> 9, pg = -cf.y >> 9, pb = -cf.z >> 9;
+                en = make_int2(pr | (pg << 8) | (pb << 16), cf.w);
+            }
+            s_ent[tid] = en;
+        }
+        __syncthreads();
+        ctx.ent_a = smem_u32(s_ent);
+        ctx.table_a = ctx.orgb_a = ctx.sub_a = 0;
+        ctx.table_g = KIND == DP_THRESH_NONE ? P->near3_table : P->thr4_table;
+        ctx.subt_g = P->thr4_sub;
+        ctx.sub_g = P->near3_sub;
+        ctx.P = P;
+        ctx.K = K;
+    }
     const int strips_per_row = (p.w + 31) >> 5;
     const uint32_t total = (uint32_t)p.frames * p.h * strips_per_row;     // < 2^31 (host check)
     const size_t src_frame = (size_t)p.src_h * p.src_w * 3;
@@ -1019,8 +1047,15 @@ __global__ void __launch_bounds__(THREADS) k_thresh_geom2(const ThreshParams p)
                 b = s_lut[b];
             }
             const float thr = threshold_at<KIND>(p, s_mat, mat_in_smem, x, y);
-            const int idx = p.integral ? pick_int<KIND>(P, s_coef, K, r, g, b, thr)
-                                       : pick_f64<KIND>(P, K, r, g, b, thr);
+            int idx;
+            if (use_table) {
+                bool slow;
+                idx = (int)v4_pick<KIND, true>(ctx, (unsigned)r | ((unsigned)g << 8) | ((unsigned)b << 16), thr, slow);
+                if (slow) idx = pick_int<KIND>(P, s_coef, K, r, g, b, thr);
+            } else {
+                idx = p.integral ? pick_int<KIND>(P, s_coef, K, r, g, b, thr)
+                                 : pick_f64<KIND>(P, K, r, g, b, thr);
+            }
             const unsigned c = (unsigned)s_orgb[4 * idx] | ((unsigned)s_orgb[4 * idx + 1] << 8) |
                                ((unsigned)s_orgb[4 * idx + 2] << 16);
             if (m == 4) {   // 12 bytes = three aligned words (lane * 12 bytes into the row image)
@@ -1115,6 +1150,7 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
         ThreshParams q = p;
         q.dspr = make_fastdiv((uint32_t)((p.w + 31) / 32));
         q.dh = make_fastdiv((uint32_t)p.h);
+        q.geom_table = p.geom_table;
         size_t smem = 256 + 1024 + (size_t)p.K * 16 + mat_bytes + 16 +
                       (size_t)(THREADS / 32) * 96 * GEOM2_MAX_M;
         long long strips = (long long)p.frames * p.h * ((p.w + 31) / 32);
@@ -1211,6 +1247,8 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
             p.dnpix = make_fastdiv((uint32_t)p.npix);
         }
     }
+    p.geom_table = (pal->dev.integral && pal->dev.K >= 2 && pal->dev.K <= 30 && !pal->has_lut &&
+                    pal->dev.thr4_table && pal->dev.near3_table) ? 1 : 0;
     cudaStream_t st = dp_stream(stream);
     switch (kind) {
         case DP_THRESH_NONE: return launch_kind<DP_THRESH_NONE>(p, geom, st);
