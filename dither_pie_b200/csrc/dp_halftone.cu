@@ -79,9 +79,11 @@ __global__ void __launch_bounds__(256) k_ht_maps(const HtParams p)
 
 // Per-cell integer RGB sums and pixel counts.  A warp walks 32 consecutive pixels; consecutive
 // pixels mostly share a cell (a cell of size c covers runs of up to ~1.4 c pixels of a row), so
-// the lanes first add up each run with a segmented shuffle scan on two packed 64-bit words and
-// only the last lane of a run touches global memory: two 64-bit reductions per run instead of
-// four 32-bit atomics per pixel.  Exact as long as a cell's channel sum is below 2^32.
+// only the last lane of each run touches global memory: two 64-bit reductions per run instead of
+// four 32-bit atomics per pixel.  Run sums come from ONE unsegmented inclusive warp scan of the
+// packed channel values (r | g << 16 and b; 32 * 255 < 2^16) -- prefix at the run's tail minus
+// prefix just before its head -- with the run boundaries taken from a ballot of "cell changed".
+// Exact as long as a cell's channel sum is below 2^32.
 __global__ void __launch_bounds__(256) k_ht_sums(const HtParams p)
 {
     __shared__ uint8_t s_lut[256];
@@ -98,25 +100,33 @@ __global__ void __launch_bounds__(256) k_ht_sums(const HtParams p)
         const int i = ch * 32 + lane;
         const bool ok = i < p.npix;
         int c = -1 - lane;                       // distinct, never a cell id
-        unsigned long long a = 0, b = 0;
+        unsigned p0 = 0, p1 = 0;
         if (ok) {
             const uint8_t *q = src + (size_t)i * 3;
             c = __ldg(p.cell + i);
-            a = (unsigned long long)s_lut[q[0]] | ((unsigned long long)s_lut[q[1]] << 32);
-            b = (unsigned long long)s_lut[q[2]] | (1ull << 32);
+            p0 = (unsigned)s_lut[q[0]] | ((unsigned)s_lut[q[1]] << 16);
+            p1 = (unsigned)s_lut[q[2]];
         }
-        // inclusive segmented scan over runs of equal c
+        const int pc = __shfl_up_sync(FULL, c, 1);
+        const unsigned heads = __ballot_sync(FULL, lane == 0 || pc != c);
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const unsigned long long ua = __shfl_up_sync(FULL, a, d), ub = __shfl_up_sync(FULL, b, d);
-            const int uc = __shfl_up_sync(FULL, c, d);
-            if (lane >= d && uc == c) {
-                a += ua;
-                b += ub;
+            const unsigned t0 = __shfl_up_sync(FULL, p0, d), t1 = __shfl_up_sync(FULL, p1, d);
+            if (lane >= d) {
+                p0 += t0;
+                p1 += t1;
             }
         }
-        const int nc = __shfl_down_sync(FULL, c, 1);
-        if (ok && (lane == 31 || nc != c)) {      // last lane of its run
+        // head of this lane's run = highest head bit at or below the lane
+        const int start = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+        const unsigned b0 = __shfl_sync(FULL, p0, (start + 31) & 31), b1 = __shfl_sync(FULL, p1, (start + 31) & 31);
+        const bool tail = lane == 31 || ((heads >> (lane + 1)) & 1u);
+        if (ok && tail) {
+            const unsigned s0 = p0 - (start ? b0 : 0u), s1 = p1 - (start ? b1 : 0u);   // fields never borrow
+            const unsigned long long a = (unsigned long long)(s0 & 0xffffu) |
+                                         ((unsigned long long)(s0 >> 16) << 32);
+            const unsigned long long b = (unsigned long long)s1 |
+                                         ((unsigned long long)(unsigned)(lane - start + 1) << 32);
             atomicAdd(sums + 2 * (size_t)c, a);
             atomicAdd(sums + 2 * (size_t)c + 1, b);
         }
