@@ -504,14 +504,16 @@ struct WarpStageT {
     unsigned char outb[32][108];
 };
 
-// Warps per block, from the registers ptxas needs without spilling the window state: 8 for the
-// 5x5 footprints (JJN, Stucki: 221 registers; capping them at 168 for 12 warps gains 4 % on
-// saturating batches but costs 9 % on a single image), 12 for Sierra and Ostromoukhov (168), 16
-// (128 registers) for the rest.
-template <int V>
+// Warps per block, from the registers ptxas needs without spilling the window state: 16 (128
+// registers) for the 3x3 and two-row footprints, 12 (168) for Sierra and Ostromoukhov.  The 5x5
+// footprints (JJN, Stucki) want 221 registers = 8 warps; capped at 168 (32 bytes of spills) they
+// run 12 warps, which is 4 % faster on saturating batches and 9 % slower on a single image, so
+// they are compiled both ways (BIG) and the launch picks.
+template <int V, bool BIG>
 constexpr int wave_max_warps()
 {
-    return (V == DP_ED_JJN || V == DP_ED_STUCKI) ? 8 : (V == DP_ED_SIERRA || V == V_OSTRO) ? 12 : 16;
+    return (V == DP_ED_JJN || V == DP_ED_STUCKI) ? (BIG ? 12 : 8)
+         : (V == DP_ED_SIERRA || V == V_OSTRO) ? 12 : 16;
 }
 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, bool valid)
@@ -528,8 +530,8 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ float to_f32(double v) { return __double2float_rn(v); }
 __device__ __forceinline__ float to_f32(float v) { return v; }
 
-template <int V>
-__global__ void __launch_bounds__(wave_max_warps<V>() * 32, 1) k_diffuse_wave(const WaveParams p)
+template <int V, bool BIG>
+__global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wave(const WaveParams p)
 {
     using SP = Spec<V>;
     using T = typename StateOf<V>::T;
@@ -1126,23 +1128,21 @@ __global__ void k_wave_init(int *progress, int *qctrl, int *queue, int units, in
     }
 }
 
-template <int V>
-int launch_wave(const WaveParams &p0, cudaStream_t st, int npat)
+// BIG selects the kernel instantiation (register budget); `big` the launch shape.
+template <int V, bool BIG>
+int launch_wave_as(const WaveParams &p0, cudaStream_t st, int npat, bool big)
 {
-    // Few bands (a single image, a small batch): 4-warp blocks so that the bands spread over
-    // the SM sub-partitions (a lone warp is latency-bound).  Many bands: one block per SM with
-    // as many warps as registers (wave_max_warps) and shared memory allow.
     using Stage = WarpStageT<typename StateOf<V>::T, Spec<V>::ROWS3 ? 6 : 3>;
     WaveParams p = p0;
     const int sms = dp_num_sms();
     const size_t base = DP_MAX_COLORS * 3 * 8 + (DP_MAX_COLORS + 1) * 16 + 256 * 8 +
                         (V == V_OSTRO ? DP_MAX_COLORS * 3 * 4 + 256 * 4 * 4 : 0) + 256 * 4;
     const size_t limit = 227 * 1024;
-    const bool big = p.total_units > sms * 8;
-    int warps = big ? wave_max_warps<V>() : 4;
+    constexpr int maxw = wave_max_warps<V, BIG>();
+    int warps = big ? maxw : 4;
     if (const char *ev = getenv("DP_WAVE_WARPS")) {   // tuning knob (tools/): 1..max warps per block
         const int w = atoi(ev);
-        if (w >= 1 && w <= wave_max_warps<V>()) warps = w;
+        if (w >= 1 && w <= maxw) warps = w;
     }
     // First table level (64 KB) in shared memory: always for latency-bound launches; for
     // saturating batches only if it does not cost warps (occupancy is worth more there).
@@ -1153,18 +1153,33 @@ int launch_wave(const WaveParams &p0, cudaStream_t st, int npat)
     // the patterns join it when they fit beside the stages
     p.pat_smem = (p.l1_smem && fixed + sizeof(Stage) * warps + (size_t)npat * 16 <= limit) ? npat : 0;
     const size_t smem = fixed + sizeof(Stage) * warps + (size_t)p.pat_smem * 16;
-    DP_CUDA(cudaFuncSetAttribute(k_diffuse_wave<V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DP_CUDA(cudaFuncSetAttribute(k_diffuse_wave<V, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     int per_sm = 0;
-    DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_diffuse_wave<V>, warps * 32,
+    DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_diffuse_wave<V, BIG>, warps * 32,
                                                           smem));
     if (per_sm < 1) per_sm = 1;
     long long blocks = ((long long)p.total_units + warps - 1) / warps;
     long long cap = (long long)sms * per_sm;
     int grid = (int)(blocks < cap ? blocks : cap);
-    k_diffuse_wave<V><<<grid, warps * 32, smem, st>>>(p);
+    k_diffuse_wave<V, BIG><<<grid, warps * 32, smem, st>>>(p);
     DP_LAUNCH_CHECK();
     return 0;
+}
+
+// Few bands (a single image, a small batch): 4-warp blocks so that the bands spread over the SM
+// sub-partitions (a lone warp is latency-bound).  Many bands: one block per SM with as many
+// warps as registers (wave_max_warps) and shared memory allow.  Only the 5x5 footprints are
+// compiled differently for the two regimes; for the others BIG merely selects the launch shape.
+template <int V>
+int launch_wave(const WaveParams &p, cudaStream_t st, int npat)
+{
+    const bool big = p.total_units > dp_num_sms() * 8;
+    if constexpr (V == DP_ED_JJN || V == DP_ED_STUCKI) {
+        return big ? launch_wave_as<V, true>(p, st, npat, true) : launch_wave_as<V, false>(p, st, npat, false);
+    } else {
+        return launch_wave_as<V, true>(p, st, npat, big);
+    }
 }
 
 template <int V>
