@@ -93,6 +93,21 @@ def test_api_surface_matches_reference_names():
     assert d2.palette == [(1, 2, 3)] and d2.dither_params == {"cell_size": 4}
 
 
+def test_median_cut_and_uniform_palettes_match_reference_golden():
+    """reduce_colors (array path for > 64 unique colours, list path below) and the uniform cube
+    against palettes produced by the live reference (tools/make_golden.py, median_cut.json)."""
+    import json
+    from PIL import Image
+    g = json.load(open(os.path.join(GOLDEN, "median_cut.json")))
+    for c in g["median_cut"]:
+        gen = {"frame": synth.frame, "noise": synth.noise_frame}.get(c["kind"])
+        arr = gen(c["h"], c["w"], c["seed"]) if gen else synth.blocks_frame(c["h"], c["w"], c["seed"], 8, 6)
+        pal = dp.ColorReducer.reduce_colors(Image.fromarray(arr, "RGB"), c["num_colors"])
+        assert [list(map(int, p)) for p in pal] == c["palette"], c
+    for n, pal in g["uniform"].items():
+        assert [list(map(int, p)) for p in dp.ColorReducer.generate_uniform_palette(int(n))] == pal, n
+
+
 def test_median_cut_and_uniform_palettes_match_reference_semantics():
     from PIL import Image
     img = Image.fromarray(synth.frame(24, 32, 3), "RGB")

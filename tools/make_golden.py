@@ -221,9 +221,32 @@ def main():
         store[f"palette_{t}"] = np.asarray(pal, np.int64)
         store[f"niter_{t}"] = np.asarray(km.n_iter_)
     np.savez_compressed(os.path.join(OUT, "kmeans.npz"), **store)
+    median_cut_golden(dl)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+def median_cut_golden(dl):
+    """---- 7. median cut / uniform palettes (ColorReducer.reduce_colors :1834-1843,
+    generate_uniform_palette :1859-1872) on seeded frames; small, so stored as JSON."""
+    cases = []
+    for (kind, hh, w, seed, nc) in [("frame", 120, 160, 5, 16), ("frame", 120, 160, 5, 12),
+                                    ("noise", 60, 80, 6, 8), ("noise", 60, 80, 6, 2),
+                                    ("blocks", 64, 64, 7, 16), ("frame", 7, 9, 8, 256),
+                                    ("frame", 120, 160, 9, 1)]:
+        img = {"frame": synth.frame, "noise": synth.noise_frame}.get(kind, None)
+        arr = img(hh, w, seed) if img else synth.blocks_frame(hh, w, seed, 8, 6)
+        pal = dl.ColorReducer.reduce_colors(Image.fromarray(arr, "RGB"), nc)
+        cases.append({"kind": kind, "h": hh, "w": w, "seed": seed, "num_colors": nc,
+                      "palette": [list(map(int, c)) for c in pal]})
+    uniform = {str(n): [list(map(int, c)) for c in dl.ColorReducer.generate_uniform_palette(n)]
+               for n in (1, 2, 8, 16, 27, 30)}
+    json.dump({"median_cut": cases, "uniform": uniform},
+              open(os.path.join(OUT, "median_cut.json"), "w"))
+
+
 if __name__ == "__main__":
-    main()
+    if "--median-cut-only" in sys.argv:   # adds median_cut.json without touching the other files
+        median_cut_golden(load()[0])
+    else:
+        main()
