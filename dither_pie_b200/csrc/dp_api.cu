@@ -225,6 +225,7 @@ int build_ed_table(const double *d_pal64, int K, PalDev &d, dp_palette *h)
     cudaFree(dmask);
     if (!ok) return 1;
     std::vector<uint16_t> l1(cells);
+    int gt4 = 0;
     std::vector<uint4> pats;
     std::map<std::array<uint32_t, 4>, int> seen;
     std::vector<int> ocells;
@@ -237,6 +238,7 @@ int build_ed_table(const double *d_pal64, int K, PalDev &d, dp_palette *h)
             if (hmask[(size_t)c * 8 + (i >> 5)] >> (i & 31) & 1u) cand[cnt++] = (uint8_t)i;
         unsigned slot[8];
         for (int k = 0; k < 8; ++k) slot[k] = (k < cnt) ? (unsigned)cand[k] * 16u : DP_ED_PAD;
+        if (cnt > 4) ++gt4;
         if (cnt > 7) {
             slot[7] = DP_ED_OVERFLOW;
             ocells.push_back(c);
@@ -280,6 +282,7 @@ int build_ed_table(const double *d_pal64, int K, PalDev &d, dp_palette *h)
     d.ed_l1 = static_cast<const uint16_t *>(dt);
     d.ed_pat = reinterpret_cast<const uint4 *>(static_cast<uint8_t *>(dt) + l1_bytes);
     d.ed_npat = (int)pats.size();
+    d.ed_gt4 = gt4;
     d.ed_flat = reinterpret_cast<const uint4 *>(static_cast<uint8_t *>(dt) + l1_bytes + pat_bytes);
     d.ed_ovf_cells = reinterpret_cast<const int *>(static_cast<uint8_t *>(dov) + o_cells);
     d.ed_ovf_off = reinterpret_cast<const uint32_t *>(static_cast<uint8_t *>(dov) + o_off);

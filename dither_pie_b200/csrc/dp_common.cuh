@@ -101,6 +101,7 @@ struct PalDev {
     const uint16_t *ed_l1;
     const uint4 *ed_pat;
     int ed_npat;
+    int ed_gt4;                   // cells with more than four candidates
     // the same information flattened, ed_flat[cell] = ed_pat[ed_l1[cell]] (512 KB): one L1-cached
     // load per pixel for saturating batches, where shared memory is better spent on more warps
     const uint4 *ed_flat;

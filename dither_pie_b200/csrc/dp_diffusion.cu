@@ -295,6 +295,10 @@ __device__ __forceinline__ int cell_of(float r, float g, float b)
 // exact minimum: if the runner-up is that far away the smallest key's row IS the answer of the
 // reference's f64 comparison loop.  Otherwise (near-tie, exact tie, or a cell with more than
 // seven candidates) the caller takes the exact path below.
+// NSLOT = 4: palettes whose cells (almost) never hold more than four candidates -- the usual
+// 2..32-colour palettes -- evaluate only the first four slots; a cell with a fifth candidate is
+// treated like a near-tie (exact path).
+template <int NSLOT>
 __device__ __forceinline__ int nearest_screen(const Search &s, const uint4 e, float r, float g,
                                               float b, bool &sure)
 {
@@ -302,7 +306,7 @@ __device__ __forceinline__ int nearest_screen(const Search &s, const uint4 e, fl
                              e.z & 0xffffu, e.z >> 16, e.w & 0xffffu};
     int k1 = 0x7fffffff, k2 = 0x7fffffff;
 #pragma unroll
-    for (int j = 0; j < 7; ++j) {
+    for (int j = 0; j < NSLOT; ++j) {
         const float4 p = lds_f32x4(s.rows_a + off[j]);
         const float dr = __fsub_rn(r, p.x), dg = __fsub_rn(g, p.y), db = __fsub_rn(b, p.z);
         const float d = __fmaf_rn(db, db, __fmaf_rn(dg, dg, __fmul_rn(dr, dr)));
@@ -312,6 +316,7 @@ __device__ __forceinline__ int nearest_screen(const Search &s, const uint4 e, fl
         k2 = min(k2, hi);
     }
     sure = ((e.w >> 16) != DP_ED_OVERFLOW) && (k2 - k1 > 2048);
+    if (NSLOT < 7) sure = sure && (off[NSLOT] == DP_ED_PAD);   // slots fill in order
     return k1 & 255;
 }
 
@@ -418,7 +423,7 @@ __device__ __noinline__ int nearest_kd_exact(const PalDev *P, const Search &s, i
 
 // work values (clamped to [0,255]) -> palette row, the reference's answer.  (r,g,b) are the f32
 // screening copies of the exact values (xr,xg,xb).
-template <bool KD>
+template <bool KD, int NSLOT>
 __device__ __forceinline__ int nearest_row(const PalDev *P, const Search &s, float r, float g,
                                            float b, double xr, double xg, double xb)
 {
@@ -431,7 +436,7 @@ __device__ __forceinline__ int nearest_row(const PalDev *P, const Search &s, flo
     } else {
         e = __ldg(s.flat + cell);
     }
-    int bi = nearest_screen(s, e, r, g, b, sure);
+    int bi = nearest_screen<NSLOT>(s, e, r, g, b, sure);
 #ifdef DP_WAVE_TIMING
     if (!sure) atomicAdd(&g_wave_timing[128 * 4], 1ull);
     if (__any_sync(__activemask(), !sure) && (threadIdx.x & 31) == (__ffs(__activemask()) - 1))
@@ -530,7 +535,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ float to_f32(double v) { return __double2float_rn(v); }
 __device__ __forceinline__ float to_f32(float v) { return v; }
 
-template <int V, bool BIG>
+template <int V, bool BIG, int NSLOT>
 __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wave(const WaveParams p)
 {
     using SP = Spec<V>;
@@ -814,7 +819,7 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                             vf[c] = narrow_nonneg(v[c]);
                         }
                         DP_STICK(1);
-                        bi = nearest_row<false>(P, srch, vf[0], vf[1], vf[2], v[0], v[1], v[2]);
+                        bi = nearest_row<false, NSLOT>(P, srch, vf[0], vf[1], vf[2], v[0], v[1], v[2]);
                         DP_STICK(2);
 #pragma unroll
                         for (int c = 0; c < 3; ++c) e[c] = __dsub_rn(v[c], lds_f64(pal_a + 24u * bi + 8u * c));
@@ -828,7 +833,7 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                             float a = __fadd_rn(fa[c], oq10[c]);
                             ov[c] = fminf(fmaxf(a, 0.f), 255.f);
                         }
-                        bi = nearest_row<true>(P, srch, ov[0], ov[1], ov[2], (double)ov[0],
+                        bi = nearest_row<true, NSLOT>(P, srch, ov[0], ov[1], ov[2], (double)ov[0],
                                                (double)ov[1], (double)ov[2]);
 #pragma unroll
                         for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], lds_f32(palf_a + 12u * bi + 4u * c));
@@ -1128,8 +1133,9 @@ __global__ void k_wave_init(int *progress, int *qctrl, int *queue, int units, in
     }
 }
 
-// BIG selects the kernel instantiation (register budget); `big` the launch shape.
-template <int V, bool BIG>
+// BIG selects the kernel instantiation (register budget); `big` the launch shape; NSLOT the
+// number of candidate slots the screening pass evaluates.
+template <int V, bool BIG, int NSLOT>
 int launch_wave_as(const WaveParams &p0, cudaStream_t st, int npat, bool big)
 {
     using Stage = WarpStageT<typename StateOf<V>::T, Spec<V>::ROWS3 ? 6 : 3>;
@@ -1153,16 +1159,16 @@ int launch_wave_as(const WaveParams &p0, cudaStream_t st, int npat, bool big)
     // the patterns join it when they fit beside the stages
     p.pat_smem = (p.l1_smem && fixed + sizeof(Stage) * warps + (size_t)npat * 16 <= limit) ? npat : 0;
     const size_t smem = fixed + sizeof(Stage) * warps + (size_t)p.pat_smem * 16;
-    DP_CUDA(cudaFuncSetAttribute(k_diffuse_wave<V, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DP_CUDA(cudaFuncSetAttribute(k_diffuse_wave<V, BIG, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     int per_sm = 0;
-    DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_diffuse_wave<V, BIG>, warps * 32,
+    DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_diffuse_wave<V, BIG, NSLOT>, warps * 32,
                                                           smem));
     if (per_sm < 1) per_sm = 1;
     long long blocks = ((long long)p.total_units + warps - 1) / warps;
     long long cap = (long long)sms * per_sm;
     int grid = (int)(blocks < cap ? blocks : cap);
-    k_diffuse_wave<V, BIG><<<grid, warps * 32, smem, st>>>(p);
+    k_diffuse_wave<V, BIG, NSLOT><<<grid, warps * 32, smem, st>>>(p);
     DP_LAUNCH_CHECK();
     return 0;
 }
@@ -1171,15 +1177,22 @@ int launch_wave_as(const WaveParams &p0, cudaStream_t st, int npat, bool big)
 // sub-partitions (a lone warp is latency-bound).  Many bands: one block per SM with as many
 // warps as registers (wave_max_warps) and shared memory allow.  Only the 5x5 footprints are
 // compiled differently for the two regimes; for the others BIG merely selects the launch shape.
-template <int V>
-int launch_wave(const WaveParams &p, cudaStream_t st, int npat)
+template <int V, int NSLOT>
+int launch_wave_n(const WaveParams &p, cudaStream_t st, int npat)
 {
     const bool big = p.total_units > dp_num_sms() * 8;
     if constexpr (V == DP_ED_JJN || V == DP_ED_STUCKI) {
-        return big ? launch_wave_as<V, true>(p, st, npat, true) : launch_wave_as<V, false>(p, st, npat, false);
+        return big ? launch_wave_as<V, true, NSLOT>(p, st, npat, true)
+                   : launch_wave_as<V, false, NSLOT>(p, st, npat, false);
     } else {
-        return launch_wave_as<V, true>(p, st, npat, big);
+        return launch_wave_as<V, true, NSLOT>(p, st, npat, big);
     }
+}
+
+template <int V>
+int launch_wave(const WaveParams &p, cudaStream_t st, int npat, bool four_slots)
+{
+    return four_slots ? launch_wave_n<V, 4>(p, st, npat) : launch_wave_n<V, 7>(p, st, npat);
 }
 
 template <int V>
@@ -1275,16 +1288,18 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
         p.progress, p.qctrl, p.queue, (int)units, frames, p.nbands);
     DP_LAUNCH_CHECK();
     const int npat = pal->dev.ed_npat;
+    // four candidate slots are enough when at most 0.1 % of the cells hold a fifth candidate
+    const bool four = pal->dev.ed_gt4 <= 32 && !getenv("DP_WAVE_SEVEN");
     switch (variant) {
-        case DP_ED_FLOYD_STEINBERG: return launch_wave<DP_ED_FLOYD_STEINBERG>(p, st, npat);
-        case DP_ED_JJN: return launch_wave<DP_ED_JJN>(p, st, npat);
-        case DP_ED_STUCKI: return launch_wave<DP_ED_STUCKI>(p, st, npat);
-        case DP_ED_BURKES: return launch_wave<DP_ED_BURKES>(p, st, npat);
-        case DP_ED_ATKINSON: return launch_wave<DP_ED_ATKINSON>(p, st, npat);
-        case DP_ED_SIERRA: return launch_wave<DP_ED_SIERRA>(p, st, npat);
-        case DP_ED_SIERRA_TWO_ROW: return launch_wave<DP_ED_SIERRA_TWO_ROW>(p, st, npat);
-        case DP_ED_SIERRA_LITE: return launch_wave<DP_ED_SIERRA_LITE>(p, st, npat);
-        default: return launch_wave<V_OSTRO>(p, st, npat);
+        case DP_ED_FLOYD_STEINBERG: return launch_wave<DP_ED_FLOYD_STEINBERG>(p, st, npat, four);
+        case DP_ED_JJN: return launch_wave<DP_ED_JJN>(p, st, npat, four);
+        case DP_ED_STUCKI: return launch_wave<DP_ED_STUCKI>(p, st, npat, four);
+        case DP_ED_BURKES: return launch_wave<DP_ED_BURKES>(p, st, npat, four);
+        case DP_ED_ATKINSON: return launch_wave<DP_ED_ATKINSON>(p, st, npat, four);
+        case DP_ED_SIERRA: return launch_wave<DP_ED_SIERRA>(p, st, npat, four);
+        case DP_ED_SIERRA_TWO_ROW: return launch_wave<DP_ED_SIERRA_TWO_ROW>(p, st, npat, four);
+        case DP_ED_SIERRA_LITE: return launch_wave<DP_ED_SIERRA_LITE>(p, st, npat, four);
+        default: return launch_wave<V_OSTRO>(p, st, npat, four);
     }
 }
 
