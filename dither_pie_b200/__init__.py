@@ -9,7 +9,7 @@ it, or a B200, is missing.  There is no CPU fallback.
 from .dithering_lib import (  # noqa: F401
     BaseDitherStrategy, BayerDitherStrategy, BlueNoiseDitherStrategy, ColorReducer, DitherMode,
     DitherUtils, ErrorDiffusionDitherStrategy, ErrorDiffusionKernel, HalftoneDitherStrategy,
-    ImageDitherer, InterleavedGradientNoiseDitherStrategy, MatrixDitherStrategy,
+    HybridDitherStrategy, ImageDitherer, InterleavedGradientNoiseDitherStrategy, MatrixDitherStrategy,
     NoDitherStrategy, OstromoukhovDitherStrategy, PaletteSource, PixelizeMethod,
     PolkaDotDitherStrategy, generate_blue_noise)
 from .video_processor import VideoProcessor, pixelize_regular, shard_frames  # noqa: F401

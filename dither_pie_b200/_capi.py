@@ -52,6 +52,7 @@ PROTOTYPES = {
     "dp_halftone": [_vp, _vp, _i, _i, _i, _i, _d, _d, _d, _d, _d, _i, _d, _vp, _vp, _vp, _vp],
     "dp_error_diffusion": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp],
     "dp_ostromoukhov": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp],
+    "dp_hybrid": [_vp, _vp, _i, _i, _i, _d, _d, _vp, _vp, _vp],
     "dp_resample_nearest": [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp],
     "dp_kmeans_accumulate": [_vp, _i64, _vp, _i, _vp, _vp],
     "dp_kmeans_update": [_vp, _i, _vp, _vp, _vp],

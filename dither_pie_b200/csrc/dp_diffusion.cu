@@ -43,28 +43,35 @@
 namespace {
 
 constexpr int V_OSTRO = 8;
+constexpr int V_HYBRID = 9;   // Floyd-Steinberg footprint, luminance/colour split of the error
+
+// footprint a variant diffuses with
+__host__ __device__ constexpr int ed_base(int v) { return v == V_HYBRID ? DP_ED_FLOYD_STEINBERG : v; }
 
 struct Tap {
     int dx, dy, w;
 };
 
-__host__ __device__ constexpr int ed_ntaps(int v)
+__host__ __device__ constexpr int ed_ntaps(int v0)
 {
+    const int v = ed_base(v0);
     return v == DP_ED_FLOYD_STEINBERG ? 4 : v == DP_ED_JJN ? 12 : v == DP_ED_STUCKI ? 12
          : v == DP_ED_BURKES ? 7 : v == DP_ED_ATKINSON ? 6 : v == DP_ED_SIERRA ? 10
          : v == DP_ED_SIERRA_TWO_ROW ? 7 : v == DP_ED_SIERRA_LITE ? 3 : /*ostro*/ 3;
 }
 
-__host__ __device__ constexpr int ed_divisor(int v)
+__host__ __device__ constexpr int ed_divisor(int v0)
 {
+    const int v = ed_base(v0);
     return v == DP_ED_FLOYD_STEINBERG ? 16 : v == DP_ED_JJN ? 48 : v == DP_ED_STUCKI ? 42
          : v == DP_ED_BURKES ? 32 : v == DP_ED_ATKINSON ? 8 : v == DP_ED_SIERRA ? 32
          : v == DP_ED_SIERRA_TWO_ROW ? 16 : v == DP_ED_SIERRA_LITE ? 4 : 1;
 }
 
 // dithering_lib.py:107-188, in the reference's order
-__host__ __device__ constexpr Tap ed_tap(int v, int k)
+__host__ __device__ constexpr Tap ed_tap(int v0, int k)
 {
+    const int v = ed_base(v0);
     constexpr Tap FS[4] = {{1, 0, 7}, {-1, 1, 3}, {0, 1, 5}, {1, 1, 1}};
     constexpr Tap JJN[12] = {{1, 0, 7}, {2, 0, 5}, {-2, 1, 3}, {-1, 1, 5}, {0, 1, 7}, {1, 1, 5},
                              {2, 1, 3}, {-2, 2, 1}, {-1, 2, 3}, {0, 2, 5}, {1, 2, 3}, {2, 2, 1}};
@@ -165,6 +172,7 @@ struct WaveParams {
     int pat_smem;       // number of candidate patterns kept in shared memory (all or none)
     int l1_smem;        // first table level in shared memory (else read through L1)
     const float *ostro_w;  // [256][4] f32 weights (c0,c1,c2)/sum, DEVICE (ostromoukhov only)
+    double hyb_lum, hyb_col;   // lum_factor, col_factor (hybrid only)
 };
 
 // Progress poll.  Relaxed (no L1 invalidation): everything the consumer reads after the poll is
@@ -823,6 +831,17 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                         DP_STICK(2);
 #pragma unroll
                         for (int c = 0; c < 3; ++c) e[c] = __dsub_rn(v[c], lds_f64(pal_a + 24u * bi + 8u * c));
+                        if constexpr (V == V_HYBRID) {
+                            // _hybrid_numba :1447-1455, one rounding per operation, in its order
+                            const double lum = __dadd_rn(
+                                __dadd_rn(__dmul_rn(0.299, e[0]), __dmul_rn(0.587, e[1])),
+                                __dmul_rn(0.114, e[2]));
+                            const double l0 = __dmul_rn(0.299, lum), l1 = __dmul_rn(0.587, lum),
+                                         l2 = __dmul_rn(0.114, lum);
+                            e[0] = __dadd_rn(__dmul_rn(p.hyb_lum, l0), __dmul_rn(p.hyb_col, __dsub_rn(e[0], l0)));
+                            e[1] = __dadd_rn(__dmul_rn(p.hyb_lum, l1), __dmul_rn(p.hyb_col, __dsub_rn(e[1], l1)));
+                            e[2] = __dadd_rn(__dmul_rn(p.hyb_lum, l2), __dmul_rn(p.hyb_col, __dsub_rn(e[2], l2)));
+                        }
                         apply_taps<V>(std::make_integer_sequence<int, SP::N>{}, e, q10, q20a, q20b,
                                       d1, d2);
                         DP_STICK(3);
@@ -978,6 +997,7 @@ struct SerialParams {
     int frames, h, w, K, serpentine, variant;
     float *ring;           // [frames][3][w][3]
     const float *ostro_w;  // ostromoukhov only
+    double hyb_lum, hyb_col;   // hybrid only
 };
 
 template <bool OSTRO>
@@ -1050,6 +1070,16 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
                         bi = nearest_first_exact(srch, cell_of((float)v[0], (float)v[1], (float)v[2]),
                                                  v[0], v[1], v[2]);
                         for (int c = 0; c < 3; ++c) e[c] = __dsub_rn(v[c], (double)s_palf[3 * bi + c]);
+                        if (p.variant == V_HYBRID) {   // _hybrid_numba :1447-1455
+                            const double lum = __dadd_rn(
+                                __dadd_rn(__dmul_rn(0.299, e[0]), __dmul_rn(0.587, e[1])),
+                                __dmul_rn(0.114, e[2]));
+                            const double cf[3] = {0.299, 0.587, 0.114};
+                            for (int c = 0; c < 3; ++c) {
+                                const double l = __dmul_rn(cf[c], lum);
+                                e[c] = __dadd_rn(__dmul_rn(p.hyb_lum, l), __dmul_rn(p.hyb_col, __dsub_rn(e[c], l)));
+                            }
+                        }
                         for (int k = 0; k < ntaps; ++k) {
                             const int nx = x + s_tdx[k] * dir;
                             const int dy = s_tdy[k];
@@ -1214,6 +1244,7 @@ int wave_tpad(int variant, int w)
         case DP_ED_SIERRA: extra = wave_extra_steps<DP_ED_SIERRA>(); break;
         case DP_ED_SIERRA_TWO_ROW: extra = wave_extra_steps<DP_ED_SIERRA_TWO_ROW>(); break;
         case DP_ED_SIERRA_LITE: extra = wave_extra_steps<DP_ED_SIERRA_LITE>(); break;
+        case V_HYBRID: extra = wave_extra_steps<V_HYBRID>(); break;
         default: extra = wave_extra_steps<V_OSTRO>(); break;
     }
     return ((w + extra + 31) >> 5) << 5;
@@ -1221,7 +1252,7 @@ int wave_tpad(int variant, int w)
 
 int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, int w, int variant,
                   int serpentine, const float *ostro_w_host, uint8_t *dst, uint8_t *dst_idx,
-                  cudaStream_t st)
+                  cudaStream_t st, double hyb_lum = 0.0, double hyb_col = 0.0)
 {
     const bool ostro = (variant == V_OSTRO);
     Workspace ws_ow;
@@ -1248,6 +1279,8 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
         sp.serpentine = serpentine;
         sp.variant = variant;
         sp.ostro_w = ostro_w;
+        sp.hyb_lum = hyb_lum;
+        sp.hyb_col = hyb_col;
         Workspace ring;
         if (ring.alloc((size_t)frames * 3 * w * 3 * sizeof(float), st)) return 1;
         sp.ring = static_cast<float *>(ring.ptr);
@@ -1275,6 +1308,8 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
     p.has_lut = pal->has_lut;
     p.K = pal->dev.K;
     p.ostro_w = ostro_w;
+    p.hyb_lum = hyb_lum;
+    p.hyb_col = hyb_col;
     Workspace hand, flags;
     if (hand.alloc((size_t)units * 6 * (size_t)wave_tpad(variant, w) * sizeof(float), st)) return 1;
     if (flags.alloc((size_t)(2 * units + 2) * sizeof(int), st)) return 1;
@@ -1299,6 +1334,7 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
         case DP_ED_SIERRA: return launch_wave<DP_ED_SIERRA>(p, st, npat, four);
         case DP_ED_SIERRA_TWO_ROW: return launch_wave<DP_ED_SIERRA_TWO_ROW>(p, st, npat, four);
         case DP_ED_SIERRA_LITE: return launch_wave<DP_ED_SIERRA_LITE>(p, st, npat, four);
+        case V_HYBRID: return launch_wave<V_HYBRID>(p, st, npat, four);
         default: return launch_wave<V_OSTRO>(p, st, npat, four);
     }
 }
@@ -1352,4 +1388,15 @@ extern "C" int dp_ostromoukhov(const dp_palette *pal, const uint8_t *src_rgb, in
     }
     return run_diffusion(pal, src_rgb, frames, h, w, V_OSTRO, serpentine ? 1 : 0, wts, dst_rgb,
                          dst_idx, dp_stream(stream));
+}
+
+extern "C" int dp_hybrid(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h, int w,
+                         double lum_factor, double col_factor, uint8_t *dst_rgb, uint8_t *dst_idx,
+                         void *stream)
+{
+    DP_REQUIRE(pal && src_rgb && dst_rgb, "null argument");
+    DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
+    if (frames == 0 || h == 0 || w == 0) return 0;
+    return run_diffusion(pal, src_rgb, frames, h, w, V_HYBRID, 0, nullptr, dst_rgb, dst_idx,
+                         dp_stream(stream), lum_factor, col_factor);
 }

@@ -5,9 +5,10 @@ dobrosketchkun/dither_pie ``dithering_lib.py`` (``__all__`` at :27-57) for every
 the per-pixel work runs in libditherpie_b200.so (hand-written CUDA, sm_100a) through ctypes.
 There is no CPU fallback: without the library or without a B200 every ``dither`` call raises.
 
-Out-of-scope modes (riemersma, wavelet, adaptive_variance, perceptual, hybrid -- SURVEY.md
+Out-of-scope modes (riemersma, wavelet, adaptive_variance, perceptual -- SURVEY.md
 section 2, rows 14-15) keep their names so that imports do not break, and raise
-NotImplementedError when used.
+NotImplementedError when used.  ``hybrid`` runs on the
+error-diffusion wavefront with the semantics of the reference's numba kernel.
 """
 from __future__ import annotations
 
@@ -397,7 +398,34 @@ RiemersmaDitherStrategy = _out_of_scope('RiemersmaDitherStrategy', ':771-841')
 WaveletDitherStrategy = _out_of_scope('WaveletDitherStrategy', ':846-941')
 AdaptiveVarianceDitherStrategy = _out_of_scope('AdaptiveVarianceDitherStrategy', ':946-1025')
 PerceptualDitherStrategy = _out_of_scope('PerceptualDitherStrategy', ':1030-1066')
-HybridDitherStrategy = _out_of_scope('HybridDitherStrategy', ':1071-1155')
+
+
+class HybridDitherStrategy(BaseDitherStrategy):
+    """:1071-1155 with the semantics of its numba core ``_hybrid_numba`` (:1396-1494), the path
+    the reference takes whenever numba imports: Floyd-Steinberg diffusion of
+    ``lum_factor * luminance part + col_factor * colour part`` of the error."""
+    _mode = "hybrid"
+
+    @staticmethod
+    def get_parameter_info() -> Dict[str, Any]:
+        return {
+            'lum_factor': {'type': 'float', 'default': 1.0, 'min': 0.0, 'max': 2.0, 'step': 0.1,
+                           'label': 'Luminance Factor',
+                           'description': 'Strength of luminance error diffusion '
+                                          '(1.0 = full, 0.0 = none)'},
+            'col_factor': {'type': 'float', 'default': 0.2, 'min': 0.0, 'max': 2.0, 'step': 0.1,
+                           'label': 'Color Factor',
+                           'description': 'Strength of color error diffusion '
+                                          '(lower = less color noise)'},
+        }
+
+    def __init__(self, lum_factor: float = 1.0, col_factor: float = 0.2):
+        self.lum_factor = lum_factor
+        self.col_factor = col_factor
+        self.fs_offsets = [(1, 0, 7 / 16), (-1, 1, 3 / 16), (0, 1, 5 / 16), (1, 1, 1 / 16)]
+
+    def get_current_parameters(self) -> Dict[str, Any]:
+        return {'lum_factor': self.lum_factor, 'col_factor': self.col_factor}
 
 
 # ----------------------------------------------------------------------------------------

@@ -381,6 +381,10 @@ class Plan:
         elif mode == "ostromoukhov":
             self.serpentine = p.get("serpentine", "false") == "true"
             self.coeffs = ostromoukhov_coeffs()
+        elif mode == "hybrid":
+            # HybridDitherStrategy.__init__ (:1101-1104); dither() passes float(...) of both (:1121)
+            self.lum_factor = float(p.get("lum_factor", 1.0))
+            self.col_factor = float(p.get("col_factor", 0.2))
         else:
             raise ValueError(f"Unrecognized or out-of-scope dither mode: {mode!r}")
         self.fused_geometry = self.kind is not None
@@ -412,6 +416,9 @@ class Plan:
             check(L.dp_error_diffusion(pal.handle, src_ptr, frames, self.h, self.w, self.variant,
                                        int(self.serpentine), dst_ptr, idx_ptr, stream),
                   "dp_error_diffusion")
+        elif self.mode == "hybrid":
+            check(L.dp_hybrid(pal.handle, src_ptr, frames, self.h, self.w, self.lum_factor,
+                              self.col_factor, dst_ptr, idx_ptr, stream), "dp_hybrid")
         else:
             check(L.dp_ostromoukhov(pal.handle, src_ptr, frames, self.h, self.w,
                                     self.coeffs.ctypes.data, int(self.serpentine), dst_ptr,

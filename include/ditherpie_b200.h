@@ -158,6 +158,19 @@ int dp_ostromoukhov(const dp_palette *pal, const uint8_t *src_rgb, int frames, i
                     void *stream);
 
 /*
+ * dp_hybrid -- HybridDitherStrategy.dither (:1071-1155) with the semantics of its numba core
+ * _hybrid_numba (:1396-1494), the canonical path when numba is importable: the Floyd-Steinberg
+ * raster loop of dp_error_diffusion (f32 state, f64 arithmetic, clamp before the strict '<'
+ * first-index lookup) whose error is split into a luminance part and a colour part before it
+ * is distributed:  lum = (0.299 e0 + 0.587 e1) + 0.114 e2;  l_c = coef_c * lum;
+ * fe_c = lum_factor * l_c + col_factor * (e_c - l_c), every operation a separately rounded f64.
+ * (same wavefront skeleton, different error transform.)
+ */
+int dp_hybrid(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h, int w,
+              double lum_factor, double col_factor, uint8_t *dst_rgb, uint8_t *dst_idx,
+              void *stream);
+
+/*
  * dp_resample_nearest -- Image.resize(NEAREST) as used by pixelize_regular
  * (video_processor.py:576) and the final up-scale (:419, dither_cli.py:565):
  * dst[f,y,x] = src[f, ytab[y], xtab[x]].  Tables are DEVICE int32.

@@ -12,6 +12,9 @@
  *                         554-556, 748-749, 1243, 1633.
  *   orc_error_diffusion   dithering_lib.py:212-308 (_error_diffusion_numba): f32 state, f64
  *                         arithmetic, one f32 rounding per accumulation, strict '<' argmin.
+ *   orc_hybrid            dithering_lib.py:1396-1494 (_hybrid_numba): the Floyd-Steinberg loop of
+ *                         orc_error_diffusion with the error split into luminance and colour
+ *                         parts (f64, one rounding per operation).
  *   orc_ostromoukhov      dithering_lib.py:1225-1269 (the live pure-Python path): all-f32
  *                         arithmetic, f32-rounded weights, KD-tree nearest (tie rules of scipy).
  *
@@ -245,6 +248,74 @@ int orc_error_diffusion(float *work, int h, int w, const float *palette, int K,
     }
     /* final clamp pass (:285-306); a no-op for visited pixels, kept for fidelity */
     for (size_t i = 0; i < (size_t)h * w * 3; ++i) {
+        float t = work[i];
+        if (t < 0.0f) t = 0.0f;
+        else if (t > 255.0f) t = 255.0f;
+        work[i] = t;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Hybrid (dithering_lib.py:1396-1494, _hybrid_numba -- the path HybridDitherStrategy.dither
+ * takes whenever numba imports, :1116-1127).  Floyd-Steinberg footprint; the error of a pixel is
+ * split into a luminance part and a colour part which are scaled separately (:1447-1455).
+ * numba types: the clamp assigns 0.0/255.0 (f64) to r,g,b so they are f64 holding f32 values;
+ * every product and sum below is f64 and separately rounded (no fast-math, no contraction).
+ * ---------------------------------------------------------------------------------------- */
+int orc_hybrid(float *work, int h, int w, const float *palette, int K, double lum_factor,
+               double col_factor, uint8_t *out_idx /* may be NULL, [h,w] */)
+{
+    static const int dxs[4] = {1, -1, 0, 1}, dys[4] = {0, 1, 1, 1};
+    static const double wts[4] = {7.0 / 16.0, 3.0 / 16.0, 5.0 / 16.0, 1.0 / 16.0};
+    for (int y = 0; y < h; ++y) {
+        for (int x = 0; x < w; ++x) {
+            float *px = work + 3 * ((size_t)y * w + x);
+            double v[3];
+            for (int c = 0; c < 3; ++c) {
+                double t = (double)px[c];
+                if (t < 0.0) t = 0.0;
+                else if (t > 255.0) t = 255.0;
+                v[c] = t;
+            }
+            int best = 0;
+            double bestd = 1e20;
+            for (int i = 0; i < K; ++i) {
+                double dr = v[0] - (double)palette[3 * i + 0];
+                double dg = v[1] - (double)palette[3 * i + 1];
+                double db = v[2] - (double)palette[3 * i + 2];
+                double d = dr * dr + dg * dg + db * db;
+                if (d < bestd) {
+                    bestd = d;
+                    best = i;
+                }
+            }
+            double e[3], fe[3];
+            for (int c = 0; c < 3; ++c) {
+                float ch = palette[3 * best + c];
+                px[c] = ch;
+                e[c] = v[c] - (double)ch;
+            }
+            if (out_idx) out_idx[(size_t)y * w + x] = (uint8_t)best;
+            {
+                static const double cf[3] = {0.299, 0.587, 0.114};
+                double lum = 0.299 * e[0] + 0.587 * e[1];
+                lum = lum + 0.114 * e[2];
+                for (int c = 0; c < 3; ++c) {
+                    double l = cf[c] * lum;
+                    fe[c] = lum_factor * l + col_factor * (e[c] - l);
+                }
+            }
+            for (int k = 0; k < 4; ++k) {
+                int nx = x + dxs[k], ny = y + dys[k];
+                if (nx >= 0 && nx < w && ny < h) {
+                    float *q = work + 3 * ((size_t)ny * w + nx);
+                    for (int c = 0; c < 3; ++c) q[c] = (float)((double)q[c] + fe[c] * wts[k]);
+                }
+            }
+        }
+    }
+    for (size_t i = 0; i < (size_t)h * w * 3; ++i) {   /* final clamp pass (:1474-1492) */
         float t = work[i];
         if (t < 0.0f) t = 0.0f;
         else if (t > 255.0f) t = 255.0f;

@@ -68,6 +68,7 @@ def _lib():
         _LIB.orc_kdtree_query.restype = ctypes.c_int
         _LIB.orc_error_diffusion.restype = ctypes.c_int
         _LIB.orc_ostromoukhov.restype = ctypes.c_int
+        _LIB.orc_hybrid.restype = ctypes.c_int
     return _LIB
 
 
@@ -383,6 +384,22 @@ def error_diffusion_indices(pixels: np.ndarray, palette: np.ndarray, h: int, w: 
     return idx.reshape(-1).astype(np.int32)
 
 
+def hybrid_indices(pixels: np.ndarray, palette: np.ndarray, h: int, w: int,
+                   lum_factor: float = 1.0, col_factor: float = 0.2) -> np.ndarray:
+    """HybridDitherStrategy.dither (:1111-1127) -> _hybrid_numba (:1396-1494)."""
+    work = np.ascontiguousarray(pixels, np.float32).reshape(h, w, 3).copy()
+    pal = np.ascontiguousarray(palette, np.float32)
+    idx = np.empty((h, w), np.uint8)
+    rc = _lib().orc_hybrid(
+        ctypes.c_void_p(work.ctypes.data), ctypes.c_int(h), ctypes.c_int(w),
+        ctypes.c_void_p(pal.ctypes.data), ctypes.c_int(pal.shape[0]),
+        ctypes.c_double(float(lum_factor)), ctypes.c_double(float(col_factor)),
+        ctypes.c_void_p(idx.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("orc_hybrid failed")
+    return idx.reshape(-1).astype(np.int32)
+
+
 _OSTRO = None
 
 
@@ -476,6 +493,9 @@ def apply_dithering(img_u8: np.ndarray, palette: Sequence[Sequence[float]], mode
                                       params.get("serpentine", "false") == "true")
     elif mode == "ostromoukhov":
         idx = ostromoukhov_indices(flat, pal, h, w, params.get("serpentine", "false") == "true")
+    elif mode == "hybrid":
+        idx = hybrid_indices(flat, pal, h, w, params.get("lum_factor", 1.0),
+                             params.get("col_factor", 0.2))
     else:
         raise ValueError(f"mode {mode!r} is outside the hot path")
     out = pal[idx, :].reshape(h, w, 3).astype(np.uint8)

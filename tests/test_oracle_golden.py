@@ -78,6 +78,17 @@ def test_diffusion_big():
     assert np.array_equal(out, g["ostro"])
 
 
+def test_hybrid_cases_bit_exact():
+    """hybrid mode (_hybrid_numba, dithering_lib.py:1396-1494) incl. gamma and extreme factors."""
+    g = load_golden("hybrid_cases.npz")
+    meta = json.load(open(os.path.join(GOLDEN, "hybrid_cases.json")))
+    assert len(meta) >= 14
+    for n, m in enumerate(meta):
+        out = O.apply_dithering(g["img_" + m["image"]], g["pal_" + m["palette"]], "hybrid",
+                                m["params"], m["gamma"])
+        assert np.array_equal(out, g[f"out_{n}"]), (n, m)
+
+
 def test_pixelize_tables():
     g = load_golden("pixelize.npz")
     meta = json.load(open(os.path.join(GOLDEN, "pixelize.json")))

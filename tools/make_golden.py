@@ -93,6 +93,8 @@ def case_list():
 def main():
     dl, vp = load()
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["hybrid"]:
+        return hybrid_golden(dl)
     import numba
     import PIL
     import scipy
@@ -222,8 +224,43 @@ def main():
         store[f"niter_{t}"] = np.asarray(km.n_iter_)
     np.savez_compressed(os.path.join(OUT, "kmeans.npz"), **store)
     median_cut_golden(dl)
+    hybrid_golden(dl)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+def hybrid_golden(dl):
+    """---- 8. hybrid mode (HybridDitherStrategy :1071-1155 -> _hybrid_numba :1396-1494) through
+    ImageDitherer.apply_dithering; own file so that it can be regenerated alone
+    (python tools/make_golden.py hybrid)."""
+    assert dl._NUMBA_AVAILABLE
+    imgs, pals = images(), palettes()
+    imgs["big"] = synth.frame(96, 160, 5)
+    store, meta = {}, []
+    n = 0
+    for iname, pname, params, gamma in [
+            ("frame", "pico8", {}, False), ("frame", "pico8", {}, True),
+            ("frame", "r64", {"lum_factor": 0.7, "col_factor": 0.9}, False),
+            ("frame", "r256", {"lum_factor": 1.3, "col_factor": 0.0}, False),
+            ("frame", "gb4", {"lum_factor": 0.0, "col_factor": 2.0}, False),
+            ("frame", "lat27", {}, False), ("frame", "one", {}, False),
+            ("noise", "c64", {}, False), ("noise", "r16", {"lum_factor": 2.0, "col_factor": 1.0}, False),
+            ("noise", "r64", {}, True), ("blocks", "pico8", {}, False),
+            ("blocks", "lat27", {"lum_factor": 1.0, "col_factor": 1.0}, False),
+            ("big", "r64", {}, False), ("big", "pico8", {"lum_factor": 0.5, "col_factor": 0.5}, False)]:
+        d = dl.ImageDitherer(num_colors=len(pals[pname]), dither_mode=dl.DitherMode.HYBRID,
+                             palette=[tuple(int(v) for v in c) for c in pals[pname]],
+                             use_gamma=gamma, dither_params=dict(params))
+        store[f"out_{n}"] = np.array(d.apply_dithering(Image.fromarray(imgs[iname], "RGB")))
+        meta.append({"image": iname, "palette": pname, "params": params, "gamma": gamma})
+        n += 1
+    for k, v in imgs.items():
+        store[f"img_{k}"] = v
+    for k, v in pals.items():
+        store[f"pal_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "hybrid_cases.npz"), **store)
+    json.dump(meta, open(os.path.join(OUT, "hybrid_cases.json"), "w"))
+    print("hybrid cases:", len(meta))
 
 
 def median_cut_golden(dl):
