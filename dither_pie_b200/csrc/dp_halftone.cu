@@ -9,6 +9,8 @@
 //   pass 2                    per cell: mean colour in f64 -> KD-tree nearest palette row
 //   pass 3                    per pixel: ink (cell colour) where 1 - gray/255 > screen, else paper
 // Algorithmic bytes: 3 read + 3 written per pixel (the maps are an implementation cost).
+#include <stdlib.h>
+
 #include "dp_search.cuh"
 
 namespace {
@@ -29,6 +31,8 @@ struct HtParams {
     uint8_t *cell_pal;   // [frames][ncells]
     int paper;
     int make_screen;
+    int has_lut;   // the palette carries a gamma input LUT (else the LUT is the identity)
+    int vec16;     // rows and buffers allow 128-bit strip loads (w % 16 == 0, 16-byte aligned)
 };
 
 // numpy's floored modulo for doubles (npy_divmod): fmod, then fix the sign.
@@ -130,6 +134,161 @@ __global__ void __launch_bounds__(256) k_ht_sums(const HtParams p)
             atomicAdd(sums + 2 * (size_t)c, a);
             atomicAdd(sums + 2 * (size_t)c + 1, b);
         }
+    }
+}
+
+// Tiled variant (the default): a block owns a 64 x 128 pixel tile and adds the run sums into a
+// shared-memory image of the cell grid the tile touches (32-bit shared atomics: r, g, b, count),
+// then flushes every touched cell ONCE with two 64-bit global reductions.  A cell of size c is
+// met by ~c rows of a tile, so this issues ~c/1.5 times fewer global reductions than one per
+// run (they are bound by the L2 atomic units).  The tile's cell range comes from its four corners
+// (the rotated coordinates are monotone in x and y, also after rounding); tiles whose range does
+// not fit the shared grid (tiny cells) are handled by k_ht_sums.
+constexpr int HT_TW = 128, HT_TH = 64, HT_CAP = 2048;
+
+__device__ __forceinline__ void ht_cell_xy(const HtParams &p, int x, int y, int &cx, int &cy)
+{
+    const double xd = (double)x, yd = (double)y, cs = (double)p.cell_size;
+    const double xr = __dsub_rn(__dmul_rn(xd, p.ca), __dmul_rn(yd, p.sa));
+    const double yr = __dadd_rn(__dmul_rn(xd, p.sa), __dmul_rn(yd, p.ca));
+    cx = (int)floor(__ddiv_rn(xr, cs));
+    cy = (int)floor(__ddiv_rn(yr, cs));
+}
+
+// MODE 0: four 32-bit shared atomics per run; 1: two (16-bit fields: a cell holds < 257 pixels,
+// cell_size <= 14); 2: no shared grid, two 64-bit global reductions per run
+template <int MODE>
+__global__ void __launch_bounds__(256) k_ht_sums_tile(const HtParams p, int tiles_x)
+{
+    __shared__ uint8_t s_lut[256];
+    __shared__ unsigned s_grid[HT_CAP * 4];
+    __shared__ int s_geo[4];   // base cell id, local width, local height
+    s_lut[threadIdx.x] = p.P->in_lut[threadIdx.x];
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int x0 = tx * HT_TW, y0 = ty * HT_TH;
+    const int x1 = min(x0 + HT_TW, p.w) - 1, y1 = min(y0 + HT_TH, p.h) - 1;
+    if (threadIdx.x == 0) {
+        int cxl = 0, cxh = 0, cyl = 0, cyh = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int cx, cy;
+            ht_cell_xy(p, (k & 1) ? x1 : x0, (k & 2) ? y1 : y0, cx, cy);
+            if (k == 0 || cx < cxl) cxl = cx;
+            if (k == 0 || cx > cxh) cxh = cx;
+            if (k == 0 || cy < cyl) cyl = cy;
+            if (k == 0 || cy > cyh) cyh = cy;
+        }
+        s_geo[0] = (cyl - p.cy_min) * p.ncx + (cxl - p.cx_min);
+        s_geo[1] = cxh - cxl + 1;
+        s_geo[2] = cyh - cyl + 1;
+    }
+    __syncthreads();
+    const int base = s_geo[0], lw = s_geo[1], lh = s_geo[2];
+    const int nloc = lw * lh;           // <= HT_CAP (checked by the host for the worst tile)
+    if (MODE != 2) {
+        if (nloc > HT_CAP) __trap();    // host bound violated: an error, never a silent overrun
+        for (int i = threadIdx.x; i < nloc * (MODE == 1 ? 2 : 4); i += 256) s_grid[i] = 0;
+        __syncthreads();
+    }
+
+    // A thread walks strips of 16 consecutive pixels of a row (48 source bytes = three 128-bit
+    // loads, 16 cell ids = four) and keeps the sums of the current run of equal cell ids in
+    // registers; a run is added to the shared grid when the cell changes and at the strip's end.
+    const int f = blockIdx.y;
+    const uint8_t *src = p.src + (size_t)f * p.npix * 3;
+    const unsigned mdiv = (unsigned)((0x100000000ull + (unsigned)p.ncx - 1) / (unsigned)p.ncx);
+    const unsigned skip = (unsigned)(p.ncx - lw);
+    const bool lut = p.has_lut != 0;
+    unsigned long long *gsums = p.sums + (size_t)f * p.ncells * 2;
+    auto flush = [&](int cell, unsigned rg, unsigned bn) {
+        if (MODE == 2) {
+            atomicAdd(gsums + 2 * (size_t)cell, (unsigned long long)(rg & 0xffffu) | ((unsigned long long)(rg >> 16) << 32));
+            atomicAdd(gsums + 2 * (size_t)cell + 1, (unsigned long long)(bn & 0xffffu) | ((unsigned long long)(bn >> 16) << 32));
+            return;
+        }
+        const unsigned d = (unsigned)(cell - base);
+        const unsigned ly = __umulhi(d, mdiv);       // d / ncx, exact for d < 2^32 / ncx
+        if (MODE == 1) {
+            unsigned *g = s_grid + 2 * (d - ly * skip);
+            atomicAdd(g, rg);
+            atomicAdd(g + 1, bn);
+        } else {
+            unsigned *g = s_grid + 4 * (d - ly * skip);  // ly * lw + lx
+            atomicAdd(g, rg & 0xffffu);
+            atomicAdd(g + 1, rg >> 16);
+            atomicAdd(g + 2, bn & 0xffffu);
+            atomicAdd(g + 3, bn >> 16);
+        }
+    };
+    constexpr int SPR = HT_TW / 16;                  // strips per tile row
+    for (int sidx = threadIdx.x; sidx < HT_TH * SPR; sidx += 256) {
+        const int r = sidx / SPR, y = y0 + r;
+        const int xs = x0 + (sidx - r * SPR) * 16;
+        if (y > y1 || xs > x1) continue;
+        const int i0 = y * p.w + xs;
+        const int n = min(16, x1 + 1 - xs);
+        unsigned wsrc[12];
+        int cid[16];
+        if (n == 16 && p.vec16) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(src + (size_t)i0 * 3);
+            const uint4 a = __ldcs(q), b = __ldcs(q + 1), c = __ldcs(q + 2);
+            wsrc[0] = a.x; wsrc[1] = a.y; wsrc[2] = a.z; wsrc[3] = a.w;
+            wsrc[4] = b.x; wsrc[5] = b.y; wsrc[6] = b.z; wsrc[7] = b.w;
+            wsrc[8] = c.x; wsrc[9] = c.y; wsrc[10] = c.z; wsrc[11] = c.w;
+            const int4 *cq = reinterpret_cast<const int4 *>(p.cell + i0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int4 t = __ldg(cq + k);
+                cid[4 * k] = t.x; cid[4 * k + 1] = t.y; cid[4 * k + 2] = t.z; cid[4 * k + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k) wsrc[k] = 0;
+            for (int k = 0; k < 3 * n; ++k)
+                wsrc[k >> 2] |= (unsigned)src[(size_t)i0 * 3 + k] << (8 * (k & 3));
+#pragma unroll
+            for (int k = 0; k < 16; ++k) cid[k] = k < n ? __ldg(p.cell + i0 + k) : -1;
+        }
+        int cur = cid[0];
+        unsigned rg = 0, bn = 0;                     // r | g << 16, b | count << 16 (<= 16 pixels)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            // pixel k: bytes 3k .. 3k+2 of the strip
+            const unsigned lo = wsrc[(3 * k) >> 2], hi = wsrc[((3 * k) >> 2) + ((3 * k) % 4 > 1 ? 1 : 0)];
+            const unsigned v = (3 * k) % 4 > 1 ? __funnelshift_r(lo, hi, 8 * ((3 * k) % 4)) : lo >> (8 * ((3 * k) % 4));
+            unsigned pr = v & 255u, pg = (v >> 8) & 255u, pb = (v >> 16) & 255u;
+            if (lut) {
+                pr = s_lut[pr];
+                pg = s_lut[pg];
+                pb = s_lut[pb];
+            }
+            if (k && cid[k] != cur) {
+                if (cur >= 0) flush(cur, rg, bn);
+                rg = bn = 0;
+                cur = cid[k];
+            }
+            if (k < n) {
+                rg += pr | (pg << 16);
+                bn += pb | 0x10000u;
+            }
+        }
+        if (cur >= 0) flush(cur, rg, bn);
+    }
+    if (MODE == 2) return;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nloc; i += 256) {
+        uint4 v;
+        if (MODE == 1) {
+            const uint2 t = reinterpret_cast<const uint2 *>(s_grid)[i];
+            v = make_uint4(t.x & 0xffffu, t.x >> 16, t.y & 0xffffu, t.y >> 16);
+        } else {
+            v = reinterpret_cast<const uint4 *>(s_grid)[i];
+        }
+        if (!v.w) continue;
+        const int ly = i / lw, lx = i - ly * lw;
+        const size_t c = (size_t)(base + ly * p.ncx + lx);
+        atomicAdd(gsums + 2 * c, (unsigned long long)v.x | ((unsigned long long)v.y << 32));
+        atomicAdd(gsums + 2 * c + 1, (unsigned long long)v.z | ((unsigned long long)v.w << 32));
     }
 }
 
@@ -294,6 +453,8 @@ extern "C" int dp_halftone(const dp_palette *pal, const uint8_t *src_rgb, int fr
     p.sharp = sharpness;
     p.sharpen = sharpness != 1.0;
     p.make_screen = screen == nullptr;
+    p.has_lut = pal->has_lut;
+    p.vec16 = (w % 16 == 0) && (reinterpret_cast<uintptr_t>(src_rgb) & 15) == 0;
 
     // cell index range: the rotated coordinates are linear in (x, y), so the extremes are at
     // the image corners; same operation order as the device (separately rounded ops)
@@ -360,7 +521,20 @@ extern "C" int dp_halftone(const dp_palette *pal, const uint8_t *src_rgb, int fr
     DP_LAUNCH_CHECK();
     int gx = (p.npix + 255) / 256;
     if (gx > sms * 8) gx = sms * 8;
-    k_ht_sums<<<dim3(gx, frames), 256, 0, st>>>(p);
+    {
+        // worst-case cell range of a tile: |d(xr)| <= TW |cos| + TH |sin| across a tile (+2 for
+        // the floor at both ends and rounding), likewise yr
+        const double ex = (HT_TW * fabs(cos_a) + HT_TH * fabs(sin_a)) / cell_size + 2.0;
+        const double ey = (HT_TW * fabs(sin_a) + HT_TH * fabs(cos_a)) / cell_size + 2.0;
+        const int tiles_x = (w + HT_TW - 1) / HT_TW, tiles_y = (h + HT_TH - 1) / HT_TH;
+        const dim3 tg(tiles_x * tiles_y, frames);
+        int mode = (ceil(ex) * ceil(ey) <= (double)HT_CAP) ? (cell_size <= 14 ? 1 : 0) : 2;
+        if (const char *ev = getenv("DP_HT_MODE")) mode = atoi(ev);   // tuning knob (tools/)
+        if (mode == 0) k_ht_sums_tile<0><<<tg, 256, 0, st>>>(p, tiles_x);
+        else if (mode == 1) k_ht_sums_tile<1><<<tg, 256, 0, st>>>(p, tiles_x);
+        else if (mode == 2) k_ht_sums_tile<2><<<tg, 256, 0, st>>>(p, tiles_x);
+        else k_ht_sums<<<dim3(gx, frames), 256, 0, st>>>(p);
+    }
     DP_LAUNCH_CHECK();
     int gc = (p.ncells + 127) / 128;
     if (gc > sms * 8) gc = sms * 8;
