@@ -4,12 +4,22 @@
 // _generate_halftone_screen_with_cells (:1646-1695).
 //
 //   pass 0 (frame-invariant)  rotated-grid cell id and dot screen per pixel, in f64 with one
-//                             rounding per numpy ufunc (no transcendental when dot_gain == 1)
+//                             rounding per numpy ufunc (no transcendental when dot_gain == 1);
+//                             the screen value s is stored as the GRAY THRESHOLD g*(s) = the
+//                             smallest f32 gray with 1 - gray/255 <= s (bisection over the f32
+//                             bit patterns with the reference's own division and subtraction):
+//                             both rounded operations are monotone, so
+//                             `1 - gray/255 > s`  <=>  `gray < g*(s)` exactly, and pass 3 needs
+//                             neither the division nor the subtraction.  Maps are cached per
+//                             device and parameter set across calls (video: same size every batch)
 //   pass 1                    exact integer RGB sums and counts per cell (atomics)
 //   pass 2                    per cell: mean colour in f64 -> KD-tree nearest palette row
 //   pass 3                    per pixel: ink (cell colour) where 1 - gray/255 > screen, else paper
 // Algorithmic bytes: 3 read + 3 written per pixel (the maps are an implementation cost).
 #include <stdlib.h>
+
+#include <mutex>
+#include <vector>
 
 #include "dp_search.cuh"
 
@@ -25,7 +35,8 @@ struct HtParams {
     double ca, sa, min_dot, span, sharp;
     int sharpen;
     int cx_min, cy_min, ncx, ncells;
-    float *screen;
+    float *screen;              // gray thresholds g*(screen value), see the file header
+    const float *user_screen;   // caller-provided screen values (dot_gain != 1) or null
     int *cell;
     unsigned long long *sums;   // [frames][ncells][2]: (sum r | sum g << 32), (sum b | count << 32)
     uint8_t *cell_pal;   // [frames][ncells]
@@ -47,6 +58,31 @@ __device__ __forceinline__ double np_mod(double a, double b)
     return m;
 }
 
+// smallest non-negative f32 g with  1 - g/255 <= s  (the reference's f32 ops, :1638-1640);
+// 0 <= s <= 1 after the reference's clip, so g = 256 always satisfies it
+__device__ __forceinline__ bool dark_le(unsigned gbits, float s)
+{
+    return __fsub_rn(1.0f, __fdiv_rn(__uint_as_float(gbits), 255.0f)) <= s;
+}
+__device__ __forceinline__ float gray_threshold(float s)
+{
+    // bit patterns of non-negative floats are ordered like the values.  g* lies within a few
+    // 1e-5 of 255 (1 - s) (two roundings of relative size 2^-24 on values <= 1): bisect a window
+    // of +-2^-12 around it, checked at both ends; fall back to the whole range [0, 256] otherwise.
+    const float g0 = 255.0f * (1.0f - s);
+    unsigned lo = __float_as_uint(fmaxf(g0 - 0.000244140625f, 0.0f));
+    unsigned hi = __float_as_uint(fminf(fmaxf(g0 + 0.000244140625f, 0.0f), 256.0f));
+    if (!dark_le(hi, s)) hi = 0x43800000u;          // 256.0f always satisfies it (0 <= s)
+    if (lo > 0u && dark_le(lo - 1u, s)) lo = 0u;    // the predicate must be false just below lo
+#pragma unroll 1
+    while (lo < hi) {
+        const unsigned mid = (lo + hi) >> 1;
+        if (dark_le(mid, s)) hi = mid;
+        else lo = mid + 1u;
+    }
+    return __uint_as_float(hi);
+}
+
 __global__ void __launch_bounds__(256) k_ht_maps(const HtParams p)
 {
     const int i = blockIdx.x * 256 + threadIdx.x;
@@ -58,7 +94,10 @@ __global__ void __launch_bounds__(256) k_ht_maps(const HtParams p)
     const int cx = (int)floor(__ddiv_rn(xr, cs));
     const int cy = (int)floor(__ddiv_rn(yr, cs));
     p.cell[i] = (cy - p.cy_min) * p.ncx + (cx - p.cx_min);
-    if (!p.make_screen) return;
+    if (!p.make_screen) {
+        p.screen[i] = gray_threshold(__ldg(p.user_screen + i));
+        return;
+    }
     const double dx = __dsub_rn(__ddiv_rn(np_mod(xr, cs), cs), 0.5);
     const double dy = __dsub_rn(__ddiv_rn(np_mod(yr, cs), cs), 0.5);
     double dist, dmax;
@@ -78,7 +117,7 @@ __global__ void __launch_bounds__(256) k_ht_maps(const HtParams p)
     t = __dadd_rn(p.min_dot, __dmul_rn(t, p.span));
     if (p.sharpen) t = __dadd_rn(0.5, __dmul_rn(__dsub_rn(t, 0.5), p.sharp));
     t = fmin(fmax(t, 0.0), 1.0);
-    p.screen[i] = __double2float_rn(t);
+    p.screen[i] = gray_threshold(__double2float_rn(t));
 }
 
 // Per-cell integer RGB sums and pixel counts.  A warp walks 32 consecutive pixels; consecutive
@@ -167,20 +206,25 @@ __global__ void __launch_bounds__(256) k_ht_sums_tile(const HtParams p, int tile
     const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
     const int x0 = tx * HT_TW, y0 = ty * HT_TH;
     const int x1 = min(x0 + HT_TW, p.w) - 1, y1 = min(y0 + HT_TH, p.h) - 1;
-    if (threadIdx.x == 0) {
-        int cxl = 0, cxh = 0, cyl = 0, cyh = 0;
+    if (threadIdx.x < 32) {
+        // one corner per lane 0..3, range by warp shuffles
+        const unsigned FULL = 0xffffffffu;
+        const int k = threadIdx.x & 3;
+        int cx, cy;
+        ht_cell_xy(p, (k & 1) ? x1 : x0, (k & 2) ? y1 : y0, cx, cy);
+        int cxl = cx, cxh = cx, cyl = cy, cyh = cy;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int cx, cy;
-            ht_cell_xy(p, (k & 1) ? x1 : x0, (k & 2) ? y1 : y0, cx, cy);
-            if (k == 0 || cx < cxl) cxl = cx;
-            if (k == 0 || cx > cxh) cxh = cx;
-            if (k == 0 || cy < cyl) cyl = cy;
-            if (k == 0 || cy > cyh) cyh = cy;
+        for (int d = 1; d < 4; d <<= 1) {
+            cxl = min(cxl, __shfl_xor_sync(FULL, cxl, d));
+            cxh = max(cxh, __shfl_xor_sync(FULL, cxh, d));
+            cyl = min(cyl, __shfl_xor_sync(FULL, cyl, d));
+            cyh = max(cyh, __shfl_xor_sync(FULL, cyh, d));
         }
-        s_geo[0] = (cyl - p.cy_min) * p.ncx + (cxl - p.cx_min);
-        s_geo[1] = cxh - cxl + 1;
-        s_geo[2] = cyh - cyl + 1;
+        if (threadIdx.x == 0) {
+            s_geo[0] = (cyl - p.cy_min) * p.ncx + (cxl - p.cx_min);
+            s_geo[1] = cxh - cxl + 1;
+            s_geo[2] = cyh - cyl + 1;
+        }
     }
     __syncthreads();
     const int base = s_geo[0], lw = s_geo[1], lh = s_geo[2];
@@ -242,10 +286,16 @@ __global__ void __launch_bounds__(256) k_ht_sums_tile(const HtParams p, int tile
                 cid[4 * k] = t.x; cid[4 * k + 1] = t.y; cid[4 * k + 2] = t.z; cid[4 * k + 3] = t.w;
             }
         } else {
+            // ragged strips / unaligned rows: byte loads, fully unrolled (no local-memory arrays)
+            const uint8_t *q = src + (size_t)i0 * 3;
 #pragma unroll
-            for (int k = 0; k < 12; ++k) wsrc[k] = 0;
-            for (int k = 0; k < 3 * n; ++k)
-                wsrc[k >> 2] |= (unsigned)src[(size_t)i0 * 3 + k] << (8 * (k & 3));
+            for (int k = 0; k < 12; ++k) {
+                unsigned wv = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (4 * k + j < 3 * n) wv |= (unsigned)q[4 * k + j] << (8 * j);
+                wsrc[k] = wv;
+            }
 #pragma unroll
             for (int k = 0; k < 16; ++k) cid[k] = k < n ? __ldg(p.cell + i0 + k) : -1;
         }
@@ -256,11 +306,13 @@ __global__ void __launch_bounds__(256) k_ht_sums_tile(const HtParams p, int tile
             // pixel k: bytes 3k .. 3k+2 of the strip
             const unsigned lo = wsrc[(3 * k) >> 2], hi = wsrc[((3 * k) >> 2) + ((3 * k) % 4 > 1 ? 1 : 0)];
             const unsigned v = (3 * k) % 4 > 1 ? __funnelshift_r(lo, hi, 8 * ((3 * k) % 4)) : lo >> (8 * ((3 * k) % 4));
-            unsigned pr = v & 255u, pg = (v >> 8) & 255u, pb = (v >> 16) & 255u;
+            unsigned prg, pbn;                        // r | g << 16,  b | 1 << 16
             if (lut) {
-                pr = s_lut[pr];
-                pg = s_lut[pg];
-                pb = s_lut[pb];
+                prg = (unsigned)s_lut[v & 255u] | ((unsigned)s_lut[(v >> 8) & 255u] << 16);
+                pbn = (unsigned)s_lut[(v >> 16) & 255u] | 0x10000u;
+            } else {
+                prg = __byte_perm(v, 0u, 0x4140);
+                pbn = __byte_perm(v, 1u, 0x5452);
             }
             if (k && cid[k] != cur) {
                 if (cur >= 0) flush(cur, rg, bn);
@@ -268,8 +320,8 @@ __global__ void __launch_bounds__(256) k_ht_sums_tile(const HtParams p, int tile
                 cur = cid[k];
             }
             if (k < n) {
-                rg += pr | (pg << 16);
-                bn += pb | 0x10000u;
+                rg += prg;
+                bn += pbn;
             }
         }
         if (cur >= 0) flush(cur, rg, bn);
@@ -355,8 +407,7 @@ __global__ void __launch_bounds__(256) k_ht_select(const HtParams p)
         // (:1605-1606, :1638-1639) f32, one rounding per operation
         float gray = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, g)),
                                __fmul_rn(0.114f, b));
-        const float dark = __fsub_rn(1.0f, __fdiv_rn(gray, 255.0f));
-        const int idx = (dark > __ldg(p.screen + i)) ? cp[__ldg(p.cell + i)] : p.paper;
+        const int idx = (gray < __ldg(p.screen + i)) ? cp[__ldg(p.cell + i)] : p.paper;
         uint8_t *o = dst + (size_t)i * 3;
         o[0] = s_orgb[4 * idx];
         o[1] = s_orgb[4 * idx + 1];
@@ -366,7 +417,13 @@ __global__ void __launch_bounds__(256) k_ht_select(const HtParams p)
 }
 
 // Four pixels per thread with word accesses (frames whose pixel count is a multiple of 4 and
-// 4-byte aligned buffers): 12 bytes in, 12 bytes out, the screen and cell maps as 128-bit loads.
+// 4-byte aligned buffers): 12 bytes in, 12 bytes out, the threshold and cell maps as 128-bit loads.
+// Byte -> float without a conversion instruction: 2^23 + byte as a bit pattern (one PRMT), and
+// fl(c * byte) = fma(c, 2^23 + byte, -c * 2^23): the fma rounds the exact product c * byte once,
+// like the reference's multiply (c * 2^23 is exact).
+// (Measured alternatives at 1080p x64: sixteen pixels per thread with 128-bit source loads 0.27 ms,
+// the same staged through shared memory with cp.async at two blocks per SM 0.43 ms, this kernel
+// 0.22 ms -- the per-thread chain load -> decide -> gather -> colour -> store wants many warps.)
 __global__ void __launch_bounds__(256) k_ht_select4(const HtParams p)
 {
     __shared__ uint8_t s_lut[256];
@@ -382,6 +439,7 @@ __global__ void __launch_bounds__(256) k_ht_select4(const HtParams p)
     unsigned *dst = reinterpret_cast<unsigned *>(p.dst + (size_t)f * p.npix * 3);
     const uint8_t *cp = p.cell_pal + (size_t)f * p.ncells;
     const int ngroups = p.npix >> 2;
+    const bool lut = p.has_lut != 0;
     for (int gi = blockIdx.x * 256 + threadIdx.x; gi < ngroups; gi += gridDim.x * 256) {
         const unsigned w0 = __ldcs(src + 3 * gi), w1 = __ldcs(src + 3 * gi + 1), w2 = __ldcs(src + 3 * gi + 2);
         const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.screen) + gi);
@@ -392,12 +450,22 @@ __global__ void __launch_bounds__(256) k_ht_select4(const HtParams p)
         unsigned col[4], idx4 = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float r = (float)s_lut[v[k] & 255u], g = (float)s_lut[(v[k] >> 8) & 255u],
-                        b = (float)s_lut[(v[k] >> 16) & 255u];
-            const float gray = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, g)),
-                                         __fmul_rn(0.114f, b));
-            const float dark = __fsub_rn(1.0f, __fdiv_rn(gray, 255.0f));
-            const int idx = (dark > scr[k]) ? (int)__ldg(cp + cel[k]) : p.paper;
+            unsigned mr, mg, mb;   // 2^23 + byte as a float bit pattern
+            if (lut) {
+                mr = 0x4b000000u | s_lut[v[k] & 255u];
+                mg = 0x4b000000u | s_lut[(v[k] >> 8) & 255u];
+                mb = 0x4b000000u | s_lut[(v[k] >> 16) & 255u];
+            } else {
+                mr = __byte_perm(v[k], 0x4b000000u, 0x7540);
+                mg = __byte_perm(v[k], 0x4b000000u, 0x7541);
+                mb = __byte_perm(v[k], 0x4b000000u, 0x7542);
+            }
+            const float gray = __fadd_rn(
+                __fadd_rn(__fmaf_rn(0.299f, __uint_as_float(mr), -0.299f * 8388608.0f),
+                          __fmaf_rn(0.587f, __uint_as_float(mg), -0.587f * 8388608.0f)),
+                __fmaf_rn(0.114f, __uint_as_float(mb), -0.114f * 8388608.0f));
+            int idx = p.paper;
+            if (gray < scr[k]) idx = (int)__ldg(cp + cel[k]);
             col[k] = s_orgb[idx];
             idx4 |= (unsigned)idx << (8 * k);
         }
@@ -416,6 +484,79 @@ struct Ws {
         if (ptr) cudaFreeAsync(ptr, st);
     }
 };
+
+// Frame-invariant maps, kept per device and parameter set between calls (a video hands over the
+// same geometry batch after batch).  Entries own plain cudaMalloc memory; `ready` orders the map
+// kernel before any consumer on another stream.  Never destroyed at exit (no CUDA calls from
+// static destructors).
+struct MapEntry {
+    int dev, h, w, cell_size, shape, sharpen;
+    double ca, sa, min_dot, span, sharp;
+    float *gthr;
+    int *cell;
+    cudaEvent_t ready;
+    unsigned long long stamp;
+};
+struct MapCache {
+    std::mutex mu;
+    std::vector<MapEntry> ent;
+    unsigned long long clock = 0;
+};
+MapCache &map_cache()
+{
+    static MapCache *c = new MapCache;
+    return *c;
+}
+constexpr size_t HT_MAP_CACHE = 4;
+
+// returns 0 and fills p.screen / p.cell; launches k_ht_maps on `st` on a miss
+int cached_maps(HtParams &p, cudaStream_t st)
+{
+    int dev = 0;
+    DP_CUDA(cudaGetDevice(&dev));
+    MapCache &mc = map_cache();
+    std::lock_guard<std::mutex> lk(mc.mu);
+    for (MapEntry &e : mc.ent) {
+        if (e.dev == dev && e.h == p.h && e.w == p.w && e.cell_size == p.cell_size && e.shape == p.shape &&
+            e.sharpen == p.sharpen && e.ca == p.ca && e.sa == p.sa && e.min_dot == p.min_dot &&
+            e.span == p.span && e.sharp == p.sharp) {
+            e.stamp = ++mc.clock;
+            p.screen = e.gthr;
+            p.cell = e.cell;
+            DP_CUDA(cudaStreamWaitEvent(st, e.ready, 0));
+            return 0;
+        }
+    }
+    if (mc.ent.size() >= HT_MAP_CACHE) {
+        size_t v = 0;
+        for (size_t i = 1; i < mc.ent.size(); ++i)
+            if (mc.ent[i].stamp < mc.ent[v].stamp) v = i;
+        // cudaFree waits for the device: no in-flight kernel can still read the evicted maps
+        cudaFree(mc.ent[v].gthr);
+        cudaFree(mc.ent[v].cell);
+        cudaEventDestroy(mc.ent[v].ready);
+        mc.ent.erase(mc.ent.begin() + v);
+    }
+    MapEntry e;
+    e.dev = dev; e.h = p.h; e.w = p.w; e.cell_size = p.cell_size; e.shape = p.shape; e.sharpen = p.sharpen;
+    e.ca = p.ca; e.sa = p.sa; e.min_dot = p.min_dot; e.span = p.span; e.sharp = p.sharp;
+    e.gthr = nullptr;
+    e.cell = nullptr;
+    e.stamp = ++mc.clock;
+    DP_CUDA(cudaMalloc(&e.gthr, (size_t)p.npix * 4));
+    if (cudaMalloc(&e.cell, (size_t)p.npix * 4) != cudaSuccess) {
+        cudaFree(e.gthr);
+        DP_REQUIRE(false, "out of device memory for the halftone maps");
+    }
+    DP_CUDA(cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming));
+    p.screen = e.gthr;
+    p.cell = e.cell;
+    k_ht_maps<<<(p.npix + 255) / 256, 256, 0, st>>>(p);
+    DP_LAUNCH_CHECK();
+    DP_CUDA(cudaEventRecord(e.ready, st));
+    mc.ent.push_back(e);
+    return 0;
+}
 
 }  // namespace
 
@@ -501,14 +642,18 @@ extern "C" int dp_halftone(const dp_palette *pal, const uint8_t *src_rgb, int fr
 
     Ws w_screen, w_cell, w_sums, w_cp;
     w_screen.st = w_cell.st = w_sums.st = w_cp.st = st;
-    if (p.make_screen) {
+    const int sms = dp_num_sms();
+    if (p.make_screen && !getenv("DP_HT_NO_MAP_CACHE")) {
+        if (cached_maps(p, st)) return 1;
+    } else {
         DP_CUDA(cudaMallocAsync(&w_screen.ptr, (size_t)p.npix * 4, st));
         p.screen = static_cast<float *>(w_screen.ptr);
-    } else {
-        p.screen = const_cast<float *>(screen);
+        p.user_screen = screen;
+        DP_CUDA(cudaMallocAsync(&w_cell.ptr, (size_t)p.npix * 4, st));
+        p.cell = static_cast<int *>(w_cell.ptr);
+        k_ht_maps<<<(p.npix + 255) / 256, 256, 0, st>>>(p);
+        DP_LAUNCH_CHECK();
     }
-    DP_CUDA(cudaMallocAsync(&w_cell.ptr, (size_t)p.npix * 4, st));
-    p.cell = static_cast<int *>(w_cell.ptr);
     size_t sums_bytes = (size_t)frames * p.ncells * 2 * sizeof(unsigned long long);
     DP_CUDA(cudaMallocAsync(&w_sums.ptr, sums_bytes, st));
     p.sums = static_cast<unsigned long long *>(w_sums.ptr);
@@ -516,9 +661,6 @@ extern "C" int dp_halftone(const dp_palette *pal, const uint8_t *src_rgb, int fr
     p.cell_pal = static_cast<uint8_t *>(w_cp.ptr);
     DP_CUDA(cudaMemsetAsync(p.sums, 0, sums_bytes, st));
 
-    const int sms = dp_num_sms();
-    k_ht_maps<<<(p.npix + 255) / 256, 256, 0, st>>>(p);
-    DP_LAUNCH_CHECK();
     int gx = (p.npix + 255) / 256;
     if (gx > sms * 8) gx = sms * 8;
     {
@@ -540,10 +682,9 @@ extern "C" int dp_halftone(const dp_palette *pal, const uint8_t *src_rgb, int fr
     if (gc > sms * 8) gc = sms * 8;
     k_ht_cells<<<dim3(gc, frames), 128, 0, st>>>(p);
     DP_LAUNCH_CHECK();
-    const bool vec4 = p.npix % 4 == 0 &&
-                      ((reinterpret_cast<uintptr_t>(src_rgb) | reinterpret_cast<uintptr_t>(dst_rgb) |
+    const bool al16 = ((reinterpret_cast<uintptr_t>(src_rgb) | reinterpret_cast<uintptr_t>(dst_rgb) |
                         reinterpret_cast<uintptr_t>(dst_idx) | reinterpret_cast<uintptr_t>(p.screen)) & 15) == 0;
-    if (vec4) {
+    if (al16 && p.npix % 4 == 0) {
         int g4 = (p.npix / 4 + 255) / 256;
         if (g4 > sms * 8) g4 = sms * 8;
         k_ht_select4<<<dim3(g4, frames), 256, 0, st>>>(p);
