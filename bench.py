@@ -474,7 +474,8 @@ def extra_modes(torch, engine, synth, sp, stream, peak):
         else:
             # config 5: 4K, 64 colours, Ostromoukhov and Sierra (per GPU; frames shard over GPUs)
             for (mode, params, tag) in (("ostromoukhov", {}, "ostromoukhov"),
-                                        ("error_diffusion", {"variant": "sierra"}, "ed_sierra")):
+                                        ("error_diffusion", {"variant": "sierra"}, "ed_sierra"),
+                                        ("hybrid", {}, "hybrid")):
                 plan = engine.Plan(mode, params, h, w)
                 ms = timed(lambda: plan.run(pal64, src.data_ptr(), nf, dst.data_ptr(), None, sp), 3)
                 crop = frames[0][:540, :960]
