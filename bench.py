@@ -434,10 +434,21 @@ def extra_modes(torch, engine, synth, sp, stream, peak):
         except Exception:
             return None
 
-    def entry(name, px, ms, alg_bytes=None, cpu=None):
+    def entry(name, px, ms, alg_bytes=None, cpu=None, write_bytes=None):
         gbs = (alg_bytes if alg_bytes is not None else BYTES_PER_PX * px) / (ms * 1e-3) / 1e9
         out[name] = {"mpx_s": px / (ms * 1e-3) / 1e6, "ms": ms, "gb_s": gbs, "hbm_frac": gbs / peak,
                      "cpu_mpx_s": cpu}
+        if write_bytes is not None:
+            # write-dominated path: also against the WRITE-ONLY bandwidth measured in this run
+            out[name]["write_gb_s"] = write_bytes / (ms * 1e-3) / 1e9
+            out[name]["write_only_peak_gb_s"] = write_peak
+            out[name]["write_frac"] = out[name]["write_gb_s"] / write_peak
+
+    # write-only HBM bandwidth (fill of 1.6 GB): the bound of the x4 up-scaling video path, whose
+    # output is 16 times its input -- a fill reaches ~3.9 TB/s on B200, a copy 6.5 TB/s (r+w)
+    fill = torch.empty(1600 * 1000 * 1000, dtype=torch.uint8, device=dev)
+    write_peak = fill.numel() / (timed(lambda: fill.fill_(1), 10) * 1e-3) / 1e9
+    del fill
 
     pico = synth.hex_palette(synth.PICO8)
     for (label, h, w, nf) in (("1080p", 1080, 1920, 64), ("4k", 2160, 3840, 16)):
@@ -470,7 +481,7 @@ def extra_modes(torch, engine, synth, sp, stream, peak):
                 plan = engine.Plan(mode, {}, 270, 480, (h, w), 4)
                 ms = timed(lambda: plan.run(pal16, src.data_ptr(), nf, dst.data_ptr(), None, sp))
                 entry(f"video1080p_pixelize270_{mode}_x4", nf * h * w, ms,
-                      nf * (3 * 480 * 270 + 3 * 1920 * 1080))
+                      nf * (3 * 480 * 270 + 3 * 1920 * 1080), write_bytes=nf * 3 * 1920 * 1080)
         else:
             # config 5: 4K, 64 colours, Ostromoukhov and Sierra (per GPU; frames shard over GPUs)
             for (mode, params, tag) in (("ostromoukhov", {}, "ostromoukhov"),

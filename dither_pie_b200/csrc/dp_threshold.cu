@@ -948,8 +948,16 @@ __global__ void __launch_bounds__(THREADS) k_thresh_geom(const ThreshParams p)
 // times into a shared row image (96*m bytes), and the warp writes that image to each of the m
 // output rows with 128-bit stores.  The lane's source pixel is fetched one strip ahead.
 // Needs 16-byte aligned output rows; otherwise k_thresh_geom.
+// The bound of this path is the WRITE-ONLY bandwidth of HBM, 3.9 TB/s on B200 (memset/fill of
+// 0.4-1.6 GB, tools/ubench/write_bw.py) against 6.5 TB/s for a copy: 398 MB of output per 64
+// 1080p frames cannot take less than 0.10 ms.  Measured alternatives: three staged kernels
+// (coalesced gather 0.036 ms, k_thresh_v4 on the low-resolution frames 0.053 ms, a pure
+// replication kernel 0.098 ms = 4.06 TB/s, i.e. at the write roofline) sum to the same 0.187 ms
+// as this fused kernel (whose dither work overlaps its stores); capping it at 64 registers for a
+// fourth resident block did not help either.
 // ---------------------------------------------------------------------------------------
 constexpr int GEOM2_MAX_M = 8;
+constexpr int GEOM2_MAT_SMEM = 4096;   // threshold matrices up to 64 x 64 (blue noise) live in shared memory
 
 template <int KIND>
 __global__ void __launch_bounds__(THREADS) k_thresh_geom2(const ThreshParams p)
@@ -959,7 +967,7 @@ __global__ void __launch_bounds__(THREADS) k_thresh_geom2(const ThreshParams p)
     uint8_t *s_orgb = s_lut + 256;
     int4 *s_coef = reinterpret_cast<int4 *>(s_orgb + 1024);
     float *s_mat = reinterpret_cast<float *>(s_coef + p.K);
-    const bool mat_in_smem = (KIND == DP_THRESH_MATRIX) && (p.mh * p.mw <= 1024);
+    const bool mat_in_smem = (KIND == DP_THRESH_MATRIX) && (p.mh * p.mw <= GEOM2_MAT_SMEM);
     uint8_t *s_row = reinterpret_cast<uint8_t *>(s_mat + (mat_in_smem ? p.mh * p.mw : 0));
     s_row += (16 - (reinterpret_cast<uintptr_t>(s_row) & 15)) & 15;
 
@@ -1007,37 +1015,63 @@ __global__ void __launch_bounds__(THREADS) k_thresh_geom2(const ThreshParams p)
     const size_t dst_frame = (size_t)p.h * m * out_w3;
     const uint32_t stride = gridDim.x * (THREADS / 32);
 
-    // strip id -> (frame, row, strip in the row)
-    auto locate = [&](uint32_t st, int &f, int &y, int &strip) {
-        const uint32_t rowid = fd_div(p.dspr, st);
-        strip = (int)(st - rowid * strips_per_row);
-        f = (int)fd_div(p.dh, rowid);
-        y = (int)(rowid - (uint32_t)f * p.h);
+    // strip id -> (frame, row, strip in the row): divisions once, then advanced incrementally by
+    // the (constant) stride of the grid
+    struct Pos {
+        int f, y, strip;
     };
-    // the three source bytes of this lane's pixel of strip `st`, as raw loads: nothing is done
+    auto locate = [&](uint32_t st) {
+        Pos q;
+        const uint32_t rowid = fd_div(p.dspr, st);
+        q.strip = (int)(st - rowid * strips_per_row);
+        q.f = (int)fd_div(p.dh, rowid);
+        q.y = (int)(rowid - (uint32_t)q.f * p.h);
+        return q;
+    };
+    const Pos dpos = locate(stride);        // stride = (df frames, dy rows, dstrip strips)
+    auto advance = [&](Pos &q) {
+        q.strip += dpos.strip;
+        const int c = q.strip >= strips_per_row ? 1 : 0;
+        q.strip -= c * strips_per_row;
+        q.y += dpos.y + c;
+        const int c2 = q.y >= p.h ? 1 : 0;
+        q.y -= c2 * p.h;
+        q.f += dpos.f + c2;
+    };
+    // the three source bytes of this lane's pixel of a strip, as raw loads: nothing is done
     // with them until the next iteration, so the loads stay in flight behind this strip's work
-    auto fetch = [&](uint32_t st, unsigned &b0, unsigned &b1, unsigned &b2) {
+    auto fetch = [&](uint32_t st, const Pos &q, unsigned &b0, unsigned &b1, unsigned &b2) {
         b0 = b1 = b2 = 0u;
         if (st >= total) return;
-        int f, y, strip;
-        locate(st, f, y, strip);
-        const int x = strip * 32 + lane;
+        const int x = q.strip * 32 + lane;
         if (x >= p.w) return;
-        const int sy = p.ytab ? __ldg(p.ytab + y) : y;
+        const int sy = p.ytab ? __ldg(p.ytab + q.y) : q.y;
         const int sx = p.xtab ? __ldg(p.xtab + x) : x;
-        const uint8_t *q = p.src + (size_t)f * src_frame + ((size_t)sy * p.src_w + sx) * 3;
-        b0 = __ldg(q);
-        b1 = __ldg(q + 1);
-        b2 = __ldg(q + 2);
+        const uint8_t *src = p.src + (size_t)q.f * src_frame + ((size_t)sy * p.src_w + sx) * 3;
+        b0 = __ldg(src);
+        b1 = __ldg(src + 1);
+        b2 = __ldg(src + 2);
     };
+    // x4 up-scale, full strips: the 4 x 384 output bytes of a strip are 96 sixteen-byte pieces,
+    // three per lane (piece j = lane + 32 i: output row j / 24, piece j % 24 of the row image)
+    size_t x4_off[3];
+    int x4_col[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int j = lane + 32 * i;
+        x4_col[i] = j % 24;
+        x4_off[i] = (size_t)(j / 24) * out_w3 + (size_t)(j % 24) * 16;
+    }
     uint32_t st = blockIdx.x * (THREADS / 32) + wib;
+    Pos cur = locate(st < total ? st : 0u), nxt = cur;
     unsigned n0, n1, n2;
-    fetch(st, n0, n1, n2);
+    fetch(st, cur, n0, n1, n2);
     for (; st < total; st += stride) {
         int r = (int)n0, g = (int)n1, b = (int)n2;
-        fetch(st + stride, n0, n1, n2);
-        int f, y, strip;
-        locate(st, f, y, strip);
+        cur = nxt;
+        advance(nxt);
+        fetch(st + stride, nxt, n0, n1, n2);
+        const int f = cur.f, y = cur.y, strip = cur.strip;
         const int x = strip * 32 + lane;
         const int nvalid = min(32, p.w - strip * 32);
         if (x < p.w) {
@@ -1078,6 +1112,12 @@ __global__ void __launch_bounds__(THREADS) k_thresh_geom2(const ThreshParams p)
         const int n16 = nbytes >> 4;          // <= 6 * GEOM2_MAX_M = 48 sixteen-byte pieces
         uint8_t *drow = p.dst + (size_t)f * dst_frame + (size_t)y * m * out_w3 + (size_t)strip * 96 * m;
         const uint4 *img4 = reinterpret_cast<const uint4 *>(rowimg);
+        if (m == 4 && nvalid == 32) {         // warp-uniform
+#pragma unroll
+            for (int i = 0; i < 3; ++i) __stcs(reinterpret_cast<uint4 *>(drow + x4_off[i]), img4[x4_col[i]]);
+            __syncwarp();
+            continue;
+        }
         const uint4 v0 = lane < n16 ? img4[lane] : make_uint4(0, 0, 0, 0);
         const uint4 v1 = lane + 32 < n16 ? img4[lane + 32] : make_uint4(0, 0, 0, 0);
         for (int rr = 0; rr < m; ++rr) {
@@ -1090,6 +1130,7 @@ __global__ void __launch_bounds__(THREADS) k_thresh_geom2(const ThreshParams p)
         __syncwarp();
     }
 }
+
 
 template <int KIND>
 int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
@@ -1151,7 +1192,8 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
         q.dspr = make_fastdiv((uint32_t)((p.w + 31) / 32));
         q.dh = make_fastdiv((uint32_t)p.h);
         q.geom_table = p.geom_table;
-        size_t smem = 256 + 1024 + (size_t)p.K * 16 + mat_bytes + 16 +
+        const size_t mat2 = (KIND == DP_THRESH_MATRIX && p.mh * p.mw <= GEOM2_MAT_SMEM) ? (size_t)p.mh * p.mw * 4 : 0;
+        size_t smem = 256 + 1024 + (size_t)p.K * 16 + mat2 + 16 +
                       (size_t)(THREADS / 32) * 96 * GEOM2_MAX_M;
         long long strips = (long long)p.frames * p.h * ((p.w + 31) / 32);
         long long want = (strips + THREADS / 32 - 1) / (THREADS / 32);

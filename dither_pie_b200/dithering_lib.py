@@ -476,38 +476,50 @@ class ColorReducer:
 
     @staticmethod
     def _median_cut_array(cols: np.ndarray, depth: int):
-        """median_cut on an int64 [N,3] array whose row order is the list order of the
+        """median_cut on a PLANAR uint8 [3,N] array whose column order is the list order of the
         reference: ``list.sort(key=channel)`` is a stable sort, so a stable argsort on the
-        channel reproduces it; the box average is the same float division of exact integer sums,
-        truncated."""
-        n = cols.shape[0]
+        channel reproduces it (numpy sorts bytes with a radix sort); the box average is the same
+        float division of exact integer sums, truncated."""
+        n = cols.shape[1]
         if depth == 0 or n == 0:
             if n == 0:
                 return [(0, 0, 0)]
-            return [tuple(int(int(sv) / n) for sv in cols.sum(axis=0))]
-        spans = (cols.max(axis=0) - cols.min(axis=0)).tolist()
+            return [tuple(int(int(sv) / n) for sv in cols.sum(axis=1, dtype=np.int64))]
+        spans = [int(cols[c].max()) - int(cols[c].min()) for c in range(3)]
         ch = spans.index(max(spans))
-        cols = cols[np.argsort(cols[:, ch], kind='stable')]
+        cols = np.take(cols, np.argsort(cols[ch], kind='stable'), axis=1)
         mid = n // 2
-        return (ColorReducer._median_cut_array(cols[:mid], depth - 1)
-                + ColorReducer._median_cut_array(cols[mid:], depth - 1))
+        return (ColorReducer._median_cut_array(cols[:, :mid], depth - 1)
+                + ColorReducer._median_cut_array(cols[:, mid:], depth - 1))
+
+    @staticmethod
+    def unique_colors_in_set_order(arr_u8: np.ndarray) -> np.ndarray:
+        """``list(set(image.getdata()))`` (:1837) as a uint8 [N,3] array: the unique colours in
+        the iteration order of a CPython set of (r, g, b) tuples, replayed natively
+        (csrc/dp_pyset.cu; host code, no GPU needed).  That order decides how equal keys fall
+        around each median (``list.sort`` is stable)."""
+        from . import _capi
+        import ctypes as C
+        flat = np.ascontiguousarray(arr_u8, np.uint8).reshape(-1, 3)
+        out = np.empty_like(flat)
+        n = C.c_int64(0)
+        _capi.check(_capi.lib().dp_unique_colors_pyset_order(
+            flat.ctypes.data, flat.shape[0], out.ctypes.data, C.byref(n)),
+            "dp_unique_colors_pyset_order")
+        return out[:n.value]
 
     @staticmethod
     def reduce_colors(image, num_colors: int):
-        """:1834-1843.  The order in which the unique colours enter the cut is the iteration
-        order of a Python ``set`` of tuples (it decides how equal keys fall around each median),
-        so the set is still built by the interpreter; the recursive sort/split/average work --
-        most of the reference's 7.6 s on a 1080p frame -- runs on arrays."""
+        """:1834-1843.  The unique colours enter the cut in CPython set order
+        (unique_colors_in_set_order); the recursive sort/split/average work -- most of the
+        reference's 7.6 s on a 1080p frame -- runs on arrays."""
         image = image.convert('RGB')
-        unique_cols = list(set(image.getdata()))
+        arr = ColorReducer.unique_colors_in_set_order(np.asarray(image, dtype=np.uint8))
         num_colors = max(1, num_colors)
         depth = int(math.log2(num_colors)) if num_colors > 1 else 0
-        if len(unique_cols) < 64:
-            return ColorReducer.median_cut(unique_cols, depth)
-        import itertools
-        arr = np.fromiter(itertools.chain.from_iterable(unique_cols), dtype=np.int64,
-                          count=3 * len(unique_cols)).reshape(-1, 3)
-        return ColorReducer._median_cut_array(arr, depth)
+        if arr.shape[0] < 64:
+            return ColorReducer.median_cut([tuple(int(v) for v in c) for c in arr], depth)
+        return ColorReducer._median_cut_array(np.ascontiguousarray(arr.T), depth)
 
     @staticmethod
     def generate_kmeans_palette(img, num_colors: int, random_state=42):

@@ -171,6 +171,18 @@ int dp_hybrid(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h, 
               void *stream);
 
 /*
+ * dp_unique_colors_pyset_order -- HOST helper (no device work) for the default palette source:
+ * `unique_cols = list(set(image.getdata()))` in ColorReducer.reduce_colors
+ * (dithering_lib.py:1837).  Median cut depends on the ITERATION ORDER of that CPython set (stable
+ * sorts keep it among equal keys), so the unique colours are returned in exactly that order by
+ * replaying CPython's tuple hash and set table (see csrc/dp_pyset.cu).  SURVEY.md section 8(f) #1.
+ *   rgb      HOST u8 [npix,3]
+ *   out_rgb  HOST u8 [npix,3] capacity; the first *n_unique rows are written
+ */
+int dp_unique_colors_pyset_order(const uint8_t *rgb, int64_t npix, uint8_t *out_rgb,
+                                 int64_t *n_unique);
+
+/*
  * dp_resample_nearest -- Image.resize(NEAREST) as used by pixelize_regular
  * (video_processor.py:576) and the final up-scale (:419, dither_cli.py:565):
  * dst[f,y,x] = src[f, ytab[y], xtab[x]].  Tables are DEVICE int32.

@@ -110,6 +110,24 @@ def test_median_cut_and_uniform_palettes_match_reference_golden():
         assert [list(map(int, p)) for p in dp.ColorReducer.generate_uniform_palette(int(n))] == pal, n
 
 
+def test_unique_colours_come_out_in_cpython_set_order():
+    """csrc/dp_pyset.cu replays CPython's tuple hash and set table: the order must equal the
+    running interpreter's own ``list(set(image.getdata()))`` (dithering_lib.py:1837) -- across
+    the growth policy's regimes (x4 below 50 000 entries, x2 above), duplicates, tiny inputs."""
+    from PIL import Image
+    rs = np.random.RandomState(5)
+    cases = [synth.frame(24, 32, 3), synth.noise_frame(60, 80, 6), synth.blocks_frame(64, 64, 7, 8, 6),
+             synth.frame(270, 480, 1), synth.noise_frame(300, 400, 2),          # > 50 000 unique colours
+             np.zeros((3, 5, 3), np.uint8), rs.randint(0, 4, (50, 50, 3)).astype(np.uint8),
+             rs.randint(0, 256, (1, 1, 3)).astype(np.uint8),
+             np.concatenate([synth.noise_frame(200, 300, 9)] * 2)]
+    for arr in cases:
+        want = list(set(Image.fromarray(arr, "RGB").getdata()))
+        got = dp.ColorReducer.unique_colors_in_set_order(arr)
+        assert got.shape == (len(want), 3)
+        assert [tuple(int(v) for v in c) for c in got] == want, arr.shape
+
+
 def test_median_cut_and_uniform_palettes_match_reference_semantics():
     from PIL import Image
     img = Image.fromarray(synth.frame(24, 32, 3), "RGB")
