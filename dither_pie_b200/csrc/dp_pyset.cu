@@ -143,3 +143,50 @@ extern "C" int dp_unique_colors_pyset_order(const uint8_t *rgb, int64_t npix, ui
     *n_unique = n;
     return 0;
 }
+
+// generate_blue_noise (dithering_lib.py:381-399): farthest-point ordering of a shuffled
+// coordinate list -- `max(coords, key=min_dist)` (first maximum in list order), value
+// i / (n - 1 + 1e-9), then every remaining point's squared distance to the pick is folded into
+// min_dist.  The distances are small integers (exact in the reference's f32 array), so the
+// replay is integer arithmetic; the reference's pure-Python double loop takes 7 s at size 64 and
+// minutes at 128.  `order`: the shuffled list as flat indices r * size + c (the caller shuffles
+// with numpy's RandomState, as the reference does).
+extern "C" int dp_blue_noise_from_order(const int32_t *order, int size, float *out)
+{
+    DP_REQUIRE(order && out && size >= 1 && size <= 1024, "bad argument");
+    const int n = size * size;
+    int32_t *rr = static_cast<int32_t *>(malloc(sizeof(int32_t) * 3 * (size_t)n));
+    DP_REQUIRE(rr, "out of host memory");
+    int32_t *cc = rr + n, *mind = cc + n;
+    for (int k = 0; k < n; ++k) {
+        rr[k] = order[k] / size;
+        cc[k] = order[k] % size;
+        mind[k] = INT32_MAX;                 // +inf
+    }
+    const double denom = (double)(n - 1) + 1e-9;
+    int live = n;                            // the list, compacted in place (order preserved)
+    for (int i = 0; i < n; ++i) {
+        int j = 0;
+        int32_t best = mind[0];
+        for (int k = 1; k < live; ++k)
+            if (mind[k] > best) {            // strict: the first maximum wins
+                best = mind[k];
+                j = k;
+            }
+        const int br = rr[j], bc = cc[j];
+        out[br * size + bc] = (float)((double)i / denom);
+        --live;
+        for (int k = j; k < live; ++k) {     // coords.remove(best)
+            rr[k] = rr[k + 1];
+            cc[k] = cc[k + 1];
+            mind[k] = mind[k + 1];
+        }
+        for (int k = 0; k < live; ++k) {
+            const int dr = rr[k] - br, dc = cc[k] - bc;
+            const int32_t d2 = dr * dr + dc * dc;
+            if (d2 < mind[k]) mind[k] = d2;
+        }
+    }
+    free(rr);
+    return 0;
+}

@@ -183,6 +183,15 @@ int dp_unique_colors_pyset_order(const uint8_t *rgb, int64_t npix, uint8_t *out_
                                  int64_t *n_unique);
 
 /*
+ * dp_blue_noise_from_order -- HOST helper: generate_blue_noise (dithering_lib.py:381-399), the
+ * farthest-point ordering of a shuffled coordinate list, replayed in integer arithmetic.
+ *   order  HOST int32 [size*size]: the shuffled list as flat indices r*size + c
+ *          (np.random.RandomState(seed).shuffle, as the reference does at :388-389)
+ *   out    HOST f32 [size,size]
+ */
+int dp_blue_noise_from_order(const int32_t *order, int size, float *out);
+
+/*
  * dp_resample_nearest -- Image.resize(NEAREST) as used by pixelize_regular
  * (video_processor.py:576) and the final up-scale (:419, dither_cli.py:565):
  * dst[f,y,x] = src[f, ytab[y], xtab[x]].  Tables are DEVICE int32.
