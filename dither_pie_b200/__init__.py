@@ -10,8 +10,8 @@ from .dithering_lib import (  # noqa: F401
     BaseDitherStrategy, BayerDitherStrategy, BlueNoiseDitherStrategy, ColorReducer, DitherMode,
     DitherUtils, ErrorDiffusionDitherStrategy, ErrorDiffusionKernel, HalftoneDitherStrategy,
     HybridDitherStrategy, ImageDitherer, InterleavedGradientNoiseDitherStrategy, MatrixDitherStrategy,
-    NoDitherStrategy, OstromoukhovDitherStrategy, PaletteSource, PixelizeMethod,
-    PolkaDotDitherStrategy, generate_blue_noise)
+    NoDitherStrategy, OstromoukhovDitherStrategy, PaletteSource, PerceptualDitherStrategy,
+    PixelizeMethod, PolkaDotDitherStrategy, generate_blue_noise)
 from .video_processor import VideoProcessor, pixelize_regular, shard_frames  # noqa: F401
 
 __version__ = "0.1.0"

@@ -44,9 +44,14 @@ namespace {
 
 constexpr int V_OSTRO = 8;
 constexpr int V_HYBRID = 9;   // Floyd-Steinberg footprint, luminance/colour split of the error
+constexpr int V_WEIGHTED = 10; // Floyd-Steinberg footprint, all-f32, per-pixel weight factor, KD-tree nearest
+                               // on the UNCLAMPED value (perceptual: dithering_lib.py:1030-1066)
 
 // footprint a variant diffuses with
-__host__ __device__ constexpr int ed_base(int v) { return v == V_HYBRID ? DP_ED_FLOYD_STEINBERG : v; }
+__host__ __device__ constexpr int ed_base(int v)
+{
+    return (v == V_HYBRID || v == V_WEIGHTED) ? DP_ED_FLOYD_STEINBERG : v;
+}
 
 struct Tap {
     int dx, dy, w;
@@ -123,6 +128,8 @@ __host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
 template <int V>
 struct Spec {
     static constexpr bool OSTRO = (V == V_OSTRO);
+    static constexpr bool WEIGHTED = (V == V_WEIGHTED);
+    static constexpr bool F32 = OSTRO || WEIGHTED;          // all-f32 state and arithmetic
     static constexpr int N = ed_ntaps(V);
     static constexpr bool ROWS3 = ed_rows3(V);
     static constexpr int A1 = ed_extent(V, 1, -1), B1 = ed_extent(V, 1, 1);
@@ -173,6 +180,7 @@ struct WaveParams {
     int l1_smem;        // first table level in shared memory (else read through L1)
     const float *ostro_w;  // [256][4] f32 weights (c0,c1,c2)/sum, DEVICE (ostromoukhov only)
     double hyb_lum, hyb_col;   // lum_factor, col_factor (hybrid only)
+    const float *plane;        // [frames][h][w] per-pixel weight factor, DEVICE (weighted only)
 };
 
 // Progress poll.  Relaxed (no L1 invalidation): everything the consumer reads after the poll is
@@ -429,6 +437,33 @@ __device__ __noinline__ int nearest_kd_exact(const PalDev *P, const Search &s, i
     return bi;
 }
 
+// KD-tree nearest of an arbitrary point (outside the colour cube the per-cell candidate lists do
+// not apply): every row, unique minimum else scipy's traversal.
+__device__ __noinline__ int nearest_kd_full(const PalDev *P, const double *s_pal, int K, double r, double g,
+                                            double b)
+{
+    double best = DP_INF_F64;
+    int bi = 0;
+    bool tie = false;
+    for (int i = 0; i < K; ++i) {
+        const double d = dist_scipy(s_pal + 3 * i, r, g, b);
+        if (d < best) {
+            best = d;
+            bi = i;
+            tie = false;
+        } else if (d == best) {
+            tie = true;
+        }
+    }
+    if (tie) {
+        int oi[1];
+        double os[1];
+        kd_emulate<1>(P, r, g, b, oi, os);
+        bi = oi[0];
+    }
+    return bi;
+}
+
 // work values (clamped to [0,255]) -> palette row, the reference's answer.  (r,g,b) are the f32
 // screening copies of the exact values (xr,xg,xb).
 template <bool KD, int NSLOT>
@@ -497,6 +532,7 @@ __device__ __forceinline__ void apply_taps(std::integer_sequence<int, Ks...>, co
 // round_to_f32), plain f32 for Ostromoukhov (whose reference arithmetic is f32 throughout).
 template <int V> struct StateOf { using T = double; };
 template <> struct StateOf<V_OSTRO> { using T = float; };
+template <> struct StateOf<V_WEIGHTED> { using T = float; };
 
 // Per-warp staging buffers (shared memory), one "chunk" = 32 pixel steps:
 //   inw  [2][32 rows][25] u32  raw source bytes (aligned words) holding the 32 pixels each lane
@@ -526,7 +562,7 @@ template <int V, bool BIG>
 constexpr int wave_max_warps()
 {
     return (V == DP_ED_JJN || V == DP_ED_STUCKI) ? (BIG ? 12 : 8)
-         : (V == DP_ED_SIERRA || V == V_OSTRO) ? 12 : 16;
+         : (V == DP_ED_SIERRA || V == V_OSTRO || V == V_WEIGHTED) ? 12 : 16;
 }
 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc, bool valid)
@@ -554,7 +590,7 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
     float4 *s_rows = reinterpret_cast<float4 *>(s_pal + DP_MAX_COLORS * 3);   // [257]
     double *s_lutd = reinterpret_cast<double *>(s_rows + DP_MAX_COLORS + 1);  // [256] (as T)
     float *s_palf = reinterpret_cast<float *>(s_lutd + 256);                  // [256*3] (Ostromoukhov)
-    float *s_ow = s_palf + (SP::OSTRO ? DP_MAX_COLORS * 3 : 0);               // [256*4] (Ostromoukhov)
+    float *s_ow = s_palf + (SP::F32 ? DP_MAX_COLORS * 3 : 0);                 // [256*4] (Ostromoukhov)
     unsigned *s_orgb = reinterpret_cast<unsigned *>(s_ow + (SP::OSTRO ? 256 * 4 : 0));   // [256]
     uint16_t *s_l1 = reinterpret_cast<uint16_t *>(s_orgb + 256);              // [32768] if l1_smem
     uint4 *s_pat = reinterpret_cast<uint4 *>(s_l1 + (p.l1_smem ? 32768 : 0)); // [p.pat_smem]
@@ -573,7 +609,7 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
     }
     for (int i = threadIdx.x; i < p.K * 3; i += NT) {
         s_pal[i] = P->pal_f64[i];
-        if (SP::OSTRO) s_palf[i] = P->pal_f32[i];
+        if (SP::F32) s_palf[i] = P->pal_f32[i];
     }
     for (int i = threadIdx.x; i < p.K; i += NT) {
         const uint8_t *o = P->out_rgb + 4 * i;
@@ -815,7 +851,7 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                 const bool active = rowok && x >= 0 && x < W;
                 if (active) {
                     int bi;
-                    if constexpr (!SP::OSTRO) {
+                    if constexpr (!SP::F32) {
                         double v[3], e[3];
                         float vf[3];
 #pragma unroll
@@ -845,6 +881,31 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                         apply_taps<V>(std::make_integer_sequence<int, SP::N>{}, e, q10, q20a, q20b,
                                       d1, d2);
                         DP_STICK(3);
+                    } else if constexpr (SP::WEIGHTED) {
+                        // perceptual (:1042-1063): no clamp, KD-tree nearest of the raw work value,
+                        // f32 error, taps scaled by the pixel's factor: err * f32(wgt * factor)
+                        float ov[3], er[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) ov[c] = __fadd_rn(fa[c], oq10[c]);
+                        const bool inside = ov[0] >= 0.f && ov[0] <= 255.f && ov[1] >= 0.f && ov[1] <= 255.f &&
+                                            ov[2] >= 0.f && ov[2] <= 255.f;
+                        if (inside)
+                            bi = nearest_row<true, NSLOT>(P, srch, ov[0], ov[1], ov[2], (double)ov[0],
+                                                          (double)ov[1], (double)ov[2]);
+                        else   // outside the colour cube the candidate tables do not apply
+                            bi = nearest_kd_full(P, srch.s_pal, p.K, (double)ov[0], (double)ov[1], (double)ov[2]);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], lds_f32(palf_a + 12u * bi + 4u * c));
+                        const float fac = __ldg(p.plane + ((size_t)f * H + y) * W + x);
+                        const float w0 = __fmul_rn(0.4375f, fac), w1 = __fmul_rn(0.1875f, fac),
+                                    w2 = __fmul_rn(0.3125f, fac), w3 = __fmul_rn(0.0625f, fac);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            oq10[c] = __fmul_rn(er[c], w0);
+                            d1[0][c] = __fadd_rn(d1[0][c], __fmul_rn(er[c], w1));
+                            d1[1][c] = __fadd_rn(d1[1][c], __fmul_rn(er[c], w2));
+                            d1[2][c] = __fadd_rn(d1[2][c], __fmul_rn(er[c], w3));
+                        }
                     } else {
                         float ov[3], er[3];
 #pragma unroll
@@ -998,6 +1059,7 @@ struct SerialParams {
     float *ring;           // [frames][3][w][3]
     const float *ostro_w;  // ostromoukhov only
     double hyb_lum, hyb_col;   // hybrid only
+    const float *plane;        // weighted only
 };
 
 template <bool OSTRO>
@@ -1061,7 +1123,28 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
                 for (int n = 0; n < W; ++n, x += dir) {
                     float *px = r0 + 3 * x;
                     int bi;
-                    if (!OSTRO) {
+                    if (!OSTRO && p.variant == V_WEIGHTED) {
+                        // perceptual (:1042-1063), see the wavefront kernel
+                        float ov[3], er[3];
+                        for (int c = 0; c < 3; ++c) ov[c] = px[c];
+                        const bool inside = ov[0] >= 0.f && ov[0] <= 255.f && ov[1] >= 0.f && ov[1] <= 255.f &&
+                                            ov[2] >= 0.f && ov[2] <= 255.f;
+                        bi = inside ? nearest_kd_exact(P, srch, cell_of(ov[0], ov[1], ov[2]), (double)ov[0],
+                                                       (double)ov[1], (double)ov[2])
+                                    : nearest_kd_full(P, s_pal, p.K, (double)ov[0], (double)ov[1], (double)ov[2]);
+                        for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], s_palf[3 * bi + c]);
+                        const float fac = p.plane[((size_t)f * H + y) * W + x];
+                        const float w0 = __fmul_rn(0.4375f, fac), w1 = __fmul_rn(0.1875f, fac),
+                                    w2 = __fmul_rn(0.3125f, fac), w3 = __fmul_rn(0.0625f, fac);
+                        for (int c = 0; c < 3; ++c) {
+                            if (x + 1 < W) r0[3 * (x + 1) + c] = __fadd_rn(r0[3 * (x + 1) + c], __fmul_rn(er[c], w0));
+                            if (y + 1 < H) {
+                                if (x > 0) r1[3 * (x - 1) + c] = __fadd_rn(r1[3 * (x - 1) + c], __fmul_rn(er[c], w1));
+                                r1[3 * x + c] = __fadd_rn(r1[3 * x + c], __fmul_rn(er[c], w2));
+                                if (x + 1 < W) r1[3 * (x + 1) + c] = __fadd_rn(r1[3 * (x + 1) + c], __fmul_rn(er[c], w3));
+                            }
+                        }
+                    } else if (!OSTRO) {
                         double v[3], e[3];
                         for (int c = 0; c < 3; ++c) {
                             double tv = (double)px[c];
@@ -1172,7 +1255,8 @@ int launch_wave_as(const WaveParams &p0, cudaStream_t st, int npat, bool big)
     WaveParams p = p0;
     const int sms = dp_num_sms();
     const size_t base = DP_MAX_COLORS * 3 * 8 + (DP_MAX_COLORS + 1) * 16 + 256 * 8 +
-                        (V == V_OSTRO ? DP_MAX_COLORS * 3 * 4 + 256 * 4 * 4 : 0) + 256 * 4;
+                        (V == V_OSTRO ? DP_MAX_COLORS * 3 * 4 + 256 * 4 * 4 : 0) +
+                        (V == V_WEIGHTED ? DP_MAX_COLORS * 3 * 4 : 0) + 256 * 4;
     const size_t limit = 227 * 1024;
     constexpr int maxw = wave_max_warps<V, BIG>();
     int warps = big ? maxw : 4;
@@ -1245,6 +1329,7 @@ int wave_tpad(int variant, int w)
         case DP_ED_SIERRA_TWO_ROW: extra = wave_extra_steps<DP_ED_SIERRA_TWO_ROW>(); break;
         case DP_ED_SIERRA_LITE: extra = wave_extra_steps<DP_ED_SIERRA_LITE>(); break;
         case V_HYBRID: extra = wave_extra_steps<V_HYBRID>(); break;
+        case V_WEIGHTED: extra = wave_extra_steps<V_WEIGHTED>(); break;
         default: extra = wave_extra_steps<V_OSTRO>(); break;
     }
     return ((w + extra + 31) >> 5) << 5;
@@ -1252,7 +1337,7 @@ int wave_tpad(int variant, int w)
 
 int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, int w, int variant,
                   int serpentine, const float *ostro_w_host, uint8_t *dst, uint8_t *dst_idx,
-                  cudaStream_t st, double hyb_lum = 0.0, double hyb_col = 0.0)
+                  cudaStream_t st, double hyb_lum = 0.0, double hyb_col = 0.0, const float *plane = nullptr)
 {
     const bool ostro = (variant == V_OSTRO);
     Workspace ws_ow;
@@ -1281,6 +1366,7 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
         sp.ostro_w = ostro_w;
         sp.hyb_lum = hyb_lum;
         sp.hyb_col = hyb_col;
+        sp.plane = plane;
         Workspace ring;
         if (ring.alloc((size_t)frames * 3 * w * 3 * sizeof(float), st)) return 1;
         sp.ring = static_cast<float *>(ring.ptr);
@@ -1310,6 +1396,7 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
     p.ostro_w = ostro_w;
     p.hyb_lum = hyb_lum;
     p.hyb_col = hyb_col;
+    p.plane = plane;
     Workspace hand, flags;
     if (hand.alloc((size_t)units * 6 * (size_t)wave_tpad(variant, w) * sizeof(float), st)) return 1;
     if (flags.alloc((size_t)(2 * units + 2) * sizeof(int), st)) return 1;
@@ -1335,6 +1422,7 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
         case DP_ED_SIERRA_TWO_ROW: return launch_wave<DP_ED_SIERRA_TWO_ROW>(p, st, npat, four);
         case DP_ED_SIERRA_LITE: return launch_wave<DP_ED_SIERRA_LITE>(p, st, npat, four);
         case V_HYBRID: return launch_wave<V_HYBRID>(p, st, npat, four);
+        case V_WEIGHTED: return launch_wave<V_WEIGHTED>(p, st, npat, four);
         default: return launch_wave<V_OSTRO>(p, st, npat, four);
     }
 }
@@ -1399,4 +1487,43 @@ extern "C" int dp_hybrid(const dp_palette *pal, const uint8_t *src_rgb, int fram
     if (frames == 0 || h == 0 || w == 0) return 0;
     return run_diffusion(pal, src_rgb, frames, h, w, V_HYBRID, 0, nullptr, dst_rgb, dst_idx,
                          dp_stream(stream), lum_factor, col_factor);
+}
+
+namespace {
+
+// perceptual factor plane (:1037, :1051-1052), all f32 with one rounding per operation:
+// gray = ((0.299 R + 0.587 G) + 0.114 B) of the ORIGINAL pixel, factor = 0.5 + 0.5 (gray / 255)
+__global__ void __launch_bounds__(256) k_perceptual_plane(const PalDev *P, const uint8_t *src, float *plane,
+                                                          long long n)
+{
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x] = P->in_lut[threadIdx.x];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const uint8_t *q = src + 3 * i;
+        const float r = (float)s_lut[q[0]], g = (float)s_lut[q[1]], b = (float)s_lut[q[2]];
+        const float gray = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, g)), __fmul_rn(0.114f, b));
+        plane[i] = __fadd_rn(0.5f, __fmul_rn(0.5f, __fdiv_rn(gray, 255.0f)));
+    }
+}
+
+}  // namespace
+
+extern "C" int dp_perceptual(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h, int w,
+                             uint8_t *dst_rgb, uint8_t *dst_idx, void *stream)
+{
+    DP_REQUIRE(pal && src_rgb && dst_rgb, "null argument");
+    DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
+    if (frames == 0 || h == 0 || w == 0) return 0;
+    cudaStream_t st = dp_stream(stream);
+    Workspace plane;
+    const long long n = (long long)frames * h * w;
+    if (plane.alloc((size_t)n * sizeof(float), st)) return 1;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)dp_num_sms() * 16;
+    k_perceptual_plane<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(
+        reinterpret_cast<const PalDev *>(pal->blob), src_rgb, static_cast<float *>(plane.ptr), n);
+    DP_LAUNCH_CHECK();
+    return run_diffusion(pal, src_rgb, frames, h, w, V_WEIGHTED, 0, nullptr, dst_rgb, dst_idx, st, 0.0, 0.0,
+                         static_cast<const float *>(plane.ptr));
 }

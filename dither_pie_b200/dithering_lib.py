@@ -5,10 +5,11 @@ dobrosketchkun/dither_pie ``dithering_lib.py`` (``__all__`` at :27-57) for every
 the per-pixel work runs in libditherpie_b200.so (hand-written CUDA, sm_100a) through ctypes.
 There is no CPU fallback: without the library or without a B200 every ``dither`` call raises.
 
-Out-of-scope modes (riemersma, wavelet, adaptive_variance, perceptual -- SURVEY.md
-section 2, rows 14-15) keep their names so that imports do not break, and raise
-NotImplementedError when used.  ``hybrid`` runs on the
-error-diffusion wavefront with the semantics of the reference's numba kernel.
+Out-of-scope modes (riemersma, wavelet, adaptive_variance -- SURVEY.md section 2, rows 14-15)
+keep their names so that imports do not break, and raise NotImplementedError when used.
+``hybrid`` and ``perceptual`` run on the error-diffusion
+wavefront: hybrid with the semantics of the reference's numba kernel, perceptual with those of
+its pure-Python loop (f32, KD-tree nearest of the unclamped value).
 """
 from __future__ import annotations
 
@@ -397,7 +398,20 @@ def _out_of_scope(name: str, where: str):
 RiemersmaDitherStrategy = _out_of_scope('RiemersmaDitherStrategy', ':771-841')
 WaveletDitherStrategy = _out_of_scope('WaveletDitherStrategy', ':846-941')
 AdaptiveVarianceDitherStrategy = _out_of_scope('AdaptiveVarianceDitherStrategy', ':946-1025')
-PerceptualDitherStrategy = _out_of_scope('PerceptualDitherStrategy', ':1030-1066')
+
+
+class PerceptualDitherStrategy(BaseDitherStrategy):
+    """:1030-1066: Floyd-Steinberg whose taps are scaled by a luminance factor of the original
+    pixel.  Only the default ``base_weights`` run on the GPU; a custom list raises."""
+    _mode = "perceptual"
+    _FS = [(1, 0, 7 / 16), (-1, 1, 3 / 16), (0, 1, 5 / 16), (1, 1, 1 / 16)]
+
+    def __init__(self, base_weights=None):
+        if base_weights is not None and [tuple(t) for t in base_weights] != self._FS:
+            raise NotImplementedError(
+                "PerceptualDitherStrategy: only the default Floyd-Steinberg base_weights are "
+                "built for B200; use the reference for custom weights")
+        self.base_weights = list(self._FS)
 
 
 class HybridDitherStrategy(BaseDitherStrategy):

@@ -376,6 +376,8 @@ class Plan:
         elif mode == "ostromoukhov":
             self.serpentine = p.get("serpentine", "false") == "true"
             self.coeffs = ostromoukhov_coeffs()
+        elif mode == "perceptual":
+            pass   # PerceptualDitherStrategy (:1030-1066) with its default Floyd-Steinberg weights
         elif mode == "hybrid":
             # HybridDitherStrategy.__init__ (:1101-1104); dither() passes float(...) of both (:1121)
             self.lum_factor = float(p.get("lum_factor", 1.0))
@@ -411,6 +413,9 @@ class Plan:
             check(L.dp_error_diffusion(pal.handle, src_ptr, frames, self.h, self.w, self.variant,
                                        int(self.serpentine), dst_ptr, idx_ptr, stream),
                   "dp_error_diffusion")
+        elif self.mode == "perceptual":
+            check(L.dp_perceptual(pal.handle, src_ptr, frames, self.h, self.w, dst_ptr, idx_ptr,
+                                  stream), "dp_perceptual")
         elif self.mode == "hybrid":
             check(L.dp_hybrid(pal.handle, src_ptr, frames, self.h, self.w, self.lum_factor,
                               self.col_factor, dst_ptr, idx_ptr, stream), "dp_hybrid")

@@ -171,6 +171,16 @@ int dp_hybrid(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h, 
               void *stream);
 
 /*
+ * dp_perceptual -- PerceptualDitherStrategy.dither (:1040-1066, pure Python in the reference,
+ * default base_weights = Floyd-Steinberg): all-f32 diffusion, KD-tree nearest of the UNCLAMPED
+ * work value, every tap scaled by the luminance factor 0.5 + 0.5 (gray / 255) of the ORIGINAL
+ * pixel (f32, one rounding per operation).  Same wavefront as dp_error_diffusion; the factor
+ * plane is produced by a small per-pixel kernel first.  
+ */
+int dp_perceptual(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h, int w,
+                  uint8_t *dst_rgb, uint8_t *dst_idx, void *stream);
+
+/*
  * dp_unique_colors_pyset_order -- HOST helper (no device work) for the default palette source:
  * `unique_cols = list(set(image.getdata()))` in ColorReducer.reduce_colors
  * (dithering_lib.py:1837).  Median cut depends on the ITERATION ORDER of that CPython set (stable

@@ -15,6 +15,9 @@
  *   orc_hybrid            dithering_lib.py:1396-1494 (_hybrid_numba): the Floyd-Steinberg loop of
  *                         orc_error_diffusion with the error split into luminance and colour
  *                         parts (f64, one rounding per operation).
+ *   orc_perceptual        dithering_lib.py:1030-1066 (PerceptualDitherStrategy, pure Python):
+ *                         all-f32 Floyd-Steinberg whose taps are scaled by a luminance factor of
+ *                         the ORIGINAL pixel; KD-tree nearest of the UNCLAMPED work value.
  *   orc_ostromoukhov      dithering_lib.py:1225-1269 (the live pure-Python path): all-f32
  *                         arithmetic, f32-rounded weights, KD-tree nearest (tie rules of scipy).
  *
@@ -388,6 +391,71 @@ int orc_ostromoukhov(float *work, int h, int w, const float *palette, int K,
         }
     }
     for (size_t i = 0; i < (size_t)h * w * 3; ++i) {
+        float t = work[i];
+        if (t < 0.0f) t = 0.0f;
+        else if (t > 255.0f) t = 255.0f;
+        work[i] = t;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Perceptual (dithering_lib.py:1030-1066, pure Python; numpy >= 2 scalar promotion: every
+ * quantity is f32, python floats are weak).
+ *   gray     = ((0.299f R + 0.587f G) + 0.114f B) of the ORIGINAL image (:1037), f32 ops
+ *   per pixel: old = work[y,x] (NOT clamped); idx = KDTree.query(old); err = old - chosen (f32);
+ *              sens = 0.5f + 0.5f * (gray / 255.0f); for the FS taps: work += err * f32(wgt * sens)
+ * ---------------------------------------------------------------------------------------- */
+int orc_perceptual(float *work, int h, int w, const float *palette, int K, const orc_kdtree *tree,
+                   uint8_t *out_idx)
+{
+    (void)K;
+    static const int dxs[4] = {1, -1, 0, 1}, dys[4] = {0, 1, 1, 1};
+    static const float wts[4] = {0.4375f, 0.1875f, 0.3125f, 0.0625f};
+    const float c299 = (float)0.299, c587 = (float)0.587, c114 = (float)0.114;
+    float *gray = (float *)malloc(sizeof(float) * (size_t)h * w);
+    if (!gray) return 1;
+    for (size_t i = 0; i < (size_t)h * w; ++i) {
+        float a = c299 * work[3 * i], b = c587 * work[3 * i + 1], c = c114 * work[3 * i + 2];
+        float ab = a + b;
+        gray[i] = ab + c;
+    }
+    for (int y = 0; y < h; ++y) {
+        for (int x = 0; x < w; ++x) {
+            float *px = work + 3 * ((size_t)y * w + x);
+            float old[3], err[3];
+            double xq[3];
+            for (int c = 0; c < 3; ++c) {
+                old[c] = px[c];
+                xq[c] = (double)px[c];
+            }
+            int32_t idx;
+            double d2;
+            kd_query_one(tree, xq, 1, &idx, &d2);
+            for (int c = 0; c < 3; ++c) {
+                float ch = palette[3 * idx + c];
+                px[c] = ch;
+                err[c] = old[c] - ch;
+            }
+            if (out_idx) out_idx[(size_t)y * w + x] = (uint8_t)idx;
+            float q = gray[(size_t)y * w + x] / 255.0f;
+            float hq = 0.5f * q;
+            float sens = 0.5f + hq;
+            for (int k = 0; k < 4; ++k) {
+                int nx = x + dxs[k], ny = y + dys[k];
+                if (nx >= 0 && nx < w && ny >= 0 && ny < h) {
+                    float wk = wts[k] * sens;
+                    float *t = work + 3 * ((size_t)ny * w + nx);
+                    for (int c = 0; c < 3; ++c) {
+                        float pr = err[c] * wk;
+                        t[c] = t[c] + pr;
+                    }
+                }
+            }
+        }
+    }
+    free(gray);
+    for (size_t i = 0; i < (size_t)h * w * 3; ++i) {   /* np.clip(work, 0, 255) (:1065) */
         float t = work[i];
         if (t < 0.0f) t = 0.0f;
         else if (t > 255.0f) t = 255.0f;

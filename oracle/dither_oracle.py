@@ -69,6 +69,7 @@ def _lib():
         _LIB.orc_error_diffusion.restype = ctypes.c_int
         _LIB.orc_ostromoukhov.restype = ctypes.c_int
         _LIB.orc_hybrid.restype = ctypes.c_int
+        _LIB.orc_perceptual.restype = ctypes.c_int
     return _LIB
 
 
@@ -400,6 +401,22 @@ def hybrid_indices(pixels: np.ndarray, palette: np.ndarray, h: int, w: int,
     return idx.reshape(-1).astype(np.int32)
 
 
+def perceptual_indices(pixels: np.ndarray, palette: np.ndarray, h: int, w: int) -> np.ndarray:
+    """PerceptualDitherStrategy.dither (:1040-1066), default base_weights (Floyd-Steinberg)."""
+    work = np.ascontiguousarray(pixels, np.float32).reshape(h, w, 3).copy()
+    pal = np.ascontiguousarray(palette, np.float32)
+    tree = export_kdtree(pal)
+    s = _kd_struct(tree)
+    idx = np.empty((h, w), np.uint8)
+    rc = _lib().orc_perceptual(
+        ctypes.c_void_p(work.ctypes.data), ctypes.c_int(h), ctypes.c_int(w),
+        ctypes.c_void_p(pal.ctypes.data), ctypes.c_int(pal.shape[0]), ctypes.byref(s),
+        ctypes.c_void_p(idx.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("orc_perceptual failed")
+    return idx.reshape(-1).astype(np.int32)
+
+
 _OSTRO = None
 
 
@@ -493,6 +510,8 @@ def apply_dithering(img_u8: np.ndarray, palette: Sequence[Sequence[float]], mode
                                       params.get("serpentine", "false") == "true")
     elif mode == "ostromoukhov":
         idx = ostromoukhov_indices(flat, pal, h, w, params.get("serpentine", "false") == "true")
+    elif mode == "perceptual":
+        idx = perceptual_indices(flat, pal, h, w)
     elif mode == "hybrid":
         idx = hybrid_indices(flat, pal, h, w, params.get("lum_factor", 1.0),
                              params.get("col_factor", 0.2))

@@ -61,6 +61,15 @@ def test_golden_hybrid_cases():
         assert mismatch(out, g[f"out_{n}"]) == 0, (n, m)
 
 
+def test_golden_perceptual_cases():
+    """perceptual mode against outputs of the live reference (pure-Python loop), incl. gamma."""
+    g = load_golden("perceptual_cases.npz")
+    meta = json.load(open(os.path.join(GOLDEN, "perceptual_cases.json")))
+    for n, m in enumerate(meta):
+        out = gpu(g["img_" + m["image"]], g["pal_" + m["palette"]], "perceptual", {}, m["gamma"])
+        assert mismatch(out, g[f"out_{n}"]) == 0, (n, m)
+
+
 def test_golden_pixelize_and_final_resize():
     g = load_golden("pixelize.npz")
     small = g["small"]
@@ -215,6 +224,28 @@ def test_hybrid_vs_oracle():
     assert np.array_equal(out.reshape(64, 300, 3).astype(np.uint8), ref)
     big = synth.frame(1080, 1920, 3)
     assert mismatch(gpu(big, PALS["pico8"], "hybrid"), O.apply_dithering(big, PALS["pico8"], "hybrid", {})) == 0
+
+
+def test_perceptual_vs_oracle():
+    """Multi-band, multi-frame, single-row (serial kernel), values leaving the colour cube
+    (two-colour and single-colour palettes push the unclamped work values far outside), 1080p."""
+    for pname, (h, w) in [("pico8", (70, 90)), ("r256", (45, 140)), ("lat27", (97, 33)),
+                          ("two", (40, 40)), ("one", (9, 9)), ("c64", (1, 77)), ("r64", (150, 211)),
+                          ("gb4", (64, 64))]:
+        frames = np.stack([synth.frame(h, w, 95 + t) for t in range(2)])
+        out = gpu(frames, PALS[pname], "perceptual")
+        for t in range(2):
+            ref = O.apply_dithering(frames[t], PALS[pname], "perceptual", {})
+            assert mismatch(out[t], ref) == 0, (pname, h, w, t)
+    img = synth.noise_frame(64, 300, 6)
+    assert mismatch(gpu(img, PALS["r64"], "perceptual", {}, True),
+                    O.apply_dithering(img, PALS["r64"], "perceptual", {}, True)) == 0
+    flat = img.reshape(-1, 3).astype(np.float32)
+    out = dp.PerceptualDitherStrategy().dither(flat, PALS["pico8"].astype(np.float32), (64, 300))
+    assert np.array_equal(out.reshape(64, 300, 3).astype(np.uint8),
+                          O.apply_dithering(img, PALS["pico8"], "perceptual", {}))
+    big = synth.frame(1080, 1920, 4)
+    assert mismatch(gpu(big, PALS["pico8"], "perceptual"), O.apply_dithering(big, PALS["pico8"], "perceptual", {})) == 0
 
 
 def test_ostromoukhov_vs_oracle():

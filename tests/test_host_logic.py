@@ -83,7 +83,11 @@ def test_api_surface_matches_reference_names():
     assert dl.ErrorDiffusionKernel.get_kernel("nope") is dl.ErrorDiffusionKernel.FLOYD_STEINBERG
     assert dl.ErrorDiffusionKernel.JJN["divisor"] == 48 and len(dl.ErrorDiffusionKernel.SIERRA["weights"]) == 10
     with pytest.raises(NotImplementedError):
-        dl.PerceptualDitherStrategy()
+        dl.AdaptiveVarianceDitherStrategy()
+    with pytest.raises(NotImplementedError):
+        dl.PerceptualDitherStrategy(base_weights=[(1, 0, 1.0)])
+    assert dl.PerceptualDitherStrategy().base_weights[0] == (1, 0, 7 / 16)
+    assert dl.ImageDitherer.get_mode_parameters(dl.DitherMode.PERCEPTUAL) is None
     assert dl.HybridDitherStrategy().get_current_parameters() == {"lum_factor": 1.0, "col_factor": 0.2}
     assert dl.ImageDitherer.get_mode_parameters(dl.DitherMode.HYBRID)["col_factor"]["default"] == 0.2
     with pytest.raises(TypeError):

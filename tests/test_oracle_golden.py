@@ -89,6 +89,16 @@ def test_hybrid_cases_bit_exact():
         assert np.array_equal(out, g[f"out_{n}"]), (n, m)
 
 
+def test_perceptual_cases_bit_exact():
+    """perceptual mode (pure-Python reference, :1030-1066): unclamped KD-tree lookups, f32."""
+    g = load_golden("perceptual_cases.npz")
+    meta = json.load(open(os.path.join(GOLDEN, "perceptual_cases.json")))
+    assert len(meta) >= 14
+    for n, m in enumerate(meta):
+        out = O.apply_dithering(g["img_" + m["image"]], g["pal_" + m["palette"]], "perceptual", {}, m["gamma"])
+        assert np.array_equal(out, g[f"out_{n}"]), (n, m)
+
+
 def test_pixelize_tables():
     g = load_golden("pixelize.npz")
     meta = json.load(open(os.path.join(GOLDEN, "pixelize.json")))

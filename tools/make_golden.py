@@ -95,6 +95,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if sys.argv[1:] == ["hybrid"]:
         return hybrid_golden(dl)
+    if sys.argv[1:] == ["perceptual"]:
+        return perceptual_golden(dl)
     import numba
     import PIL
     import scipy
@@ -225,6 +227,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "kmeans.npz"), **store)
     median_cut_golden(dl)
     hybrid_golden(dl)
+    perceptual_golden(dl)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
@@ -261,6 +264,33 @@ def hybrid_golden(dl):
     np.savez_compressed(os.path.join(OUT, "hybrid_cases.npz"), **store)
     json.dump(meta, open(os.path.join(OUT, "hybrid_cases.json"), "w"))
     print("hybrid cases:", len(meta))
+
+
+def perceptual_golden(dl):
+    """---- 9. perceptual mode (PerceptualDitherStrategy :1030-1066, pure Python + KDTree) through
+    ImageDitherer.apply_dithering; own file (python tools/make_golden.py perceptual)."""
+    imgs, pals = images(), palettes()
+    imgs["wide"] = synth.frame(70, 90, 5)      # three row bands
+    store, meta = {}, []
+    n = 0
+    for iname, pname, gamma in [
+            ("frame", "pico8", False), ("frame", "pico8", True), ("frame", "r64", False),
+            ("frame", "r256", False), ("frame", "gb4", False), ("frame", "lat27", False),
+            ("frame", "one", False), ("noise", "c64", False), ("noise", "r16", False),
+            ("noise", "r64", True), ("blocks", "pico8", False), ("blocks", "lat27", False),
+            ("wide", "r64", False), ("wide", "gb4", False)]:
+        d = dl.ImageDitherer(num_colors=len(pals[pname]), dither_mode=dl.DitherMode.PERCEPTUAL,
+                             palette=[tuple(int(v) for v in c) for c in pals[pname]], use_gamma=gamma)
+        store[f"out_{n}"] = np.array(d.apply_dithering(Image.fromarray(imgs[iname], "RGB")))
+        meta.append({"image": iname, "palette": pname, "gamma": gamma})
+        n += 1
+    for k, v in imgs.items():
+        store[f"img_{k}"] = v
+    for k, v in pals.items():
+        store[f"pal_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "perceptual_cases.npz"), **store)
+    json.dump(meta, open(os.path.join(OUT, "perceptual_cases.json"), "w"))
+    print("perceptual cases:", len(meta))
 
 
 def median_cut_golden(dl):
