@@ -7,7 +7,7 @@ package does not touch CUDA; the first call that needs the GPU loads the library
 it, or a B200, is missing.  There is no CPU fallback.
 """
 from .dithering_lib import (  # noqa: F401
-    BaseDitherStrategy, BayerDitherStrategy, BlueNoiseDitherStrategy, ColorReducer, DitherMode,
+    AdaptiveVarianceDitherStrategy, BaseDitherStrategy, BayerDitherStrategy, BlueNoiseDitherStrategy, ColorReducer, DitherMode,
     DitherUtils, ErrorDiffusionDitherStrategy, ErrorDiffusionKernel, HalftoneDitherStrategy,
     HybridDitherStrategy, ImageDitherer, InterleavedGradientNoiseDitherStrategy, MatrixDitherStrategy,
     NoDitherStrategy, OstromoukhovDitherStrategy, PaletteSource, PerceptualDitherStrategy,

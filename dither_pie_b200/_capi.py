@@ -54,6 +54,7 @@ PROTOTYPES = {
     "dp_ostromoukhov": [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp],
     "dp_hybrid": [_vp, _vp, _i, _i, _i, _d, _d, _vp, _vp, _vp],
     "dp_perceptual": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp],
+    "dp_adaptive_variance": [_vp, _vp, _i, _i, _i, _d, _i, _vp, _vp, _vp],
     "dp_unique_colors_pyset_order": [_vp, _i64, _vp, _vp],
     "dp_blue_noise_from_order": [_vp, _i, _vp],
     "dp_resample_nearest": [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp],

@@ -1527,3 +1527,107 @@ extern "C" int dp_perceptual(const dp_palette *pal, const uint8_t *src_rgb, int 
     return run_diffusion(pal, src_rgb, frames, h, w, V_WEIGHTED, 0, nullptr, dst_rgb, dst_idx, st, 0.0, 0.0,
                          static_cast<const float *>(plane.ptr));
 }
+
+namespace {
+
+// ---- adaptive variance: the gate plane (AdaptiveVarianceDitherStrategy, :989-1025) -------------
+// gray and gray^2 of the original pixels (f32, one rounding per operation; numpy squares with a
+// multiply)
+__global__ void __launch_bounds__(256) k_av_gray(const PalDev *P, const uint8_t *src, float *g, float *g2,
+                                                 long long n)
+{
+    __shared__ uint8_t s_lut[256];
+    s_lut[threadIdx.x] = P->in_lut[threadIdx.x];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const uint8_t *q = src + 3 * i;
+        const float r = (float)s_lut[q[0]], gg = (float)s_lut[q[1]], b = (float)s_lut[q[2]];
+        const float gray = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, gg)), __fmul_rn(0.114f, b));
+        g[i] = gray;
+        g2[i] = __fmul_rn(gray, gray);
+    }
+}
+
+// scipy.ndimage.uniform_filter1d (scipy 1.18, third-party; ni_filters.c NI_UniformFilter1D) along
+// one axis, mode='nearest', origin 0, f32 in / f32 out: the line is extended by `rad` edge copies
+// and walked with a RUNNING SUM in double -- tmp = sum of the first window; out[0] = tmp / size;
+// then tmp += new - old; out[l] = tmp / size -- one thread per line, two planes per launch.
+// `stride` = element distance along the line, lines are enumerated by `line_of`.
+__global__ void __launch_bounds__(128) k_av_uniform(const float *in_a, const float *in_b, float *out_a,
+                                                    float *out_b, int frames, int h, int w, int axis, int rad)
+{
+    const long long nlines = (long long)frames * (axis == 0 ? w : h);
+    const int len = axis == 0 ? h : w;
+    const long long stride = axis == 0 ? w : 1;
+    const double size = (double)(2 * rad + 1);
+    for (long long t = (long long)blockIdx.x * 128 + threadIdx.x; t < 2 * nlines; t += (long long)gridDim.x * 128) {
+        const bool second = t >= nlines;
+        const long long line = second ? t - nlines : t;
+        const float *in = second ? in_b : in_a;
+        float *out = second ? out_b : out_a;
+        const long long f = line / (axis == 0 ? w : h);
+        const long long k = line - f * (axis == 0 ? w : h);
+        const long long base = f * (long long)h * w + (axis == 0 ? k : k * w);
+        auto at = [&](int i) -> double {
+            i = i < 0 ? 0 : (i >= len ? len - 1 : i);
+            return (double)in[base + (long long)i * stride];
+        };
+        double tmp = 0.0;
+        for (int j = -rad; j <= rad; ++j) tmp = __dadd_rn(tmp, at(j));
+        out[base] = __double2float_rn(__ddiv_rn(tmp, size));
+        for (int l = 1; l < len; ++l) {
+            tmp = __dadd_rn(tmp, __dsub_rn(at(l + rad), at(l - 1 - rad)));
+            out[base + (long long)l * stride] = __double2float_rn(__ddiv_rn(tmp, size));
+        }
+    }
+}
+
+// var = max(0, mean_sq - mean^2) (f32), gate = var >= f32(threshold) -> factor 1 or 0
+__global__ void __launch_bounds__(256) k_av_gate(const float *mean, const float *mean_sq, float thr, float *plane,
+                                                 long long n)
+{
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float m = mean[i];
+        const float var = fmaxf(0.0f, __fsub_rn(mean_sq[i], __fmul_rn(m, m)));
+        plane[i] = var >= thr ? 1.0f : 0.0f;
+    }
+}
+
+}  // namespace
+
+extern "C" int dp_adaptive_variance(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h, int w,
+                                    double var_threshold, int window_radius, uint8_t *dst_rgb,
+                                    uint8_t *dst_idx, void *stream)
+{
+    DP_REQUIRE(pal && src_rgb && dst_rgb, "null argument");
+    DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
+    DP_REQUIRE(window_radius >= 0 && window_radius <= 64, "window radius out of range");
+    if (frames == 0 || h == 0 || w == 0) return 0;
+    cudaStream_t st = dp_stream(stream);
+    const long long n = (long long)frames * h * w;
+    Workspace wa, wb, wc, wd;
+    if (wa.alloc((size_t)n * 4, st) || wb.alloc((size_t)n * 4, st) || wc.alloc((size_t)n * 4, st) ||
+        wd.alloc((size_t)n * 4, st))
+        return 1;
+    float *A = static_cast<float *>(wa.ptr), *B = static_cast<float *>(wb.ptr), *C = static_cast<float *>(wc.ptr),
+          *D = static_cast<float *>(wd.ptr);
+    const long long cap = (long long)dp_num_sms() * 16;
+    const long long blocks = (n + 255) / 256;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+    k_av_gray<<<grid, 256, 0, st>>>(reinterpret_cast<const PalDev *>(pal->blob), src_rgb, A, B, n);
+    DP_LAUNCH_CHECK();
+    const float *mean = A, *mean_sq = B;
+    if (window_radius >= 1) {   // size = 2 r + 1 > 1 on both axes: axis 0, then axis 1 on its f32 result
+        const long long l0 = 2ll * frames * w, l1 = 2ll * frames * h;
+        k_av_uniform<<<(int)((l0 + 127) / 128 < cap ? (l0 + 127) / 128 : cap), 128, 0, st>>>(A, B, C, D, frames, h, w,
+                                                                                          0, window_radius);
+        DP_LAUNCH_CHECK();
+        k_av_uniform<<<(int)((l1 + 127) / 128 < cap ? (l1 + 127) / 128 : cap), 128, 0, st>>>(C, D, A, B, frames, h, w,
+                                                                                          1, window_radius);
+        DP_LAUNCH_CHECK();
+    }
+    // python float threshold meets an f32 array element: numpy (NEP 50) compares in f32
+    k_av_gate<<<grid, 256, 0, st>>>(mean, mean_sq, (float)var_threshold, C, n);
+    DP_LAUNCH_CHECK();
+    return run_diffusion(pal, src_rgb, frames, h, w, V_WEIGHTED, 0, nullptr, dst_rgb, dst_idx, st, 0.0, 0.0, C);
+}

@@ -5,11 +5,11 @@ dobrosketchkun/dither_pie ``dithering_lib.py`` (``__all__`` at :27-57) for every
 the per-pixel work runs in libditherpie_b200.so (hand-written CUDA, sm_100a) through ctypes.
 There is no CPU fallback: without the library or without a B200 every ``dither`` call raises.
 
-Out-of-scope modes (riemersma, wavelet, adaptive_variance -- SURVEY.md section 2, rows 14-15)
-keep their names so that imports do not break, and raise NotImplementedError when used.
-``hybrid`` and ``perceptual`` run on the error-diffusion
-wavefront: hybrid with the semantics of the reference's numba kernel, perceptual with those of
-its pure-Python loop (f32, KD-tree nearest of the unclamped value).
+Out-of-scope modes (riemersma, wavelet -- SURVEY.md section 2, rows 14-15) keep their names so
+that imports do not break, and raise NotImplementedError when used.  ``hybrid``, ``perceptual``
+and ``adaptive_variance`` run on the error-diffusion wavefront:
+hybrid with the semantics of the reference's numba kernel, the other two with those of their
+pure-Python loops (f32, KD-tree nearest of the unclamped value).
 """
 from __future__ import annotations
 
@@ -397,7 +397,30 @@ def _out_of_scope(name: str, where: str):
 
 RiemersmaDitherStrategy = _out_of_scope('RiemersmaDitherStrategy', ':771-841')
 WaveletDitherStrategy = _out_of_scope('WaveletDitherStrategy', ':846-941')
-AdaptiveVarianceDitherStrategy = _out_of_scope('AdaptiveVarianceDitherStrategy', ':946-1025')
+
+
+class AdaptiveVarianceDitherStrategy(BaseDitherStrategy):
+    """:946-1025: Floyd-Steinberg that distributes a pixel's error only where the local variance
+    of the gray image reaches ``var_threshold``."""
+    _mode = "adaptive_variance"
+
+    @staticmethod
+    def get_parameter_info() -> Dict[str, Any]:
+        return {
+            'var_threshold': {'type': 'float', 'default': 300.0, 'min': 0.0, 'max': 1000.0,
+                              'step': 10.0, 'label': 'Variance Threshold',
+                              'description': 'Threshold for local variance to trigger error diffusion'},
+            'window_radius': {'type': 'int', 'default': 1, 'min': 1, 'max': 5,
+                              'label': 'Window Radius',
+                              'description': 'Radius of window for computing local variance'},
+        }
+
+    def __init__(self, var_threshold: float = 300.0, window_radius: int = 1):
+        self.var_threshold = var_threshold
+        self.window_radius = window_radius
+
+    def get_current_parameters(self) -> Dict[str, Any]:
+        return {'var_threshold': self.var_threshold, 'window_radius': self.window_radius}
 
 
 class PerceptualDitherStrategy(BaseDitherStrategy):

@@ -376,6 +376,10 @@ class Plan:
         elif mode == "ostromoukhov":
             self.serpentine = p.get("serpentine", "false") == "true"
             self.coeffs = ostromoukhov_coeffs()
+        elif mode == "adaptive_variance":
+            # AdaptiveVarianceDitherStrategy.__init__ (:979-981)
+            self.var_threshold = float(p.get("var_threshold", 300.0))
+            self.window_radius = int(p.get("window_radius", 1))
         elif mode == "perceptual":
             pass   # PerceptualDitherStrategy (:1030-1066) with its default Floyd-Steinberg weights
         elif mode == "hybrid":
@@ -413,6 +417,10 @@ class Plan:
             check(L.dp_error_diffusion(pal.handle, src_ptr, frames, self.h, self.w, self.variant,
                                        int(self.serpentine), dst_ptr, idx_ptr, stream),
                   "dp_error_diffusion")
+        elif self.mode == "adaptive_variance":
+            check(L.dp_adaptive_variance(pal.handle, src_ptr, frames, self.h, self.w,
+                                         self.var_threshold, self.window_radius, dst_ptr, idx_ptr,
+                                         stream), "dp_adaptive_variance")
         elif self.mode == "perceptual":
             check(L.dp_perceptual(pal.handle, src_ptr, frames, self.h, self.w, dst_ptr, idx_ptr,
                                   stream), "dp_perceptual")

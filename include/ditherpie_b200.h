@@ -181,6 +181,18 @@ int dp_perceptual(const dp_palette *pal, const uint8_t *src_rgb, int frames, int
                   uint8_t *dst_rgb, uint8_t *dst_idx, void *stream);
 
 /*
+ * dp_adaptive_variance -- AdaptiveVarianceDitherStrategy.dither (:989-1025, pure Python in the
+ * reference): all-f32 Floyd-Steinberg on the UNCLAMPED work values with KD-tree nearest, the
+ * error of a pixel being distributed only where the local variance of the original gray image
+ * (scipy.ndimage.uniform_filter of gray and gray^2, size 2*window_radius+1, mode 'nearest';
+ * :1021-1025) is >= var_threshold.  The gate plane is computed on the device by replaying
+ * scipy's running-sum filter, then the weighted wavefront of dp_perceptual runs with factors 0/1.
+ */
+int dp_adaptive_variance(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h, int w,
+                         double var_threshold, int window_radius, uint8_t *dst_rgb,
+                         uint8_t *dst_idx, void *stream);
+
+/*
  * dp_unique_colors_pyset_order -- HOST helper (no device work) for the default palette source:
  * `unique_cols = list(set(image.getdata()))` in ColorReducer.reduce_colors
  * (dithering_lib.py:1837).  Median cut depends on the ITERATION ORDER of that CPython set (stable

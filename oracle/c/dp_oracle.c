@@ -18,6 +18,9 @@
  *   orc_perceptual        dithering_lib.py:1030-1066 (PerceptualDitherStrategy, pure Python):
  *                         all-f32 Floyd-Steinberg whose taps are scaled by a luminance factor of
  *                         the ORIGINAL pixel; KD-tree nearest of the UNCLAMPED work value.
+ *   orc_adaptive          dithering_lib.py:989-1015 (AdaptiveVarianceDitherStrategy, pure Python):
+ *                         all-f32 Floyd-Steinberg, unclamped KD-tree lookups, the error of a
+ *                         pixel distributed only where the caller's gate plane is set.
  *   orc_ostromoukhov      dithering_lib.py:1225-1269 (the live pure-Python path): all-f32
  *                         arithmetic, f32-rounded weights, KD-tree nearest (tie rules of scipy).
  *
@@ -456,6 +459,57 @@ int orc_perceptual(float *work, int h, int w, const float *palette, int K, const
     }
     free(gray);
     for (size_t i = 0; i < (size_t)h * w * 3; ++i) {   /* np.clip(work, 0, 255) (:1065) */
+        float t = work[i];
+        if (t < 0.0f) t = 0.0f;
+        else if (t > 255.0f) t = 255.0f;
+        work[i] = t;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Adaptive variance (dithering_lib.py:989-1015, pure Python): as orc_perceptual without the
+ * luminance factor; `gate` (u8 [h,w]) = var_map >= var_threshold, computed by the caller with
+ * scipy's uniform_filter exactly as the reference does (:1021-1025).
+ * ---------------------------------------------------------------------------------------- */
+int orc_adaptive(float *work, int h, int w, const float *palette, int K, const orc_kdtree *tree,
+                 const uint8_t *gate, uint8_t *out_idx)
+{
+    (void)K;
+    static const int dxs[4] = {1, -1, 0, 1}, dys[4] = {0, 1, 1, 1};
+    static const float wts[4] = {0.4375f, 0.1875f, 0.3125f, 0.0625f};
+    for (int y = 0; y < h; ++y) {
+        for (int x = 0; x < w; ++x) {
+            float *px = work + 3 * ((size_t)y * w + x);
+            float old[3], err[3];
+            double xq[3];
+            for (int c = 0; c < 3; ++c) {
+                old[c] = px[c];
+                xq[c] = (double)px[c];
+            }
+            int32_t idx;
+            double d2;
+            kd_query_one(tree, xq, 1, &idx, &d2);
+            for (int c = 0; c < 3; ++c) {
+                float ch = palette[3 * idx + c];
+                px[c] = ch;
+                err[c] = old[c] - ch;
+            }
+            if (out_idx) out_idx[(size_t)y * w + x] = (uint8_t)idx;
+            if (!gate[(size_t)y * w + x]) continue;
+            for (int k = 0; k < 4; ++k) {
+                int nx = x + dxs[k], ny = y + dys[k];
+                if (nx >= 0 && nx < w && ny < h) {
+                    float *t = work + 3 * ((size_t)ny * w + nx);
+                    for (int c = 0; c < 3; ++c) {
+                        float pr = err[c] * wts[k];
+                        t[c] = t[c] + pr;
+                    }
+                }
+            }
+        }
+    }
+    for (size_t i = 0; i < (size_t)h * w * 3; ++i) {
         float t = work[i];
         if (t < 0.0f) t = 0.0f;
         else if (t > 255.0f) t = 255.0f;

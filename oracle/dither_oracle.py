@@ -70,6 +70,7 @@ def _lib():
         _LIB.orc_ostromoukhov.restype = ctypes.c_int
         _LIB.orc_hybrid.restype = ctypes.c_int
         _LIB.orc_perceptual.restype = ctypes.c_int
+        _LIB.orc_adaptive.restype = ctypes.c_int
     return _LIB
 
 
@@ -417,6 +418,64 @@ def perceptual_indices(pixels: np.ndarray, palette: np.ndarray, h: int, w: int) 
     return idx.reshape(-1).astype(np.int32)
 
 
+def uniform_filter_nearest(a: np.ndarray, size: int) -> np.ndarray:
+    """scipy.ndimage.uniform_filter(a f32 [h,w], size, mode='nearest') restated (scipy 1.18.1,
+    third-party; NI_UniformFilter1D): axis 0 then axis 1, each pass a RUNNING SUM in double over
+    the edge-extended line (tmp = first window; out = tmp / size; tmp += new - old), f32 between
+    passes.  Checked against scipy itself in tests/test_oracle_golden.py."""
+    out = np.asarray(a, np.float32)
+    if size <= 1:
+        return out.copy()
+    r = size // 2
+    for axis in (0, 1):
+        lines = np.moveaxis(out, axis, 1).astype(np.float64)          # [lines, length]
+        ext = np.concatenate([np.repeat(lines[:, :1], r, 1), lines,
+                              np.repeat(lines[:, -1:], size - r - 1, 1)], 1)
+        res = np.empty_like(lines)
+        tmp = np.zeros(lines.shape[0])
+        for k in range(size):
+            tmp = tmp + ext[:, k]
+        res[:, 0] = tmp / float(size)
+        for l in range(1, lines.shape[1]):
+            tmp = tmp + (ext[:, l + size - 1] - ext[:, l - 1])
+            res[:, l] = tmp / float(size)
+        out = np.moveaxis(res.astype(np.float32), 1, axis)
+    return np.ascontiguousarray(out)
+
+
+def variance_gate(pixels: np.ndarray, h: int, w: int, var_threshold: float = 300.0,
+                  window_radius: int = 1) -> np.ndarray:
+    """AdaptiveVarianceDitherStrategy (:993-996, :1021-1025) with scipy's own uniform_filter, as
+    the reference calls it: gray (f32) -> local variance -> `>= var_threshold`."""
+    from scipy.ndimage import uniform_filter
+    pix = np.asarray(pixels, np.float32).reshape(h, w, 3)
+    gray = 0.299 * pix[:, :, 0] + 0.587 * pix[:, :, 1] + 0.114 * pix[:, :, 2]
+    size = 2 * window_radius + 1
+    g = gray.astype(np.float32)
+    mean_sq = uniform_filter(g ** 2, size=size, mode='nearest')
+    sq_mean = uniform_filter(g, size=size, mode='nearest') ** 2
+    var = np.maximum(0.0, mean_sq - sq_mean)
+    return np.ascontiguousarray(var >= var_threshold).astype(np.uint8)
+
+
+def adaptive_indices(pixels: np.ndarray, palette: np.ndarray, h: int, w: int,
+                     var_threshold: float = 300.0, window_radius: int = 1) -> np.ndarray:
+    """AdaptiveVarianceDitherStrategy.dither (:989-1019)."""
+    work = np.ascontiguousarray(pixels, np.float32).reshape(h, w, 3).copy()
+    pal = np.ascontiguousarray(palette, np.float32)
+    gate = variance_gate(pixels, h, w, var_threshold, window_radius)
+    tree = export_kdtree(pal)
+    s = _kd_struct(tree)
+    idx = np.empty((h, w), np.uint8)
+    rc = _lib().orc_adaptive(
+        ctypes.c_void_p(work.ctypes.data), ctypes.c_int(h), ctypes.c_int(w),
+        ctypes.c_void_p(pal.ctypes.data), ctypes.c_int(pal.shape[0]), ctypes.byref(s),
+        ctypes.c_void_p(gate.ctypes.data), ctypes.c_void_p(idx.ctypes.data))
+    if rc != 0:
+        raise RuntimeError("orc_adaptive failed")
+    return idx.reshape(-1).astype(np.int32)
+
+
 _OSTRO = None
 
 
@@ -512,6 +571,9 @@ def apply_dithering(img_u8: np.ndarray, palette: Sequence[Sequence[float]], mode
         idx = ostromoukhov_indices(flat, pal, h, w, params.get("serpentine", "false") == "true")
     elif mode == "perceptual":
         idx = perceptual_indices(flat, pal, h, w)
+    elif mode == "adaptive_variance":
+        idx = adaptive_indices(flat, pal, h, w, params.get("var_threshold", 300.0),
+                               params.get("window_radius", 1))
     elif mode == "hybrid":
         idx = hybrid_indices(flat, pal, h, w, params.get("lum_factor", 1.0),
                              params.get("col_factor", 0.2))

@@ -16,7 +16,7 @@ def declared_symbols():
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
     for must in ("dp_palette_create", "dp_threshold_dither", "dp_halftone", "dp_error_diffusion",
-                 "dp_ostromoukhov", "dp_hybrid", "dp_perceptual", "dp_resample_nearest", "dp_kmeans_accumulate",
+                 "dp_ostromoukhov", "dp_hybrid", "dp_perceptual", "dp_adaptive_variance", "dp_resample_nearest", "dp_kmeans_accumulate",
                  "dp_kmeans_update", "dp_last_error"):
         assert must in syms
 

@@ -70,6 +70,16 @@ def test_golden_perceptual_cases():
         assert mismatch(out, g[f"out_{n}"]) == 0, (n, m)
 
 
+def test_golden_adaptive_cases():
+    """adaptive_variance against outputs of the live reference (pure Python + scipy filter)."""
+    g = load_golden("adaptive_cases.npz")
+    meta = json.load(open(os.path.join(GOLDEN, "adaptive_cases.json")))
+    for n, m in enumerate(meta):
+        out = gpu(g["img_" + m["image"]], g["pal_" + m["palette"]], "adaptive_variance", m["params"],
+                  m["gamma"])
+        assert mismatch(out, g[f"out_{n}"]) == 0, (n, m)
+
+
 def test_golden_pixelize_and_final_resize():
     g = load_golden("pixelize.npz")
     small = g["small"]
@@ -246,6 +256,28 @@ def test_perceptual_vs_oracle():
                           O.apply_dithering(img, PALS["pico8"], "perceptual", {}))
     big = synth.frame(1080, 1920, 4)
     assert mismatch(gpu(big, PALS["pico8"], "perceptual"), O.apply_dithering(big, PALS["pico8"], "perceptual", {})) == 0
+
+
+def test_adaptive_variance_vs_oracle():
+    """Gate plane (running-sum filter replay, radii 1..5, lines shorter than the window, thresholds
+    that are not f32 numbers) and the gated diffusion; multi-band, multi-frame, single row, 1080p."""
+    cases = [{}, {"var_threshold": 0.0}, {"var_threshold": 33.3, "window_radius": 2},
+             {"var_threshold": 500.1, "window_radius": 5}, {"var_threshold": 1e9}]
+    for pname, (h, w) in [("pico8", (70, 90)), ("r256", (45, 140)), ("lat27", (97, 33)), ("two", (40, 40)),
+                          ("one", (9, 9)), ("c64", (1, 77)), ("r64", (150, 211)), ("gb4", (3, 4))]:
+        frames = np.stack([synth.frame(h, w, 97 + t) if t == 0 else synth.noise_frame(h, w, 97 + t)
+                           for t in range(2)])
+        for params in cases:
+            out = gpu(frames, PALS[pname], "adaptive_variance", params)
+            for t in range(2):
+                ref = O.apply_dithering(frames[t], PALS[pname], "adaptive_variance", params)
+                assert mismatch(out[t], ref) == 0, (pname, h, w, params, t)
+    img = synth.noise_frame(64, 300, 6)
+    assert mismatch(gpu(img, PALS["r64"], "adaptive_variance", {"var_threshold": 900.0}, True),
+                    O.apply_dithering(img, PALS["r64"], "adaptive_variance", {"var_threshold": 900.0}, True)) == 0
+    big = synth.frame(1080, 1920, 4)
+    assert mismatch(gpu(big, PALS["pico8"], "adaptive_variance", {"var_threshold": 60.0}),
+                    O.apply_dithering(big, PALS["pico8"], "adaptive_variance", {"var_threshold": 60.0})) == 0
 
 
 def test_ostromoukhov_vs_oracle():

@@ -83,7 +83,9 @@ def test_api_surface_matches_reference_names():
     assert dl.ErrorDiffusionKernel.get_kernel("nope") is dl.ErrorDiffusionKernel.FLOYD_STEINBERG
     assert dl.ErrorDiffusionKernel.JJN["divisor"] == 48 and len(dl.ErrorDiffusionKernel.SIERRA["weights"]) == 10
     with pytest.raises(NotImplementedError):
-        dl.AdaptiveVarianceDitherStrategy()
+        dl.RiemersmaDitherStrategy()
+    assert dl.AdaptiveVarianceDitherStrategy().get_current_parameters() == {
+        "var_threshold": 300.0, "window_radius": 1}
     with pytest.raises(NotImplementedError):
         dl.PerceptualDitherStrategy(base_weights=[(1, 0, 1.0)])
     assert dl.PerceptualDitherStrategy().base_weights[0] == (1, 0, 7 / 16)

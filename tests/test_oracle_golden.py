@@ -99,6 +99,31 @@ def test_perceptual_cases_bit_exact():
         assert np.array_equal(out, g[f"out_{n}"]), (n, m)
 
 
+def test_adaptive_cases_bit_exact():
+    """adaptive_variance mode (pure-Python reference, :946-1025) incl. gamma, radii 1..5,
+    thresholds that are not f32 numbers."""
+    g = load_golden("adaptive_cases.npz")
+    meta = json.load(open(os.path.join(GOLDEN, "adaptive_cases.json")))
+    assert len(meta) >= 14
+    for n, m in enumerate(meta):
+        out = O.apply_dithering(g["img_" + m["image"]], g["pal_" + m["palette"]], "adaptive_variance",
+                                m["params"], m["gamma"])
+        assert np.array_equal(out, g[f"out_{n}"]), (n, m)
+
+
+def test_uniform_filter_restatement_equals_scipy():
+    """The running-sum restatement of scipy.ndimage.uniform_filter (the arithmetic the CUDA gate
+    kernel replays) against scipy itself, bit for bit."""
+    from scipy.ndimage import uniform_filter
+    rs = np.random.RandomState(3)
+    for (h, w) in ((1, 1), (1, 9), (7, 1), (13, 17), (40, 56), (3, 200)):
+        for scale in (1.0, 255.0, 65025.0, 1e-3):
+            a = (rs.rand(h, w) * scale).astype(np.float32)
+            for size in (1, 3, 5, 7, 11):
+                assert np.array_equal(O.uniform_filter_nearest(a, size),
+                                      uniform_filter(a, size=size, mode='nearest')), (h, w, scale, size)
+
+
 def test_pixelize_tables():
     g = load_golden("pixelize.npz")
     meta = json.load(open(os.path.join(GOLDEN, "pixelize.json")))

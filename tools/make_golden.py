@@ -97,6 +97,8 @@ def main():
         return hybrid_golden(dl)
     if sys.argv[1:] == ["perceptual"]:
         return perceptual_golden(dl)
+    if sys.argv[1:] == ["adaptive"]:
+        return adaptive_golden(dl)
     import numba
     import PIL
     import scipy
@@ -228,6 +230,7 @@ def main():
     median_cut_golden(dl)
     hybrid_golden(dl)
     perceptual_golden(dl)
+    adaptive_golden(dl)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
@@ -291,6 +294,40 @@ def perceptual_golden(dl):
     np.savez_compressed(os.path.join(OUT, "perceptual_cases.npz"), **store)
     json.dump(meta, open(os.path.join(OUT, "perceptual_cases.json"), "w"))
     print("perceptual cases:", len(meta))
+
+
+def adaptive_golden(dl):
+    """---- 10. adaptive_variance mode (AdaptiveVarianceDitherStrategy :946-1025, pure Python +
+    KDTree + scipy.ndimage.uniform_filter); own file (python tools/make_golden.py adaptive)."""
+    imgs, pals = images(), palettes()
+    imgs["wide"] = synth.frame(70, 90, 5)
+    store, meta = {}, []
+    n = 0
+    for iname, pname, params, gamma in [
+            ("frame", "pico8", {}, False), ("frame", "pico8", {}, True),
+            ("frame", "r64", {"var_threshold": 50.0}, False),
+            ("frame", "r256", {"var_threshold": 0.0}, False),
+            ("frame", "gb4", {"var_threshold": 120.5, "window_radius": 2}, False),
+            ("frame", "lat27", {"var_threshold": 77.7, "window_radius": 5}, False),
+            ("frame", "one", {}, False), ("noise", "c64", {}, False),
+            ("noise", "r16", {"var_threshold": 2500.0}, False),
+            ("noise", "r64", {"var_threshold": 4000.3, "window_radius": 3}, True),
+            ("blocks", "pico8", {"var_threshold": 10.0}, False),
+            ("blocks", "lat27", {"var_threshold": 1000.0, "window_radius": 4}, False),
+            ("wide", "r64", {"var_threshold": 60.0}, False), ("wide", "gb4", {"var_threshold": 0.1}, False)]:
+        d = dl.ImageDitherer(num_colors=len(pals[pname]), dither_mode=dl.DitherMode.ADAPTIVE_VARIANCE,
+                             palette=[tuple(int(v) for v in c) for c in pals[pname]], use_gamma=gamma,
+                             dither_params=dict(params))
+        store[f"out_{n}"] = np.array(d.apply_dithering(Image.fromarray(imgs[iname], "RGB")))
+        meta.append({"image": iname, "palette": pname, "params": params, "gamma": gamma})
+        n += 1
+    for k, v in imgs.items():
+        store[f"img_{k}"] = v
+    for k, v in pals.items():
+        store[f"pal_{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "adaptive_cases.npz"), **store)
+    json.dump(meta, open(os.path.join(OUT, "adaptive_cases.json"), "w"))
+    print("adaptive cases:", len(meta))
 
 
 def median_cut_golden(dl):
