@@ -486,7 +486,8 @@ def extra_modes(torch, engine, synth, sp, stream, peak):
             # config 5: 4K, 64 colours, Ostromoukhov and Sierra (per GPU; frames shard over GPUs)
             for (mode, params, tag) in (("ostromoukhov", {}, "ostromoukhov"),
                                         ("error_diffusion", {"variant": "sierra"}, "ed_sierra"),
-                                        ("hybrid", {}, "hybrid")):
+                                        ("hybrid", {}, "hybrid"), ("perceptual", {}, "perceptual"),
+                                        ("adaptive_variance", {"var_threshold": 60.0}, "adaptive_variance")):
                 plan = engine.Plan(mode, params, h, w)
                 ms = timed(lambda: plan.run(pal64, src.data_ptr(), nf, dst.data_ptr(), None, sp), 3)
                 crop = frames[0][:540, :960]

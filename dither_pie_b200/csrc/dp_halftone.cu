@@ -60,27 +60,39 @@ __device__ __forceinline__ double np_mod(double a, double b)
 
 // smallest non-negative f32 g with  1 - g/255 <= s  (the reference's f32 ops, :1638-1640);
 // 0 <= s <= 1 after the reference's clip, so g = 256 always satisfies it
-__device__ __forceinline__ bool dark_le(unsigned gbits, float s)
-{
-    return __fsub_rn(1.0f, __fdiv_rn(__uint_as_float(gbits), 255.0f)) <= s;
-}
 __device__ __forceinline__ float gray_threshold(float s)
 {
-    // bit patterns of non-negative floats are ordered like the values.  g* lies within a few
-    // 1e-5 of 255 (1 - s) (two roundings of relative size 2^-24 on values <= 1): bisect a window
-    // of +-2^-12 around it, checked at both ends; fall back to the whole range [0, 256] otherwise.
-    const float g0 = 255.0f * (1.0f - s);
-    unsigned lo = __float_as_uint(fmaxf(g0 - 0.000244140625f, 0.0f));
-    unsigned hi = __float_as_uint(fminf(fmaxf(g0 + 0.000244140625f, 0.0f), 256.0f));
-    if (!dark_le(hi, s)) hi = 0x43800000u;          // 256.0f always satisfies it (0 <= s)
-    if (lo > 0u && dark_le(lo - 1u, s)) lo = 0u;    // the predicate must be false just below lo
+    // Bit patterns of non-negative floats are ordered like the values, and both rounded operations
+    // are monotone, so  fl(1 - fl(g / 255)) <= s  <=>  fl(g / 255) >= q*  with q* the smallest q
+    // satisfying fl(1 - q) <= s.  Stage 1 bisects q* (an add per step, no division); stage 2 finds
+    // the smallest g whose quotient reaches q* among the few floats around q* * 255 (the division
+    // is correctly rounded, so the answer lies within a couple of ulps of the product).
+    unsigned lo = 0u, hi = 0x40000000u;              // 0.0f .. 2.0f; fl(1 - 2) = -1 <= s always
 #pragma unroll 1
-    while (lo < hi) {
+    for (int it = 0; it < 31; ++it) {
         const unsigned mid = (lo + hi) >> 1;
-        if (dark_le(mid, s)) hi = mid;
-        else lo = mid + 1u;
+        const bool le = __fsub_rn(1.0f, __uint_as_float(mid)) <= s;
+        hi = (lo < hi && le) ? mid : hi;
+        lo = (lo < hi && !le) ? mid + 1u : lo;
     }
-    return __uint_as_float(hi);
+    const float qs = __uint_as_float(hi);
+    if (hi == 0u) return 0.0f;                       // s >= 1: every gray qualifies, ink never
+    const unsigned g0 = __float_as_uint(__fmul_rn(qs, 255.0f));
+    unsigned g = g0 > 8u ? g0 - 8u : 0u;
+    if (g > 0u && __fdiv_rn(__uint_as_float(g), 255.0f) >= qs) {
+        // (never observed) the window does not bracket the answer: whole-range bisection
+        unsigned a = 0u, b = 0x44000000u;            // 512.0f / 255 > 2 >= q*
+#pragma unroll 1
+        while (a < b) {
+            const unsigned mid = (a + b) >> 1;
+            if (__fdiv_rn(__uint_as_float(mid), 255.0f) >= qs) b = mid;
+            else a = mid + 1u;
+        }
+        return __uint_as_float(b);
+    }
+#pragma unroll 1
+    while (__fdiv_rn(__uint_as_float(g), 255.0f) < qs) ++g;   // <= 16 steps
+    return __uint_as_float(g);
 }
 
 __global__ void __launch_bounds__(256) k_ht_maps(const HtParams p)
