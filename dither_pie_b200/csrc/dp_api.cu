@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <array>
 #include <map>
+#include <mutex>
 
 #include "dp_search.cuh"
 
@@ -176,8 +177,12 @@ __global__ void __launch_bounds__(256) k_thr_masks(const int4 *__restrict__ coef
 //   max_{x in box} (|x-p_j|^2 - |x-p_i|^2) < 0;
 // the expression is linear in x, so the maximum sits at the corner picked coordinate-wise by
 // the sign of (p_j - p_i).  One block per cell; the result is a 256-bit mask of survivors.
+// `unbounded`: the boxes of the outermost cells extend to infinity on their outer sides, so that
+// the cell of a CLAMPED point lists every row that can be nearest to the unclamped point (the
+// modes that look up unclamped work values: perceptual, adaptive variance).  The maximum over a
+// half-infinite box is +inf unless the expression does not grow in that direction.
 __global__ void __launch_bounds__(256) k_ed_masks(const double *__restrict__ pal, int K,
-                                                  uint32_t *__restrict__ masks)
+                                                  uint32_t *__restrict__ masks, int unbounded)
 {
     __shared__ double s_p[DP_MAX_COLORS * 3];
     __shared__ double s_n[DP_MAX_COLORS];
@@ -193,6 +198,7 @@ __global__ void __launch_bounds__(256) k_ed_masks(const double *__restrict__ pal
     if (threadIdx.x < 8) s_mask[threadIdx.x] = 0;
     __syncthreads();
     const double lo[3] = {8.0 * (cell >> 10), 8.0 * ((cell >> 5) & 31), 8.0 * (cell & 31)};
+    const int ci[3] = {cell >> 10, (cell >> 5) & 31, cell & 31};
     const int i = threadIdx.x;
     if (i < K) {
         bool dominated = false;
@@ -203,6 +209,7 @@ __global__ void __launch_bounds__(256) k_ed_masks(const double *__restrict__ pal
                 const double dlt = s_p[3 * j + c] - s_p[3 * i + c];
                 const double x = dlt > 0.0 ? lo[c] : lo[c] + 8.0;
                 mx += -2.0 * x * dlt;
+                if (unbounded && ((dlt > 0.0 && ci[c] == 0) || (dlt < 0.0 && ci[c] == 31))) mx = 1e300;
             }
             dominated = mx < -1e-6;
         }
@@ -213,13 +220,13 @@ __global__ void __launch_bounds__(256) k_ed_masks(const double *__restrict__ pal
 }
 
 // masks -> device tables (host side; palette creation is set-up)
-int build_ed_table(const double *d_pal64, int K, PalDev &d, dp_palette *h)
+int build_ed_table(const double *d_pal64, int K, PalDev &d, void **out_table, void **out_ovf, int unbounded)
 {
     const int cells = 32768;
     uint32_t *dmask = nullptr;
     std::vector<uint32_t> hmask((size_t)cells * 8);
     if (cudaMalloc(&dmask, (size_t)cells * 32) != cudaSuccess) return 1;
-    k_ed_masks<<<cells, 256>>>(d_pal64, K, dmask);
+    k_ed_masks<<<cells, 256>>>(d_pal64, K, dmask, unbounded);
     bool ok = cudaMemcpy(hmask.data(), dmask, (size_t)cells * 32, cudaMemcpyDeviceToHost) ==
               cudaSuccess;
     cudaFree(dmask);
@@ -288,8 +295,8 @@ int build_ed_table(const double *d_pal64, int K, PalDev &d, dp_palette *h)
     d.ed_ovf_off = reinterpret_cast<const uint32_t *>(static_cast<uint8_t *>(dov) + o_off);
     d.ed_ovf = static_cast<uint8_t *>(dov) + o_list;
     d.ed_novf = (int)n;
-    h->ed_table = dt;
-    h->ed_ovf = dov;
+    *out_table = dt;
+    *out_ovf = dov;
     return 0;
 }
 
@@ -560,7 +567,7 @@ extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out
         delete h;
         return 1;
     }
-    if (build_ed_table(d.pal_f64, K, d, h)) {
+    if (build_ed_table(d.pal_f64, K, d, &h->ed_table, &h->ed_ovf, 0)) {
         dp_set_error("palette nearest-row table build failed: %s",
                      cudaGetErrorString(cudaGetLastError()));
         cudaFree(blob);
@@ -675,6 +682,9 @@ extern "C" int dp_palette_destroy(dp_palette *pal)
     if (!pal) return 0;
     if (pal->ed_table) cudaFree(pal->ed_table);
     if (pal->ed_ovf) cudaFree(pal->ed_ovf);
+    if (pal->ext_table) cudaFree(pal->ext_table);
+    if (pal->ext_ovf) cudaFree(pal->ext_ovf);
+    if (pal->ext_dev) cudaFree(pal->ext_dev);
     if (pal->thr_table) cudaFree(pal->thr_table);
     if (pal->thr_ovf) cudaFree(pal->thr_ovf);
     if (pal->thr4_table) cudaFree(pal->thr4_table);
@@ -684,6 +694,39 @@ extern "C" int dp_palette_destroy(dp_palette *pal)
     if (pal->tie_table) cudaFree(pal->tie_table);
     if (pal->blob) cudaFree(pal->blob);
     delete pal;
+    return 0;
+}
+
+// Second device copy of the palette descriptor whose nearest-row tables were built with unbounded
+// outer cells (see k_ed_masks); built on first use, under a lock (palettes are shared by threads).
+int dp_palette_ext(dp_palette *pal, const PalDev **dev, int *npat, int *gt4)
+{
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pal->ext_dev) {
+        PalDev dx = pal->dev;
+        void *t = nullptr, *o = nullptr, *dd = nullptr;
+        if (build_ed_table(pal->dev.pal_f64, pal->dev.K, dx, &t, &o, 1)) {
+            dp_set_error("unbounded nearest-row table build failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return 1;
+        }
+        if (cudaMalloc(&dd, sizeof(PalDev)) != cudaSuccess ||
+            cudaMemcpy(dd, &dx, sizeof(PalDev), cudaMemcpyHostToDevice) != cudaSuccess) {
+            dp_set_error("palette descriptor upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            cudaFree(t);
+            cudaFree(o);
+            if (dd) cudaFree(dd);
+            return 1;
+        }
+        pal->ext_table = t;
+        pal->ext_ovf = o;
+        pal->ext_npat = dx.ed_npat;
+        pal->ext_gt4 = dx.ed_gt4;
+        pal->ext_dev = dd;
+    }
+    *dev = static_cast<const PalDev *>(pal->ext_dev);
+    *npat = pal->ext_npat;
+    *gt4 = pal->ext_gt4;
     return 0;
 }
 

@@ -125,9 +125,18 @@ struct dp_palette {
     void *tie_table;
     void *ed_table;   // one allocation: level 1 | patterns | flat
     void *ed_ovf;     // one allocation: cells | offsets | lists
+    // lazily built twin with unbounded outer cells (dp_palette_ext): tables, a device copy of
+    // `dev` pointing at them, and the two counters the launch code needs
+    void *ext_table;
+    void *ext_ovf;
+    void *ext_dev;
+    int ext_npat, ext_gt4;
     float host_pal[DP_MAX_COLORS * 3];
 };
 
+// descriptor + nearest-row tables with unbounded outer cells, for the modes that look up
+// UNCLAMPED work values (built on first use)
+int dp_palette_ext(dp_palette *pal, const PalDev **dev, int *npat, int *gt4);
 // number of SMs of the current device (cached)
 int dp_num_sms();
 // make the device's default stream-ordered memory pool keep its memory between calls

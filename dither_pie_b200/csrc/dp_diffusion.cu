@@ -467,10 +467,9 @@ __device__ __noinline__ int nearest_kd_full(const PalDev *P, const double *s_pal
 // work values (clamped to [0,255]) -> palette row, the reference's answer.  (r,g,b) are the f32
 // screening copies of the exact values (xr,xg,xb).
 template <bool KD, int NSLOT>
-__device__ __forceinline__ int nearest_row(const PalDev *P, const Search &s, float r, float g,
-                                           float b, double xr, double xg, double xb)
+__device__ __forceinline__ int nearest_row_in(const PalDev *P, const Search &s, int cell, float r, float g,
+                                              float b, double xr, double xg, double xb)
 {
-    const int cell = cell_of(r, g, b);
     bool sure;
     uint4 e;
     if (s.l1_a) {
@@ -488,6 +487,13 @@ __device__ __forceinline__ int nearest_row(const PalDev *P, const Search &s, flo
     if (!sure)
         bi = KD ? nearest_kd_exact(P, s, cell, xr, xg, xb) : nearest_first_exact(s, cell, xr, xg, xb);
     return bi;
+}
+
+template <bool KD, int NSLOT>
+__device__ __forceinline__ int nearest_row(const PalDev *P, const Search &s, float r, float g,
+                                           float b, double xr, double xg, double xb)
+{
+    return nearest_row_in<KD, NSLOT>(P, s, cell_of(r, g, b), r, g, b, xr, xg, xb);
 }
 
 // One tap, everything about it known at compile time (weight = f64(f32(w)) / divisor, the
@@ -690,6 +696,7 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
         T emitA[3] = {0, 0, 0}, emitB[3] = {0, 0, 0};
         double q10[3] = {0., 0., 0.}, q20a[3] = {0., 0., 0.}, q20b[3] = {0., 0., 0.};
         float oq10[3] = {0.f, 0.f, 0.f};
+        float fac_nxt = 0.f;   // weighted variant: the factor of the NEXT pixel of this lane's row
 #pragma unroll
         for (int j = 0; j < SP::W1; ++j) d1[j][0] = d1[j][1] = d1[j][2] = 0;
 #pragma unroll
@@ -796,6 +803,13 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
 #ifdef DP_WAVE_TIMING
                 long long _stick = clock64();
 #endif
+                float fac = 0.f;
+                if constexpr (SP::WEIGHTED) {
+                    // one step ahead: the load is in flight during this step's search and taps
+                    fac = fac_nxt;
+                    const int xn = x + 1;
+                    fac_nxt = (rowok && xn >= 0 && xn < W) ? __ldg(p.plane + ((size_t)f * H + y) * W + xn) : 0.f;
+                }
                 T fa[3], fb[3];
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -882,21 +896,20 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                                       d1, d2);
                         DP_STICK(3);
                     } else if constexpr (SP::WEIGHTED) {
-                        // perceptual (:1042-1063): no clamp, KD-tree nearest of the raw work value,
+                        // perceptual (:1042-1063): no clamp, KD-tree nearest of the raw work value
+                        // (NaN cannot arise: the work values stay finite),
                         // f32 error, taps scaled by the pixel's factor: err * f32(wgt * factor)
                         float ov[3], er[3];
 #pragma unroll
                         for (int c = 0; c < 3; ++c) ov[c] = __fadd_rn(fa[c], oq10[c]);
-                        const bool inside = ov[0] >= 0.f && ov[0] <= 255.f && ov[1] >= 0.f && ov[1] <= 255.f &&
-                                            ov[2] >= 0.f && ov[2] <= 255.f;
-                        if (inside)
-                            bi = nearest_row<true, NSLOT>(P, srch, ov[0], ov[1], ov[2], (double)ov[0],
-                                                          (double)ov[1], (double)ov[2]);
-                        else   // outside the colour cube the candidate tables do not apply
-                            bi = nearest_kd_full(P, srch.s_pal, p.K, (double)ov[0], (double)ov[1], (double)ov[2]);
+                        // p.P is the descriptor whose outer cells are unbounded: the cell of the
+                        // CLAMPED value lists every row that can be nearest to the value itself
+                        bi = nearest_row_in<true, NSLOT>(
+                            P, srch, cell_of(fminf(fmaxf(ov[0], 0.f), 255.f), fminf(fmaxf(ov[1], 0.f), 255.f),
+                                             fminf(fmaxf(ov[2], 0.f), 255.f)),
+                            ov[0], ov[1], ov[2], (double)ov[0], (double)ov[1], (double)ov[2]);
 #pragma unroll
                         for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], lds_f32(palf_a + 12u * bi + 4u * c));
-                        const float fac = __ldg(p.plane + ((size_t)f * H + y) * W + x);
                         const float w0 = __fmul_rn(0.4375f, fac), w1 = __fmul_rn(0.1875f, fac),
                                     w2 = __fmul_rn(0.3125f, fac), w3 = __fmul_rn(0.0625f, fac);
 #pragma unroll
@@ -1409,9 +1422,10 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
     k_wave_init<<<(int)((units + 255) / 256 < 1024 ? (units + 255) / 256 : 1024), 256, 0, st>>>(
         p.progress, p.qctrl, p.queue, (int)units, frames, p.nbands);
     DP_LAUNCH_CHECK();
-    const int npat = pal->dev.ed_npat;
+    int npat = pal->dev.ed_npat, gt4 = pal->dev.ed_gt4;
+    if (variant == V_WEIGHTED && dp_palette_ext(const_cast<dp_palette *>(pal), &p.P, &npat, &gt4)) return 1;
     // four candidate slots are enough when at most 0.1 % of the cells hold a fifth candidate
-    const bool four = pal->dev.ed_gt4 <= 32 && !getenv("DP_WAVE_SEVEN");
+    const bool four = gt4 <= 32 && !getenv("DP_WAVE_SEVEN");
     switch (variant) {
         case DP_ED_FLOYD_STEINBERG: return launch_wave<DP_ED_FLOYD_STEINBERG>(p, st, npat, four);
         case DP_ED_JJN: return launch_wave<DP_ED_JJN>(p, st, npat, four);
@@ -1552,6 +1566,8 @@ __global__ void __launch_bounds__(256) k_av_gray(const PalDev *P, const uint8_t 
 // one axis, mode='nearest', origin 0, f32 in / f32 out: the line is extended by `rad` edge copies
 // and walked with a RUNNING SUM in double -- tmp = sum of the first window; out[0] = tmp / size;
 // then tmp += new - old; out[l] = tmp / size -- one thread per line, two planes per launch.
+// (A warp-per-32-rows variant that stages tiles through shared memory for coalesced row traffic
+// measured slower: 28 ms against 14 ms for 64 4K frames -- its loads serialise.)
 // `stride` = element distance along the line, lines are enumerated by `line_of`.
 __global__ void __launch_bounds__(128) k_av_uniform(const float *in_a, const float *in_b, float *out_a,
                                                     float *out_b, int frames, int h, int w, int axis, int rad)
