@@ -17,7 +17,10 @@ pal = engine.get_palette(synth.random_palette(K))
 img = np.stack([synth.frame(h, w, 1 + t % 2) for t in range(frames)])
 src = _capi.DeviceBuffer(img.nbytes).upload(img)
 dst = _capi.DeviceBuffer(img.nbytes)
-plan = engine.Plan("error_diffusion", {"variant": variant}, h, w)
+if variant in ("perceptual", "ostromoukhov", "hybrid", "adaptive_variance"):
+    plan = engine.Plan(variant, {}, h, w)      # the other wavefront instantiations
+else:
+    plan = engine.Plan("error_diffusion", {"variant": variant}, h, w)
 buf = (C.c_ulonglong * 532)()
 for rep in range(2):
     plan.run(pal, src.ptr, frames, dst.ptr, None, None)
