@@ -349,10 +349,16 @@ struct CandList {
     int n;
 };
 
-__device__ __forceinline__ CandList cand_list(const Search &s, int cell)
+__device__ __forceinline__ uint4 fetch_pattern(const Search &s, int cell)
+{
+    return __ldg(s.pat + __ldg(s.l1 + cell));
+}
+
+// `e`: the cell's pattern (the screening pass has it in registers already)
+__device__ __forceinline__ CandList cand_list(const Search &s, int cell, const uint4 e)
 {
     CandList L;
-    L.e = __ldg(s.pat + __ldg(s.l1 + cell));
+    L.e = e;
     L.ovf = nullptr;
     if ((L.e.w >> 16) == DP_ED_OVERFLOW) {
         const PalDev *P = s.P;
@@ -385,10 +391,10 @@ __device__ __forceinline__ int cand_at(const CandList &L, int j)
 
 // numba path (:254-263), exact: strict '<' over f64 distances, first index wins.  The candidate
 // list of the pixel's cell holds every row that can be nearest there, in ascending order.
-__device__ __noinline__ int nearest_first_exact(const Search &s, int cell, double r, double g,
+__device__ __noinline__ int nearest_first_exact(const Search &s, int cell, const uint4 e, double r, double g,
                                                 double b)
 {
-    const CandList L = cand_list(s, cell);
+    const CandList L = cand_list(s, cell, e);
     double best = 1e20;
     int bi = 0;
     for (int j = 0; j < L.n; ++j) {
@@ -410,10 +416,10 @@ __device__ __forceinline__ double dist_scipy(const double *pp, double r, double 
 }
 
 // KD-tree nearest (:1243), exact: unique minimum among the candidates, else replay scipy.
-__device__ __noinline__ int nearest_kd_exact(const PalDev *P, const Search &s, int cell, double r,
-                                             double g, double b)
+__device__ __noinline__ int nearest_kd_exact(const PalDev *P, const Search &s, int cell, const uint4 e,
+                                             double r, double g, double b)
 {
-    const CandList L = cand_list(s, cell);
+    const CandList L = cand_list(s, cell, e);
     double best = DP_INF_F64;
     int bi = 0;
     bool tie = false;
@@ -466,9 +472,29 @@ __device__ __noinline__ int nearest_kd_full(const PalDev *P, const double *s_pal
 
 // work values (clamped to [0,255]) -> palette row, the reference's answer.  (r,g,b) are the f32
 // screening copies of the exact values (xr,xg,xb).
-template <bool KD, int NSLOT>
+// f32 screening of EVERY row (same keys and margin as nearest_screen): for cells whose candidate
+// list overflows the pattern -- frequent only in the unbounded outer cells of the unclamped
+// modes -- this beats walking the overflow list (a binary search through global memory).
+__device__ __noinline__ int nearest_all_rows(const PalDev *P, const Search &s, int K, float r, float g, float b,
+                                             double xr, double xg, double xb)
+{
+    int k1 = 0x7fffffff, k2 = 0x7fffffff;
+    for (int i = 0; i < K; ++i) {
+        const float4 p = lds_f32x4(s.rows_a + 16u * i);
+        const float dr = __fsub_rn(r, p.x), dg = __fsub_rn(g, p.y), db = __fsub_rn(b, p.z);
+        const float d = __fmaf_rn(db, db, __fmaf_rn(dg, dg, __fmul_rn(dr, dr)));
+        const int key = (__float_as_int(d) & (int)0xffffff00) | __float_as_int(p.w);
+        const int hi = max(k1, key);
+        k1 = min(k1, key);
+        k2 = min(k2, hi);
+    }
+    if (k2 - k1 > 2048) return k1 & 255;
+    return nearest_kd_full(P, s.s_pal, K, xr, xg, xb);
+}
+
+template <bool KD, int NSLOT, bool ALLROWS = false>
 __device__ __forceinline__ int nearest_row_in(const PalDev *P, const Search &s, int cell, float r, float g,
-                                              float b, double xr, double xg, double xb)
+                                              float b, double xr, double xg, double xb, int K = 0)
 {
     bool sure;
     uint4 e;
@@ -484,8 +510,12 @@ __device__ __forceinline__ int nearest_row_in(const PalDev *P, const Search &s, 
     if (__any_sync(__activemask(), !sure) && (threadIdx.x & 31) == (__ffs(__activemask()) - 1))
         atomicAdd(&g_wave_timing[128 * 4 + 1], 1ull);
 #endif
-    if (!sure)
-        bi = KD ? nearest_kd_exact(P, s, cell, xr, xg, xb) : nearest_first_exact(s, cell, xr, xg, xb);
+    if (!sure) {
+        if (ALLROWS && (e.w >> 16) == DP_ED_OVERFLOW)
+            bi = nearest_all_rows(P, s, K, r, g, b, xr, xg, xb);
+        else
+            bi = KD ? nearest_kd_exact(P, s, cell, e, xr, xg, xb) : nearest_first_exact(s, cell, e, xr, xg, xb);
+    }
     return bi;
 }
 
@@ -904,10 +934,10 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                         for (int c = 0; c < 3; ++c) ov[c] = __fadd_rn(fa[c], oq10[c]);
                         // p.P is the descriptor whose outer cells are unbounded: the cell of the
                         // CLAMPED value lists every row that can be nearest to the value itself
-                        bi = nearest_row_in<true, NSLOT>(
+                        bi = nearest_row_in<true, NSLOT, true>(
                             P, srch, cell_of(fminf(fmaxf(ov[0], 0.f), 255.f), fminf(fmaxf(ov[1], 0.f), 255.f),
                                              fminf(fmaxf(ov[2], 0.f), 255.f)),
-                            ov[0], ov[1], ov[2], (double)ov[0], (double)ov[1], (double)ov[2]);
+                            ov[0], ov[1], ov[2], (double)ov[0], (double)ov[1], (double)ov[2], p.K);
 #pragma unroll
                         for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], lds_f32(palf_a + 12u * bi + 4u * c));
                         const float w0 = __fmul_rn(0.4375f, fac), w1 = __fmul_rn(0.1875f, fac),
@@ -1142,7 +1172,8 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
                         for (int c = 0; c < 3; ++c) ov[c] = px[c];
                         const bool inside = ov[0] >= 0.f && ov[0] <= 255.f && ov[1] >= 0.f && ov[1] <= 255.f &&
                                             ov[2] >= 0.f && ov[2] <= 255.f;
-                        bi = inside ? nearest_kd_exact(P, srch, cell_of(ov[0], ov[1], ov[2]), (double)ov[0],
+                        const int wcell = inside ? cell_of(ov[0], ov[1], ov[2]) : 0;
+                        bi = inside ? nearest_kd_exact(P, srch, wcell, fetch_pattern(srch, wcell), (double)ov[0],
                                                        (double)ov[1], (double)ov[2])
                                     : nearest_kd_full(P, s_pal, p.K, (double)ov[0], (double)ov[1], (double)ov[2]);
                         for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], s_palf[3 * bi + c]);
@@ -1163,8 +1194,8 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
                             double tv = (double)px[c];
                             v[c] = tv < 0.0 ? 0.0 : (tv > 255.0 ? 255.0 : tv);
                         }
-                        bi = nearest_first_exact(srch, cell_of((float)v[0], (float)v[1], (float)v[2]),
-                                                 v[0], v[1], v[2]);
+                        const int scell = cell_of((float)v[0], (float)v[1], (float)v[2]);
+                        bi = nearest_first_exact(srch, scell, fetch_pattern(srch, scell), v[0], v[1], v[2]);
                         for (int c = 0; c < 3; ++c) e[c] = __dsub_rn(v[c], (double)s_palf[3 * bi + c]);
                         if (p.variant == V_HYBRID) {   // _hybrid_numba :1447-1455
                             const double lum = __dadd_rn(
@@ -1189,7 +1220,8 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
                             float a = px[c];
                             ov[c] = a < 0.f ? 0.f : (a > 255.f ? 255.f : a);
                         }
-                        bi = nearest_kd_exact(P, srch, cell_of(ov[0], ov[1], ov[2]), (double)ov[0],
+                        const int ocell = cell_of(ov[0], ov[1], ov[2]);
+                        bi = nearest_kd_exact(P, srch, ocell, fetch_pattern(srch, ocell), (double)ov[0],
                                               (double)ov[1], (double)ov[2]);
                         for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], s_palf[3 * bi + c]);
                         float lum = __fmul_rn(0.299f, ov[0]);
