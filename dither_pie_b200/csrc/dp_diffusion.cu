@@ -1598,8 +1598,6 @@ __global__ void __launch_bounds__(256) k_av_gray(const PalDev *P, const uint8_t 
 // one axis, mode='nearest', origin 0, f32 in / f32 out: the line is extended by `rad` edge copies
 // and walked with a RUNNING SUM in double -- tmp = sum of the first window; out[0] = tmp / size;
 // then tmp += new - old; out[l] = tmp / size -- one thread per line, two planes per launch.
-// (A warp-per-32-rows variant that stages tiles through shared memory for coalesced row traffic
-// measured slower: 28 ms against 14 ms for 64 4K frames -- its loads serialise.)
 // `stride` = element distance along the line, lines are enumerated by `line_of`.
 __global__ void __launch_bounds__(128) k_av_uniform(const float *in_a, const float *in_b, float *out_a,
                                                     float *out_b, int frames, int h, int w, int axis, int rad)
@@ -1626,6 +1624,71 @@ __global__ void __launch_bounds__(128) k_av_uniform(const float *in_a, const flo
         for (int l = 1; l < len; ++l) {
             tmp = __dadd_rn(tmp, __dsub_rn(at(l + rad), at(l - 1 - rad)));
             out[base + (long long)l * stride] = __double2float_rn(__ddiv_rn(tmp, size));
+        }
+    }
+}
+
+// The same filter along rows (axis 1) with coalesced traffic: a warp owns 32 consecutive rows of
+// one plane and walks them in tiles of AVR_TW columns.  The tile plus its halo is loaded with the
+// lane as the column index (32 independent loads per column group, fully unrolled) into shared
+// memory; lane r then advances the running sum of ITS row through the tile sequentially -- the
+// same operations in the same order as k_av_uniform -- and the results go back through shared
+// memory as coalesced stores.
+constexpr int AVR_MAXRAD = 16, AVR_TW = 96;
+__global__ void __launch_bounds__(32) k_av_uniform_rows(const float *in_a, const float *in_b, float *out_a,
+                                                        float *out_b, int frames, int h, int w, int rad)
+{
+    __shared__ float s_in[32][AVR_TW + 2 * AVR_MAXRAD + 3];   // odd row length: no bank conflicts
+    __shared__ float s_out[32][AVR_TW + 1];
+    const int lane = threadIdx.x;
+    const long long rows_total = (long long)frames * h;       // rows of consecutive frames are contiguous
+    const long long ngroups = (rows_total + 31) / 32;
+    const double size = (double)(2 * rad + 1);
+    const int tw = AVR_TW + 2 * rad + 1;                       // tile columns x0-rad-1 .. x0+AVR_TW-1+rad
+    for (long long gidx = blockIdx.x; gidx < 2 * ngroups; gidx += gridDim.x) {
+        const bool second = gidx >= ngroups;
+        const long long g = second ? gidx - ngroups : gidx;
+        const float *in = second ? in_b : in_a;
+        float *out = second ? out_b : out_a;
+        const long long row0 = g * 32;
+        const int nrows = (int)(rows_total - row0 < 32 ? rows_total - row0 : 32);
+        const bool rowok = lane < nrows;
+        double tmp = 0.0;
+        for (int x0 = 0; x0 < w; x0 += AVR_TW) {
+            for (int c0 = 0; c0 < tw; c0 += 32) {
+                const int c = c0 + lane;
+                int x = x0 - rad - 1 + c;
+                x = x < 0 ? 0 : (x >= w ? w - 1 : x);          // mode='nearest'
+                float v[32];
+#pragma unroll
+                for (int r = 0; r < 32; ++r) v[r] = (r < nrows && c < tw) ? in[(row0 + r) * w + x] : 0.f;
+                if (c < tw) {
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) s_in[r][c] = v[r];
+                }
+            }
+            __syncwarp();
+            const int nout = w - x0 < AVR_TW ? w - x0 : AVR_TW;
+            if (rowok) {
+                const float *line = s_in[lane];                // line[c] = element x0 - rad - 1 + c
+                for (int k = 0; k < nout; ++k) {
+                    if (x0 + k == 0) {
+                        tmp = 0.0;
+                        for (int j = 0; j <= 2 * rad; ++j) tmp = __dadd_rn(tmp, (double)line[1 + j]);
+                    } else {
+                        tmp = __dadd_rn(tmp, __dsub_rn((double)line[k + 2 * rad + 1], (double)line[k]));
+                    }
+                    s_out[lane][k] = __double2float_rn(__ddiv_rn(tmp, size));
+                }
+            }
+            __syncwarp();
+            for (int c0 = 0; c0 < nout; c0 += 32) {
+                const int c = c0 + lane;
+#pragma unroll
+                for (int r = 0; r < 32; ++r)
+                    if (r < nrows && c < nout) out[(row0 + r) * w + x0 + c] = s_out[r][c];
+            }
+            __syncwarp();
         }
     }
 }
@@ -1670,8 +1733,14 @@ extern "C" int dp_adaptive_variance(const dp_palette *pal, const uint8_t *src_rg
         k_av_uniform<<<(int)((l0 + 127) / 128 < cap ? (l0 + 127) / 128 : cap), 128, 0, st>>>(A, B, C, D, frames, h, w,
                                                                                           0, window_radius);
         DP_LAUNCH_CHECK();
-        k_av_uniform<<<(int)((l1 + 127) / 128 < cap ? (l1 + 127) / 128 : cap), 128, 0, st>>>(C, D, A, B, frames, h, w,
-                                                                                          1, window_radius);
+        if (window_radius <= AVR_MAXRAD && getenv("DP_AV_TILED_ROWS")) {   // off until validated on the GPU
+            const long long groups = 2 * (((long long)frames * h + 31) / 32);
+            k_av_uniform_rows<<<(int)(groups < cap * 2 ? groups : cap * 2), 32, 0, st>>>(C, D, A, B, frames, h, w,
+                                                                                     window_radius);
+        } else {
+            k_av_uniform<<<(int)((l1 + 127) / 128 < cap ? (l1 + 127) / 128 : cap), 128, 0, st>>>(C, D, A, B, frames, h,
+                                                                                              w, 1, window_radius);
+        }
         DP_LAUNCH_CHECK();
     }
     // python float threshold meets an f32 array element: numpy (NEP 50) compares in f32
