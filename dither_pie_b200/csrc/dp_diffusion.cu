@@ -1733,7 +1733,7 @@ extern "C" int dp_adaptive_variance(const dp_palette *pal, const uint8_t *src_rg
         k_av_uniform<<<(int)((l0 + 127) / 128 < cap ? (l0 + 127) / 128 : cap), 128, 0, st>>>(A, B, C, D, frames, h, w,
                                                                                           0, window_radius);
         DP_LAUNCH_CHECK();
-        if (window_radius <= AVR_MAXRAD && getenv("DP_AV_TILED_ROWS")) {   // off until validated on the GPU
+        if (window_radius <= AVR_MAXRAD && !getenv("DP_AV_SIMPLE_ROWS")) {
             const long long groups = 2 * (((long long)frames * h + 31) / 32);
             k_av_uniform_rows<<<(int)(groups < cap * 2 ? groups : cap * 2), 32, 0, st>>>(C, D, A, B, frames, h, w,
                                                                                      window_radius);
