@@ -53,6 +53,50 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate(
     }
 }
 
+// Per-iteration candidate grid (the argmin structure of the dither kernels, rebuilt for the moving
+// centres): colour space in 16^3 boxes of 16^3 byte colours; a centre is dropped from a box when
+// another centre is strictly nearer at EVERY point of the box -- the difference of two squared
+// distances is linear in the point, so its maximum sits at a corner (exact test in double with a
+// 1e-6 margin).  One warp per box, lane = centre.  Entry: up to four surviving centres, ascending,
+// one per byte (255 = none); 0xffffffff = more than four (the pixel loop then scans all centres).
+__global__ void __launch_bounds__(256) k_kmeans_grid(const double *__restrict__ centers, int K,
+                                                     uint32_t *__restrict__ grid)
+{
+    const int cell = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (cell >= 4096) return;
+    const double lo[3] = {16.0 * (cell >> 8), 16.0 * ((cell >> 4) & 15), 16.0 * (cell & 15)};
+    bool alive = false;
+    if (lane < K) {
+        const double ci[3] = {centers[3 * lane], centers[3 * lane + 1], centers[3 * lane + 2]};
+        const double ni = ci[0] * ci[0] + ci[1] * ci[1] + ci[2] * ci[2];
+        alive = true;
+        for (int j = 0; j < K && alive; ++j) {
+            if (j == lane) continue;
+            const double cj[3] = {centers[3 * j], centers[3 * j + 1], centers[3 * j + 2]};
+            double mx = (cj[0] * cj[0] + cj[1] * cj[1] + cj[2] * cj[2]) - ni;   // |c_j|^2 - |c_i|^2
+            for (int a = 0; a < 3; ++a) {
+                const double dlt = ci[a] - cj[a];
+                mx += 2.0 * (dlt > 0.0 ? lo[a] + 15.0 : lo[a]) * dlt;
+            }
+            if (mx < -1e-6) alive = false;   // centre j is strictly nearer everywhere in the box
+        }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) {
+        uint32_t e = 0xffffffffu;
+        if (__popc(m) <= 4) {
+            e = 0;
+            for (int k = 0; k < 4; ++k) {
+                const unsigned idx = m ? (unsigned)(__ffs(m) - 1) : 255u;
+                if (m) m &= m - 1;
+                e |= idx << (8 * k);
+            }
+        }
+        grid[cell] = e;
+    }
+}
+
 // K <= 32: no atomics in the pixel loop.  A warp labels 32 pixels at a time; the labels are
 // screened in f32 against all centres (two smallest distances kept) and only pixels whose two
 // best distances are closer than the f32 error bound repeat the exact f64 comparison (strict
@@ -61,14 +105,17 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate(
 // k keeps the running 64-bit totals of cluster k in registers; one flush per warp at the end.
 __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate_warp(
     const uint8_t *__restrict__ px, long long n, const double *__restrict__ centers, int K,
-    unsigned long long *__restrict__ sums)
+    unsigned long long *__restrict__ sums, const uint32_t *__restrict__ grid)
 {
     __shared__ double s_c[32 * 3];
-    __shared__ float4 s_cf[32];
+    __shared__ float4 s_cf[33];          // [32] = pad entry, far outside the colour cube
+    __shared__ uint32_t s_grid[4096];
     if (threadIdx.x < K * 3) s_c[threadIdx.x] = centers[threadIdx.x];
     if (threadIdx.x < K)
         s_cf[threadIdx.x] = make_float4((float)centers[3 * threadIdx.x], (float)centers[3 * threadIdx.x + 1],
                                         (float)centers[3 * threadIdx.x + 2], 0.f);
+    if (threadIdx.x == 32) s_cf[32] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
+    for (int i = threadIdx.x; i < 4096; i += KM_THREADS) s_grid[i] = grid[i];
     __syncthreads();
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -88,19 +135,35 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate_warp(
             const float fr = (float)r, fg = (float)g, fb = (float)b;
             float d1 = 3.0e38f, d2 = 3.0e38f;
             int bi = 0;
+            // the box of the pixel lists every centre that can be nearest to it (k_kmeans_grid)
+            const uint32_t e = s_grid[((r >> 4) << 8) | ((g >> 4) << 4) | (b >> 4)];
+            const bool few = e != 0xffffffffu;
+            if (few) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {   // ascending candidates; 255 -> the pad entry
+                    const int k = (int)((e >> (8 * q)) & 255u);
+                    const float4 c = s_cf[k < 32 ? k : 32];
+                    const float e0 = fr - c.x, e1 = fg - c.y, e2 = fb - c.z;
+                    const float d = fmaf(e2, e2, fmaf(e1, e1, e0 * e0));
+                    d2 = fminf(d2, fmaxf(d1, d));
+                    bi = d < d1 ? k : bi;
+                    d1 = fminf(d1, d);
+                }
+            } else {
 #pragma unroll 4
-            for (int k = 0; k < K; ++k) {     // branch-free: lanes of a warp disagree on every test
-                const float4 c = s_cf[k];
-                const float e0 = fr - c.x, e1 = fg - c.y, e2 = fb - c.z;
-                const float d = fmaf(e2, e2, fmaf(e1, e1, e0 * e0));
-                d2 = fminf(d2, fmaxf(d1, d));
-                bi = d < d1 ? k : bi;
-                d1 = fminf(d1, d);
+                for (int k = 0; k < K; ++k) {     // branch-free: lanes of a warp disagree on every test
+                    const float4 c = s_cf[k];
+                    const float e0 = fr - c.x, e1 = fg - c.y, e2 = fb - c.z;
+                    const float d = fmaf(e2, e2, fmaf(e1, e1, e0 * e0));
+                    d2 = fminf(d2, fmaxf(d1, d));
+                    bi = d < d1 ? k : bi;
+                    d1 = fminf(d1, d);
+                }
             }
             // centre rounded to f32 (<= 255 * 2^-24) and the rounded difference give |e32 - e| <= 3.1e-5
             // per channel, so |d32 - D| <= 1.07e-4 sqrt(D) + 1.8e-7 D; twice that (both distances)
-            // is below the margin used here for every D in [0, 195075]
-            if (d2 - d1 <= 3.0e-4f * sqrtf(d2) + 5.0e-7f * d2 + 3.0e-4f) {
+            // is below the margin used here for every D in [0, 195075]  (d2 = pad: never ambiguous)
+            if (d2 < 1.0e30f && d2 - d1 <= 3.0e-4f * sqrtf(d2) + 5.0e-7f * d2 + 3.0e-4f) {
                 const double x0 = r, x1 = g, x2 = b;
                 double best = 1e300;
                 for (int k = 0; k < K; ++k) {
@@ -180,9 +243,14 @@ extern "C" int dp_kmeans_accumulate(const uint8_t *pixels, int64_t n, const doub
     if (K <= 32) {
         long long blocks = ((n + 31) / 32 + KM_THREADS / 32 - 1) / (KM_THREADS / 32);
         int grid = (int)(blocks < cap ? blocks : cap);   // 8 resident blocks of 8 warps per SM
-        k_kmeans_accumulate_warp<<<grid, KM_THREADS, 0, dp_stream(stream)>>>(pixels, n, centers, K,
-                                                                             sums);
-        DP_LAUNCH_CHECK();
+        cudaStream_t st = dp_stream(stream);
+        uint32_t *cgrid = nullptr;
+        DP_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&cgrid), 4096 * sizeof(uint32_t), st));
+        k_kmeans_grid<<<512, 256, 0, st>>>(centers, K, cgrid);
+        k_kmeans_accumulate_warp<<<grid, KM_THREADS, 0, st>>>(pixels, n, centers, K, sums, cgrid);
+        const cudaError_t le = cudaGetLastError();
+        cudaFreeAsync(cgrid, st);
+        DP_CUDA(le);
         return 0;
     }
     long long chunks = (n + KM_PIX_PER_BLOCK - 1) / KM_PIX_PER_BLOCK;
