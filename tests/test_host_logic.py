@@ -141,3 +141,28 @@ def test_median_cut_and_uniform_palettes_match_reference_semantics():
     assert len(pal) == 8 and all(len(c) == 3 for c in pal)
     assert dp.ColorReducer.generate_uniform_palette(8)[-1] == (255, 255, 255)
     assert dp.ColorReducer.generate_uniform_palette(1) == [(128, 128, 128)]
+
+
+def test_native_blue_noise_equals_the_restated_loop():
+    """dp_blue_noise_from_order (native farthest-point replay) against the oracle's numpy
+    restatement of generate_blue_noise (:381-399) on sizes / seeds the golden file does not hold."""
+    from oracle import dither_oracle as O
+    for size, seed in ((1, 0), (2, 3), (7, 11), (16, 1), (24, 99), (48, 42)):
+        assert np.array_equal(engine.blue_noise_matrix(size, seed), O.blue_noise_matrix(size, seed)), (size, seed)
+
+
+def test_array_median_cut_equals_the_list_restatement():
+    """The planar array cut (stable radix argsort) against the literal list restatement of
+    ColorReducer.median_cut (:1822-1832) fed with the interpreter's own set order."""
+    from PIL import Image
+    rs = np.random.RandomState(11)
+    for arr, nc in ((synth.frame(60, 90, 2), 16), (synth.noise_frame(40, 50, 3), 8),
+                    (rs.randint(0, 6, (80, 80, 3)).astype(np.uint8) * 50, 32),
+                    (synth.blocks_frame(64, 96, 4, 4, 5), 4), (synth.frame(100, 150, 5), 256)):
+        img = Image.fromarray(arr, "RGB")
+        uniq = list(set(img.getdata()))
+        assert len(uniq) >= 64
+        depth = int(np.log2(nc))
+        want = dp.ColorReducer.median_cut(list(uniq), depth)
+        got = dp.ColorReducer.reduce_colors(img, nc)
+        assert [tuple(int(v) for v in c) for c in got] == [tuple(int(v) for v in c) for c in want], nc
