@@ -355,18 +355,21 @@ def run_gpu(args):
     avg_kernel_ms = sum(kernel_ms) / len(kernel_ms)
     alg_bytes = BYTES_PER_PX * B * H4K * W4K
     achieved = alg_bytes / (avg_kernel_ms * 1e-3) / 1e9
-    # DRAM traffic per launch: 7.85 GB for 128 4K frames in the ncu --set full capture of
-    # k_diffuse_wave<floyd_steinberg> (profiles/r1f_diffuse_wave_fs_K256_4k_x128.txt), i.e.
-    # 7.39 B/pixel against 6 algorithmic -- the hand-off streams and the candidate table
-    traffic = 7.849621e9 / (128 * H4K * W4K) * (B * H4K * W4K)
+    # DRAM traffic per launch for 128 4K frames in the ncu --set full captures of this round:
+    # 7.795 GB for k_diffuse_wave<floyd_steinberg>, 8.194 GB for <jjn> (the two ends of the step's
+    # three launches; profiles/r1l_diffuse_wave_{fs,jjn}_K256_4k_x128.txt), i.e. 7.3-7.7 B/pixel
+    # against 6 algorithmic -- the hand-off streams and the candidate table
+    traffic = 0.5 * (7.794756e9 + 8.194386e9) / (128 * H4K * W4K) * (B * H4K * W4K)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
-                                  "profiles/r1f_diffuse_wave_fs_K256_4k_x128.txt (scaled by frames)",
+                                  "mean of profiles/r1l_diffuse_wave_{fs,jjn}_K256_4k_x128.txt "
+                                  "(scaled by frames)",
                 "kernel": "k_diffuse_wave",
                 "peak_source": peak_src, "avg_launch_ms": avg_kernel_ms,
                 "note": "error diffusion is bounded by its per-pixel dependency chain (~1100 cycles "
-                        "per wavefront step, 314 instructions) and by instruction issue, not by HBM; "
+                        "per wavefront step; 342 instructions per step for Floyd-Steinberg, 629 for "
+                        "JJN, 58-63 % of the issue slots used) and by instruction issue, not by HBM; "
                         "see DESIGN.md"}
 
     line = {
