@@ -615,6 +615,14 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ float to_f32(double v) { return __double2float_rn(v); }
 __device__ __forceinline__ float to_f32(float v) { return v; }
 
+#ifndef DP_WAVE_UNROLL_5X5
+#define DP_WAVE_UNROLL_5X5 2
+#endif
+__host__ __device__ constexpr int wave_step_unroll(int v)
+{
+    return (v == DP_ED_JJN || v == DP_ED_STUCKI) ? DP_WAVE_UNROLL_5X5 : 1;
+}
+
 template <int V, bool BIG, int NSLOT>
 __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wave(const WaveParams p)
 {
@@ -827,7 +835,9 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
             // ---- 32 pixel steps --------------------------------------------------------
             const unsigned char *feed = reinterpret_cast<const unsigned char *>(st.inw[ch & 1][lane]) + my_o;
             unsigned char *ob = st.outb[lane] + my_m;
-#pragma unroll 1
+            // the 5x5 footprints shift two five-entry register windows every step (60 moves): two
+            // steps per loop iteration let the compiler rename across the pair instead
+#pragma unroll(wave_step_unroll(V))
             for (int sidx = 0; sidx < 32; ++sidx) {
                 const int x = x00 + sidx - SP::S * lane;
 #ifdef DP_WAVE_TIMING
