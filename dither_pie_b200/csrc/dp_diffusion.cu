@@ -615,12 +615,15 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __device__ __forceinline__ float to_f32(double v) { return __double2float_rn(v); }
 __device__ __forceinline__ float to_f32(float v) { return v; }
 
+#ifndef DP_WAVE_UNROLL_OTHER
+#define DP_WAVE_UNROLL_OTHER 1
+#endif
 #ifndef DP_WAVE_UNROLL_5X5
 #define DP_WAVE_UNROLL_5X5 2
 #endif
 __host__ __device__ constexpr int wave_step_unroll(int v)
 {
-    return (v == DP_ED_JJN || v == DP_ED_STUCKI) ? DP_WAVE_UNROLL_5X5 : 1;
+    return (v == DP_ED_JJN || v == DP_ED_STUCKI) ? DP_WAVE_UNROLL_5X5 : DP_WAVE_UNROLL_OTHER;
 }
 
 template <int V, bool BIG, int NSLOT>
