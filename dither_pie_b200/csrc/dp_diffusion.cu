@@ -616,7 +616,7 @@ __device__ __forceinline__ float to_f32(double v) { return __double2float_rn(v);
 __device__ __forceinline__ float to_f32(float v) { return v; }
 
 #ifndef DP_WAVE_UNROLL_OTHER
-#define DP_WAVE_UNROLL_OTHER 1
+#define DP_WAVE_UNROLL_OTHER 2
 #endif
 #ifndef DP_WAVE_UNROLL_5X5
 #define DP_WAVE_UNROLL_5X5 2
