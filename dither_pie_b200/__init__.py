@@ -12,6 +12,6 @@ from .dithering_lib import (  # noqa: F401
     HybridDitherStrategy, ImageDitherer, InterleavedGradientNoiseDitherStrategy, MatrixDitherStrategy,
     NoDitherStrategy, OstromoukhovDitherStrategy, PaletteSource, PerceptualDitherStrategy,
     PixelizeMethod, PolkaDotDitherStrategy, generate_blue_noise)
-from .video_processor import VideoProcessor, pixelize_regular, shard_frames  # noqa: F401
+from .video_processor import NeuralPixelizer, VideoProcessor, pixelize_regular, shard_frames  # noqa: F401
 
 __version__ = "0.1.0"

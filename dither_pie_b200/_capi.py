@@ -43,6 +43,17 @@ PROTOTYPES = {
     "dp_stream_create": [C.POINTER(_vp)],
     "dp_stream_destroy": [_vp],
     "dp_stream_sync": [_vp],
+    "dp_event_create": [C.POINTER(_vp), _i],
+    "dp_event_destroy": [_vp],
+    "dp_event_record": [_vp, _vp],
+    "dp_stream_wait_event": [_vp, _vp],
+    "dp_event_sync": [_vp],
+    "dp_event_elapsed_ms": [_vp, _vp, C.POINTER(C.c_float)],
+    "dp_host_register": [_vp, _sz],
+    "dp_host_unregister": [_vp],
+    "dp_host_is_pinned": [_vp, C.POINTER(C.c_int)],
+    "dp_range_push": [C.c_char_p],
+    "dp_range_pop": [],
     "dp_palette_create": [_vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                           C.POINTER(_vp)],
     "dp_palette_destroy": [_vp],

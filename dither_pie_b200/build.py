@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if (force or procs or not os.path.exists(LIB)
             or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs)):
         cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
-               "-o", LIB, *objs, "-lcudart"]
+               "-o", LIB, *objs, "-lcudart", "-ldl"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
@@ -77,7 +77,7 @@ def build_timing() -> str:
                            os.path.join(CSRC, "dp_diffusion.cu"), "-o", tobj])
     others = [os.path.join(OBJ_DIR, s[:-3] + ".o") for s in sources() if s != "dp_diffusion.cu"]
     subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
-                           "-o", out, tobj, *others, "-lcudart"])
+                           "-o", out, tobj, *others, "-lcudart", "-ldl"])
     return out
 
 

@@ -8,6 +8,8 @@
 #include <map>
 #include <mutex>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "dp_search.cuh"
 
 // ---------------------------------------------------------------------------------------
@@ -124,6 +126,76 @@ extern "C" int dp_stream_destroy(void *stream)
 extern "C" int dp_stream_sync(void *stream)
 {
     DP_CUDA(cudaStreamSynchronize(dp_stream(stream)));
+    return 0;
+}
+extern "C" int dp_event_create(void **event, int timing)
+{
+    DP_REQUIRE(event, "null argument");
+    cudaEvent_t e;
+    DP_CUDA(cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming));
+    *event = e;
+    return 0;
+}
+extern "C" int dp_event_destroy(void *event)
+{
+    DP_CUDA(cudaEventDestroy(reinterpret_cast<cudaEvent_t>(event)));
+    return 0;
+}
+extern "C" int dp_event_record(void *event, void *stream)
+{
+    DP_CUDA(cudaEventRecord(reinterpret_cast<cudaEvent_t>(event), dp_stream(stream)));
+    return 0;
+}
+extern "C" int dp_stream_wait_event(void *stream, void *event)
+{
+    DP_CUDA(cudaStreamWaitEvent(dp_stream(stream), reinterpret_cast<cudaEvent_t>(event), 0));
+    return 0;
+}
+extern "C" int dp_event_sync(void *event)
+{
+    DP_CUDA(cudaEventSynchronize(reinterpret_cast<cudaEvent_t>(event)));
+    return 0;
+}
+extern "C" int dp_event_elapsed_ms(void *start, void *stop, float *ms)
+{
+    DP_REQUIRE(ms, "null argument");
+    DP_CUDA(cudaEventElapsedTime(ms, reinterpret_cast<cudaEvent_t>(start), reinterpret_cast<cudaEvent_t>(stop)));
+    return 0;
+}
+extern "C" int dp_host_register(void *hptr, size_t bytes)
+{
+    DP_REQUIRE(hptr && bytes, "null argument");
+    DP_CUDA(cudaHostRegister(hptr, bytes, cudaHostRegisterDefault));
+    return 0;
+}
+extern "C" int dp_host_is_pinned(const void *hptr, int *pinned)
+{
+    DP_REQUIRE(hptr && pinned, "null argument");
+    cudaPointerAttributes at;
+    const cudaError_t e = cudaPointerGetAttributes(&at, hptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();   // unregistered memory may report an error on older drivers
+        *pinned = 0;
+        return 0;
+    }
+    *pinned = at.type == cudaMemoryTypeHost ? 1 : 0;
+    return 0;
+}
+extern "C" int dp_host_unregister(void *hptr)
+{
+    DP_CUDA(cudaHostUnregister(hptr));
+    return 0;
+}
+// NVTX ranges around the entry points (the reference has no tracing at all);
+// no-ops unless a profiler that collects NVTX is attached.
+extern "C" int dp_range_push(const char *name)
+{
+    nvtxRangePushA(name ? name : "dp");
+    return 0;
+}
+extern "C" int dp_range_pop(void)
+{
+    nvtxRangePop();
     return 0;
 }
 

@@ -36,6 +36,7 @@
 // (W + S*(H-1) pixel steps per frame) and fp64 issue, not HBM.
 #include <stdlib.h>
 
+#include <mutex>
 #include <utility>
 
 #include "dp_search.cuh"
@@ -191,6 +192,20 @@ __device__ __forceinline__ int ld_poll(const int *p)
     int v;
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+// Spin-wait guard.  The protocol cannot deadlock (a band's predecessor is always running), so a
+// wait is bounded by the predecessor's progress; the guard only turns a protocol BUG into an
+// error instead of a hang.  Every spin sleeps >= ~100 ns, so 2^30 spins are at least 100 s of
+// waiting (far more under compute-sanitizer or a debugger, where each spin is slower): a slow
+// predecessor is not mistaken for a bug.
+#define DP_SPIN_LIMIT (1u << 30)
+// Executed by EVERY lane once a poll has succeeded (the polled value reaches the lanes by
+// shuffle): orders this thread's later loads of the producer's data after the observation of the
+// flag -- the acquire side of the producer's fence + st.release, per the PTX memory model
+// (fence-fence synchronisation through the relaxed load that observed the release).
+__device__ __forceinline__ void acquire_fence()
+{
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 __device__ __forceinline__ void st_release(int *p, int v)
 {
@@ -709,13 +724,15 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
         slot = __shfl_sync(FULL, slot, 0);
         if (slot >= p.total_units) break;
         int unit = 0;
-        for (unsigned spins = 0;; ++spins) {
+        for (unsigned spins = 1;; ++spins) {
             if (lane == 0) unit = ld_poll(p.queue + slot);
             unit = __shfl_sync(FULL, unit, 0);
             if (unit > 0) break;
             __nanosleep(200);
-            if (spins > (1u << 26)) __trap();  // protocol bug -> error, not a hang
+            if (spins > DP_SPIN_LIMIT) __trap();
         }
+        acquire_fence();
+        __syncwarp();
         unit -= 1;                          // storage index of the hand-off streams: f * nbands + band
         const int f = unit / p.nbands;
         const int band = unit - f * p.nbands;
@@ -756,6 +773,7 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
         const int my_o = (int)(feed0 & 3);
         const long long out0 = ((long long)y * W + (-SP::BMAX - SP::S * lane)) * 3;
         const int my_m = (int)((reinterpret_cast<uintptr_t>(dst_f) + (unsigned long long)out0) & 3);
+        const bool rgb_out = p.dst != nullptr;   // null: index-plane-only output (idx_f is set)
 
         // rows of chunk `c` -> st.inw[c & 1] (asynchronous; completion via cp_async_wait)
         auto issue_rows = [&](int c) {
@@ -789,13 +807,15 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                 const int need = min(t0 + 32, W + SP::BMAX);
                 if (need > avail) {
                     int v = 0;
-                    for (unsigned spins = 0;; ++spins) {
+                    for (unsigned spins = 1;; ++spins) {
                         if (lane == 0) v = ld_poll(prog_in);
                         v = __shfl_sync(FULL, v, 0);
                         if (v >= need) break;
                         __nanosleep(100);
-                        if (spins > (1u << 24)) __trap();  // protocol bug -> error, not a hang
+                        if (spins > DP_SPIN_LIMIT) __trap();
                     }
+                    acquire_fence();
+                    __syncwarp();
                     avail = v;
                 }
             }
@@ -1075,7 +1095,7 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                 const int xfirst = x00 - SP::S * lane;          // column of this lane's step 0
                 const long long obyte = out0 + 96ll * ch;       // its byte offset in the frame
                 unsigned *ow = reinterpret_cast<unsigned *>(st.outb[lane]);
-                if (rowok && xfirst + 31 >= 0 && xfirst - 1 < W) {
+                if (rgb_out && rowok && xfirst + 31 >= 0 && xfirst - 1 < W) {
                     const bool lead_ok = xfirst >= 1 || (xfirst == 0 && my_m == 0);
                     if (lead_ok && xfirst + 32 < W) {
                         unsigned *g = reinterpret_cast<unsigned *>(dst_f + (obyte - my_m));
@@ -1257,10 +1277,12 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
                                 r1[3 * x + c] = __fadd_rn(r1[3 * x + c], __fmul_rn(er[c], w2));
                         }
                     }
-                    uint8_t *o = dst_f + ((size_t)y * W + x) * 3;
-                    o[0] = s_orgb[4 * bi];
-                    o[1] = s_orgb[4 * bi + 1];
-                    o[2] = s_orgb[4 * bi + 2];
+                    if (p.dst) {   // (null: index-plane-only output)
+                        uint8_t *o = dst_f + ((size_t)y * W + x) * 3;
+                        o[0] = s_orgb[4 * bi];
+                        o[1] = s_orgb[4 * bi + 1];
+                        o[2] = s_orgb[4 * bi + 2];
+                    }
                     if (idx_f) idx_f[(size_t)y * W + x] = (uint8_t)bi;
                 }
             }
@@ -1340,6 +1362,10 @@ int launch_wave_as(const WaveParams &p0, cudaStream_t st, int npat, bool big)
     long long blocks = ((long long)p.total_units + warps - 1) / warps;
     long long cap = (long long)sms * per_sm;
     int grid = (int)(blocks < cap ? blocks : cap);
+    if (const char *ev = getenv("DP_WAVE_GRID")) {   // test knob: fewer blocks than the device holds
+        const int g = atoi(ev);
+        if (g >= 1 && g < grid) grid = g;
+    }
     k_diffuse_wave<V, BIG, NSLOT><<<grid, warps * 32, smem, st>>>(p);
     DP_LAUNCH_CHECK();
     return 0;
@@ -1398,15 +1424,25 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
                   cudaStream_t st, double hyb_lum = 0.0, double hyb_col = 0.0, const float *plane = nullptr)
 {
     const bool ostro = (variant == V_OSTRO);
-    Workspace ws_ow;
     const float *ostro_w = nullptr;
     if (ostro) {
-        if (ws_ow.alloc(256 * 4 * sizeof(float), st)) return 1;
-        DP_CUDA(cudaMemcpyAsync(ws_ow.ptr, ostro_w_host, 256 * 4 * sizeof(float),
-                                cudaMemcpyHostToDevice, st));
-        // the host array is a temporary of the caller: make the copy complete before returning
-        DP_CUDA(cudaStreamSynchronize(st));
-        ostro_w = static_cast<const float *>(ws_ow.ptr);
+        // The weight table depends only on the caller's coefficient table: keep one device copy
+        // per device (re-uploaded, synchronously, only when the contents change) so that a call
+        // neither allocates nor synchronises the stream -- a frame pipeline keeps overlapping.
+        static std::mutex mu;
+        static float *dev_w[64] = {nullptr};
+        static float host_w[64][256 * 4];
+        int dev = 0;
+        DP_CUDA(cudaGetDevice(&dev));
+        DP_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+        std::lock_guard<std::mutex> lk(mu);
+        if (!dev_w[dev] || memcmp(host_w[dev], ostro_w_host, sizeof(host_w[dev])) != 0) {
+            if (!dev_w[dev]) DP_CUDA(cudaMalloc(reinterpret_cast<void **>(&dev_w[dev]), sizeof(host_w[dev])));
+            else DP_CUDA(cudaDeviceSynchronize());   // a running kernel may still read the old table
+            DP_CUDA(cudaMemcpy(dev_w[dev], ostro_w_host, sizeof(host_w[dev]), cudaMemcpyHostToDevice));
+            memcpy(host_w[dev], ostro_w_host, sizeof(host_w[dev]));
+        }
+        ostro_w = dev_w[dev];
     }
     if (serpentine || h < 2) {
         SerialParams sp;
@@ -1506,7 +1542,8 @@ extern "C" int dp_error_diffusion(const dp_palette *pal, const uint8_t *src_rgb,
                                   int w, int variant, int serpentine, uint8_t *dst_rgb,
                                   uint8_t *dst_idx, void *stream)
 {
-    DP_REQUIRE(pal && src_rgb && dst_rgb, "null argument");
+    DP_REQUIRE(pal && src_rgb, "null argument");
+    DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
     DP_REQUIRE(variant >= DP_ED_FLOYD_STEINBERG && variant <= DP_ED_SIERRA_LITE,
                "unknown error-diffusion variant");
@@ -1519,7 +1556,8 @@ extern "C" int dp_ostromoukhov(const dp_palette *pal, const uint8_t *src_rgb, in
                                int w, const int32_t *coeffs, int serpentine, uint8_t *dst_rgb,
                                uint8_t *dst_idx, void *stream)
 {
-    DP_REQUIRE(pal && src_rgb && dst_rgb && coeffs, "null argument");
+    DP_REQUIRE(pal && src_rgb && coeffs, "null argument");
+    DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
     if (frames == 0 || h == 0 || w == 0) return 0;
     // weights as the reference forms them: float32(c / (c0+c1+c2)), c/d in f64 (:1252-1266);
@@ -1541,7 +1579,8 @@ extern "C" int dp_hybrid(const dp_palette *pal, const uint8_t *src_rgb, int fram
                          double lum_factor, double col_factor, uint8_t *dst_rgb, uint8_t *dst_idx,
                          void *stream)
 {
-    DP_REQUIRE(pal && src_rgb && dst_rgb, "null argument");
+    DP_REQUIRE(pal && src_rgb, "null argument");
+    DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
     if (frames == 0 || h == 0 || w == 0) return 0;
     return run_diffusion(pal, src_rgb, frames, h, w, V_HYBRID, 0, nullptr, dst_rgb, dst_idx,
@@ -1571,7 +1610,8 @@ __global__ void __launch_bounds__(256) k_perceptual_plane(const PalDev *P, const
 extern "C" int dp_perceptual(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h, int w,
                              uint8_t *dst_rgb, uint8_t *dst_idx, void *stream)
 {
-    DP_REQUIRE(pal && src_rgb && dst_rgb, "null argument");
+    DP_REQUIRE(pal && src_rgb, "null argument");
+    DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
     if (frames == 0 || h == 0 || w == 0) return 0;
     cudaStream_t st = dp_stream(stream);
@@ -1723,7 +1763,8 @@ extern "C" int dp_adaptive_variance(const dp_palette *pal, const uint8_t *src_rg
                                     double var_threshold, int window_radius, uint8_t *dst_rgb,
                                     uint8_t *dst_idx, void *stream)
 {
-    DP_REQUIRE(pal && src_rgb && dst_rgb, "null argument");
+    DP_REQUIRE(pal && src_rgb, "null argument");
+    DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
     DP_REQUIRE(window_radius >= 0 && window_radius <= 64, "window radius out of range");
     if (frames == 0 || h == 0 || w == 0) return 0;

@@ -420,10 +420,12 @@ __global__ void __launch_bounds__(256) k_ht_select(const HtParams p)
         float gray = __fadd_rn(__fadd_rn(__fmul_rn(0.299f, r), __fmul_rn(0.587f, g)),
                                __fmul_rn(0.114f, b));
         const int idx = (gray < __ldg(p.screen + i)) ? cp[__ldg(p.cell + i)] : p.paper;
-        uint8_t *o = dst + (size_t)i * 3;
-        o[0] = s_orgb[4 * idx];
-        o[1] = s_orgb[4 * idx + 1];
-        o[2] = s_orgb[4 * idx + 2];
+        if (p.dst) {   // (null: index-plane-only output)
+            uint8_t *o = dst + (size_t)i * 3;
+            o[0] = s_orgb[4 * idx];
+            o[1] = s_orgb[4 * idx + 1];
+            o[2] = s_orgb[4 * idx + 2];
+        }
         if (p.dst_idx) p.dst_idx[(size_t)f * p.npix + i] = (uint8_t)idx;
     }
 }
@@ -481,9 +483,11 @@ __global__ void __launch_bounds__(256) k_ht_select4(const HtParams p)
             col[k] = s_orgb[idx];
             idx4 |= (unsigned)idx << (8 * k);
         }
-        __stcs(dst + 3 * gi, col[0] | (col[1] << 24));
-        __stcs(dst + 3 * gi + 1, (col[1] >> 8) | (col[2] << 16));
-        __stcs(dst + 3 * gi + 2, (col[2] >> 16) | (col[3] << 8));
+        if (p.dst) {   // (null: index-plane-only output)
+            __stcs(dst + 3 * gi, col[0] | (col[1] << 24));
+            __stcs(dst + 3 * gi + 1, (col[1] >> 8) | (col[2] << 16));
+            __stcs(dst + 3 * gi + 2, (col[2] >> 16) | (col[3] << 8));
+        }
         if (p.dst_idx) reinterpret_cast<unsigned *>(p.dst_idx + (size_t)f * p.npix)[gi] = idx4;
     }
 }
@@ -577,7 +581,8 @@ extern "C" int dp_halftone(const dp_palette *pal, const uint8_t *src_rgb, int fr
                            double min_dot, double max_dot, int shape, double sharpness,
                            const float *screen, uint8_t *dst_rgb, uint8_t *dst_idx, void *stream)
 {
-    DP_REQUIRE(pal && src_rgb && dst_rgb, "null argument");
+    DP_REQUIRE(pal && src_rgb, "null argument");
+    DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0 && cell_size >= 1, "bad size");
     DP_REQUIRE(shape >= 0 && shape <= 2, "unknown dot shape");
     DP_REQUIRE(screen || dot_gain == 1.0,

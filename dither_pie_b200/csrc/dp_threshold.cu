@@ -249,15 +249,17 @@ __global__ void __launch_bounds__(THREADS) k_thresh_tile(const ThreshParams p)
 
         // ---- store: 128-bit writes for the aligned interior, bytes for the fringes
         {
-            const int head = (16 - mis_out) & 15;           // bytes before the first aligned word
-            const int hb = min(head, nbytes);
-            if (tid < hb) gdst[tid] = s_out[mis_out + tid];
-            const int nmid = (nbytes - hb) >> 4;
-            uint4 *g4 = reinterpret_cast<uint4 *>(gdst + hb);
-            const uint4 *s4 = reinterpret_cast<const uint4 *>(s_out + mis_out + hb);
-            for (int i = tid; i < nmid; i += THREADS) __stcs(g4 + i, s4[i]);
-            const int tail0 = hb + (nmid << 4);
-            if (tid < nbytes - tail0) gdst[tail0 + tid] = s_out[mis_out + tail0 + tid];
+            if (p.dst) {   // (null: index-plane-only output)
+                const int head = (16 - mis_out) & 15;           // bytes before the first aligned word
+                const int hb = min(head, nbytes);
+                if (tid < hb) gdst[tid] = s_out[mis_out + tid];
+                const int nmid = (nbytes - hb) >> 4;
+                uint4 *g4 = reinterpret_cast<uint4 *>(gdst + hb);
+                const uint4 *s4 = reinterpret_cast<const uint4 *>(s_out + mis_out + hb);
+                for (int i = tid; i < nmid; i += THREADS) __stcs(g4 + i, s4[i]);
+                const int tail0 = hb + (nmid << 4);
+                if (tid < nbytes - tail0) gdst[tail0 + tid] = s_out[mis_out + tail0 + tid];
+            }
             if (p.dst_idx) {
                 uint8_t *gi = p.dst_idx + (size_t)f * p.npix + px0;
                 for (int i = tid; i < npx; i += THREADS) gi[i] = s_idx[i];
@@ -504,10 +506,12 @@ __global__ void __launch_bounds__(THREADS) k_thresh_fast(const ThreshParams p)
                 reinterpret_cast<unsigned *>(p.dst_idx + (size_t)f * p.npix + px0)[gi] = idx4;
         }
         __syncwarp();
+        if (p.dst) {   // (null: index-plane-only output)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int i = j * 32 + lane;
-            if (i < n16) __stcs(d4 + i, io4[i]);
+            for (int j = 0; j < 3; ++j) {
+                const int i = j * 32 + lane;
+                if (i < n16) __stcs(d4 + i, io4[i]);
+            }
         }
         __syncwarp();
     }
@@ -871,7 +875,7 @@ __global__ void __launch_bounds__(v4_threads<KIND>(), 1) k_thresh_v4(const Thres
         // generic-proxy writes -> visible to the async proxy, then one bulk store by lane 0
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) {
+        if (lane == 0 && p.dst) {   // (null dst: index-plane-only output)
             const uint32_t n16 = min(96u, n16_total - b16);
             bulk_store(d4 + b16, io_a + buf * 1536, n16 * 16u);
         }
@@ -929,7 +933,7 @@ __global__ void __launch_bounds__(THREADS) k_thresh_geom(const ThreshParams p)
                              : pick_f64<KIND>(P, K, r, g, b, thr);
         const uint8_t o0 = s_orgb[4 * idx], o1 = s_orgb[4 * idx + 1], o2 = s_orgb[4 * idx + 2];
         uint8_t *d = p.dst + (size_t)f * dst_frame + ((size_t)y * m * out_w + (size_t)x * m) * 3;
-        for (int yy = 0; yy < m; ++yy) {
+        for (int yy = 0; p.dst && yy < m; ++yy) {   // (null dst: index-plane-only output)
             uint8_t *row = d + (size_t)yy * out_w * 3;
             for (int xx = 0; xx < m; ++xx) {
                 row[3 * xx] = o0;
@@ -1108,6 +1112,7 @@ __global__ void __launch_bounds__(THREADS) k_thresh_geom2(const ThreshParams p)
             if (p.dst_idx) p.dst_idx[((size_t)f * p.h + y) * p.w + x] = (uint8_t)idx;
         }
         __syncwarp();
+        if (!p.dst) continue;                 // index-plane-only output (warp-uniform)
         const int nbytes = nvalid * m * 3;
         const int n16 = nbytes >> 4;          // <= 6 * GEOM2_MAX_M = 48 sixteen-byte pieces
         uint8_t *drow = p.dst + (size_t)f * dst_frame + (size_t)y * m * out_w3 + (size_t)strip * 96 * m;
@@ -1218,7 +1223,8 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
                                    float ign_scale, uint8_t *dst_rgb, uint8_t *dst_idx,
                                    void *stream)
 {
-    DP_REQUIRE(pal && src_rgb && dst_rgb && geo, "null argument");
+    DP_REQUIRE(pal && src_rgb && geo, "null argument");
+    DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && geo->h >= 0 && geo->w >= 0, "negative size");
     DP_REQUIRE(kind >= DP_THRESH_NONE && kind <= DP_THRESH_IGN, "unknown threshold kind");
     if (frames == 0 || geo->h == 0 || geo->w == 0) return 0;
@@ -1299,7 +1305,10 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
     }
 }
 
-// Host-buffer convenience: H2D, kernel, D2H and a stream synchronise inside the call.
+// Host-buffer convenience: H2D, kernel, D2H and a stream synchronise inside the call.  The call
+// runs on a private non-blocking stream (never the legacy default stream, which would serialise
+// with every other stream of the process) and takes its device buffers from the retained
+// stream-ordered pool (no cudaMalloc / cudaFree per call).
 extern "C" int dp_threshold_dither_host(const dp_palette *pal, const uint8_t *src_rgb_host,
                                         int frames, int h, int w, int kind,
                                         const float *matrix_host, int mat_h, int mat_w,
@@ -1308,50 +1317,48 @@ extern "C" int dp_threshold_dither_host(const dp_palette *pal, const uint8_t *sr
 {
     DP_REQUIRE(pal && src_rgb_host && dst_rgb_host, "null argument");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
+    if (kind == DP_THRESH_MATRIX) DP_REQUIRE(matrix_host && mat_h > 0 && mat_w > 0, "threshold matrix missing");
     const size_t bytes = (size_t)frames * h * w * 3;
     if (bytes == 0) return 0;
+    int dev = 0;
+    DP_CUDA(cudaGetDevice(&dev));
+    if (dp_retain_pool(dev)) return 1;
     cudaStream_t st = nullptr;
+    DP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     uint8_t *dsrc = nullptr, *ddst = nullptr;
     float *dmat = nullptr;
-    int rc = 0;
-    auto cleanup = [&]() {
-        if (dsrc) cudaFree(dsrc);
-        if (ddst) cudaFree(ddst);
-        if (dmat) cudaFree(dmat);
+    auto fail = [&](const char *what) {
+        dp_set_error("dp_threshold_dither_host: %s: %s", what, cudaGetErrorString(cudaGetLastError()));
+        if (dsrc) cudaFreeAsync(dsrc, st);
+        if (ddst) cudaFreeAsync(ddst, st);
+        if (dmat) cudaFreeAsync(dmat, st);
+        cudaStreamSynchronize(st);
+        cudaStreamDestroy(st);
+        return 1;
     };
-    if (cudaMalloc(&dsrc, bytes) != cudaSuccess || cudaMalloc(&ddst, bytes) != cudaSuccess) {
-        dp_set_error("cudaMalloc failed in dp_threshold_dither_host");
-        cleanup();
-        return 1;
-    }
-    if (kind == DP_THRESH_MATRIX) {
-        if (!matrix_host || mat_h <= 0 || mat_w <= 0 ||
-            cudaMalloc(&dmat, (size_t)mat_h * mat_w * 4) != cudaSuccess ||
-            cudaMemcpyAsync(dmat, matrix_host, (size_t)mat_h * mat_w * 4, cudaMemcpyHostToDevice,
-                            st) != cudaSuccess) {
-            dp_set_error("threshold matrix upload failed");
-            cleanup();
-            return 1;
-        }
-    }
-    if (cudaMemcpyAsync(dsrc, src_rgb_host, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
-        dp_set_error("H2D copy failed");
-        cleanup();
-        return 1;
-    }
+    if (cudaMallocAsync(reinterpret_cast<void **>(&dsrc), bytes, st) != cudaSuccess ||
+        cudaMallocAsync(reinterpret_cast<void **>(&ddst), bytes, st) != cudaSuccess)
+        return fail("device allocation");
+    if (kind == DP_THRESH_MATRIX &&
+        (cudaMallocAsync(reinterpret_cast<void **>(&dmat), (size_t)mat_h * mat_w * 4, st) != cudaSuccess ||
+         cudaMemcpyAsync(dmat, matrix_host, (size_t)mat_h * mat_w * 4, cudaMemcpyHostToDevice, st) != cudaSuccess))
+        return fail("threshold matrix upload");
+    if (cudaMemcpyAsync(dsrc, src_rgb_host, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return fail("H2D copy");
     dp_geometry geo;
     memset(&geo, 0, sizeof(geo));
     geo.src_h = geo.h = h;
     geo.src_w = geo.w = w;
     geo.upscale = 1;
-    rc = dp_threshold_dither(pal, dsrc, frames, &geo, kind, dmat, mat_h, mat_w, ign_xoff, ign_yoff,
-                             ign_scale, ddst, nullptr, st);
-    if (rc == 0 && (cudaMemcpyAsync(dst_rgb_host, ddst, bytes, cudaMemcpyDeviceToHost, st) !=
-                        cudaSuccess ||
-                    cudaStreamSynchronize(st) != cudaSuccess)) {
-        dp_set_error("D2H copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-        rc = 1;
-    }
-    cleanup();
+    int rc = dp_threshold_dither(pal, dsrc, frames, &geo, kind, dmat, mat_h, mat_w, ign_xoff, ign_yoff,
+                                 ign_scale, ddst, nullptr, st);
+    if (rc == 0 && (cudaMemcpyAsync(dst_rgb_host, ddst, bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                    cudaStreamSynchronize(st) != cudaSuccess))
+        return fail("D2H copy");
+    cudaFreeAsync(dsrc, st);
+    cudaFreeAsync(ddst, st);
+    if (dmat) cudaFreeAsync(dmat, st);
+    cudaStreamSynchronize(st);
+    cudaStreamDestroy(st);
     return rc;
 }

@@ -44,6 +44,13 @@ def init_process_group(backend: Optional[str] = None):
     return dist.get_rank(), dist.get_world_size()
 
 
+def barrier() -> None:
+    """Process-group barrier (no-op for a single process)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.barrier()
+
+
 def allreduce_sums_(sums) -> None:
     """In-place SUM all-reduce of an int64 tensor of per-cluster (sum r, sum g, sum b, count).
     Integers: the result -- hence every centre -- is independent of the number of shards and of

@@ -135,8 +135,8 @@ class BaseDitherStrategy:
             raise NotImplementedError
         img = _pixels_to_u8(pixels, image_size)
         pal = np.asarray(palette_arr)
-        _, idx = engine.dither_frames(img, pal, self._mode, self.get_current_parameters(),
-                                      use_gamma=False, return_indices=True, search_space=True)
+        idx = engine.dither_frames(img, pal, self._mode, self.get_current_parameters(),
+                                   use_gamma=False, search_space=True, indices_only=True)
         return pal[idx.reshape(-1).astype(np.int32), :]
 
     @staticmethod
@@ -167,30 +167,32 @@ class MatrixDitherStrategy(BaseDitherStrategy):
 
 
 def _run_matrix(img_u8: np.ndarray, palette_arr: np.ndarray, matrix: np.ndarray) -> np.ndarray:
-    """Custom-matrix path for MatrixDitherStrategy subclasses constructed directly."""
+    """Custom-matrix path for MatrixDitherStrategy subclasses constructed directly: the index
+    plane only, device buffers from the engine's buffer cache."""
     import ctypes as C
-    from ._capi import DeviceBuffer, Geometry, check, lib, sync
+    from ._capi import Geometry, check, lib, sync
     h, w, _ = img_u8.shape
     pal = engine.get_palette(palette_arr, False, True)
     geo = Geometry()
     geo.src_h = geo.h = h
     geo.src_w = geo.w = w
     geo.upscale = 1
-    src = DeviceBuffer(max(img_u8.nbytes, 4)).upload(np.ascontiguousarray(img_u8))
-    dst = DeviceBuffer(max(img_u8.nbytes, 4))
-    ib = DeviceBuffer(max(h * w, 4))
     mat = engine.device_table(np.ascontiguousarray(matrix, np.float32))
+    src = engine._acquire(max(img_u8.nbytes, 4)).upload(np.ascontiguousarray(img_u8))
+    ib = engine._acquire(max(h * w, 4))
     try:
         check(lib().dp_threshold_dither(pal.handle, src.ptr, 1, C.byref(geo), 1, mat.ptr,
-                                        matrix.shape[0], matrix.shape[1], 0.0, 0.0, 1.0, dst.ptr,
+                                        matrix.shape[0], matrix.shape[1], 0.0, 0.0, 1.0, None,
                                         ib.ptr, None), "dp_threshold_dither")
         idx = np.empty((h, w), np.uint8)
         ib.download(idx)
         sync()
-    finally:
+    except BaseException:
         src.free()
-        dst.free()
         ib.free()
+        raise
+    engine._release(src)
+    engine._release(ib)
     return idx
 
 

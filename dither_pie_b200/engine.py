@@ -240,17 +240,23 @@ _tab_cache: Dict[tuple, DeviceBuffer] = {}
 _tab_lock = threading.Lock()
 
 
+_TAB_CACHE_MAX_BYTES = 64 << 20
+
+
 def device_table(arr: np.ndarray) -> DeviceBuffer:
+    """Small constant tables (threshold matrices, index tables) by content; LRU bounded by bytes."""
     arr = np.ascontiguousarray(arr)
     key = (arr.dtype.str, arr.shape, arr.tobytes(), _capi.ensure_device())
     with _tab_lock:
-        buf = _tab_cache.get(key)
+        buf = _tab_cache.pop(key, None)
         if buf is None:
             buf = DeviceBuffer(max(arr.nbytes, 4)).upload(arr)
             _capi.sync()
-            if len(_tab_cache) > 256:
-                _tab_cache.clear()
-            _tab_cache[key] = buf
+        _tab_cache[key] = buf
+        total = sum(b.nbytes for b in _tab_cache.values())
+        while total > _TAB_CACHE_MAX_BYTES and len(_tab_cache) > 1:
+            k0 = next(iter(_tab_cache))
+            total -= _tab_cache.pop(k0).nbytes
     return buf
 
 
@@ -315,6 +321,33 @@ def halftone_screen_host(h, w, cell_size, angle, dot_gain, min_dot_size, max_dot
     return np.clip(t, 0.0, 1.0).astype(np.float32)
 
 
+# Host-built halftone screens (dot_gain != 1 needs pow()): frame-invariant, so one device copy
+# per (size, parameters, device), kept in an LRU bounded by total bytes (a 4K screen is 33 MB).
+_screen_cache: "Dict[tuple, DeviceBuffer]" = {}
+_screen_lock = threading.Lock()
+_SCREEN_CACHE_MAX_BYTES = 512 << 20
+
+
+def _halftone_screen_device(h: int, w: int, ht: dict) -> DeviceBuffer:
+    key = (int(h), int(w), ht["cell_size"], ht["angle"], ht["dot_gain"], ht["min_dot_size"],
+           ht["max_dot_size"], ht["shape"], ht["sharpness"], _capi.ensure_device())
+    with _screen_lock:
+        buf = _screen_cache.pop(key, None)
+        if buf is not None:
+            _screen_cache[key] = buf          # most recently used last
+            return buf
+    arr = halftone_screen_host(h, w, **ht)
+    buf = DeviceBuffer(max(arr.nbytes, 4)).upload(arr)
+    _capi.sync()
+    with _screen_lock:
+        _screen_cache[key] = buf
+        total = sum(b.nbytes for b in _screen_cache.values())
+        while total > _SCREEN_CACHE_MAX_BYTES and len(_screen_cache) > 1:
+            k0 = next(iter(_screen_cache))
+            total -= _screen_cache.pop(k0).nbytes   # dropped; freed when no Plan holds it any more
+    return buf
+
+
 class Plan:
     """Everything a (mode, params, geometry) needs on the device besides the palette.
     Built once, reused for every frame batch (the reference rebuilds its strategy per call,
@@ -369,7 +402,7 @@ class Plan:
                            shape=p.get("shape", "circle"), sharpness=float(p.get("sharpness", 1.5)))
             self.ht_screen = None
             if self.ht["dot_gain"] != 1.0:
-                self.ht_screen = device_table(halftone_screen_host(self.h, self.w, **self.ht))
+                self.ht_screen = _halftone_screen_device(self.h, self.w, self.ht)
         elif mode == "error_diffusion":
             self.variant = ED_VARIANTS.get(p.get("variant", "atkinson"), 0)  # unknown -> FS (:203)
             self.serpentine = p.get("serpentine", "false") == "true"
@@ -394,7 +427,8 @@ class Plan:
     def run(self, pal: PaletteHandle, src_ptr: int, frames: int, dst_ptr: int,
             idx_ptr: Optional[int] = None, stream=None):
         """src: u8 [frames, src_h, src_w, 3]; dst: u8 [frames, out_h, out_w, 3] (threshold
-        family: pixelize/upscale fused; other modes need identity geometry)."""
+        family: pixelize/upscale fused; other modes need identity geometry).  ``dst_ptr`` may be
+        None when ``idx_ptr`` (u8 [frames, h, w]) is given: index-plane-only output."""
         L = lib()
         if self.kind is not None:
             mat = self.matrix.ptr if self.matrix is not None else None
@@ -431,6 +465,80 @@ class Plan:
             check(L.dp_ostromoukhov(pal.handle, src_ptr, frames, self.h, self.w,
                                     self.coeffs.ctypes.data, int(self.serpentine), dst_ptr,
                                     idx_ptr, stream), "dp_ostromoukhov")
+
+
+class ChainPlan:
+    """pixelize -> dither -> final resize as separate device passes, for the modes whose kernels run
+    at identity geometry (halftone, the diffusion family) or for output sizes that are not an exact
+    multiple (odd sizes bumped to even, video_processor.py:412-417).  Same interface as Plan.run;
+    the intermediate frames live in device buffers owned by the chain (sized for ``max_frames``)."""
+
+    def __init__(self, mode: str, params: Optional[dict], src_hw: Tuple[int, int],
+                 dither_hw: Tuple[int, int], out_hw: Tuple[int, int], max_frames: int):
+        self.src_h, self.src_w = src_hw
+        self.h, self.w = dither_hw
+        self.out_h, self.out_w = out_hw
+        self.upscale = 1
+        self.max_frames = int(max_frames)
+        self.inner = Plan(mode, params, self.h, self.w)
+        self.mode = mode
+        self.pre = (self.src_h, self.src_w) != (self.h, self.w)
+        self.post = (self.out_h, self.out_w) != (self.h, self.w)
+        n = max(self.max_frames * self.h * self.w * 3, 16)
+        self.small = _acquire(n) if self.pre else None       # from the device buffer cache
+        self.dith = _acquire(n) if self.post else None
+        self.fused_geometry = False
+
+    def run(self, pal: PaletteHandle, src_ptr: int, frames: int, dst_ptr: Optional[int],
+            idx_ptr: Optional[int] = None, stream=None):
+        assert frames <= self.max_frames
+        cur = src_ptr
+        if self.pre:
+            resample(src_ptr, frames, self.src_h, self.src_w, self.h, self.w, self.small.ptr, stream)
+            cur = self.small.ptr
+        if self.post and dst_ptr is not None:
+            self.inner.run(pal, cur, frames, self.dith.ptr, idx_ptr, stream)
+            resample(self.dith.ptr, frames, self.h, self.w, self.out_h, self.out_w, dst_ptr, stream)
+        else:
+            self.inner.run(pal, cur, frames, dst_ptr, idx_ptr, stream)
+
+    def close(self):
+        """Call after the stream the chain ran on has been synchronised."""
+        for b in (self.small, self.dith):
+            if b is not None:
+                _release(b)
+        self.small = self.dith = None
+
+
+def video_geometry(H: int, W: int, pixelize_max_size: Optional[int], final_multiplier: Optional[int],
+                   even_final: bool = True):
+    """(dither size, output size) of _process_single_frame (video_processor.py:443-462):
+    pixelize_regular to even dimensions, then the integer up-scale with odd sizes bumped to even
+    (``even_final``; the CLI image path, dither_cli.py:559-566, does not bump)."""
+    if pixelize_max_size:
+        w, h = even_dimensions(W, H, int(pixelize_max_size))
+    else:
+        h, w = H, W
+    m = int(final_multiplier) if final_multiplier else 1
+    oh, ow = h * m, w * m
+    if even_final and final_multiplier:
+        oh += oh % 2
+        ow += ow % 2
+    return (h, w), (oh, ow), m
+
+
+def make_plan(mode: str, params: Optional[dict], H: int, W: int,
+              pixelize_max_size: Optional[int] = None, final_multiplier: Optional[int] = None,
+              even_final: bool = True, max_frames: int = 1):
+    """The cheapest device plan for (mode, geometry): the fused pixelize -> dither -> up-scale
+    kernel when the mode has one and the output is an exact multiple, else a ChainPlan."""
+    (h, w), (oh, ow), m = video_geometry(H, W, pixelize_max_size, final_multiplier, even_final)
+    probe = Plan(mode, params, h, w)
+    if (h, w) == (H, W) and (oh, ow) == (h, w):
+        return probe
+    if probe.fused_geometry and (oh, ow) == (h * m, w * m):
+        return Plan(mode, params, h, w, (H, W), m)
+    return ChainPlan(mode, params, (H, W), (h, w), (oh, ow), max_frames)
 
 
 def resample(src_ptr: int, frames: int, src_h: int, src_w: int, dst_h: int, dst_w: int,
@@ -482,12 +590,16 @@ def _release(buf: DeviceBuffer):
 def dither_frames(frames_u8: np.ndarray, palette, mode: str, params: Optional[dict] = None,
                   use_gamma: bool = False, pixelize_max_size: Optional[int] = None,
                   final_multiplier: Optional[int] = None, even_final: bool = True,
-                  return_indices: bool = False, search_space: bool = False):
-    """uint8 [F,H,W,3] (or [H,W,3]) -> uint8 [F,H',W',3] through the GPU.
+                  return_indices: bool = False, search_space: bool = False,
+                  indices_only: bool = False):
+    """uint8 [F,H,W,3] (or [H,W,3]) -> uint8 [F,H',W',3] through the GPU (simple synchronous
+    path: one upload, the kernels, one download; clips go through pipeline.FramePipeline).
 
     pixelize_max_size: regular pixelization first (video_processor.py:563-577).
     final_multiplier:  integer up-scale afterwards (video_processor.py:393-420 when
                        ``even_final`` else dither_cli.py:559-566).
+    return_indices:    also return the palette-index plane u8 [F,h,w] of the dithered image.
+    indices_only:      return ONLY the index plane (the colour bytes are never produced).
     """
     arr = np.ascontiguousarray(frames_u8, dtype=np.uint8)
     single = arr.ndim == 3
@@ -495,54 +607,26 @@ def dither_frames(frames_u8: np.ndarray, palette, mode: str, params: Optional[di
         arr = arr[None]
     F, H, W, _ = arr.shape
     pal = get_palette(palette, use_gamma, search_space)
-    if pixelize_max_size:
-        w, h = even_dimensions(W, H, int(pixelize_max_size))
-    else:
-        h, w = H, W
-    m = int(final_multiplier) if final_multiplier else 1
-    oh, ow = h * m, w * m
-    if even_final and final_multiplier:
-        oh += oh % 2
-        ow += ow % 2
-    exact_multiple = (oh, ow) == (h * m, w * m)
-
+    (h, w), (oh, ow), m = video_geometry(H, W, pixelize_max_size, final_multiplier, even_final)
+    want_idx = return_indices or indices_only
+    plan = make_plan(mode, params, H, W, pixelize_max_size, final_multiplier, even_final, max_frames=F)
     bufs = []
     try:
         src = _acquire(max(arr.nbytes, 4)).upload(arr)
         bufs.append(src)
-        probe = Plan(mode, params, h, w)
-        fused = probe.fused_geometry
-        idx_buf = None
-        if fused and exact_multiple:
-            plan = Plan(mode, params, h, w, (H, W), m)
+        dst = idx_buf = None
+        if not indices_only:
             dst = _acquire(max(F * oh * ow * 3, 4))
             bufs.append(dst)
-            if return_indices:
-                idx_buf = _acquire(max(F * h * w, 4))
-                bufs.append(idx_buf)
-            plan.run(pal, src.ptr, F, dst.ptr, idx_buf.ptr if idx_buf else None)
-        else:
-            cur, ch, cw = src, H, W
-            if (h, w) != (H, W):
-                small = _acquire(max(F * h * w * 3, 4))
-                bufs.append(small)
-                resample(src.ptr, F, H, W, h, w, small.ptr)
-                cur, ch, cw = small, h, w
-            dith = _acquire(max(F * h * w * 3, 4))
-            bufs.append(dith)
-            if return_indices:
-                idx_buf = _acquire(max(F * h * w, 4))
-                bufs.append(idx_buf)
-            probe.run(pal, cur.ptr, F, dith.ptr, idx_buf.ptr if idx_buf else None)
-            dst = dith
-            if (oh, ow) != (h, w):
-                dst = _acquire(max(F * oh * ow * 3, 4))
-                bufs.append(dst)
-                resample(dith.ptr, F, h, w, oh, ow, dst.ptr)
-        out = np.empty((F, oh, ow, 3), np.uint8)
-        dst.download(out)
-        idx = None
-        if return_indices:
+        if want_idx:
+            idx_buf = _acquire(max(F * h * w, 4))
+            bufs.append(idx_buf)
+        plan.run(pal, src.ptr, F, dst.ptr if dst else None, idx_buf.ptr if idx_buf else None)
+        out = idx = None
+        if dst is not None:
+            out = np.empty((F, oh, ow, 3), np.uint8)
+            dst.download(out)
+        if want_idx:
             idx = np.empty((F, h, w), np.uint8)
             idx_buf.download(idx)
         _capi.sync()
@@ -550,9 +634,15 @@ def dither_frames(frames_u8: np.ndarray, palette, mode: str, params: Optional[di
         for b in bufs:      # state unknown (a kernel may still run): do not recycle
             b.free()
         raise
+    finally:
+        if hasattr(plan, "close"):
+            _capi.sync()
+            plan.close()
     for b in bufs:
         _release(b)
     if single:
-        out = out[0]
+        out = out[0] if out is not None else None
         idx = idx[0] if idx is not None else None
+    if indices_only:
+        return idx
     return (out, idx) if return_indices else out

@@ -11,6 +11,12 @@
  * dobrosketchkun/dither_pie).  The Python binding a maintainer would add is shown in
  * INTEGRATION.md; dither_pie_b200/_capi.py is that binding.
  *
+ * Output planes.  Every dither entry point writes `dst_rgb` (the palette colours, what
+ * ImageDitherer.apply_dithering returns, dithering_lib.py:1984-1992) and/or `dst_idx` (one
+ * palette row per dithered pixel -- the palette-index image).  Either may be NULL, not both:
+ * with dst_rgb == NULL only the index plane is produced (1 byte per pixel instead of 3, which
+ * is what a caller that owns the palette needs to bring back over PCIe).
+ *
  * Return value: 0 on success, non-zero on error; dp_last_error() returns the message of the
  * last failing call on the calling thread.  There is no CPU fallback anywhere.
  */
@@ -43,6 +49,22 @@ int dp_memset(void *dst, int value, size_t bytes, void *stream);
 int dp_stream_create(void **stream);
 int dp_stream_destroy(void *stream);
 int dp_stream_sync(void *stream); /* NULL = default stream */
+/* events: ordering between the copy-in / kernel / copy-out streams of a frame pipeline (the
+ * GPU-side replacement of the reference's batch loop, video_processor.py:304-346) and timing */
+int dp_event_create(void **event, int timing);
+int dp_event_destroy(void *event);
+int dp_event_record(void *event, void *stream);
+int dp_stream_wait_event(void *stream, void *event);
+int dp_event_sync(void *event);
+int dp_event_elapsed_ms(void *start, void *stop, float *ms);
+/* page-lock a caller-owned host buffer in place (e.g. the numpy array a frame reader fills) so
+ * that dp_memcpy_* on it are true asynchronous DMA transfers */
+int dp_host_register(void *hptr, size_t bytes);
+int dp_host_unregister(void *hptr);
+int dp_host_is_pinned(const void *hptr, int *pinned); /* dp_host_alloc'ed or registered memory */
+/* NVTX ranges (visible to profilers that collect NVTX; no-ops otherwise) */
+int dp_range_push(const char *name);
+int dp_range_pop(void);
 
 /* ---------------------------------------------------------------------------------------
  * Palette handle.
@@ -105,7 +127,7 @@ enum {
  *   matrix      DEVICE f32 [mat_h, mat_w] (DP_THRESH_MATRIX), tiled over the dithered image
  *   ign_*       f32 constants of :546-549 already rounded to f32 by the caller:
  *               x' = (x + ign_xoff) * ign_scale,  y' = (y + ign_yoff) * ign_scale
- *   dst_rgb     DEVICE u8 [frames, h*upscale, w*upscale, 3]
+ *   dst_rgb     DEVICE u8 [frames, h*upscale, w*upscale, 3], or NULL (index plane only)
  *   dst_idx     DEVICE u8 [frames, h, w] palette row per dithered pixel, or NULL
  */
 int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb, int frames,

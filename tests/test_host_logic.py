@@ -166,3 +166,63 @@ def test_array_median_cut_equals_the_list_restatement():
         want = dp.ColorReducer.median_cut(list(uniq), depth)
         got = dp.ColorReducer.reduce_colors(img, nc)
         assert [tuple(int(v) for v in c) for c in got] == [tuple(int(v) for v in c) for c in want], nc
+
+
+def test_fix_failed_frames_copies_the_nearest_good_frame():
+    """video_processor.py:53-96: previous frames first, then following ones."""
+    from dither_pie_b200.video_processor import VideoProcessor
+    out = np.arange(6, dtype=np.uint8).reshape(6, 1, 1, 1).repeat(3, axis=3).copy()
+    lost = VideoProcessor._fix_failed_frames([0, 1, 4], out)
+    assert lost == []
+    assert out[:, 0, 0, 0].tolist() == [2, 2, 2, 3, 3, 5]
+    out2 = np.zeros((2, 1, 1, 3), np.uint8)
+    assert VideoProcessor._fix_failed_frames([0, 1], out2) == [0, 1]
+
+
+def test_video_processor_worker_and_rank_bookkeeping(monkeypatch):
+    from dither_pie_b200.video_processor import NeuralPixelizer, VideoProcessor, _unpack_pixelize
+    monkeypatch.setenv("RANK", "3")
+    monkeypatch.setenv("WORLD_SIZE", "8")
+    vp = VideoProcessor()
+    assert (vp.rank, vp.world, vp.num_workers) == (3, 8, 8)
+    assert VideoProcessor(num_workers=2).num_workers == 2
+    assert _unpack_pixelize(None) is None
+    assert _unpack_pixelize(("regular", 64)) == 64
+    assert _unpack_pixelize((dp.PixelizeMethod.REGULAR, 65)) == 65
+    assert _unpack_pixelize(("none", 64)) is None
+    with pytest.raises(NotImplementedError):
+        _unpack_pixelize(("neural", 64))
+    assert NeuralPixelizer._compute_even_dimensions(1920, 1080, 270) == (480, 270)
+    with pytest.raises(NotImplementedError):
+        NeuralPixelizer().pixelize(None, 64)
+
+
+def test_video_geometry_matches_the_reference_rules():
+    # pixelize to even dims, x m, odd sizes bumped to even only on the video path
+    assert engine.video_geometry(1080, 1920, 270, 4) == ((270, 480), (1080, 1920), 4)
+    assert engine.video_geometry(90, 150, 31, 3, True) == ((30, 50), (90, 150), 3)
+    assert engine.video_geometry(45, 75, None, 3, True) == ((45, 75), (136, 226), 3)
+    assert engine.video_geometry(45, 75, None, 3, False) == ((45, 75), (135, 225), 3)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference checkout")
+def test_reference_cli_imports_against_the_drop_in_modules():
+    """the reference's front end loads with the two hot-path modules
+    swapped for this package (it imports VideoProcessor, NeuralPixelizer, pixelize_regular and the
+    dithering_lib names unconditionally, dither_cli.py:26)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, types\n"
+        "sys.path.insert(0, %r); sys.path.insert(1, '/root/reference')\n"
+        "sys.modules.setdefault('pywt', types.ModuleType('pywt'))\n"
+        "import dither_pie_b200.dithering_lib as dl, dither_pie_b200.video_processor as vp\n"
+        "sys.modules['dithering_lib'] = dl; sys.modules['video_processor'] = vp\n"
+        "import dither_cli\n"
+        "assert dither_cli.VideoProcessor is vp.VideoProcessor\n"
+        "assert dither_cli.ImageDitherer is dl.ImageDitherer\n"
+        "import pathlib\n"
+        "cfg = dither_cli.validate_config({'input': 'a.png', 'output': 'b.png'}, pathlib.Path('cfg.json'), True)\n"
+        "print('ok', sorted(cfg)[:3])\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.stdout, r.stderr[-800:])

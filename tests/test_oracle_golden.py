@@ -154,3 +154,17 @@ def test_kdtree_single_colour_palette(k):
     assert idx[0, 0] == 0 and d2[0, 0] == 81 + 324 + 729
     if k == 2:
         assert idx[0, 1] == 1 and np.isinf(d2[0, 1])  # scipy: index n, distance inf
+
+
+def test_big_cases_from_the_live_reference():
+    """540x960 outputs of the reference itself (tools/make_golden.py --big): the oracle pinned at
+    the BASELINE configs' kernels and palette sizes, beyond the small cases."""
+    g = load_golden("big_cases.npz")
+    img = g["img"]
+    for key, pk, mode, params in (("ed_jjn", "pal256", "error_diffusion", {"variant": "jjn"}),
+                                  ("ed_atkinson", "pal256", "error_diffusion", {"variant": "atkinson"}),
+                                  ("ed_sierra", "pal64", "error_diffusion", {"variant": "sierra"}),
+                                  ("bayer8", "pal16", "bayer", {"size": "8x8"}),
+                                  ("blue", "pal16", "blue_noise", {"size": 64, "seed": 42})):
+        assert np.array_equal(O.apply_dithering(img, g[pk], mode, params), g[key]), key
+    assert np.array_equal(O.apply_dithering(g["ostro_img"], g["pal64"], "ostromoukhov"), g["ostro"])

@@ -349,8 +349,37 @@ def median_cut_golden(dl):
               open(os.path.join(OUT, "median_cut.json"), "w"))
 
 
+def big_golden(dl):
+    """540x960 outputs of the live reference (a quarter of a 1080p frame; 17 row bands per frame
+    for the wavefront kernel): the BASELINE configs' kernels and palette sizes, so that the oracle
+    itself is pinned beyond the small cases.  Ostromoukhov (pure Python in the reference, ~14 kpx/s)
+    is stored on a 270x480 crop.  tests/golden/big_cases.npz."""
+    img = synth.frame(1080, 1920, 1)[:540, :960].copy()
+    pal16 = synth.hex_palette(synth.PICO8)
+    pal64, pal256 = synth.random_palette(64), synth.random_palette(256)
+    store = {"img": img, "pal16": pal16, "pal64": pal64, "pal256": pal256}
+
+    def run(arr, pal, mode, params):
+        d = dl.ImageDitherer(num_colors=len(pal), dither_mode=dl.DitherMode(mode),
+                             palette=[tuple(int(v) for v in c) for c in pal], dither_params=dict(params))
+        return np.array(d.apply_dithering(Image.fromarray(arr, "RGB")))
+
+    store["ed_jjn"] = run(img, pal256, "error_diffusion", {"variant": "jjn"})
+    store["ed_atkinson"] = run(img, pal256, "error_diffusion", {"variant": "atkinson"})
+    store["ed_sierra"] = run(img, pal64, "error_diffusion", {"variant": "sierra"})
+    store["bayer8"] = run(img, pal16, "bayer", {"size": "8x8"})
+    store["blue"] = run(img, pal16, "blue_noise", {"size": 64, "seed": 42})
+    crop = synth.frame(2160, 3840, 2000)[:270, :480].copy()
+    store["ostro_img"] = crop
+    store["ostro"] = run(crop, pal64, "ostromoukhov", {})
+    np.savez_compressed(os.path.join(OUT, "big_cases.npz"), **store)
+    print("big_cases.npz:", os.path.getsize(os.path.join(OUT, "big_cases.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    if "--median-cut-only" in sys.argv:   # adds median_cut.json without touching the other files
+    if "--big" in sys.argv:               # adds big_cases.npz without touching the other files
+        big_golden(load()[0])
+    elif "--median-cut-only" in sys.argv:   # adds median_cut.json without touching the other files
         median_cut_golden(load()[0])
     else:
         main()
