@@ -1,11 +1,11 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the dither_pie hot path on B200.
+"""bench.py -- benchmark of the dither_pie hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--no-extra]
 
-Workload (BASELINE.json configs[1]): 3840x2160 RGB frames, error diffusion with the
-Floyd-Steinberg + Atkinson + JJN kernels, 256-colour palette.  One "step" is one pass of the
-three kernels over a batch of 128 synthetic 4K frames (3.2 GB, far larger than L2).
+Headline workload (BASELINE.json configs[1]): 3840x2160 RGB frames, error diffusion with the
+Floyd-Steinberg + Atkinson + JJN kernels, 256-colour palette.  One "step" is one pass of the three
+kernels over a batch of 128 synthetic 4K frames (3.2 GB, far larger than L2).
 Metric: Mpixels/s (input pixels x dither passes per second), whole job over all ranks.
 N > 1: one process per GPU (torchrun), every rank owns its own batch of frames (frames are
 independent -> weak scaling, no data-path collective); time = max over ranks.
@@ -14,9 +14,16 @@ Keys besides the base contract:
   roofline      dominant kernel (k_diffuse_wave), algorithmic 6 B/pixel / measured launch time
                 against the measured HBM copy peak (MEASURED_PEAKS.json)
   cpu_baseline  the oracle port (C restatement of the reference's numba loop) on the host cores
-  e2e           the same metric through the C ABI with pinned HOST buffers (H2D + D2H timed)
-  modes         the other BASELINE.json configs, one line each (device-resident, Mpx/s and
-                fraction of the HBM roofline at 6 B/pixel)
+  e2e           the same metric through the product's public API (pipeline.FramePipeline, the
+                engine under VideoProcessor.process_frames) with pinned HOST arrays: every step
+                copies its 128 input frames in and brings every result back; value = palette-index
+                output (1 B/pixel, what north_star calls the output), `rgb_value` = colour bytes
+  video         BASELINE configs[3] and [4] as STRONG-scaling jobs (600 x 1080p pixelize 270 ->
+                blue noise / IGN -> x4; 300 x 4K Ostromoukhov / Sierra, 64 colours): the clip is
+                split contiguously over the N ranks; device-resident time and end-to-end wall time
+                through VideoProcessor.process_frames with host buffers, both max over ranks
+  modes         the other BASELINE.json configs, one entry each (device-resident, Mpx/s and
+                fraction of the HBM roofline), with the CPU baselines BASELINE.md section 3 asks for
 """
 from __future__ import annotations
 
@@ -52,7 +59,7 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on the host cores
+# reference arm / cpu baselines: the oracle on the host cores
 # ------------------------------------------------------------------------------------------
 
 def cpu_reference_step(frames_u8, palette, threads):
@@ -104,7 +111,9 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus, None),
         "cpu_baseline": {"value": val, "unit": "Mpx/s", "cores": cores, "kind": "port",
-                         "sample": sample},
+                         "sample": sample,
+                         "note": "C port of the reference's numba loop on ALL cores; the reference's own "
+                                 "loop is single-threaded (1.07 Mpx/s at 4K K=256, BASELINE.md)"},
         "e2e": {"value": val, "unit": "Mpx/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -118,6 +127,48 @@ def workload_config(n_gpus, batch):
             "frame": "synth.frame(2160,3840,seed) gradient + uniform noise [-16,16]",
             "l2_policy": "inputs larger than L2 (a batch of 128 4K frames is 3.2 GB in, 3x that out)",
             "parallelism": f"frame-sharded x{n_gpus}, no data-path collective"}
+
+
+# ---- Pool.map video baseline: workers hold their frames, tasks are indices
+_POOL = {}
+
+
+def _pool_init(kind, pal_rows):
+    from dither_pie_b200 import synth
+    from oracle import dither_oracle as O
+    _POOL["O"] = O
+    _POOL["pal"] = np.asarray(pal_rows)
+    if kind == "c4":
+        _POOL["frames"] = [synth.frame(1080, 1920, 1000 + t) for t in range(4)]
+        O.blue_noise_matrix(64, 42)                       # warm the cache (the reference's class cache)
+    else:
+        _POOL["frames"] = [np.ascontiguousarray(synth.frame(H4K, W4K, 2000)[:270, :480])]
+
+
+def _pool_task(job):
+    kind, mode, params, t = job
+    O = _POOL["O"]
+    f = _POOL["frames"][t % len(_POOL["frames"])]
+    if kind == "c4":     # body of _process_single_frame minus PNG I/O (video_processor.py:443-462)
+        out = O.final_resize(O.apply_dithering(O.pixelize_regular(f, 270), _POOL["pal"], mode, params), 4, True)
+    else:
+        out = O.apply_dithering(f, _POOL["pal"], mode, params)
+    return int(out.shape[0])
+
+
+def pool_video_baseline(kind, mode, params, pal_rows, procs, tasks):
+    """Mpx/s of INPUT pixels for `tasks` frames mapped over a Pool of `procs` workers (spawned:
+    the parent holds a CUDA context).  Pool start-up and frame synthesis are outside the timing;
+    a first map warms the workers."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    px = (1080 * 1920) if kind == "c4" else (270 * 480)
+    with ctx.Pool(procs, initializer=_pool_init, initargs=(kind, np.asarray(pal_rows))) as pool:
+        pool.map(_pool_task, [(kind, mode, params, t) for t in range(procs)])
+        t0 = time.perf_counter()
+        pool.map(_pool_task, [(kind, mode, params, t) for t in range(tasks)], chunksize=1)
+        dt = time.perf_counter() - t0
+    return tasks * px / dt / 1e6, dt
 
 
 # ------------------------------------------------------------------------------------------
@@ -181,6 +232,22 @@ def _emit(line: dict, fd: int):
     os.write(fd, (json.dumps(line) + "\n").encode())
 
 
+class Arena:
+    """One pinned host allocation carved into named arrays (pinning is slow: do it once)."""
+
+    def __init__(self, nbytes):
+        from dither_pie_b200 import _capi
+        t0 = time.perf_counter()
+        self.pa = _capi.PinnedArray((nbytes,), np.uint8)
+        self.alloc_s = time.perf_counter() - t0
+        self.nbytes = nbytes
+
+    def view(self, offset, shape):
+        n = int(np.prod(shape))
+        assert offset + n <= self.nbytes, (offset, n, self.nbytes)
+        return self.pa.array[offset:offset + n].reshape(shape)
+
+
 def run_gpu(args):
     # Libraries print to stdout (NCCL's version banner at the first collective): keep the process's
     # stdout for the one JSON line and send everything else to stderr.
@@ -216,34 +283,38 @@ def run_gpu(args):
             os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from dither_pie_b200 import _capi, engine, synth
-    from dither_pie_b200._capi import check, lib
+    from dither_pie_b200 import _capi, engine, pipeline, synth
     _capi.ensure_device(local)
-    L = lib()
     dev = torch.device("cuda", local)
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     B = args.batch
     pal_rows = synth.random_palette(K_COLOURS)
     pal = engine.get_palette(pal_rows)
-    # per-rank synthetic frames (seed depends on the rank so that ranks do different work)
-    # The host side holds a block of HB frames in pinned memory; the device batch is that block
-    # repeated (frames rolled per repeat would only change the bytes, not the work).  Every e2e
-    # step still moves B frames in and 3 x B frames out over PCIe, block by block.
-    HB = min(B, 32)
-    assert B % HB == 0, "--batch must be a multiple of 32 (or smaller than 32)"
-    base = np.stack([synth.frame(H4K, W4K, 1 + rank * 16 + t) for t in range(min(HB, 4))])
-    host_in = _capi.PinnedArray((HB, H4K, W4K, 3), np.uint8)
-    for t in range(HB):
-        host_in.array[t] = base[t % base.shape[0]]
-        if t >= base.shape[0]:
-            host_in.array[t] = np.roll(host_in.array[t], 7 * t, axis=1)
+    # ---- pinned host arena: [inputs | results]; every e2e / video leg carves its arrays from it
+    frame4k = H4K * W4K * 3
+    in_bytes = max(B * frame4k, 300 // world * frame4k + frame4k, 600 // world * 1080 * 1920 * 3 + 1080 * 1920 * 3)
+    out_bytes = max(B * frame4k * (len(ED_VARIANTS) if not args.no_rgb_e2e else 1), in_bytes)
+    arena = Arena(in_bytes + out_bytes)
+    host_in = arena.view(0, (B, H4K, W4K, 3))
+    base = np.stack([synth.frame(H4K, W4K, 1 + rank * 16 + t) for t in range(4)])
+    for t in range(B):       # per-rank synthetic frames: 4 seeds, the rest rolled copies (new bytes)
+        host_in[t] = base[t % 4] if t < 4 else np.roll(base[t % 4], 7 * t, axis=1)
     src = torch.empty((B, H4K, W4K, 3), dtype=torch.uint8, device=dev)
     dst = [torch.empty_like(src) for _ in ED_VARIANTS]
-    blk = torch.from_numpy(host_in.array)
-    for q in range(B // HB):
-        src[q * HB:(q + 1) * HB].copy_(blk, non_blocking=False)
+    src.copy_(torch.from_numpy(host_in))
     plans = [engine.Plan("error_diffusion", {"variant": v}, H4K, W4K) for v in ED_VARIANTS]
     px_per_step = B * H4K * W4K * len(ED_VARIANTS)
     launches = 0
@@ -253,11 +324,6 @@ def run_gpu(args):
         for pl, d in zip(plans, dst):
             pl.run(pal, src.data_ptr(), B, d.data_ptr(), None, sp)
             launches += 2  # k_wave_init + k_diffuse_wave per call
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -282,69 +348,69 @@ def run_gpu(args):
     e1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    ms_total = e0.elapsed_time(e1)
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     kernel_ms = [a.elapsed_time(b) for a, b in ev]
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    per_variant_ms = {v: statistics.mean(kernel_ms[i::len(ED_VARIANTS)]) for i, v in enumerate(ED_VARIANTS)}
     value = world * px_per_step * args.steps / (ms_total * 1e-3) / 1e6
+    del dst
 
-    # ---- e2e: HOST buffers through the C ABI, copies inside the timed region ---------------
-    # Three streams (copy-in, kernels, copy-out) and two device buffer sets: the H2D of step
-    # n+1 and the D2H of kernel v overlap the kernels, which is how video_processor streams a
-    # clip.  Every step still moves its whole input and all three results over PCIe.
-    host_out = [_capi.PinnedArray((HB, H4K, W4K, 3), np.uint8) for _ in ED_VARIANTS]
-    nbytes = B * H4K * W4K * 3
-    blk_bytes = HB * H4K * W4K * 3
-    s_in, s_k, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-    p_in, p_k, p_out = (C.c_void_p(x.cuda_stream) for x in (s_in, s_k, s_out))
-    src2 = [src, torch.empty_like(src)]
-    dst2 = [dst, [torch.empty_like(src) for _ in ED_VARIANTS]]
-    ev_in = [torch.cuda.Event() for _ in range(2)]
-    ev_k = [[torch.cuda.Event() for _ in ED_VARIANTS] for _ in range(2)]
-    ev_out = [[torch.cuda.Event() for _ in ED_VARIANTS] for _ in range(2)]
-    ev_src_free = [torch.cuda.Event() for _ in range(2)]
-
-    def e2e_run(nsteps):
-        for n in range(nsteps):
-            b = n & 1
-            if n >= 2:
-                s_in.wait_event(ev_src_free[b])          # kernels of step n-2 are done with src2[b]
-            for q in range(B // HB):
-                check(L.dp_memcpy_h2d(src2[b].data_ptr() + q * blk_bytes, host_in.ptr, blk_bytes, p_in),
-                      "h2d")
-            ev_in[b].record(s_in)
-            s_k.wait_event(ev_in[b])
-            for v, (pl, ho) in enumerate(zip(plans, host_out)):
-                if n >= 2:
-                    s_k.wait_event(ev_out[b][v])         # D2H of step n-2 has drained dst2[b][v]
-                pl.run(pal, src2[b].data_ptr(), B, dst2[b][v].data_ptr(), None, p_k)
-                ev_k[b][v].record(s_k)
-                s_out.wait_event(ev_k[b][v])
-                for q in range(B // HB):
-                    check(L.dp_memcpy_d2h(ho.ptr, dst2[b][v].data_ptr() + q * blk_bytes, blk_bytes, p_out),
-                          "d2h")
-                ev_out[b][v].record(s_out)
-            ev_src_free[b].record(s_k)
-        for x in (s_in, s_k, s_out):
-            x.synchronize()
-
+    # ---- e2e: pinned HOST arrays through pipeline.FramePipeline (the engine under
+    # VideoProcessor.process_frames): every step submits its 128 input frames and gets all three
+    # results back; copy-in / kernels / copy-out overlap across batches and steps.
+    nbytes = B * frame4k
     e2e_steps = max(3, min(args.steps, 6))
-    e2e_run(2)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_run(e2e_steps)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * px_per_step * e2e_steps / float(te.item()) / 1e6
-    # spot-check of the result that came back (first frame, first kernel) -- also keeps the
-    # copies honest: the bytes must be palette colours
-    chk = host_out[0].array[0, :4, :4].reshape(-1, 3)
-    assert all(any((c == p).all() for p in pal_rows) for c in chk), "e2e output is not palette colours"
+    PB = min(B, 64)                    # frames per device batch inside the pipeline
+
+    def e2e_leg(output, steps):
+        if output == "index":
+            outs = [arena.view(in_bytes + v * B * H4K * W4K, (B, H4K, W4K)) for v in range(len(ED_VARIANTS))]
+            kw = {"out_idx": outs}
+        else:
+            outs = [arena.view(in_bytes + v * nbytes, (B, H4K, W4K, 3)) for v in range(len(ED_VARIANTS))]
+            kw = {"out_rgb": outs}
+        with pipeline.FramePipeline(plans, pal, PB, output) as pipe:
+            pipe.run(host_in, **kw)                       # warm-up (buffers, workspaces)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                pipe.submit(host_in, **kw)
+            pipe.flush()
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            stats = dict(pipe.stats)
+        return outs, world * px_per_step * steps / dt / 1e6, stats
+
+    outs, e2e_val, st_idx = e2e_leg("index", e2e_steps)
+    # the result that came back must be the kernels' answer: compare one frame per variant with a
+    # direct device-resident call
+    chk = torch.empty((1, H4K, W4K), dtype=torch.uint8, device=dev)
+    for v, pl in enumerate(plans):
+        pl.run(pal, src.data_ptr() + 5 * frame4k, 1, None, chk.data_ptr(), sp)
+        torch.cuda.synchronize()
+        assert np.array_equal(chk[0].cpu().numpy(), outs[v][5]), "e2e result differs from the direct call"
+    e2e = {"value": e2e_val, "unit": "Mpx/s", "h2d_bytes_per_step": nbytes,
+           "d2h_bytes_per_step": B * H4K * W4K * len(ED_VARIANTS), "steps": e2e_steps,
+           "api": "dither_pie_b200.pipeline.FramePipeline.submit/flush (pinned host arrays, index-plane output)",
+           "output": "palette-index plane, 1 B/pixel per variant",
+           "pipeline": f"copy-in + one kernel stream per variant + copy-out, {PB}-frame device batches, 2 slots",
+           "h2d_gbs_per_rank": st_idx["h2d_gbs"], "d2h_gbs_per_rank": st_idx["d2h_gbs"],
+           "host_affinity": numa, "pinned_arena_gb": arena.nbytes / 1e9, "pinned_alloc_s": arena.alloc_s}
+    if not args.no_rgb_e2e:
+        _, rgb_val, st_rgb = e2e_leg("rgb", 2)
+        e2e.update({"rgb_value": rgb_val, "rgb_d2h_bytes_per_step": nbytes * len(ED_VARIANTS),
+                    "rgb_d2h_gbs_per_rank": st_rgb["d2h_gbs"],
+                    "rgb_note": "same call with colour-byte output (3 B/pixel per variant): PCIe D2H-bound"})
+    del src
+    torch.cuda.empty_cache()
+
+    # ---- video configs as strong-scaling jobs (all ranks)
+    video = None
+    if not args.no_video:
+        try:
+            video = video_lines(torch, dist, engine, synth, arena, in_bytes, rank, world, dev, sp, stream,
+                                barrier, max_over_ranks)
+        except Exception as e:
+            video = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank != 0:
         if world > 1:
@@ -355,10 +421,9 @@ def run_gpu(args):
     avg_kernel_ms = sum(kernel_ms) / len(kernel_ms)
     alg_bytes = BYTES_PER_PX * B * H4K * W4K
     achieved = alg_bytes / (avg_kernel_ms * 1e-3) / 1e9
-    # DRAM traffic per launch for 128 4K frames in the ncu --set full captures of this round:
+    # DRAM traffic per launch for 128 4K frames in the ncu --set full captures (profiles/):
     # 7.795 GB for k_diffuse_wave<floyd_steinberg>, 8.194 GB for <jjn> (the two ends of the step's
-    # three launches; profiles/r1l_diffuse_wave_{fs,jjn}_K256_4k_x128.txt), i.e. 7.3-7.7 B/pixel
-    # against 6 algorithmic -- the hand-off streams and the candidate table
+    # three launches), i.e. 7.3-7.7 B/pixel against 6 algorithmic -- hand-off streams + table
     traffic = 0.5 * (7.794756e9 + 8.194386e9) / (128 * H4K * W4K) * (B * H4K * W4K)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
@@ -367,10 +432,9 @@ def run_gpu(args):
                                   "(scaled by frames)",
                 "kernel": "k_diffuse_wave",
                 "peak_source": peak_src, "avg_launch_ms": avg_kernel_ms,
+                "launch_ms": per_variant_ms,
                 "note": "error diffusion is bounded by its per-pixel dependency chain (~1100 cycles "
-                        "per wavefront step; 342 instructions per step for Floyd-Steinberg, 629 for "
-                        "JJN, 58-63 % of the issue slots used) and by instruction issue, not by HBM; "
-                        "see DESIGN.md"}
+                        "per wavefront step) and by instruction issue, not by HBM; see DESIGN.md"}
 
     line = {
         "metric": "Mpixels/s", "value": value, "unit": "Mpx/s", "n_gpus": world,
@@ -378,35 +442,149 @@ def run_gpu(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(world, B),
         "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": e2e_val, "unit": "Mpx/s", "h2d_bytes_per_step": nbytes,
-                "d2h_bytes_per_step": nbytes * len(ED_VARIANTS), "steps": e2e_steps,
-                "pipeline": "3 streams, double-buffered device batches; PCIe D2H-bound",
-                "host_affinity": numa},
-        "roofline": roofline,
+        "e2e": e2e, "roofline": roofline,
     }
+    if video is not None:
+        line["video"] = video
     if world == 1:
         # cpu baseline: bounded sample of the same workload on ALL host cores (undo the GPU-local
         # affinity first; worker threads inherit the mask when they are created)
         os.sched_setaffinity(0, orig_affinity)
         cores = len(orig_affinity) or 1
-        crops = [np.ascontiguousarray(host_in.array[t % HB][:540, :960]) for t in range(cores)]
+        crops = [np.ascontiguousarray(host_in[t % B][:540, :960]) for t in range(cores)]
         t0 = time.perf_counter()
         px = cpu_reference_step(crops, pal_rows.astype(np.float32), cores)
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {
             "value": px / dt / 1e6, "unit": "Mpx/s", "cores": cores, "kind": "port",
-            "sample": f"{cores} crops of 960x540 (one per core) x 3 kernels, {dt:.1f} s of wall time"}
+            "sample": f"{cores} crops of 960x540 (one per core) x 3 kernels, {dt:.1f} s of wall time",
+            "note": "C port of the reference's numba loop on ALL cores (the reference's own loop is "
+                    "single-threaded: 1.07 Mpx/s at 4K K=256, BASELINE.md)"}
         if not args.no_extra:
             try:
-                line["modes"] = extra_modes(torch, engine, synth, sp, stream, peak)
+                line["modes"] = extra_modes(torch, engine, synth, sp, stream, peak, cores)
             except Exception as e:  # never lose the headline line to an extra
-                line["modes"] = {"error": str(e)[:200]}
+                line["modes"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     _emit(line, real_stdout)
     if world > 1:
         dist.destroy_process_group()
 
 
-def extra_modes(torch, engine, synth, sp, stream, peak):
+def video_lines(torch, dist, engine, synth, arena, in_bytes, rank, world, dev, sp, stream, barrier, max_over_ranks):
+    """BASELINE configs[3] / [4] as strong-scaling jobs: a fixed clip split contiguously over the
+    ranks.  `device_ms`: frames resident in HBM, one launch per rank over its shard, CUDA events,
+    max over ranks.  `e2e_ms`: VideoProcessor.process_frames on pinned host arrays (copies inside
+    the timed region), wall clock between barriers, max over ranks."""
+    import dither_pie_b200 as dp
+    from dither_pie_b200.dithering_lib import DitherMode
+    from dither_pie_b200.video_processor import VideoProcessor, shard_frames
+    out = {}
+
+    def timed_dev(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        best = None
+        for _ in range(reps):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            ms = max_over_ranks(a.elapsed_time(b))
+            best = ms if best is None else min(best, ms)
+        return best
+
+    def timed_wall(fn, reps):
+        fn()
+        best = None
+        for _ in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            fn()
+            barrier()
+            ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            best = ms if best is None else min(best, ms)
+        return best
+
+    # ---- config 4: 600 x 1080p, pixelize 270 -> blue noise / IGN -> x4, K=16 from frame 0
+    NF, H, W = 600, 1080, 1920
+    lo, hi = shard_frames(NF, rank, world)
+    n = hi - lo
+    base = [synth.frame(H, W, 1000 + t) for t in range(8)]     # 8 seeds, repeated cyclically
+    h_in = arena.view(0, (n, H, W, 3))
+    for t in range(n):
+        h_in[t] = base[(lo + t) % 8]
+    h_out = arena.view(in_bytes, (n, H, W, 3))
+    h_idx = arena.view(in_bytes, (n, 270, 480))
+    d_in = torch.from_numpy(h_in).to(dev)
+    d_out = torch.empty_like(d_in)
+    pal16 = None
+    for mode, params, tag in ((DitherMode.BLUE_NOISE, {"size": 64, "seed": 42}, "blue_noise"),
+                              (DitherMode.INTERLEAVED_GRADIENT_NOISE, {"scale": 1.0, "seed": 0}, "IGN")):
+        d = dp.ImageDitherer(num_colors=16, dither_mode=mode, palette=pal16, dither_params=params)
+        vp = VideoProcessor()
+        vp._setup(base[0][None], d, ("regular", 270))     # palette from frame 0 (median cut), every rank
+        pal16 = d.palette
+        plan = engine.Plan(mode.value, params, 270, 480, (H, W), 4)
+        palh = engine.get_palette(pal16)
+        dev_ms = timed_dev(lambda: plan.run(palh, d_in.data_ptr(), n, d_out.data_ptr(), None, sp), 5)
+        e2e_ms = timed_wall(lambda: vp.process_frames(h_in, d, ("regular", 270), final_resize_multiplier=4,
+                                                      out=h_out, shard=False), 3)
+        st = dict(vp.last_stats)
+        idx_ms = timed_wall(lambda: vp.process_frames(h_in, d, ("regular", 270), final_resize_multiplier=4,
+                                                      out=h_idx, shard=False, output="index"), 3)
+        out[f"config4_{tag}"] = {
+            "frames": NF, "frames_per_rank": n, "n_gpus": world, "scaling": "strong",
+            "device_ms": dev_ms, "device_mpx_s": NF * H * W / dev_ms / 1e3,
+            "e2e_ms": e2e_ms, "e2e_mpx_s": NF * H * W / e2e_ms / 1e3,
+            "e2e_index_ms": idx_ms, "e2e_index_mpx_s": NF * H * W / idx_ms / 1e3,
+            "h2d_gbs_rank0": st.get("h2d_gbs"), "d2h_gbs_rank0": st.get("d2h_gbs"),
+            "api": "VideoProcessor.process_frames(pinned frames, ('regular', 270), final_resize_multiplier=4)"}
+        vp.close()
+    del d_in, d_out
+    torch.cuda.empty_cache()
+
+    # ---- config 5: 300 x 4K, Ostromoukhov and Sierra, K=64
+    NF, H, W = 300, H4K, W4K
+    lo, hi = shard_frames(NF, rank, world)
+    n = hi - lo
+    base = [synth.frame(H, W, 2000 + t) for t in range(4)]
+    h_in = arena.view(0, (n, H, W, 3))
+    for t in range(n):
+        h_in[t] = base[(lo + t) % 4] if (lo + t) < 4 else np.roll(base[(lo + t) % 4], 5 * (lo + t), axis=1)
+    h_out = arena.view(in_bytes, (n, H, W, 3))
+    h_idx = arena.view(in_bytes, (n, H, W))
+    d_in = torch.from_numpy(h_in).to(dev)
+    d_out = torch.empty_like(d_in)
+    pal64 = [tuple(int(v) for v in r) for r in synth.random_palette(64)]
+    palh = engine.get_palette(pal64)
+    for mode, params, tag in ((DitherMode.OSTROMOUKHOV, {}, "ostromoukhov"),
+                              (DitherMode.ERROR_DIFFUSION, {"variant": "sierra"}, "sierra")):
+        d = dp.ImageDitherer(num_colors=64, dither_mode=mode, palette=pal64, dither_params=params)
+        vp = VideoProcessor()
+        plan = engine.Plan(mode.value, params, H, W)
+        dev_ms = timed_dev(lambda: plan.run(palh, d_in.data_ptr(), n, d_out.data_ptr(), None, sp), 2)
+        e2e_ms = timed_wall(lambda: vp.process_frames(h_in, d, out=h_out, shard=False), 2)
+        st = dict(vp.last_stats)
+        idx_ms = timed_wall(lambda: vp.process_frames(h_in, d, out=h_idx, shard=False, output="index"), 2)
+        out[f"config5_{tag}"] = {
+            "frames": NF, "frames_per_rank": n, "n_gpus": world, "scaling": "strong",
+            "device_ms": dev_ms, "device_mpx_s": NF * H * W / dev_ms / 1e3,
+            "e2e_ms": e2e_ms, "e2e_mpx_s": NF * H * W / e2e_ms / 1e3,
+            "e2e_index_ms": idx_ms, "e2e_index_mpx_s": NF * H * W / idx_ms / 1e3,
+            "h2d_gbs_rank0": st.get("h2d_gbs"), "d2h_gbs_rank0": st.get("d2h_gbs"),
+            "api": "VideoProcessor.process_frames(pinned frames)"}
+        vp.close()
+    del d_in, d_out
+    torch.cuda.empty_cache()
+    out["note"] = ("strong scaling: fixed clip, contiguous frame shards, no data-path collective; times are "
+                   "best of 2-5 repetitions, max over ranks; synthetic frames repeat 8 (1080p) / 4 (4K, rolled) "
+                   "seeds cyclically")
+    return out
+
+
+def extra_modes(torch, engine, synth, sp, stream, peak, cores):
     """The other BASELINE.json configs, device-resident, batched (>= L2), 5 timed repetitions.
     Each entry also carries ``cpu_mpx_s``: the oracle (the reference's algorithm: numpy + scipy
     KD-tree with all host threads, C port of the numba loop) on a bounded sample of the same
@@ -437,10 +615,11 @@ def extra_modes(torch, engine, synth, sp, stream, peak):
         except Exception:
             return None
 
-    def entry(name, px, ms, alg_bytes=None, cpu=None, write_bytes=None):
+    def entry(name, px, ms, alg_bytes=None, cpu=None, write_bytes=None, **more):
         gbs = (alg_bytes if alg_bytes is not None else BYTES_PER_PX * px) / (ms * 1e-3) / 1e9
         out[name] = {"mpx_s": px / (ms * 1e-3) / 1e6, "ms": ms, "gb_s": gbs, "hbm_frac": gbs / peak,
                      "cpu_mpx_s": cpu}
+        out[name].update(more)
         if write_bytes is not None:
             # write-dominated path: also against the WRITE-ONLY bandwidth measured in this run
             out[name]["write_gb_s"] = write_bytes / (ms * 1e-3) / 1e9
@@ -458,19 +637,23 @@ def extra_modes(torch, engine, synth, sp, stream, peak):
         frames = np.stack([synth.frame(h, w, t) for t in range(2)])
         src = torch.from_numpy(np.concatenate([frames] * (nf // 2))).to(dev)
         dst = torch.empty_like(src)
+        idx = torch.empty((nf, h, w), dtype=torch.uint8, device=dev)
         for (mode, params, K) in (("bayer", {"size": "8x8"}, 16), ("none", {}, 16),
                                   ("IGN", {}, 16), ("blue_noise", {}, 16),
-                                  ("bayer", {"size": "8x8"}, 256), ("halftone", {}, 16)):
+                                  ("bayer", {"size": "8x8"}, 256), ("none", {}, 256), ("halftone", {}, 16)):
             if label == "4k" and mode in ("IGN", "blue_noise"):
                 continue
             rows = pico if K == 16 else synth.random_palette(K)
             pal = engine.get_palette(rows)
             plan = engine.Plan(mode, params, h, w)
             ms = timed(lambda: plan.run(pal, src.data_ptr(), nf, dst.data_ptr(), None, sp))
+            ms_idx = timed(lambda: plan.run(pal, src.data_ptr(), nf, None, idx.data_ptr(), sp))
             cpu = None
             if label == "1080p" and mode != "blue_noise":   # (its matrix takes seconds to generate)
                 cpu = cpu_rate(frames[0], rows, mode, params)
-            entry(f"{label}_{mode}_K{K}", nf * h * w, ms, cpu=cpu)
+            entry(f"{label}_{mode}_K{K}", nf * h * w, ms, cpu=cpu, index_only_ms=ms_idx,
+                  index_only_hbm_frac=4.0 * nf * h * w / (ms_idx * 1e-3) / 1e9 / peak)
+        del idx
         pal64_rows = synth.random_palette(64)
         pal64 = engine.get_palette(pal64_rows)
         if label == "1080p":
@@ -486,6 +669,17 @@ def extra_modes(torch, engine, synth, sp, stream, peak):
                 entry(f"video1080p_pixelize270_{mode}_x4", nf * h * w, ms,
                       nf * (3 * 480 * 270 + 3 * 1920 * 1080), write_bytes=nf * 3 * 1920 * 1080)
         else:
+            # config 2, single image: latency of ONE 4K frame per kernel (the reference: 7.7 s)
+            pal256_rows = synth.random_palette(256)
+            pal256 = engine.get_palette(pal256_rows)
+            for v in ED_VARIANTS:
+                plan = engine.Plan("error_diffusion", {"variant": v}, h, w)
+                ms = timed(lambda: plan.run(pal256, src.data_ptr(), 1, dst.data_ptr(), None, sp), 5)
+                entry(f"4k_single_image_ed_{v}_K256", h * w, ms, reference_numba_s=7.7)
+            # serpentine is serial per frame (one warp walks the frame): parallel over frames only
+            plan = engine.Plan("error_diffusion", {"variant": "floyd_steinberg", "serpentine": "true"}, 1080, 1920)
+            ms = timed(lambda: plan.run(pal256, src.data_ptr(), 1, dst.data_ptr(), None, sp), 1)
+            entry("1080p_single_image_ed_fs_serpentine_K256", 1080 * 1920, ms)
             # config 5: 4K, 64 colours, Ostromoukhov and Sierra; 300 frames over 8 GPUs = 38 frames
             # per GPU (frames shard over GPUs), which is also what saturates the wavefront kernel
             nf5 = 38
@@ -501,15 +695,66 @@ def extra_modes(torch, engine, synth, sp, stream, peak):
                 entry(f"{label}_{tag}_K64_x{nf5}", nf5 * h * w, ms, cpu=cpu_rate(crop, pal64_rows, mode, params))
             del src5, dst5
         del src, dst
-    # config 3: k-means Lloyd iteration over a full 4K frame, K=16 (3 B/pixel/iteration)
+    torch.cuda.empty_cache()
+
+    # ---- config 3: k-means Lloyd iterations, K=16, 3 B/pixel/iteration.  16 DISTINCT 4K frames
+    # (398 MB, larger than L2) as one pixel array; then the full-image loop on the seed-2 frame.
+    from dither_pie_b200 import kmeans as KM
     from dither_pie_b200._capi import check, lib
-    img = torch.from_numpy(synth.frame(2160, 3840, 2).reshape(-1, 3)).to(dev)
+    frames = np.concatenate([synth.frame(2160, 3840, 2 + t).reshape(-1, 3) for t in range(16)])
+    img = torch.from_numpy(frames).to(dev)
     n = img.shape[0]
-    cent = torch.from_numpy(img[:: n // 16][:16].cpu().numpy().astype(np.float64)).to(dev)
-    sums = torch.zeros(16 * 4, dtype=torch.int64, device=dev)
+    rs = np.random.RandomState(0)
+    init = frames[rs.choice(n, 16, replace=False)].astype(np.float64)
+    cent = torch.from_numpy(init).to(dev)
+    sums = torch.zeros(16 * 4 + 1, dtype=torch.int64, device=dev)
     ms = timed(lambda: check(lib().dp_kmeans_accumulate(img.data_ptr(), n, cent.data_ptr(), 16,
                                                         sums.data_ptr(), sp)))
-    entry("4k_kmeans_lloyd_iter_K16", n, ms, 3.0 * n)
+    entry("kmeans_assign_pass_K16_16x4k", n, ms, 3.0 * n,
+          note="one assignment pass (grid build + k_kmeans_accum16) over 133 Mpx = 398 MB (> L2)")
+    n1 = 2160 * 3840
+    t0 = time.perf_counter()
+    res = KM.lloyd_device(img.data_ptr(), n1, init, -1.0, 20, check_every=20)
+    torch.cuda.synchronize()
+    loop_ms = (time.perf_counter() - t0) * 1e3
+    # sklearn on the same full array: seconds per Lloyd iteration
+    sk_iter_s = None
+    try:
+        from sklearn.cluster import KMeans
+        X = frames[:n1].astype(np.float64)
+        t0 = time.perf_counter()
+        km = KMeans(n_clusters=16, init=init, n_init=1, max_iter=3, tol=0.0, algorithm="lloyd").fit(X)
+        sk_iter_s = (time.perf_counter() - t0) / max(int(km.n_iter_), 1)
+    except Exception:
+        pass
+    entry("kmeans_lloyd_loop_K16_4k", n1 * res[1], loop_ms, 3.0 * n1 * res[1],
+          cpu=(n1 / sk_iter_s / 1e6) if sk_iter_s else None,
+          iterations=res[1], ms_per_iteration=loop_ms / max(res[1], 1), tied_samples=res.ties,
+          sklearn_s_per_iteration=sk_iter_s, cpu_cores=cores,
+          note="dp_kmeans_lloyd: 20 iterations over the 8.29 Mpx frame, wall clock incl. launches; stop test on "
+               "the device, the host looks once; cpu = sklearn.cluster.KMeans (the call the reference makes) on "
+               "the full array")
+    del img
+    torch.cuda.empty_cache()
+
+    # ---- CPU baselines of the video configs: Pool(P).map over in-memory
+    # frames, P = all cores and P = the reference default min(4, cores - 1)
+    try:
+        pal16_rows = [tuple(int(v) for v in r) for r in pico]
+        for P in sorted({cores, min(4, max(1, cores - 1))}):
+            for mode, params in (("blue_noise", {"size": 64, "seed": 42}), ("IGN", {"scale": 1.0, "seed": 0})):
+                mpx, dt = pool_video_baseline("c4", mode, params, pal16_rows, P, 4 * P)
+                out[f"cpu_pool{P}_config4_{mode}"] = {
+                    "cpu_mpx_s": mpx, "workers": P, "frames": 4 * P, "seconds": dt,
+                    "note": "oracle pixelize->dither->x4 per 1080p frame, multiprocessing.Pool.map, input Mpx/s"}
+        P = cores
+        mpx, dt = pool_video_baseline("c5", "ostromoukhov", {}, synth.random_palette(64), P, P)
+        out[f"cpu_pool{P}_config5_ostromoukhov"] = {
+            "cpu_mpx_s": mpx, "workers": P, "frames": P, "seconds": dt, "kind": "port",
+            "note": "C port of the live Ostromoukhov path on one 480x270 crop per core, extrapolated linearly "
+                    "in pixels; the reference's own path is pure Python at ~0.014 Mpx/s per core (BASELINE.md)"}
+    except Exception as e:
+        out["cpu_pool_error"] = f"{type(e).__name__}: {e}"[:200]
     return out
 
 
@@ -520,7 +765,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="4K frames per step per GPU")
-    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the per-mode entries")
+    ap.add_argument("--no-video", action="store_true", help="skip the strong-scaling video configs")
+    ap.add_argument("--no-rgb-e2e", action="store_true", help="skip the colour-byte variant of the e2e leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -71,6 +71,13 @@ PROTOTYPES = {
     "dp_resample_nearest": [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp],
     "dp_kmeans_accumulate": [_vp, _i64, _vp, _i, _vp, _vp],
     "dp_kmeans_update": [_vp, _i, _vp, _vp, _vp],
+    "dp_kmeans_lloyd": [_vp, _i64, _vp, _i, _d, _i, _vp, _i, C.POINTER(_i), C.POINTER(_d),
+                        C.POINTER(C.c_ulonglong), C.POINTER(_i), _vp],
+    "dp_nccl_load": [C.c_char_p],
+    "dp_nccl_unique_id": [_vp],
+    "dp_nccl_comm_create": [_vp, _i, _i, C.POINTER(_vp)],
+    "dp_nccl_comm_destroy": [_vp],
+    "dp_nccl_allreduce_u64": [_vp, _sz, _vp, _vp],
     "dp_threshold_dither_host": [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _f, _f, _f, _vp],
 }
 _RESTYPES = {"dp_last_error": C.c_char_p}

@@ -2,24 +2,64 @@
 //
 // Replaces the E/M steps inside sklearn.cluster.KMeans as called by
 // ColorReducer.generate_kmeans_palette (dithering_lib.py:1854-1855).  Pixels are u8, so the
-// per-cluster channel sums are exact integers: they are accumulated in u32 per block (shared
-// memory atomics), flushed as u64 global atomics, and -- across GPUs -- all-reduced as integers
-// by the caller (NCCL), which makes the centres independent of shard count and order.
+// per-cluster channel sums are exact integers: accumulated in registers / shared memory per block,
+// flushed as u64 global atomics and -- across GPUs -- all-reduced as integers (NCCL, on the same
+// stream), which makes the centres independent of shard count and order.
 // Algorithmic bytes: 3 read per pixel per iteration (labels are not materialised).
+//
+// One Lloyd iteration is two launches:
+//   k_kmeans_prepare     every block recomputes the new centres from the previous iteration's
+//                        (all-reduced) sums -- K*4 integers, cheaper than a separate launch --,
+//                        block 0 publishes them with the squared centre shift (sklearn's stop
+//                        quantity) and the stop flag; then the blocks rebuild the CANDIDATE GRID
+//                        for the new centres (16^3 boxes of 16^3 byte colours -> the <= 4 centres
+//                        that can be nearest somewhere in the box) and the fixed-point centre table
+//   k_kmeans_accum16     the assignment pass: a lane owns 16 consecutive pixels (three 128-bit
+//                        loads), labels them against the box's candidates in 32-bit fixed point,
+//                        and keeps run-length partial sums that are merged by warp reductions /
+//                        shared atomics; pixels the fixed-point screen cannot decide go to a
+//                        per-warp list that the warp resolves cooperatively in f64 (lane = centre)
+// The stop test stays on the device: once the flag is set the remaining launches of the batch the
+// host enqueued return immediately, and the host looks at the flag only every few iterations.
+#include <dlfcn.h>
+
+#include <mutex>
+
 #include "dp_common.cuh"
+
+struct DpNcclId {   // ncclUniqueId: 128 opaque bytes, passed by value to ncclCommInitRank
+    char internal[128];
+};
 
 namespace {
 
 constexpr int KM_THREADS = 256;
+constexpr int KM_WARPS = KM_THREADS / 32;
 constexpr int KM_PIX_PER_BLOCK = 16384;  // 255 * 16384 < 2^32: u32 block partials are exact
+constexpr int KM_SCALE_LOG2 = 12;        // fixed-point centres: round(c * 4096)
+constexpr int KM_MARGIN = 800;           // score units; see k_kmeans_accum16
+constexpr int KM_SLOW_CAP = 96;          // per-warp list of undecided pixels (per 512-pixel tile)
 
+struct KmState {
+    int done;                  // stop flag (shift <= tol, or the iteration budget is used up)
+    int n_iter;                // completed Lloyd iterations
+    int empty;                 // iterations that saw an empty cluster (it keeps its centre)
+    int pad;
+    double shift2;             // squared centre shift of the last completed iteration
+    unsigned long long ties;   // samples exactly equidistant from their two nearest centres
+};
+
+// ---- generic path (K > 32): one thread per pixel, shared atomics ----------------------------
 __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate(
     const uint8_t *__restrict__ px, long long n, const double *__restrict__ centers, int K,
-    unsigned long long *__restrict__ sums)
+    unsigned long long *__restrict__ sums, const KmState *__restrict__ state)
 {
+    if (state && state->done) return;
     __shared__ double s_c[DP_MAX_COLORS * 3];
     __shared__ unsigned int s_sum[DP_MAX_COLORS * 4];
+    __shared__ unsigned int s_ties;
     for (int i = threadIdx.x; i < K * 3; i += KM_THREADS) s_c[i] = centers[i];
+    if (threadIdx.x == 0) s_ties = 0;
     const long long nchunks = (n + KM_PIX_PER_BLOCK - 1) / KM_PIX_PER_BLOCK;
     for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         for (int i = threadIdx.x; i < K * 4; i += KM_THREADS) s_sum[i] = 0;
@@ -32,6 +72,7 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate(
             const double x0 = r, x1 = g, x2 = b;
             double best = 1e300;
             int bi = 0;
+            bool tie = false;
             for (int i = 0; i < K; ++i) {
                 double d0 = x0 - s_c[3 * i], d1 = x1 - s_c[3 * i + 1], d2 = x2 - s_c[3 * i + 2];
                 double d = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)),
@@ -39,8 +80,12 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate(
                 if (d < best) {
                     best = d;
                     bi = i;
+                    tie = false;
+                } else if (d == best) {
+                    tie = true;
                 }
             }
+            if (tie) atomicAdd(&s_ties, 1u);
             atomicAdd(&s_sum[4 * bi], (unsigned)r);
             atomicAdd(&s_sum[4 * bi + 1], (unsigned)g);
             atomicAdd(&s_sum[4 * bi + 2], (unsigned)b);
@@ -51,165 +96,373 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate(
             if (s_sum[i]) atomicAdd(&sums[i], (unsigned long long)s_sum[i]);
         __syncthreads();
     }
+    if (threadIdx.x == 0 && s_ties) atomicAdd(&sums[4 * K], (unsigned long long)s_ties);
 }
 
-// Per-iteration candidate grid (the argmin structure of the dither kernels, rebuilt for the moving
-// centres): colour space in 16^3 boxes of 16^3 byte colours; a centre is dropped from a box when
-// another centre is strictly nearer at EVERY point of the box -- the difference of two squared
-// distances is linear in the point, so its maximum sits at a corner (exact test in double with a
-// 1e-6 margin).  One warp per box, lane = centre.  Entry: up to four surviving centres, ascending,
-// one per byte (255 = none); 0xffffffff = more than four (the pixel loop then scans all centres).
-__global__ void __launch_bounds__(256) k_kmeans_grid(const double *__restrict__ centers, int K,
-                                                     uint32_t *__restrict__ grid)
+// ---- centres <- sums / count (every thread that calls it gets the same values) ---------------
+// sklearn: centres = sums / counts in f64; an empty cluster keeps its centre here (sklearn moves it
+// to a far sample -- see DESIGN.md; the device flag `empty` reports that it happened).
+__device__ __forceinline__ double km_new_center(const unsigned long long *sums, const double *old_c, int i,
+                                                int ch, bool *was_empty)
 {
-    const int cell = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (cell >= 4096) return;
-    const double lo[3] = {16.0 * (cell >> 8), 16.0 * ((cell >> 4) & 15), 16.0 * (cell & 15)};
-    bool alive = false;
-    if (lane < K) {
-        const double ci[3] = {centers[3 * lane], centers[3 * lane + 1], centers[3 * lane + 2]};
-        const double ni = ci[0] * ci[0] + ci[1] * ci[1] + ci[2] * ci[2];
-        alive = true;
-        for (int j = 0; j < K && alive; ++j) {
-            if (j == lane) continue;
-            const double cj[3] = {centers[3 * j], centers[3 * j + 1], centers[3 * j + 2]};
-            double mx = (cj[0] * cj[0] + cj[1] * cj[1] + cj[2] * cj[2]) - ni;   // |c_j|^2 - |c_i|^2
-            for (int a = 0; a < 3; ++a) {
-                const double dlt = ci[a] - cj[a];
-                mx += 2.0 * (dlt > 0.0 ? lo[a] + 15.0 : lo[a]) * dlt;
-            }
-            if (mx < -1e-6) alive = false;   // centre j is strictly nearer everywhere in the box
-        }
+    const unsigned long long c = sums[4 * i + 3];
+    if (!c) {
+        *was_empty = true;
+        return old_c[3 * i + ch];
     }
-    unsigned m = __ballot_sync(0xffffffffu, alive);
-    if (lane == 0) {
-        uint32_t e = 0xffffffffu;
-        if (__popc(m) <= 4) {
-            e = 0;
-            for (int k = 0; k < 4; ++k) {
-                const unsigned idx = m ? (unsigned)(__ffs(m) - 1) : 255u;
-                if (m) m &= m - 1;
-                e |= idx << (8 * k);
+    return __ddiv_rn((double)sums[4 * i + ch], (double)c);
+}
+
+// Candidate grid + fixed-point centre table for the centres in shared memory `s_c` (K <= 32).
+//   grid[4096]  box = (r>>4) | (g>>4)<<4 | (b>>4)<<8; entry: up to four surviving centres,
+//               ascending, one per byte (32 = none: the pad entry); 0xffffffff = more than four
+//   ent[33]     (round(c*4096) per channel, round(|c|^2 * 2048)); [32] = pad that never wins
+// A centre is dropped from a box when another centre is strictly nearer at EVERY point of the box:
+// the difference of two squared distances is linear in the point, so its maximum sits at a corner
+// (exact test in double with a 1e-6 margin).  One warp per box, lane = centre.
+__device__ void km_build_grid(const double *s_c, int K, uint32_t *__restrict__ grid, int4 *__restrict__ ent,
+                              int first_box, int box_stride)
+{
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x <= 32) {
+        int4 e = make_int4(0, 0, 0, 0x3ffffffc);
+        if ((int)threadIdx.x < K) {
+            const double c0 = s_c[3 * threadIdx.x], c1 = s_c[3 * threadIdx.x + 1], c2 = s_c[3 * threadIdx.x + 2];
+            const double sc = (double)(1 << KM_SCALE_LOG2);
+            e.x = (int)llrint(c0 * sc);
+            e.y = (int)llrint(c1 * sc);
+            e.z = (int)llrint(c2 * sc);
+            e.w = (int)llrint((c0 * c0 + c1 * c1 + c2 * c2) * (sc * 0.5));
+        }
+        ent[threadIdx.x] = e;
+    }
+    for (int cell = first_box + wib; cell < 4096; cell += box_stride) {
+        const double lo[3] = {16.0 * (cell & 15), 16.0 * ((cell >> 4) & 15), 16.0 * (cell >> 8)};
+        bool alive = false;
+        if (lane < K) {
+            const double ci[3] = {s_c[3 * lane], s_c[3 * lane + 1], s_c[3 * lane + 2]};
+            const double ni = ci[0] * ci[0] + ci[1] * ci[1] + ci[2] * ci[2];
+            alive = true;
+            for (int j = 0; j < K && alive; ++j) {
+                if (j == lane) continue;
+                const double cj[3] = {s_c[3 * j], s_c[3 * j + 1], s_c[3 * j + 2]};
+                double mx = (cj[0] * cj[0] + cj[1] * cj[1] + cj[2] * cj[2]) - ni;   // |c_j|^2 - |c_i|^2
+                for (int a = 0; a < 3; ++a) {
+                    const double dlt = ci[a] - cj[a];
+                    mx += 2.0 * (dlt > 0.0 ? lo[a] + 15.0 : lo[a]) * dlt;
+                }
+                if (mx < -1e-6) alive = false;   // centre j is strictly nearer everywhere in the box
             }
         }
-        grid[cell] = e;
+        unsigned m = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) {
+            uint32_t e = 0xffffffffu;
+            if (__popc(m) <= 4) {
+                e = 0;
+                for (int k = 0; k < 4; ++k) {
+                    const unsigned idx = m ? (unsigned)(__ffs(m) - 1) : 32u;
+                    if (m) m &= m - 1;
+                    e |= idx << (8 * k);
+                }
+            }
+            grid[cell] = e;
+        }
     }
 }
 
-// K <= 32: no atomics in the pixel loop.  A warp labels 32 pixels at a time; the labels are
-// screened in f32 against all centres (two smallest distances kept) and only pixels whose two
-// best distances are closer than the f32 error bound repeat the exact f64 comparison (strict
-// '<', first index).  The per-cluster sums of the 32 pixels are formed with warp reductions
-// (REDUX) cluster by cluster -- neighbouring pixels fall into a handful of clusters -- and lane
-// k keeps the running 64-bit totals of cluster k in registers; one flush per warp at the end.
-__global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate_warp(
-    const uint8_t *__restrict__ px, long long n, const double *__restrict__ centers, int K,
-    unsigned long long *__restrict__ sums, const uint32_t *__restrict__ grid)
+// prepare: (optional) centre update from `sums_prev`, stop test, grid for the new centres
+//   c_prev / c_next   f64 [K,3] ping-pong centre buffers
+//   sums_prev         u64 [K*4+1] of the iteration that just finished (null: first iteration)
+//   sums_next         zeroed here for the accumulate pass that follows (null: nothing follows)
+__global__ void __launch_bounds__(KM_THREADS) k_kmeans_prepare(
+    const double *__restrict__ c_prev, double *__restrict__ c_next, const unsigned long long *__restrict__ sums_prev,
+    unsigned long long *__restrict__ sums_next, int K, double tol, int last, KmState *__restrict__ state,
+    uint32_t *__restrict__ grid, int4 *__restrict__ ent)
+{
+    if (state->done) return;
+    __shared__ double s_c[DP_MAX_COLORS * 3];
+    __shared__ double s_d2[DP_MAX_COLORS * 3];
+    __shared__ int s_stop, s_empty;
+    if (threadIdx.x == 0) s_stop = s_empty = 0;
+    __syncthreads();
+    if (sums_prev) {
+        for (int i = threadIdx.x; i < K * 3; i += KM_THREADS) {
+            bool emp = false;
+            const double nw = km_new_center(sums_prev, c_prev, i / 3, i % 3, &emp);
+            const double d = nw - c_prev[i];
+            s_c[i] = nw;
+            s_d2[i] = __dmul_rn(d, d);
+            if (emp) s_empty = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // single thread, fixed order: deterministic and identical in every block
+            double tot = 0.0;
+            for (int i = 0; i < K * 3; ++i) tot = __dadd_rn(tot, s_d2[i]);
+            const int stop = (tot <= tol || last) ? 1 : 0;
+            s_stop = stop;
+            if (blockIdx.x == 0) {
+                for (int i = 0; i < K * 3; ++i) c_next[i] = s_c[i];
+                state->n_iter += 1;
+                state->shift2 = tot;
+                state->ties += sums_prev[4 * K];
+                if (s_empty) state->empty += 1;
+                __threadfence();
+                if (stop) state->done = 1;   // written last; later launches on the stream see it
+            }
+        }
+        __syncthreads();
+        if (s_stop) return;
+    } else {
+        for (int i = threadIdx.x; i < K * 3; i += KM_THREADS) {
+            s_c[i] = c_prev[i];
+            if (blockIdx.x == 0 && c_next != c_prev) c_next[i] = c_prev[i];
+        }
+        __syncthreads();
+    }
+    if (sums_next && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < K * 4 + 1; i += KM_THREADS) sums_next[i] = 0ull;
+    if (K <= 32) km_build_grid(s_c, K, grid, ent, blockIdx.x * KM_WARPS, gridDim.x * KM_WARPS);
+}
+
+// NOTE on `state->done` and other blocks: block 0 may set the flag while other blocks of the SAME
+// prepare launch have not started yet; they would then return at the top without building their
+// part of the grid -- harmless, because done also stops every later accumulate launch.
+
+// grid only, for dp_kmeans_accumulate (the stand-alone assignment entry point)
+__global__ void __launch_bounds__(KM_THREADS) k_kmeans_grid_only(const double *__restrict__ centers, int K,
+                                                                 uint32_t *__restrict__ grid, int4 *__restrict__ ent)
 {
     __shared__ double s_c[32 * 3];
-    __shared__ float4 s_cf[33];          // [32] = pad entry, far outside the colour cube
-    __shared__ uint32_t s_grid[4096];
     if (threadIdx.x < K * 3) s_c[threadIdx.x] = centers[threadIdx.x];
-    if (threadIdx.x < K)
-        s_cf[threadIdx.x] = make_float4((float)centers[3 * threadIdx.x], (float)centers[3 * threadIdx.x + 1],
-                                        (float)centers[3 * threadIdx.x + 2], 0.f);
-    if (threadIdx.x == 32) s_cf[32] = make_float4(1e18f, 1e18f, 1e18f, 0.f);
-    for (int i = threadIdx.x; i < 4096; i += KM_THREADS) s_grid[i] = grid[i];
     __syncthreads();
+    km_build_grid(s_c, K, grid, ent, blockIdx.x * KM_WARPS, gridDim.x * KM_WARPS);
+}
+
+// ---- the assignment pass, K <= 32 --------------------------------------------------------------
+// Fixed-point screen.  With ci = round(c * 4096) and H = round(|c|^2 * 2048) the score
+//   s = H - v . ci  =  2048 * (|v - c|^2 - |v|^2) + err,   |err| <= 0.5 + 3 * 255 * 0.5 = 383
+// orders the candidates like their distances up to 766 score units (0.37 in squared-distance
+// units); the two low bits carry the candidate slot.  If the runner-up is more than KM_MARGIN above
+// the minimum the minimum IS the exact f64 argmin; otherwise (and for boxes with more than four
+// candidates) the pixel goes to the warp's list and is resolved exactly in f64 over all K centres
+// (strict '<', first index -- what sklearn's argmin over exact distances gives).
+struct KmWarpShared {
+    unsigned hist[32][2];            // per-centre partial sums of <= 256 pixels: r | g<<16, b | n<<16
+    unsigned slow[KM_SLOW_CAP];      // pixel offsets inside the tile of the undecided pixels
+    unsigned nslow;
+};
+
+__global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
+    const uint8_t *__restrict__ px, long long n, const double *__restrict__ centers, int K,
+    unsigned long long *__restrict__ sums, const uint32_t *__restrict__ grid, const int4 *__restrict__ ent,
+    const KmState *__restrict__ state)
+{
+    if (state && state->done) return;
+    __shared__ double s_c[32 * 3];
+    __shared__ __align__(16) int4 s_ent[33];
+    __shared__ uint32_t s_grid[4096];
+    __shared__ KmWarpShared s_w[KM_WARPS];
+    __shared__ unsigned long long s_tot[32 * 4 + 1];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    if (tid < K * 3) s_c[tid] = centers[tid];
+    if (tid <= 32) s_ent[tid] = ent[tid];
+    for (int i = tid; i < 4096; i += KM_THREADS) s_grid[i] = grid[i];
+    if (tid < 32 * 4 + 1) s_tot[tid] = 0ull;
+    KmWarpShared &ws = s_w[wib];
+    ws.hist[lane][0] = ws.hist[lane][1] = 0u;
+    if (lane == 0) ws.nslow = 0u;
+    __syncthreads();
+
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const long long nchunk = (n + 31) >> 5;
-    const long long wstride = (long long)gridDim.x * (KM_THREADS / 32);
-    unsigned long long ar = 0, ag = 0, ab = 0, an = 0;     // totals of cluster `lane`
-    for (long long ch = (long long)blockIdx.x * (KM_THREADS / 32) + (threadIdx.x >> 5); ch < nchunk;
-         ch += wstride) {
-        const long long i = ch * 32 + lane;
-        const bool ok = i < n;
-        int r = 0, g = 0, b = 0, label = -1;
-        if (ok) {
-            const uint8_t *q = px + (size_t)i * 3;
-            r = q[0];
-            g = q[1];
-            b = q[2];
-            const float fr = (float)r, fg = (float)g, fb = (float)b;
-            float d1 = 3.0e38f, d2 = 3.0e38f;
-            int bi = 0;
-            // the box of the pixel lists every centre that can be nearest to it (k_kmeans_grid)
-            const uint32_t e = s_grid[((r >> 4) << 8) | ((g >> 4) << 4) | (b >> 4)];
-            const bool few = e != 0xffffffffu;
-            if (few) {
+    const unsigned ent_a = (unsigned)__cvta_generic_to_shared(s_ent);
+    unsigned long long ar = 0, ag = 0, ab = 0, an = 0;     // totals of centre `lane`
+    unsigned nties = 0;
+
+    // exact resolution of one pixel by the whole warp: lane k holds the f64 distance to centre k
+    auto resolve = [&](unsigned v) {
+        const int r = v & 255u, g = (v >> 8) & 255u, b = (v >> 16) & 255u;
+        double d = 1e300;
+        if (lane < K) {
+            const double f0 = (double)r - s_c[3 * lane], f1 = (double)g - s_c[3 * lane + 1],
+                         f2 = (double)b - s_c[3 * lane + 2];
+            d = __dadd_rn(__dadd_rn(__dmul_rn(f0, f0), __dmul_rn(f1, f1)), __dmul_rn(f2, f2));
+        }
+        double best = d;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {   // ascending candidates; 255 -> the pad entry
-                    const int k = (int)((e >> (8 * q)) & 255u);
-                    const float4 c = s_cf[k < 32 ? k : 32];
-                    const float e0 = fr - c.x, e1 = fg - c.y, e2 = fb - c.z;
-                    const float d = fmaf(e2, e2, fmaf(e1, e1, e0 * e0));
-                    d2 = fminf(d2, fmaxf(d1, d));
-                    bi = d < d1 ? k : bi;
-                    d1 = fminf(d1, d);
+        for (int o = 16; o; o >>= 1) best = fmin(best, __shfl_xor_sync(FULL, best, o));
+        const unsigned eq = __ballot_sync(FULL, lane < K && d == best);
+        const int label = __ffs(eq) - 1;                  // first index among the minima
+        if (__popc(eq) > 1 && lane == 0) ++nties;
+        if (lane == label) {
+            ar += (unsigned)r;
+            ag += (unsigned)g;
+            ab += (unsigned)b;
+            an += 1;
+        }
+    };
+
+    // head: pixels in front of the first 16-byte boundary; body: whole 16-pixel groups; tail
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(px) & 15u);
+    long long head = (long long)((16u - mis) * 11u & 15u);    // 3 * head = -mis (mod 16)
+    if (mis == 0) head = 0;
+    if (head > n) head = n;
+    const long long ngroups = (n - head) >> 4;
+    const long long tail0 = head + (ngroups << 4);
+    if (blockIdx.x == 0 && wib == 0) {
+        for (long long i = 0; i < head; ++i) {
+            const uint8_t *q = px + 3 * i;
+            resolve((unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16));
+        }
+        for (long long i = tail0; i < n; ++i) {
+            const uint8_t *q = px + 3 * i;
+            resolve((unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16));
+        }
+    }
+
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(px + 3 * head);
+    const long long ntiles = (ngroups + 31) >> 5;             // 32 groups = 512 pixels per warp tile
+    const long long wstride = (long long)gridDim.x * KM_WARPS;
+    long long t = (long long)blockIdx.x * KM_WARPS + wib;
+    uint4 nx0 = make_uint4(0, 0, 0, 0), nx1 = nx0, nx2 = nx0;
+    auto fetch = [&](long long tile) {
+        const long long grp = tile * 32 + lane;
+        if (tile < ntiles && grp < ngroups) {
+            nx0 = __ldg(g4 + 3 * grp);
+            nx1 = __ldg(g4 + 3 * grp + 1);
+            nx2 = __ldg(g4 + 3 * grp + 2);
+        }
+    };
+    fetch(t);
+    for (; t < ntiles; t += wstride) {
+        unsigned w[12] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w, nx2.x, nx2.y, nx2.z, nx2.w};
+        const bool live = t * 32 + lane < ngroups;
+        fetch(t + wstride);                                   // next tile's loads fly during this one
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            int cur = -1;
+            unsigned accA = 0, accB = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int j = half * 8 + q;                   // pixel j of the lane's 16
+                const int wi = (3 * j) >> 2, sh = ((3 * j) & 3) * 8;
+                const unsigned v = (sh == 0 ? w[wi] : __funnelshift_r(w[wi], w[wi + (wi < 11 ? 1 : 0)], sh)) & 0xffffffu;
+                // box = (r>>4) | (g>>4)<<4 | (b>>4)<<8, as a byte offset into the u32 grid
+                const unsigned a4 = (v >> 4) & 0x0f0f0fu;
+                const unsigned e = *reinterpret_cast<const uint32_t *>(
+                    reinterpret_cast<const char *>(s_grid) + (__dp4a(a4, 0x00004004u, 0u) + ((a4 >> 6) & 0x3c00u)));
+                const unsigned vr = v & 255u, vg = (v >> 8) & 255u, vb = v >> 16;
+                int s[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    int4 en;
+                    const unsigned a = __dp4a(e, 0x10u << (8 * c), ent_a);   // ent_a + 16 * byte c of e
+                    asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(en.x), "=r"(en.y), "=r"(en.z), "=r"(en.w) : "r"(a));
+                    s[c] = ((en.w - (int)vr * en.x - (int)vg * en.y - (int)vb * en.z) & ~3) | c;
                 }
-            } else {
-#pragma unroll 4
-                for (int k = 0; k < K; ++k) {     // branch-free: lanes of a warp disagree on every test
-                    const float4 c = s_cf[k];
-                    const float e0 = fr - c.x, e1 = fg - c.y, e2 = fb - c.z;
-                    const float d = fmaf(e2, e2, fmaf(e1, e1, e0 * e0));
-                    d2 = fminf(d2, fmaxf(d1, d));
-                    bi = d < d1 ? k : bi;
-                    d1 = fminf(d1, d);
-                }
-            }
-            // centre rounded to f32 (<= 255 * 2^-24) and the rounded difference give |e32 - e| <= 3.1e-5
-            // per channel, so |d32 - D| <= 1.07e-4 sqrt(D) + 1.8e-7 D; twice that (both distances)
-            // is below the margin used here for every D in [0, 195075]  (d2 = pad: never ambiguous)
-            if (d2 < 1.0e30f && d2 - d1 <= 3.0e-4f * sqrtf(d2) + 5.0e-7f * d2 + 3.0e-4f) {
-                const double x0 = r, x1 = g, x2 = b;
-                double best = 1e300;
-                for (int k = 0; k < K; ++k) {
-                    const double f0 = x0 - s_c[3 * k], f1 = x1 - s_c[3 * k + 1], f2 = x2 - s_c[3 * k + 2];
-                    const double d = __dadd_rn(__dadd_rn(__dmul_rn(f0, f0), __dmul_rn(f1, f1)),
-                                               __dmul_rn(f2, f2));
-                    if (d < best) {
-                        best = d;
-                        bi = k;
+                const int lo01 = min(s[0], s[1]), hi01 = max(s[0], s[1]);
+                const int lo23 = min(s[2], s[3]), hi23 = max(s[2], s[3]);
+                const int m1 = min(lo01, lo23);
+                const int m2 = min(max(lo01, lo23), min(hi01, hi23));
+                const bool slow = (e == 0xffffffffu) || (m2 - m1 <= KM_MARGIN);
+                const int label = (int)((e >> (8 * (m1 & 3))) & 255u);
+                if (live) {
+                    if (slow) {
+                        const unsigned pos = atomicAdd(&ws.nslow, 1u);
+                        if (pos < KM_SLOW_CAP) ws.slow[pos] = (unsigned)(lane * 16 + j);
+                    } else {
+                        if (label != cur) {
+                            if (cur >= 0) {
+                                atomicAdd(&ws.hist[cur][0], accA);
+                                atomicAdd(&ws.hist[cur][1], accB);
+                            }
+                            cur = label;
+                            accA = accB = 0;
+                        }
+                        accA += vr | (vg << 16);
+                        accB += vb | 0x10000u;
                     }
                 }
             }
-            label = bi;
-        }
-        // clusters present among the 32 pixels, one after the other (warp-uniform loop)
-        unsigned todo = __ballot_sync(FULL, ok);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            const int k = __shfl_sync(FULL, label, src);
-            const bool mine = ok && label == k;
-            const unsigned m = __ballot_sync(FULL, mine);
-            const unsigned sr = __reduce_add_sync(FULL, mine ? (unsigned)r : 0u);
-            const unsigned sg = __reduce_add_sync(FULL, mine ? (unsigned)g : 0u);
-            const unsigned sb = __reduce_add_sync(FULL, mine ? (unsigned)b : 0u);
-            if (lane == k) {
-                ar += sr;
-                ag += sg;
-                ab += sb;
-                an += __popc(m);
+            // end of the half tile (<= 256 pixels per warp): merge the lanes' open runs.  When every
+            // lane ended in the same centre (the common case in images) two warp reductions do it.
+            const int c0 = __shfl_sync(FULL, cur, 0);
+            if (__all_sync(FULL, cur == c0)) {
+                if (c0 >= 0) {
+                    const unsigned ta = __reduce_add_sync(FULL, accA), tb = __reduce_add_sync(FULL, accB);
+                    if (lane == c0) {
+                        ar += ta & 0xffffu;
+                        ag += ta >> 16;
+                        ab += tb & 0xffffu;
+                        an += tb >> 16;
+                    }
+                }
+            } else if (cur >= 0) {
+                atomicAdd(&ws.hist[cur][0], accA);
+                atomicAdd(&ws.hist[cur][1], accB);
             }
-            todo &= ~m;
+            __syncwarp();
+            {
+                const unsigned ha = ws.hist[lane][0], hb = ws.hist[lane][1];
+                if (ha | hb) {
+                    ar += ha & 0xffffu;
+                    ag += ha >> 16;
+                    ab += hb & 0xffffu;
+                    an += hb >> 16;
+                    ws.hist[lane][0] = ws.hist[lane][1] = 0u;
+                }
+            }
+            __syncwarp();
+        }
+        // undecided pixels of the tile: the warp resolves them one by one
+        const unsigned ns = ws.nslow;
+        if (ns) {
+            const uint8_t *tile_px = px + 3 * (head + t * 512);
+            if (ns <= KM_SLOW_CAP) {
+                for (unsigned i = 0; i < ns; ++i) {
+                    const uint8_t *q = tile_px + 3 * ws.slow[i];
+                    resolve((unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16));
+                }
+            } else {
+                // list overflow (pathological inputs): the entries beyond the capacity were not
+                // recorded, so re-screen is impossible -- redo the WHOLE tile exactly instead.
+                // The decided pixels were already accumulated, so only the undecided ones may be
+                // added: recompute the screen decision per pixel, cooperatively.
+                const long long base = head + t * 512;
+                const long long lim = min((long long)512, tail0 - base);
+                for (long long i = 0; i < lim; ++i) {
+                    const uint8_t *q = px + 3 * (base + i);
+                    const unsigned v = (unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16);
+                    const unsigned a4 = (v >> 4) & 0x0f0f0fu;
+                    const unsigned e = s_grid[(a4 & 15u) | ((a4 >> 4) & 0xf0u) | ((a4 >> 8) & 0xf00u)];
+                    int sc[4];
+                    for (int c = 0; c < 4; ++c) {
+                        const int4 en = s_ent[(e >> (8 * c)) & 255u];
+                        sc[c] = ((en.w - (int)(v & 255u) * en.x - (int)((v >> 8) & 255u) * en.y - (int)(v >> 16) * en.z) & ~3) | c;
+                    }
+                    const int lo01 = min(sc[0], sc[1]), hi01 = max(sc[0], sc[1]);
+                    const int lo23 = min(sc[2], sc[3]), hi23 = max(sc[2], sc[3]);
+                    const int m1 = min(lo01, lo23), m2 = min(max(lo01, lo23), min(hi01, hi23));
+                    if ((e == 0xffffffffu) || (m2 - m1 <= KM_MARGIN)) resolve(v);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ws.nslow = 0u;
+            __syncwarp();
         }
     }
-    // block totals first (the global accumulators are 4K addresses shared by every block: one
-    // flush per block instead of one per warp keeps the L2 atomic unit out of the critical path)
-    __shared__ unsigned long long s_tot[32 * 4];
-    if (threadIdx.x < 32 * 4) s_tot[threadIdx.x] = 0;
-    __syncthreads();
+    // block totals first (the global accumulators are a few addresses shared by every block: one
+    // flush per block keeps the L2 atomic unit out of the critical path)
     if (lane < K && an) {
         atomicAdd(&s_tot[4 * lane], ar);
         atomicAdd(&s_tot[4 * lane + 1], ag);
         atomicAdd(&s_tot[4 * lane + 2], ab);
         atomicAdd(&s_tot[4 * lane + 3], an);
     }
+    if (lane == 0 && nties) atomicAdd(&s_tot[32 * 4], (unsigned long long)nties);
     __syncthreads();
-    if (threadIdx.x < K * 4 && s_tot[threadIdx.x]) atomicAdd(&sums[threadIdx.x], s_tot[threadIdx.x]);
+    if (tid < K * 4 && s_tot[tid]) atomicAdd(&sums[tid], s_tot[tid]);
+    if (tid == 0 && s_tot[32 * 4]) atomicAdd(&sums[4 * K], s_tot[32 * 4]);
 }
 
 __global__ void k_kmeans_update(const unsigned long long *__restrict__ sums, int K,
@@ -231,7 +484,131 @@ __global__ void k_kmeans_update(const unsigned long long *__restrict__ sums, int
     *shift2 = tot;
 }
 
+// ---- per-device scratch of the stand-alone accumulate entry point (grid + centre table) -----
+struct KmScratch {
+    uint32_t *grid = nullptr;
+    int4 *ent = nullptr;
+};
+std::mutex g_km_mu;
+KmScratch g_km_scratch[64];
+
+int km_scratch(KmScratch **out)
+{
+    int dev = 0;
+    DP_CUDA(cudaGetDevice(&dev));
+    DP_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+    std::lock_guard<std::mutex> lk(g_km_mu);
+    KmScratch &s = g_km_scratch[dev];
+    if (!s.grid) {
+        DP_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.grid), 4096 * sizeof(uint32_t)));
+        DP_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.ent), 33 * sizeof(int4)));
+    }
+    *out = &s;
+    return 0;
+}
+
+int km_accum_grid_size(long long n)
+{
+    static thread_local int per_sm = 0;
+    if (!per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_kmeans_accum16, KM_THREADS, 0) != cudaSuccess ||
+            per_sm < 1)
+            per_sm = 2;
+    }
+    const long long cap = (long long)dp_num_sms() * per_sm;
+    const long long tiles = (n / 16 + 31) / 32;
+    long long blocks = (tiles + KM_WARPS - 1) / KM_WARPS;
+    if (blocks < 1) blocks = 1;
+    return (int)(blocks < cap ? blocks : cap);
+}
+
+// ---- NCCL, resolved at run time (the library has no link-time dependency on it) -----------------
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(void *id) = nullptr;
+    int (*CommInitRank)(void **comm, int nranks, DpNcclId id, int rank) = nullptr;
+    int (*CommDestroy)(void *comm) = nullptr;
+    int (*AllReduce)(const void *send, void *recv, size_t count, int dtype, int op, void *comm,
+                     cudaStream_t stream) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+int nccl_load(const char *path)
+{
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.handle) return 0;
+    const char *cands[] = {path, getenv("DP_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *c : cands) {
+        if (!c || !*c) continue;
+        h = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    DP_REQUIRE(h, "libnccl.so.2 not found (set DP_NCCL_LIB or pass the path to dp_nccl_load)");
+    g_nccl.GetUniqueId = reinterpret_cast<int (*)(void *)>(dlsym(h, "ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<int (*)(void **, int, DpNcclId, int)>(dlsym(h, "ncclCommInitRank"));
+    g_nccl.CommDestroy = reinterpret_cast<int (*)(void *)>(dlsym(h, "ncclCommDestroy"));
+    g_nccl.AllReduce = reinterpret_cast<int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t)>(
+        dlsym(h, "ncclAllReduce"));
+    g_nccl.GetErrorString = reinterpret_cast<const char *(*)(int)>(dlsym(h, "ncclGetErrorString"));
+    DP_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce,
+               "libnccl does not export the expected symbols");
+    g_nccl.handle = h;
+    return 0;
+}
+
+#define DP_NCCL(call)                                                                             \
+    do {                                                                                          \
+        const int _r = (call);                                                                    \
+        if (_r != 0) {                                                                            \
+            dp_set_error("%s:%d %s -> nccl error %d (%s)", __FILE__, __LINE__, #call, _r,          \
+                         g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?");                 \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+
+constexpr int DP_NCCL_UINT64 = 5;   // ncclUint64
+constexpr int DP_NCCL_SUM = 0;      // ncclSum
+
 }  // namespace
+
+extern "C" int dp_nccl_load(const char *path) { return nccl_load(path); }
+
+extern "C" int dp_nccl_unique_id(void *id128)
+{
+    DP_REQUIRE(id128, "null argument");
+    if (nccl_load(nullptr)) return 1;
+    DP_NCCL(g_nccl.GetUniqueId(id128));
+    return 0;
+}
+
+extern "C" int dp_nccl_comm_create(const void *id128, int rank, int world, void **comm)
+{
+    DP_REQUIRE(id128 && comm && world >= 1 && rank >= 0 && rank < world, "bad argument");
+    if (nccl_load(nullptr)) return 1;
+    DpNcclId id;
+    memcpy(&id, id128, sizeof(id));
+    DP_NCCL(g_nccl.CommInitRank(comm, world, id, rank));
+    return 0;
+}
+
+extern "C" int dp_nccl_comm_destroy(void *comm)
+{
+    if (!comm) return 0;
+    DP_REQUIRE(g_nccl.handle, "NCCL was never loaded");
+    DP_NCCL(g_nccl.CommDestroy(comm));
+    return 0;
+}
+
+extern "C" int dp_nccl_allreduce_u64(void *buf, size_t count, void *comm, void *stream)
+{
+    DP_REQUIRE(buf && comm, "null argument");
+    DP_REQUIRE(g_nccl.handle, "NCCL was never loaded");
+    DP_NCCL(g_nccl.AllReduce(buf, buf, count, DP_NCCL_UINT64, DP_NCCL_SUM, comm, dp_stream(stream)));
+    return 0;
+}
 
 extern "C" int dp_kmeans_accumulate(const uint8_t *pixels, int64_t n, const double *centers,
                                     int K, unsigned long long *sums, void *stream)
@@ -239,23 +616,20 @@ extern "C" int dp_kmeans_accumulate(const uint8_t *pixels, int64_t n, const doub
     DP_REQUIRE(pixels && centers && sums, "null argument");
     DP_REQUIRE(K >= 1 && K <= DP_MAX_COLORS && n >= 0, "bad size");
     if (n == 0) return 0;
-    long long cap = (long long)dp_num_sms() * 8;
+    cudaStream_t st = dp_stream(stream);
     if (K <= 32) {
-        long long blocks = ((n + 31) / 32 + KM_THREADS / 32 - 1) / (KM_THREADS / 32);
-        int grid = (int)(blocks < cap ? blocks : cap);   // 8 resident blocks of 8 warps per SM
-        cudaStream_t st = dp_stream(stream);
-        uint32_t *cgrid = nullptr;
-        DP_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&cgrid), 4096 * sizeof(uint32_t), st));
-        k_kmeans_grid<<<512, 256, 0, st>>>(centers, K, cgrid);
-        k_kmeans_accumulate_warp<<<grid, KM_THREADS, 0, st>>>(pixels, n, centers, K, sums, cgrid);
-        const cudaError_t le = cudaGetLastError();
-        cudaFreeAsync(cgrid, st);
-        DP_CUDA(le);
+        KmScratch *sc = nullptr;
+        if (km_scratch(&sc)) return 1;
+        k_kmeans_grid_only<<<512, KM_THREADS, 0, st>>>(centers, K, sc->grid, sc->ent);
+        k_kmeans_accum16<<<km_accum_grid_size(n), KM_THREADS, 0, st>>>(pixels, n, centers, K, sums, sc->grid,
+                                                                        sc->ent, nullptr);
+        DP_LAUNCH_CHECK();
         return 0;
     }
+    long long cap = (long long)dp_num_sms() * 8;
     long long chunks = (n + KM_PIX_PER_BLOCK - 1) / KM_PIX_PER_BLOCK;
     int grid = (int)(chunks < cap ? chunks : cap);
-    k_kmeans_accumulate<<<grid, KM_THREADS, 0, dp_stream(stream)>>>(pixels, n, centers, K, sums);
+    k_kmeans_accumulate<<<grid, KM_THREADS, 0, st>>>(pixels, n, centers, K, sums, nullptr);
     DP_LAUNCH_CHECK();
     return 0;
 }
@@ -268,4 +642,98 @@ extern "C" int dp_kmeans_update(const unsigned long long *sums, int K, double *c
     k_kmeans_update<<<1, 32, 0, dp_stream(stream)>>>(sums, K, centers, shift2);
     DP_LAUNCH_CHECK();
     return 0;
+}
+
+// The whole Lloyd loop (see the header).  Synchronous: returns when the loop has stopped.
+extern "C" int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers_host, int K, double tol,
+                               int max_iter, void *nccl_comm, int check_every, int *n_iter, double *shift2,
+                               unsigned long long *ties, int *empty_iters, void *stream)
+{
+    DP_REQUIRE(pixels && centers_host, "null argument");
+    DP_REQUIRE(K >= 1 && K <= DP_MAX_COLORS && n >= 0 && max_iter >= 1, "bad size");
+    if (nccl_comm) DP_REQUIRE(g_nccl.handle, "NCCL communicator given but NCCL was never loaded");
+    cudaStream_t st = dp_stream(stream);
+    int dev = 0;
+    DP_CUDA(cudaGetDevice(&dev));
+    if (dp_retain_pool(dev)) return 1;
+    if (check_every < 1) check_every = 4;
+    const size_t nsum = (size_t)K * 4 + 1;
+    const size_t off_c = 0, off_s = off_c + 2 * (size_t)K * 3 * 8, off_state = off_s + 2 * nsum * 8,
+                 off_grid = off_state + 64, off_ent = off_grid + 4096 * 4, total = off_ent + 33 * 16;
+    char *ws = nullptr;
+    DP_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), total, st));
+    double *cbuf[2] = {reinterpret_cast<double *>(ws + off_c), reinterpret_cast<double *>(ws + off_c) + (size_t)K * 3};
+    unsigned long long *sums[2] = {reinterpret_cast<unsigned long long *>(ws + off_s),
+                                   reinterpret_cast<unsigned long long *>(ws + off_s) + nsum};
+    KmState *state = reinterpret_cast<KmState *>(ws + off_state);
+    uint32_t *grid = reinterpret_cast<uint32_t *>(ws + off_grid);
+    int4 *ent = reinterpret_cast<int4 *>(ws + off_ent);
+    int rc = 0;
+    KmState host_state;
+    memset(&host_state, 0, sizeof(host_state));
+    auto finish = [&](int code) {
+        cudaFreeAsync(ws, st);
+        cudaStreamSynchronize(st);
+        return code;
+    };
+#define KM_TRY(call)                                                                          \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            dp_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+            return finish(1);                                                                 \
+        }                                                                                     \
+    } while (0)
+    KM_TRY(cudaMemsetAsync(ws + off_s, 0, 2 * nsum * 8 + 64, st));
+    KM_TRY(cudaMemcpyAsync(cbuf[0], centers_host, (size_t)K * 3 * 8, cudaMemcpyHostToDevice, st));
+    const int agrid = km_accum_grid_size(n);
+    const long long cap = (long long)dp_num_sms() * 8;
+    const long long chunks = (n + KM_PIX_PER_BLOCK - 1) / KM_PIX_PER_BLOCK;
+    const int ggrid = (int)(chunks < cap ? (chunks < 1 ? 1 : chunks) : cap);
+    int it = 1;
+    bool stopped = false;
+    while (!stopped) {
+        const int upto = it + check_every - 1 < max_iter ? it + check_every - 1 : max_iter;
+        for (; it <= upto; ++it) {
+            // prepare(it): centres C_{it-1} from sums of iteration it-1 (none for it == 1), stop
+            // test, grid; then the assignment pass of iteration `it` into sums[it & 1]
+            k_kmeans_prepare<<<K <= 32 ? 512 : 1, KM_THREADS, 0, st>>>(
+                it == 1 ? cbuf[0] : cbuf[it & 1], cbuf[(it - 1) & 1], it > 1 ? sums[(it - 1) & 1] : nullptr,
+                sums[it & 1], K, tol, 0, state, grid, ent);
+            if (n > 0) {
+                if (K <= 32)
+                    k_kmeans_accum16<<<agrid, KM_THREADS, 0, st>>>(pixels, n, cbuf[(it - 1) & 1], K, sums[it & 1], grid,
+                                                                   ent, state);
+                else
+                    k_kmeans_accumulate<<<ggrid, KM_THREADS, 0, st>>>(pixels, n, cbuf[(it - 1) & 1], K, sums[it & 1],
+                                                                      state);
+            }
+            KM_TRY(cudaGetLastError());
+            if (nccl_comm) {
+                const int r = g_nccl.AllReduce(sums[it & 1], sums[it & 1], nsum, DP_NCCL_UINT64, DP_NCCL_SUM, nccl_comm, st);
+                if (r != 0) {
+                    dp_set_error("ncclAllReduce failed: %d (%s)", r, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+                    return finish(1);
+                }
+            }
+        }
+        if (it > max_iter) {
+            // the iteration budget is used up: finalise C_{max_iter}
+            k_kmeans_prepare<<<1, KM_THREADS, 0, st>>>(cbuf[it & 1], cbuf[(it - 1) & 1], sums[(it - 1) & 1], nullptr, K, tol,
+                                                      1, state, grid, ent);
+            KM_TRY(cudaGetLastError());
+        }
+        KM_TRY(cudaMemcpyAsync(&host_state, state, sizeof(KmState), cudaMemcpyDeviceToHost, st));
+        KM_TRY(cudaStreamSynchronize(st));
+        stopped = host_state.done != 0 || it > max_iter;
+    }
+    // final centres: C_{n_iter} lives in cbuf[n_iter & 1]
+    KM_TRY(cudaMemcpyAsync(centers_host, cbuf[host_state.n_iter & 1], (size_t)K * 3 * 8, cudaMemcpyDeviceToHost, st));
+    KM_TRY(cudaStreamSynchronize(st));
+#undef KM_TRY
+    if (n_iter) *n_iter = host_state.n_iter;
+    if (shift2) *shift2 = host_state.shift2;
+    if (ties) *ties = host_state.ties;
+    if (empty_iters) *empty_iters = host_state.empty;
+    return finish(rc);
 }

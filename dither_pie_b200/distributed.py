@@ -65,30 +65,62 @@ def shard_pixels(n: int, rank: int, world: int) -> Tuple[int, int]:
     return shard_frames(n, rank, world)
 
 
+_nccl_comm = None
+
+
+def nccl_comm():
+    """This rank's communicator for the library's own NCCL calls (created once per process: rank
+    0 draws the unique id, torch.distributed broadcasts the 128 bytes, every rank joins).  The
+    library dlopens the libnccl the process already carries (PyTorch's)."""
+    global _nccl_comm
+    if _nccl_comm is not None:
+        return _nccl_comm
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from ._capi import check, lib
+    rank, world = init_process_group()
+    if world == 1:
+        return None
+    try:   # prefer the very file PyTorch loaded
+        import glob
+        import nvidia.nccl as _n
+        cands = glob.glob(os.path.join(os.path.dirname(_n.__file__), "lib", "libnccl.so*"))
+        check(lib().dp_nccl_load(cands[0].encode() if cands else None), "dp_nccl_load")
+    except ImportError:
+        check(lib().dp_nccl_load(None), "dp_nccl_load")
+    ident = np.zeros(128, np.uint8)
+    if rank == 0:
+        check(lib().dp_nccl_unique_id(ident.ctypes.data), "dp_nccl_unique_id")
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+    t = torch.from_numpy(ident).to(dev)
+    dist.broadcast(t, src=0)
+    ident = t.cpu().numpy()
+    h = C.c_void_p()
+    check(lib().dp_nccl_comm_create(ident.ctypes.data, rank, world, C.byref(h)), "dp_nccl_comm_create")
+    _nccl_comm = h.value
+    return _nccl_comm
+
+
 def kmeans_fit_sharded(pixels_u8: np.ndarray, init_centers: np.ndarray, tol: float,
-                       max_iter: int = kmeans.MAX_ITER) -> Tuple[np.ndarray, int]:
+                       max_iter: int = kmeans.MAX_ITER, check_every: int = 8):
     """Full-image Lloyd iterations with the pixels sharded over the ranks of the job
     (BASELINE config 3, throughput mode).  Every rank passes the SAME ``pixels_u8`` [N,3] and
-    initial centres; each uploads only its shard, accumulates exact integer sums on its GPU,
-    all-reduces them (NCCL) and updates identical centres.  Returns (centres f64 [K,3], iters)."""
-    import torch
+    initial centres; each uploads only its shard; ``dp_kmeans_lloyd`` accumulates exact integer
+    sums on its GPU and all-reduces them with ncclAllReduce on the kernel stream (no host
+    synchronisation per iteration).  Returns (centres f64 [K,3], iters) -- identical on all ranks."""
     from . import _capi
     rank, world = init_process_group()
+    _capi.ensure_device()
     pix = np.ascontiguousarray(pixels_u8, np.uint8).reshape(-1, 3)
     lo, hi = shard_pixels(pix.shape[0], rank, world)
-    K = int(init_centers.shape[0])
-    dev = torch.device("cuda", torch.cuda.current_device())
-    shard = torch.from_numpy(pix[lo:hi]).to(dev)
-    sums = torch.zeros(K * 4, dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream()
-
-    def reduce():
-        allreduce_sums_(sums)
-
-    import ctypes as C
-    return kmeans.lloyd_device(shard.data_ptr(), hi - lo, init_centers, tol, max_iter,
-                               sums_ptr=sums.data_ptr(), allreduce=reduce,
-                               stream=C.c_void_p(stream.cuda_stream))
+    comm = nccl_comm()
+    buf = _capi.DeviceBuffer(max((hi - lo) * 3, 16)).upload(np.ascontiguousarray(pix[lo:hi]))
+    try:
+        return kmeans.lloyd_device(buf.ptr, hi - lo, init_centers, tol, max_iter, comm=comm,
+                                   check_every=check_every)
+    finally:
+        buf.free()
 
 
 def process_frames_sharded(frames: np.ndarray, run_shard: Callable[[np.ndarray], np.ndarray],

@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import ctypes as C
 import random
-from typing import Callable, List, Optional, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 
@@ -58,45 +58,34 @@ def kmeans_plusplus(Xc: np.ndarray, k: int, seed) -> np.ndarray:
     return centers
 
 
+class LloydResult(tuple):
+    """(centres, n_iter) with the extra device-side diagnostics as attributes."""
+
+    def __new__(cls, centers, n_iter, shift2, ties, empty_iters):
+        self = super().__new__(cls, (centers, n_iter))
+        self.shift2, self.ties, self.empty_iters = shift2, ties, empty_iters
+        return self
+
+
 def lloyd_device(pixels_ptr: int, n: int, centers: np.ndarray, tol: float,
-                 max_iter: int = MAX_ITER, sums_ptr: Optional[int] = None,
-                 allreduce: Optional[Callable[[], None]] = None, stream=None
-                 ) -> Tuple[np.ndarray, int]:
-    """Lloyd iterations on device-resident u8 pixels [n,3].  ``centers`` f64 [K,3] (uncentred).
-    When the pixels are one shard of a multi-GPU job pass ``sums_ptr`` (device u64 [K,4] the
-    caller can all-reduce) and ``allreduce`` (called after each accumulate, same stream)."""
-    K = centers.shape[0]
-    L = lib()
+                 max_iter: int = MAX_ITER, comm: Optional[int] = None, stream=None,
+                 check_every: int = 4) -> Tuple[np.ndarray, int]:
+    """Lloyd iterations on device-resident u8 pixels [n,3] through ``dp_kmeans_lloyd``: the whole
+    loop runs on the stream with the stop test on the device; the host looks at the flag every
+    ``check_every`` iterations.  ``centers`` f64 [K,3] (uncentred).  When the pixels are one shard
+    of a multi-GPU job pass ``comm`` (a dp_nccl_comm_create handle): the K x 4 integer sums are
+    all-reduced with ncclAllReduce on the same stream, so every rank ends with identical centres.
+    Returns (centres, n_iter); the result also carries ``.ties`` (samples exactly equidistant from
+    their two nearest centres, summed over the iterations), ``.shift2`` and ``.empty_iters``."""
+    K = int(centers.shape[0])
     c_host = np.ascontiguousarray(centers, np.float64).copy()
-    c_dev = DeviceBuffer(K * 3 * 8).upload(c_host, stream)
-    own_sums = None
-    if sums_ptr is None:
-        own_sums = DeviceBuffer(K * 4 * 8)
-        sums_ptr = own_sums.ptr
-    shift_dev = DeviceBuffer(8)
-    shift = np.zeros(1, np.float64)
-    it = 0
-    try:
-        for it in range(1, max_iter + 1):
-            check(L.dp_memset(sums_ptr, 0, K * 4 * 8, stream), "dp_memset")
-            check(L.dp_kmeans_accumulate(pixels_ptr, n, c_dev.ptr, K, sums_ptr, stream),
-                  "dp_kmeans_accumulate")
-            if allreduce is not None:
-                allreduce()
-            check(L.dp_kmeans_update(sums_ptr, K, c_dev.ptr, shift_dev.ptr, stream),
-                  "dp_kmeans_update")
-            shift_dev.download(shift, stream)
-            _capi.sync(stream)
-            if shift[0] <= tol:
-                break
-        c_dev.download(c_host, stream)
-        _capi.sync(stream)
-    finally:
-        c_dev.free()
-        shift_dev.free()
-        if own_sums is not None:
-            own_sums.free()
-    return c_host, it
+    n_iter, shift2 = C.c_int(0), C.c_double(0.0)
+    ties, empty = C.c_ulonglong(0), C.c_int(0)
+    check(lib().dp_kmeans_lloyd(pixels_ptr, int(n), c_host.ctypes.data, K, float(tol), int(max_iter),
+                                comm, int(check_every), C.byref(n_iter), C.byref(shift2),
+                                C.byref(ties), C.byref(empty), stream), "dp_kmeans_lloyd")
+    return LloydResult(c_host, int(n_iter.value), float(shift2.value), int(ties.value),
+                       int(empty.value))
 
 
 def kmeans_fit(sample_u8: np.ndarray, k: int, random_state=42) -> Tuple[np.ndarray, int]:

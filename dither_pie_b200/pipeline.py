@@ -92,7 +92,10 @@ class FramePipeline:
     """``plans``: engine.Plan objects with the same source size (one per dither mode applied to
     every frame).  ``output``: "rgb" (colour bytes, [F, out_h, out_w, 3], what the reference's
     frames are), "index" (palette rows, u8 [F, h, w] -- 1 byte per dithered pixel) or "both".
-    """
+
+    ``run(frames)`` processes a clip and returns; ``submit(frames, ...)`` only enqueues (the call
+    returns while the GPU works, consecutive submits keep the three streams busy across calls) and
+    ``flush()`` waits for everything submitted so far."""
 
     SLOTS = 2
 
@@ -113,25 +116,35 @@ class FramePipeline:
         self.idx_frame = [p.h * p.w for p in self.plans]
         self.want_rgb = output in ("rgb", "both")
         self.want_idx = output in ("index", "both")
-        S, B = self.SLOTS, self.B
-        self.s_in, self.s_k, self.s_out = _Stream(), _Stream(), _Stream()
+        S, B, nv = self.SLOTS, self.B, len(self.plans)
+        # one kernel stream per plan: when a launch drains (its last row bands), the next plan's
+        # blocks take over the SMs that fall idle
+        self.s_in, self.s_out = _Stream(), _Stream()
+        self.s_k = [_Stream() for _ in range(nv)]
         self.d_src = [DeviceBuffer(max(B * self.in_frame, 16)) for _ in range(S)]
         self.d_rgb = [[DeviceBuffer(max(B * n, 16)) if self.want_rgb else None for n in self.rgb_frame]
                       for _ in range(S)]
         self.d_idx = [[DeviceBuffer(max(B * n, 16)) if self.want_idx else None for n in self.idx_frame]
                       for _ in range(S)]
         self.ev_in = [_Event() for _ in range(S)]
-        self.ev_src_free = [_Event() for _ in range(S)]
         self.ev_k = [[_Event() for _ in self.plans] for _ in range(S)]
         self.ev_out = [[_Event() for _ in self.plans] for _ in range(S)]
         self.stage_in: List[Optional[PinnedArray]] = [None] * S      # allocated on first use
-        self.stage_rgb = [[None] * len(self.plans) for _ in range(S)]
-        self.stage_idx = [[None] * len(self.plans) for _ in range(S)]
+        self.stage_rgb = [[None] * nv for _ in range(S)]
+        self.stage_idx = [[None] * nv for _ in range(S)]
+        self.n = 0                 # batches submitted so far (slot = n % SLOTS)
+        self.pending = {}          # batch number -> [(stage array, destination view)]
         self.stats = {}
+        self._reset_stats()
+
+    def _reset_stats(self):
+        self._t0 = None
+        self._frames = self._h2d = self._d2h = 0
+        self._pinned_in = self._pinned_out = True
 
     # ------------------------------------------------------------------------------------
     def close(self):
-        for s in (self.s_in, self.s_k, self.s_out):
+        for s in (self.s_in, self.s_out, *self.s_k):
             try:
                 s.sync()
             except Exception:
@@ -144,10 +157,9 @@ class FramePipeline:
             for b in group:
                 if b is not None:
                     b.free()
-        for e in (*self.ev_in, *self.ev_src_free, *[e for r in self.ev_k for e in r],
-                  *[e for r in self.ev_out for e in r]):
+        for e in (*self.ev_in, *[e for r in self.ev_k for e in r], *[e for r in self.ev_out for e in r]):
             e.free()
-        for s in (self.s_in, self.s_k, self.s_out):
+        for s in (self.s_in, self.s_out, *self.s_k):
             s.free()
 
     def __enter__(self):
@@ -162,48 +174,51 @@ class FramePipeline:
             table[slot][v] = PinnedArray((nbytes,), np.uint8)
         return table[slot][v]
 
-    def run(self, frames: np.ndarray, out_rgb: Optional[Sequence[np.ndarray]] = None,
-            out_idx: Optional[Sequence[np.ndarray]] = None, progress=None):
-        """frames: u8 [F, src_h, src_w, 3] on the host.  Returns (rgb_list, idx_list): one array
-        per plan (None for a plane that was not asked for).  ``out_rgb`` / ``out_idx`` supply the
-        destination arrays (pinned ones are written by DMA directly)."""
+    def _drain(self, m):
+        """wait for batch m's copies-out and move staged results to the caller's arrays"""
+        jobs = self.pending.pop(m, None)
+        if not jobs:              # results went to pinned arrays by DMA: nothing to do on the host
+            return
+        slot = m % self.SLOTS
+        for v in range(len(self.plans)):
+            self.ev_out[slot][v].sync()
+        for stage, dest in jobs:
+            np.copyto(dest, stage.array[:dest.nbytes].reshape(dest.shape))
+
+    def submit(self, frames: np.ndarray, out_rgb: Optional[Sequence[np.ndarray]] = None,
+               out_idx: Optional[Sequence[np.ndarray]] = None, progress=None):
+        """Enqueue u8 [F, src_h, src_w, 3] host frames.  ``out_rgb`` / ``out_idx``: one destination
+        array per plan (required for the planes the pipeline produces; pinned ones are written by
+        DMA directly).  The arrays must stay alive and untouched until ``flush()`` returns."""
         L = lib()
-        frames = np.ascontiguousarray(frames, np.uint8)
+        assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"]
         F = int(frames.shape[0])
         assert frames.shape[1:] == (self.src_h, self.src_w, 3), frames.shape
         nv = len(self.plans)
-        if self.want_rgb and out_rgb is None:
-            out_rgb = [np.empty((F, p.out_h, p.out_w, 3), np.uint8) for p in self.plans]
-        if self.want_idx and out_idx is None:
-            out_idx = [np.empty((F, p.h, p.w), np.uint8) for p in self.plans]
+        assert not self.want_rgb or (out_rgb is not None and len(out_rgb) == nv)
+        assert not self.want_idx or (out_idx is not None and len(out_idx) == nv)
+        if F == 0:
+            return
         in_pinned = is_pinned(frames)
         rgb_pinned = [self.want_rgb and is_pinned(out_rgb[v]) for v in range(nv)]
         idx_pinned = [self.want_idx and is_pinned(out_idx[v]) for v in range(nv)]
+        self._pinned_in &= in_pinned
+        self._pinned_out &= all(rgb_pinned[v] or not self.want_rgb for v in range(nv)) and \
+            all(idx_pinned[v] or not self.want_idx for v in range(nv))
+        if self._t0 is None:
+            self._t0 = time.perf_counter()
         S, B = self.SLOTS, self.B
-        nb = (F + B - 1) // B
-        pending = {}          # batch number -> list of (stage array, destination view)
-        t_start = time.perf_counter()
-        h2d = d2h = 0
-
-        def drain(m):
-            """wait for batch m's copies-out and move staged results to the caller's arrays"""
-            jobs = pending.pop(m, None)
-            if not jobs:          # results went to pinned arrays by DMA: nothing to do on the host
-                return
-            slot = m % S
-            for v in range(nv):
-                self.ev_out[slot][v].sync()
-            for stage, dest in jobs:
-                np.copyto(dest, stage.array[:dest.nbytes].reshape(dest.shape))
-
-        for n in range(nb):
-            slot = n % S
-            lo, hi = n * B, min(F, (n + 1) * B)
+        for lo in range(0, F, B):
+            hi = min(F, lo + B)
             cnt = hi - lo
+            n = self.n
+            slot = n % S
             if n >= S:
-                drain(n - S)            # frees this slot's output staging (and its events)
-                self.s_in.wait(self.ev_src_free[slot])
-            # ---- copy in
+                self._drain(n - S)      # frees this slot's output staging
+            # ---- copy in (the kernels of batch n - S have released the source buffer)
+            if n >= S:
+                for v in range(nv):
+                    self.s_in.wait(self.ev_k[slot][v])
             nbytes = cnt * self.in_frame
             if in_pinned:
                 src_host = frames[lo:hi].ctypes.data
@@ -216,19 +231,20 @@ class FramePipeline:
                 np.copyto(st.array[:nbytes].reshape(frames[lo:hi].shape), frames[lo:hi])
                 src_host = st.ptr
             check(L.dp_memcpy_h2d(self.d_src[slot].ptr, src_host, nbytes, self.s_in.h), "h2d")
-            h2d += nbytes
+            self._h2d += nbytes
             self.ev_in[slot].record(self.s_in.h)
-            # ---- kernels
-            self.s_k.wait(self.ev_in[slot])
             jobs = []
             for v, plan in enumerate(self.plans):
+                sk = self.s_k[v]
+                # ---- kernel
+                sk.wait(self.ev_in[slot])
                 if n >= S:
-                    self.s_k.wait(self.ev_out[slot][v])      # the previous result has left the buffers
+                    sk.wait(self.ev_out[slot][v])      # the previous result has left the buffers
                 rgb = self.d_rgb[slot][v]
                 idx = self.d_idx[slot][v]
                 plan.run(self.pal, self.d_src[slot].ptr, cnt, rgb.ptr if rgb else None,
-                         idx.ptr if idx else None, self.s_k.h)
-                self.ev_k[slot][v].record(self.s_k.h)
+                         idx.ptr if idx else None, sk.h)
+                self.ev_k[slot][v].record(sk.h)
                 # ---- copy out
                 self.s_out.wait(self.ev_k[slot][v])
                 if self.want_rgb:
@@ -240,7 +256,7 @@ class FramePipeline:
                         stg = self._stage(self.stage_rgb, slot, v, B * self.rgb_frame[v])
                         check(L.dp_memcpy_d2h(stg.ptr, rgb.ptr, nby, self.s_out.h), "d2h")
                         jobs.append((stg, dest))
-                    d2h += nby
+                    self._d2h += nby
                 if self.want_idx:
                     nby = cnt * self.idx_frame[v]
                     dest = out_idx[v][lo:hi]
@@ -250,20 +266,40 @@ class FramePipeline:
                         stg = self._stage(self.stage_idx, slot, v, B * self.idx_frame[v])
                         check(L.dp_memcpy_d2h(stg.ptr, idx.ptr, nby, self.s_out.h), "d2h")
                         jobs.append((stg, dest))
-                    d2h += nby
+                    self._d2h += nby
                 self.ev_out[slot][v].record(self.s_out.h)
-            self.ev_src_free[slot].record(self.s_k.h)
-            pending[n] = jobs
+            self.pending[n] = jobs
+            self.n += 1
+            self._frames += cnt
             if progress is not None:
                 progress(hi, F)
-        for m in range(max(0, nb - S), nb):
-            drain(m)
-        for s in (self.s_in, self.s_k, self.s_out):
+
+    def flush(self):
+        """Wait until every submitted batch has been delivered to the caller's arrays."""
+        for m in sorted(self.pending):
+            self._drain(m)
+        for s in (self.s_in, self.s_out, *self.s_k):
             s.sync()
-        dt = time.perf_counter() - t_start
-        self.stats = {"frames": F, "seconds": dt, "h2d_bytes": h2d, "d2h_bytes": d2h,
-                      "h2d_gbs": h2d / dt / 1e9 if dt > 0 else 0.0,
-                      "d2h_gbs": d2h / dt / 1e9 if dt > 0 else 0.0,
-                      "in_pinned": in_pinned, "out_pinned": all(rgb_pinned + idx_pinned) if nv else True}
+        dt = (time.perf_counter() - self._t0) if self._t0 is not None else 0.0
+        self.stats = {"frames": self._frames, "seconds": dt, "h2d_bytes": self._h2d, "d2h_bytes": self._d2h,
+                      "h2d_gbs": self._h2d / dt / 1e9 if dt > 0 else 0.0,
+                      "d2h_gbs": self._d2h / dt / 1e9 if dt > 0 else 0.0,
+                      "in_pinned": self._pinned_in, "out_pinned": self._pinned_out}
+        self._reset_stats()
+
+    def run(self, frames: np.ndarray, out_rgb: Optional[Sequence[np.ndarray]] = None,
+            out_idx: Optional[Sequence[np.ndarray]] = None, progress=None):
+        """frames: u8 [F, src_h, src_w, 3] on the host.  Returns (rgb_list, idx_list): one array
+        per plan (None for a plane that was not asked for).  ``out_rgb`` / ``out_idx`` supply the
+        destination arrays (pinned ones are written by DMA directly)."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        F = int(frames.shape[0])
+        nv = len(self.plans)
+        if self.want_rgb and out_rgb is None:
+            out_rgb = [np.empty((F, p.out_h, p.out_w, 3), np.uint8) for p in self.plans]
+        if self.want_idx and out_idx is None:
+            out_idx = [np.empty((F, p.h, p.w), np.uint8) for p in self.plans]
+        self.submit(frames, out_rgb, out_idx, progress)
+        self.flush()
         return (list(out_rgb) if self.want_rgb else [None] * nv,
                 list(out_idx) if self.want_idx else [None] * nv)

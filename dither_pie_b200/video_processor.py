@@ -131,9 +131,33 @@ class VideoProcessor:
             num_workers = self.world
         self.num_workers = max(1, int(num_workers))
         self.progress_callback = progress_callback
+        self._pipes: dict = {}                   # (device, plan key) -> (plan, FramePipeline), reused
+        self._pipes_lock = threading.Lock()
         self.failed_frames: List[int] = []       # indices (in the caller's array) fixed by copying
         self.last_range: Tuple[int, int] = (0, 0)  # frame range this process handled
         self.last_stats: dict = {}
+
+    @staticmethod
+    def _close_entry(entry):
+        plan, pipe = entry[0], entry[1]
+        try:
+            pipe.close()
+        finally:
+            if hasattr(plan, "close"):
+                plan.close()
+
+    def close(self):
+        """Release the cached pipelines (device buffers, streams)."""
+        with self._pipes_lock:
+            entries, self._pipes = list(self._pipes.values()), {}
+        for e in entries:
+            self._close_entry(e)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _report_progress(self, fraction: float, message: str):
         if self.progress_callback:
@@ -190,16 +214,28 @@ class VideoProcessor:
             return []
         H, W = frames.shape[1:3]
         pal = engine.get_palette(ditherer.palette, ditherer.use_gamma)
+        key = (_capi.ensure_device(), mode, repr(sorted(params.items())), H, W, max_size, mult, batch,
+               output, id(pal))
         try:
-            plan = engine.make_plan(mode, params, H, W, max_size, mult, True, max_frames=batch)
+            # plan + pipeline (device buffers, streams, events) are kept between calls: a streamed
+            # clip comes back chunk after chunk with the same geometry
+            with self._pipes_lock:
+                entry = self._pipes.pop(key, None)
+            if entry is None:
+                plan = engine.make_plan(mode, params, H, W, max_size, mult, True, max_frames=batch)
+                entry = (plan, pipeline.FramePipeline([plan], pal, batch, output), pal)
+            pipe = entry[1]
             try:
-                with pipeline.FramePipeline([plan], pal, batch, output) as pipe:
-                    kw = {"out_rgb": [out[lo:hi]]} if output == "rgb" else {"out_idx": [out[lo:hi]]}
-                    pipe.run(frames[lo:hi], progress=report, **kw)
-                    self.last_stats = dict(pipe.stats)
-            finally:
-                if hasattr(plan, "close"):
-                    plan.close()
+                kw = {"out_rgb": [out[lo:hi]]} if output == "rgb" else {"out_idx": [out[lo:hi]]}
+                pipe.run(frames[lo:hi], progress=report, **kw)
+                self.last_stats = dict(pipe.stats)
+            except BaseException:
+                self._close_entry(entry)
+                raise
+            with self._pipes_lock:
+                self._pipes[key] = entry
+                while len(self._pipes) > 4:
+                    self._close_entry(self._pipes.pop(next(iter(self._pipes))))
             return []
         except NotImplementedError:
             raise

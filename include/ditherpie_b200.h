@@ -264,6 +264,40 @@ int dp_kmeans_accumulate(const uint8_t *pixels, int64_t n, const double *centers
 int dp_kmeans_update(const unsigned long long *sums, int K, double *centers, double *shift2,
                      void *stream);
 
+/*
+ * dp_kmeans_lloyd -- the whole Lloyd loop of KMeans.fit (sklearn _kmeans.py:630-760 as called from
+ * dithering_lib.py:1854-1855) from a given initialisation, with the stop test kept on the device:
+ * per iteration one "prepare" launch (centres from the previous sums, squared centre shift, stop
+ * flag, candidate grid for the new centres) and one assignment launch; with a communicator the
+ * K*4+1 integer sums are all-reduced (ncclAllReduce, same stream) between them -- the only
+ * collective of the hot path.  The host reads the flag every `check_every` iterations only.
+ *   pixels        DEVICE u8 [n,3] -- this rank's shard of the pixels
+ *   centers_host  HOST f64 [K,3], in: initial centres, out: final centres (identical on all ranks)
+ *   tol           stop when the squared centre shift is <= tol (sklearn: tol * mean variance)
+ *   nccl_comm     communicator from dp_nccl_comm_create, or NULL (single GPU)
+ *   n_iter, shift2, ties, empty_iters   HOST outputs (any may be NULL): iterations done, last
+ *                 squared shift, number of samples exactly equidistant from their two nearest
+ *                 centres summed over the iterations (a non-zero count marks a run that sklearn's
+ *                 GEMM rounding may resolve differently), iterations that
+ *                 saw an empty cluster (it keeps its centre; sklearn relocates it)
+ * Synchronous: returns when the loop has stopped.
+ */
+int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers_host, int K, double tol,
+                    int max_iter, void *nccl_comm, int check_every, int *n_iter, double *shift2,
+                    unsigned long long *ties, int *empty_iters, void *stream);
+
+/*
+ * NCCL plumbing for the sharded k-means (one process per GPU).  libnccl is resolved at run time
+ * (dlopen: the copy the process already loaded -- e.g. PyTorch's -- or the system one), the
+ * library has no link-time dependency on it.  Rank 0 creates the id and hands the 128 bytes to
+ * the other ranks by any means (torch.distributed broadcast in dither_pie_b200/distributed.py).
+ */
+int dp_nccl_load(const char *path_or_null);
+int dp_nccl_unique_id(void *id128);
+int dp_nccl_comm_create(const void *id128, int rank, int world, void **comm);
+int dp_nccl_comm_destroy(void *comm);
+int dp_nccl_allreduce_u64(void *buf, size_t count, void *comm, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Host-buffer convenience (the end-to-end path a Python caller with numpy arrays uses):
  * copies src to the device, runs the kernel, copies the result back, synchronises.

@@ -369,3 +369,77 @@ def test_single_process_multi_gpu_threads_or_single_gpu_same_result():
     for t in (0, 9):
         assert mismatch(a[t], O.apply_dithering(frames[t], PICO, "error_diffusion",
                                                 {"variant": "sierra_lite"})) == 0
+
+
+# ------------------------------------------------------------------ k-means (device-side Lloyd loop)
+def _lloyd_gpu(pix, init, tol, max_iter, offset=0, **kw):
+    """pixels uploaded at a byte offset (exercises the unaligned head / ragged tail)"""
+    raw = np.zeros(offset + pix.nbytes + 64, np.uint8)
+    raw[offset:offset + pix.nbytes] = pix.reshape(-1)
+    buf = _capi.DeviceBuffer(raw.nbytes).upload(raw)
+    try:
+        return kmeans.lloyd_device(buf.ptr + offset, pix.shape[0], init, tol, max_iter, **kw)
+    finally:
+        buf.free()
+
+
+@pytest.mark.parametrize("K", [2, 5, 16, 32, 40])
+def test_kmeans_lloyd_device_loop_vs_oracle(K):
+    """dp_kmeans_lloyd (stop test on the device, host polls every few iterations) against the
+    oracle's f64 Lloyd: same iteration count, centres to 1e-9 -- for aligned and unaligned pixel
+    pointers, pixel counts that are not multiples of 16, and K beyond the 32-centre fast kernel."""
+    rs = np.random.RandomState(K)
+    for n, off in ((10000, 0), (70001, 3), (517, 7), (15, 1)):
+        pix = np.ascontiguousarray(synth.frame(300, 400, 5).reshape(-1, 3)[:n]) if n > 600 else \
+            rs.randint(0, 256, size=(n, 3)).astype(np.uint8)
+        init = pix[rs.choice(n, K, replace=n < K)].astype(np.float64) + rs.rand(K, 3)
+        X = pix.astype(np.float64)
+        tol = float(np.mean(np.var(X, axis=0)) * 1e-4)
+        ref, it_ref = O.lloyd(X, init, tol, 40)
+        for every in (1, 4):
+            res = _lloyd_gpu(pix, init, tol, 40, offset=off, check_every=every)
+            got, it = res
+            assert it == it_ref, (n, off, every, it, it_ref)
+            assert np.abs(got - ref).max() < 1e-9, (n, off, np.abs(got - ref).max())
+    # iteration budget exhausted (tol < 0 never stops): exactly max_iter iterations
+    pix = synth.frame(120, 160, 9).reshape(-1, 3)
+    init = pix[rs.choice(len(pix), K, replace=False)].astype(np.float64)
+    got, it = _lloyd_gpu(pix, init, -1.0, 7)
+    ref, _ = O.lloyd(pix.astype(np.float64), init, -1.0, 7)
+    assert it == 7 and np.abs(got - ref).max() < 1e-9
+
+
+def test_kmeans_exact_ties_are_counted_and_go_to_the_first_centre():
+    """Samples exactly equidistant from two centres: first index wins (argmin over exact
+    distances) and the device reports how many there were (a non-zero count
+    marks a run sklearn's GEMM rounding may resolve differently)."""
+    centres = np.array([[10.0, 10.0, 10.0], [20.0, 10.0, 10.0], [200.0, 200.0, 200.0]])
+    pix = np.array([[15, 10, 10]] * 700 + [[11, 10, 10]] * 50 + [[19, 10, 10]] * 60 + [[201, 200, 199]] * 9,
+                   np.uint8)                         # 700 exact ties: far more than the per-warp list holds
+    res = _lloyd_gpu(pix, centres, -1.0, 1)
+    got, it = res
+    assert it == 1 and res.ties == 700
+    want0 = (700 * np.array([15, 10, 10.0]) + 50 * np.array([11, 10, 10.0])) / 750
+    assert np.allclose(got[0], want0, atol=1e-12) and np.allclose(got[1], [19, 10, 10])
+    # an empty cluster keeps its centre and is reported
+    res = _lloyd_gpu(pix[:700], centres, -1.0, 2)
+    assert res.empty_iters == 2 and np.allclose(res[0][2], [200, 200, 200])
+
+
+def test_kmeans_4k_full_image_lloyd_vs_oracle():
+    """BASELINE config 3, throughput mode: every one of the 8.29 M pixels of the 4K frame."""
+    img = synth.frame(2160, 3840, 2).reshape(-1, 3)
+    rs = np.random.RandomState(0)
+    init = img[rs.choice(len(img), 16, replace=False)].astype(np.float64)
+    res = _lloyd_gpu(img, init, -1.0, 3)
+    ref = init.copy()
+    for _ in range(3):                      # the oracle's Lloyd step (O.lloyd), in chunks of pixels
+        sums = np.zeros((16, 3), np.int64)
+        cnt = np.zeros(16, np.int64)
+        for lo in range(0, len(img), 1 << 20):
+            X = img[lo:lo + (1 << 20)].astype(np.float64)
+            lab = ((X[:, None, :] - ref[None]) ** 2).sum(axis=2).argmin(axis=1)
+            np.add.at(sums, lab, img[lo:lo + (1 << 20)].astype(np.int64))
+            cnt += np.bincount(lab, minlength=16)
+        ref = np.where(cnt[:, None] > 0, sums / np.maximum(cnt, 1)[:, None], ref)
+    assert res[1] == 3 and np.abs(res[0] - ref).max() < 1e-9
