@@ -36,9 +36,6 @@ namespace {
 constexpr int KM_THREADS = 256;
 constexpr int KM_WARPS = KM_THREADS / 32;
 constexpr int KM_PIX_PER_BLOCK = 16384;  // 255 * 16384 < 2^32: u32 block partials are exact
-constexpr int KM_SCALE_LOG2 = 12;        // fixed-point centres: round(c * 4096)
-constexpr int KM_MARGIN = 800;           // score units; see k_kmeans_accum16
-constexpr int KM_SLOW_CAP = 96;          // per-warp list of undecided pixels (per 512-pixel tile)
 
 struct KmState {
     int done;                  // stop flag (shift <= tol, or the iteration budget is used up)
@@ -116,7 +113,8 @@ __device__ __forceinline__ double km_new_center(const unsigned long long *sums, 
 // Candidate grid + fixed-point centre table for the centres in shared memory `s_c` (K <= 32).
 //   grid[4096]  box = (r>>4) | (g>>4)<<4 | (b>>4)<<8; entry: up to four surviving centres,
 //               ascending, one per byte (32 = none: the pad entry); 0xffffffff = more than four
-//   ent[33]     (round(c*4096) per channel, round(|c|^2 * 2048)); [32] = pad that never wins
+//   ent[4][33]  per candidate slot: (-4 round(1024 c) per channel, round(2048 |c|^2) with the slot number
+//               in its two low bits); [.][32] = pad that never wins
 // A centre is dropped from a box when another centre is strictly nearer at EVERY point of the box:
 // the difference of two squared distances is linear in the point, so its maximum sits at a corner
 // (exact test in double with a 1e-6 margin).  One warp per box, lane = centre.
@@ -124,15 +122,16 @@ __device__ void km_build_grid(const double *s_c, int K, uint32_t *__restrict__ g
                               int first_box, int box_stride)
 {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    if (blockIdx.x == 0 && threadIdx.x <= 32) {
-        int4 e = make_int4(0, 0, 0, 0x3ffffffc);
-        if ((int)threadIdx.x < K) {
-            const double c0 = s_c[3 * threadIdx.x], c1 = s_c[3 * threadIdx.x + 1], c2 = s_c[3 * threadIdx.x + 2];
-            const double sc = (double)(1 << KM_SCALE_LOG2);
-            e.x = (int)llrint(c0 * sc);
-            e.y = (int)llrint(c1 * sc);
-            e.z = (int)llrint(c2 * sc);
-            e.w = (int)llrint((c0 * c0 + c1 * c1 + c2 * c2) * (sc * 0.5));
+    if (blockIdx.x == 0 && threadIdx.x < 4 * 33) {
+        // ent[slot][k]: NEGATED fixed-point centre (multiples of 4) and H with the slot in its low bits
+        const int slot = threadIdx.x / 33, k = threadIdx.x % 33;
+        int4 e = make_int4(0, 0, 0, 0x3ffffffc | slot);   // [32] = pad that never wins
+        if (k < K) {
+            const double c0 = s_c[3 * k], c1 = s_c[3 * k + 1], c2 = s_c[3 * k + 2];
+            e.x = -4 * (int)llrint(c0 * 1024.0);
+            e.y = -4 * (int)llrint(c1 * 1024.0);
+            e.z = -4 * (int)llrint(c2 * 1024.0);
+            e.w = (((int)llrint((c0 * c0 + c1 * c1 + c2 * c2) * 2048.0)) & ~3) | slot;
         }
         ent[threadIdx.x] = e;
     }
@@ -240,42 +239,62 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_grid_only(const double *_
 }
 
 // ---- the assignment pass, K <= 32 --------------------------------------------------------------
-// Fixed-point screen.  With ci = round(c * 4096) and H = round(|c|^2 * 2048) the score
-//   s = H - v . ci  =  2048 * (|v - c|^2 - |v|^2) + err,   |err| <= 0.5 + 3 * 255 * 0.5 = 383
-// orders the candidates like their distances up to 766 score units (0.37 in squared-distance
-// units); the two low bits carry the candidate slot.  If the runner-up is more than KM_MARGIN above
-// the minimum the minimum IS the exact f64 argmin; otherwise (and for boxes with more than four
+// Fixed-point screen.  The centre table holds ci = 4 * round(c * 1024) per channel (NEGATED) and
+// H = round(|c|^2 * 2048) with its two low bits replaced by the candidate's slot number, one copy
+// of the table per slot.  The score
+//   s = H - v . ci  =  2048 * (|v - c|^2 - |v|^2) + err,   |err| <= 3 * 255 * 2 + 4 = 1534
+// orders the candidates like their distances up to 3068 score units (1.5 in squared-distance
+// units), and because v . ci is a multiple of 4 its two low bits still name the slot: the minimum
+// of the four scores carries its own index.  If the runner-up is more than KM_MARGIN above the
+// minimum the minimum IS the exact f64 argmin; otherwise (and for boxes with more than four
 // candidates) the pixel goes to the warp's list and is resolved exactly in f64 over all K centres
 // (strict '<', first index -- what sklearn's argmin over exact distances gives).
+//
+// Sums without atomics and without data-dependent branches: every LANE owns a private set of bins
+// in shared memory, bins[label][lane] = (r | g << 16, b | n << 16) -- consecutive lanes are
+// consecutive 8-byte words, so the accesses are conflict-free -- and adds each of its pixels with
+// one 64-bit load and store.  Undecided pixels add to a dummy row.  Every 16 tiles (256 pixels per
+// lane, the most the 16-bit fields can hold) the warp folds the bins into lane k's 64-bit totals
+// of centre k with warp reductions.
+constexpr int KM_MARGIN = 3200;          // score units, see above
+constexpr int KM_SLOW_CAP = 96;          // per-warp list of undecided pixels (per 512-pixel tile)
+constexpr int KM_DRAIN_TILES = 16;
+
 struct KmWarpShared {
-    unsigned hist[32][2];            // per-centre partial sums of <= 256 pixels: r | g<<16, b | n<<16
     unsigned slow[KM_SLOW_CAP];      // pixel offsets inside the tile of the undecided pixels
     unsigned nslow;
+    unsigned pad[3];
 };
 
+template <int KP>   // bins rows = KP + 1 (KP = 16 or 32 centres, + the dummy row)
 __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
     const uint8_t *__restrict__ px, long long n, const double *__restrict__ centers, int K,
     unsigned long long *__restrict__ sums, const uint32_t *__restrict__ grid, const int4 *__restrict__ ent,
     const KmState *__restrict__ state)
 {
     if (state && state->done) return;
-    __shared__ double s_c[32 * 3];
-    __shared__ __align__(16) int4 s_ent[33];
-    __shared__ uint32_t s_grid[4096];
-    __shared__ KmWarpShared s_w[KM_WARPS];
-    __shared__ unsigned long long s_tot[32 * 4 + 1];
+    extern __shared__ __align__(16) unsigned char km_smem[];
+    uint2 *s_bins = reinterpret_cast<uint2 *>(km_smem);                         // [warps][KP+1][32]
+    uint32_t *s_grid = reinterpret_cast<uint32_t *>(s_bins + KM_WARPS * (KP + 1) * 32);   // [4096]
+    int4 *s_ent = reinterpret_cast<int4 *>(s_grid + 4096);                      // [4][33]
+    double *s_c = reinterpret_cast<double *>(s_ent + 4 * 33);                   // [32*3]
+    KmWarpShared *s_w = reinterpret_cast<KmWarpShared *>(s_c + 32 * 3);         // [warps]
+    unsigned long long *s_tot = reinterpret_cast<unsigned long long *>(s_w + KM_WARPS);   // [32*4+1]
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     if (tid < K * 3) s_c[tid] = centers[tid];
-    if (tid <= 32) s_ent[tid] = ent[tid];
+    if (tid < 4 * 33) s_ent[tid] = ent[tid];
     for (int i = tid; i < 4096; i += KM_THREADS) s_grid[i] = grid[i];
+    for (int i = tid; i < KM_WARPS * (KP + 1) * 32; i += KM_THREADS) s_bins[i] = make_uint2(0u, 0u);
     if (tid < 32 * 4 + 1) s_tot[tid] = 0ull;
     KmWarpShared &ws = s_w[wib];
-    ws.hist[lane][0] = ws.hist[lane][1] = 0u;
     if (lane == 0) ws.nslow = 0u;
     __syncthreads();
 
     const unsigned FULL = 0xffffffffu;
     const unsigned ent_a = (unsigned)__cvta_generic_to_shared(s_ent);
+    const unsigned grid_a = (unsigned)__cvta_generic_to_shared(s_grid);
+    // this lane's column of bins: row k at bins_a + 256 * k
+    const unsigned bins_a = (unsigned)__cvta_generic_to_shared(s_bins + (size_t)wib * (KP + 1) * 32 + lane);
     unsigned long long ar = 0, ag = 0, ab = 0, an = 0;     // totals of centre `lane`
     unsigned nties = 0;
 
@@ -300,6 +319,23 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
             ab += (unsigned)b;
             an += 1;
         }
+    };
+    // fold the lanes' private bins into the 64-bit totals (lane k owns centre k)
+    auto drain = [&]() {
+        for (int k = 0; k < K; ++k) {
+            uint2 bin;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bin.x), "=r"(bin.y) : "r"(bins_a + 256u * k));
+            asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(bins_a + 256u * k), "r"(0u) : "memory");
+            const unsigned sr = __reduce_add_sync(FULL, bin.x & 0xffffu), sg = __reduce_add_sync(FULL, bin.x >> 16);
+            const unsigned sb = __reduce_add_sync(FULL, bin.y & 0xffffu), sn = __reduce_add_sync(FULL, bin.y >> 16);
+            if (lane == k) {
+                ar += sr;
+                ag += sg;
+                ab += sb;
+                an += sn;
+            }
+        }
+        asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(bins_a + 256u * KP), "r"(0u) : "memory");   // dummy row
     };
 
     // head: pixels in front of the first 16-byte boundary; body: whole 16-pixel groups; tail
@@ -334,87 +370,56 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
         }
     };
     fetch(t);
+    int since_drain = 0;
     for (; t < ntiles; t += wstride) {
         unsigned w[12] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w, nx2.x, nx2.y, nx2.z, nx2.w};
         const bool live = t * 32 + lane < ngroups;
         fetch(t + wstride);                                   // next tile's loads fly during this one
+        unsigned slowmask = live ? 0u : 0xffffu;              // dead lanes: every pixel to the dummy row
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            int cur = -1;
-            unsigned accA = 0, accB = 0;
+        for (int j = 0; j < 16; ++j) {                        // pixel j of the lane's 16
+            const int wi = (3 * j) >> 2, sh = ((3 * j) & 3) * 8;
+            const unsigned v = sh == 0 ? w[wi] : __funnelshift_r(w[wi], w[wi + (wi < 11 ? 1 : 0)], sh);
+            // box = (r>>4) | (g>>4)<<4 | (b>>4)<<8, as a byte offset into the u32 grid
+            const unsigned a4 = (v >> 4) & 0x0f0f0fu;
+            unsigned e;
+            asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(__dp4a(a4, 0x00004004u, grid_a) + ((a4 >> 6) & 0x3c00u)));
+            const int vr = (int)__byte_perm(v, 0u, 0x4440), vg = (int)__byte_perm(v, 0u, 0x4441),
+                      vb = (int)__byte_perm(v, 0u, 0x4442);
+            int s[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int j = half * 8 + q;                   // pixel j of the lane's 16
-                const int wi = (3 * j) >> 2, sh = ((3 * j) & 3) * 8;
-                const unsigned v = (sh == 0 ? w[wi] : __funnelshift_r(w[wi], w[wi + (wi < 11 ? 1 : 0)], sh)) & 0xffffffu;
-                // box = (r>>4) | (g>>4)<<4 | (b>>4)<<8, as a byte offset into the u32 grid
-                const unsigned a4 = (v >> 4) & 0x0f0f0fu;
-                const unsigned e = *reinterpret_cast<const uint32_t *>(
-                    reinterpret_cast<const char *>(s_grid) + (__dp4a(a4, 0x00004004u, 0u) + ((a4 >> 6) & 0x3c00u)));
-                const unsigned vr = v & 255u, vg = (v >> 8) & 255u, vb = v >> 16;
-                int s[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    int4 en;
-                    const unsigned a = __dp4a(e, 0x10u << (8 * c), ent_a);   // ent_a + 16 * byte c of e
-                    asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(en.x), "=r"(en.y), "=r"(en.z), "=r"(en.w) : "r"(a));
-                    s[c] = ((en.w - (int)vr * en.x - (int)vg * en.y - (int)vb * en.z) & ~3) | c;
-                }
-                const int lo01 = min(s[0], s[1]), hi01 = max(s[0], s[1]);
-                const int lo23 = min(s[2], s[3]), hi23 = max(s[2], s[3]);
-                const int m1 = min(lo01, lo23);
-                const int m2 = min(max(lo01, lo23), min(hi01, hi23));
-                const bool slow = (e == 0xffffffffu) || (m2 - m1 <= KM_MARGIN);
-                const int label = (int)((e >> (8 * (m1 & 3))) & 255u);
-                if (live) {
-                    if (slow) {
-                        const unsigned pos = atomicAdd(&ws.nslow, 1u);
-                        if (pos < KM_SLOW_CAP) ws.slow[pos] = (unsigned)(lane * 16 + j);
-                    } else {
-                        if (label != cur) {
-                            if (cur >= 0) {
-                                atomicAdd(&ws.hist[cur][0], accA);
-                                atomicAdd(&ws.hist[cur][1], accB);
-                            }
-                            cur = label;
-                            accA = accB = 0;
-                        }
-                        accA += vr | (vg << 16);
-                        accB += vb | 0x10000u;
-                    }
-                }
+            for (int c = 0; c < 4; ++c) {
+                int4 en;   // slot c's copy of the table: ent_a + 528 * c + 16 * byte c of e
+                const unsigned a = __dp4a(e, 0x10u << (8 * c), ent_a + 528u * c);
+                asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(en.x), "=r"(en.y), "=r"(en.z), "=r"(en.w) : "r"(a));
+                s[c] = vb * en.z + (vg * en.y + (vr * en.x + en.w));
             }
-            // end of the half tile (<= 256 pixels per warp): merge the lanes' open runs.  When every
-            // lane ended in the same centre (the common case in images) two warp reductions do it.
-            const int c0 = __shfl_sync(FULL, cur, 0);
-            if (__all_sync(FULL, cur == c0)) {
-                if (c0 >= 0) {
-                    const unsigned ta = __reduce_add_sync(FULL, accA), tb = __reduce_add_sync(FULL, accB);
-                    if (lane == c0) {
-                        ar += ta & 0xffffu;
-                        ag += ta >> 16;
-                        ab += tb & 0xffffu;
-                        an += tb >> 16;
-                    }
-                }
-            } else if (cur >= 0) {
-                atomicAdd(&ws.hist[cur][0], accA);
-                atomicAdd(&ws.hist[cur][1], accB);
-            }
-            __syncwarp();
-            {
-                const unsigned ha = ws.hist[lane][0], hb = ws.hist[lane][1];
-                if (ha | hb) {
-                    ar += ha & 0xffffu;
-                    ag += ha >> 16;
-                    ab += hb & 0xffffu;
-                    an += hb >> 16;
-                    ws.hist[lane][0] = ws.hist[lane][1] = 0u;
-                }
-            }
-            __syncwarp();
+            const int lo01 = min(s[0], s[1]), hi01 = max(s[0], s[1]);
+            const int lo23 = min(s[2], s[3]), hi23 = max(s[2], s[3]);
+            const int m1 = min(lo01, lo23);
+            const int m2 = min(max(lo01, lo23), min(hi01, hi23));
+            const bool slow = (e == 0xffffffffu) || (m2 - m1 <= KM_MARGIN) || !live;
+            const unsigned label = slow ? (unsigned)KP : __byte_perm(e, 0u, ((unsigned)m1 & 3u) | 0x4440u);
+            if (slow) slowmask |= 1u << j;
+            // bins[label][lane] += (r | g << 16, b | 1 << 16)
+            const unsigned ba = bins_a + 256u * label;
+            uint2 bin;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bin.x), "=r"(bin.y) : "r"(ba));
+            bin.x += __byte_perm(v, 0u, 0x4140);
+            bin.y += __byte_perm(v, 1u, 0x7472);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ba), "r"(bin.x), "r"(bin.y) : "memory");
         }
-        // undecided pixels of the tile: the warp resolves them one by one
+        // undecided pixels of the tile: onto the warp's list, then the warp resolves them one by one
+        if (live && slowmask) {
+            unsigned m = slowmask;
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const unsigned pos = atomicAdd(&ws.nslow, 1u);
+                if (pos < KM_SLOW_CAP) ws.slow[pos] = (unsigned)(lane * 16 + j);
+            }
+        }
+        __syncwarp();
         const unsigned ns = ws.nslow;
         if (ns) {
             const uint8_t *tile_px = px + 3 * (head + t * 512);
@@ -424,10 +429,8 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
                     resolve((unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16));
                 }
             } else {
-                // list overflow (pathological inputs): the entries beyond the capacity were not
-                // recorded, so re-screen is impossible -- redo the WHOLE tile exactly instead.
-                // The decided pixels were already accumulated, so only the undecided ones may be
-                // added: recompute the screen decision per pixel, cooperatively.
+                // list overflow (pathological inputs): redo the tile's undecided pixels by
+                // re-screening every pixel of the tile, cooperatively
                 const long long base = head + t * 512;
                 const long long lim = min((long long)512, tail0 - base);
                 for (long long i = 0; i < lim; ++i) {
@@ -437,8 +440,8 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
                     const unsigned e = s_grid[(a4 & 15u) | ((a4 >> 4) & 0xf0u) | ((a4 >> 8) & 0xf00u)];
                     int sc[4];
                     for (int c = 0; c < 4; ++c) {
-                        const int4 en = s_ent[(e >> (8 * c)) & 255u];
-                        sc[c] = ((en.w - (int)(v & 255u) * en.x - (int)((v >> 8) & 255u) * en.y - (int)(v >> 16) * en.z) & ~3) | c;
+                        const int4 en = s_ent[33 * c + ((e >> (8 * c)) & 255u) % 33u];
+                        sc[c] = (int)(v >> 16) * en.z + ((int)((v >> 8) & 255u) * en.y + ((int)(v & 255u) * en.x + en.w));
                     }
                     const int lo01 = min(sc[0], sc[1]), hi01 = max(sc[0], sc[1]);
                     const int lo23 = min(sc[2], sc[3]), hi23 = max(sc[2], sc[3]);
@@ -450,7 +453,12 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
             if (lane == 0) ws.nslow = 0u;
             __syncwarp();
         }
+        if (++since_drain == KM_DRAIN_TILES) {
+            drain();
+            since_drain = 0;
+        }
     }
+    drain();
     // block totals first (the global accumulators are a few addresses shared by every block: one
     // flush per block keeps the L2 atomic unit out of the critical path)
     if (lane < K && an) {
@@ -463,6 +471,12 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
     __syncthreads();
     if (tid < K * 4 && s_tot[tid]) atomicAdd(&sums[tid], s_tot[tid]);
     if (tid == 0 && s_tot[32 * 4]) atomicAdd(&sums[4 * K], s_tot[32 * 4]);
+}
+
+inline size_t km_accum_smem(int KP)
+{
+    return (size_t)KM_WARPS * (KP + 1) * 32 * 8 + 4096 * 4 + 4 * 33 * 16 + 32 * 3 * 8 + KM_WARPS * sizeof(KmWarpShared) +
+           (32 * 4 + 1) * 8;
 }
 
 __global__ void k_kmeans_update(const unsigned long long *__restrict__ sums, int K,
@@ -501,25 +515,42 @@ int km_scratch(KmScratch **out)
     KmScratch &s = g_km_scratch[dev];
     if (!s.grid) {
         DP_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.grid), 4096 * sizeof(uint32_t)));
-        DP_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.ent), 33 * sizeof(int4)));
+        DP_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.ent), 4 * 33 * sizeof(int4)));
     }
     *out = &s;
     return 0;
 }
 
-int km_accum_grid_size(long long n)
+// launch of the assignment pass: bins for 16 or 32 centres, as many resident blocks as fit
+template <int KP>
+int km_launch_accum_kp(const uint8_t *pixels, long long n, const double *centers, int K, unsigned long long *sums,
+                       const uint32_t *grid, const int4 *ent, const KmState *state, cudaStream_t st)
 {
-    static thread_local int per_sm = 0;
-    if (!per_sm) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_kmeans_accum16, KM_THREADS, 0) != cudaSuccess ||
-            per_sm < 1)
-            per_sm = 2;
+    static thread_local int per_sm[64] = {0};
+    int dev = 0;
+    DP_CUDA(cudaGetDevice(&dev));
+    const size_t smem = km_accum_smem(KP);
+    if (dev >= 0 && dev < 64 && !per_sm[dev]) {
+        DP_CUDA(cudaFuncSetAttribute(k_kmeans_accum16<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int ps = 0;
+        DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, k_kmeans_accum16<KP>, KM_THREADS, smem));
+        per_sm[dev] = ps < 1 ? 1 : ps;
     }
-    const long long cap = (long long)dp_num_sms() * per_sm;
+    const long long cap = (long long)dp_num_sms() * (dev >= 0 && dev < 64 ? per_sm[dev] : 1);
     const long long tiles = (n / 16 + 31) / 32;
     long long blocks = (tiles + KM_WARPS - 1) / KM_WARPS;
     if (blocks < 1) blocks = 1;
-    return (int)(blocks < cap ? blocks : cap);
+    k_kmeans_accum16<KP><<<(int)(blocks < cap ? blocks : cap), KM_THREADS, smem, st>>>(pixels, n, centers, K, sums, grid,
+                                                                                       ent, state);
+    DP_LAUNCH_CHECK();
+    return 0;
+}
+
+int km_launch_accum(const uint8_t *pixels, long long n, const double *centers, int K, unsigned long long *sums,
+                    const uint32_t *grid, const int4 *ent, const KmState *state, cudaStream_t st)
+{
+    return K <= 16 ? km_launch_accum_kp<16>(pixels, n, centers, K, sums, grid, ent, state, st)
+                   : km_launch_accum_kp<32>(pixels, n, centers, K, sums, grid, ent, state, st);
 }
 
 // ---- NCCL, resolved at run time (the library has no link-time dependency on it) -----------------
@@ -621,10 +652,8 @@ extern "C" int dp_kmeans_accumulate(const uint8_t *pixels, int64_t n, const doub
         KmScratch *sc = nullptr;
         if (km_scratch(&sc)) return 1;
         k_kmeans_grid_only<<<512, KM_THREADS, 0, st>>>(centers, K, sc->grid, sc->ent);
-        k_kmeans_accum16<<<km_accum_grid_size(n), KM_THREADS, 0, st>>>(pixels, n, centers, K, sums, sc->grid,
-                                                                        sc->ent, nullptr);
         DP_LAUNCH_CHECK();
-        return 0;
+        return km_launch_accum(pixels, n, centers, K, sums, sc->grid, sc->ent, nullptr, st);
     }
     long long cap = (long long)dp_num_sms() * 8;
     long long chunks = (n + KM_PIX_PER_BLOCK - 1) / KM_PIX_PER_BLOCK;
@@ -659,7 +688,7 @@ extern "C" int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers
     if (check_every < 1) check_every = 4;
     const size_t nsum = (size_t)K * 4 + 1;
     const size_t off_c = 0, off_s = off_c + 2 * (size_t)K * 3 * 8, off_state = off_s + 2 * nsum * 8,
-                 off_grid = off_state + 64, off_ent = off_grid + 4096 * 4, total = off_ent + 33 * 16;
+                 off_grid = off_state + 64, off_ent = off_grid + 4096 * 4, total = off_ent + 4 * 33 * 16;
     char *ws = nullptr;
     DP_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), total, st));
     double *cbuf[2] = {reinterpret_cast<double *>(ws + off_c), reinterpret_cast<double *>(ws + off_c) + (size_t)K * 3};
@@ -686,7 +715,6 @@ extern "C" int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers
     } while (0)
     KM_TRY(cudaMemsetAsync(ws + off_s, 0, 2 * nsum * 8 + 64, st));
     KM_TRY(cudaMemcpyAsync(cbuf[0], centers_host, (size_t)K * 3 * 8, cudaMemcpyHostToDevice, st));
-    const int agrid = km_accum_grid_size(n);
     const long long cap = (long long)dp_num_sms() * 8;
     const long long chunks = (n + KM_PIX_PER_BLOCK - 1) / KM_PIX_PER_BLOCK;
     const int ggrid = (int)(chunks < cap ? (chunks < 1 ? 1 : chunks) : cap);
@@ -701,10 +729,10 @@ extern "C" int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers
                 it == 1 ? cbuf[0] : cbuf[it & 1], cbuf[(it - 1) & 1], it > 1 ? sums[(it - 1) & 1] : nullptr,
                 sums[it & 1], K, tol, 0, state, grid, ent);
             if (n > 0) {
-                if (K <= 32)
-                    k_kmeans_accum16<<<agrid, KM_THREADS, 0, st>>>(pixels, n, cbuf[(it - 1) & 1], K, sums[it & 1], grid,
-                                                                   ent, state);
-                else
+                if (K <= 32) {
+                    if (km_launch_accum(pixels, n, cbuf[(it - 1) & 1], K, sums[it & 1], grid, ent, state, st))
+                        return finish(1);
+                } else
                     k_kmeans_accumulate<<<ggrid, KM_THREADS, 0, st>>>(pixels, n, cbuf[(it - 1) & 1], K, sums[it & 1],
                                                                       state);
             }
