@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(256) k_thr_masks(const int4 *__restrict__ coef
 {
     __shared__ int4 s_coef[DP_MAX_COLORS];
     __shared__ uint32_t s_mask[8];
-    for (int i = threadIdx.x; i < K; i += 256) s_coef[i] = coef[i];
+    for (int i = threadIdx.x; i < K; i += blockDim.x) s_coef[i] = coef[i];   // (launched with 64..256 threads)
     if (threadIdx.x < 8) s_mask[threadIdx.x] = 0;
     __syncthreads();
     const int n = 256 >> shift;            // cells per axis
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) k_thr_masks(const int4 *__restrict__ coef
     const int cr = cell / (n * n), cg = (cell / n) % n, cb = cell % n;
     uint32_t local[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const int total = side * side * side;
-    for (int t = threadIdx.x; t < total; t += 256) {
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
         const int r = (cr << shift) + t / (side * side);
         const int g = (cg << shift) + (t / side) % side;
         const int b = (cb << shift) + t % side;
@@ -516,6 +516,88 @@ bool build_compact_table(const int4 *d_coef, int K, int nearest_only, int slots,
     return true;
 }
 
+// The same tables for 31 <= K <= 256 (format: PalDev::thr4_wide in dp_common.cuh): plain row
+// numbers, `slots` distinct ascending rows per entry (filled up with non-candidates), sub-cell
+// entries for the cells with more candidates.
+bool build_compact_table_wide(const int4 *d_coef, int K, int nearest_only, int slots, void **out_table,
+                              void **out_sub, int *out_nsub)
+{
+    std::vector<uint32_t> m3((size_t)32768 * 8);
+    uint32_t *dm = nullptr;
+    bool ok = cudaMalloc(&dm, (size_t)32768 * 32) == cudaSuccess;
+    if (ok) {
+        k_thr_masks<<<32768, 256>>>(d_coef, K, 3, dm, nearest_only);
+        ok = cudaMemcpy(m3.data(), dm, (size_t)32768 * 32, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    if (dm) cudaFree(dm);
+    if (!ok) return false;
+    const uint32_t marker_top = slots == 4 ? 0u : 0u;   // markers have a top byte of 0
+    auto pack = [K, slots](const uint32_t *mask, bool &over) -> uint32_t {
+        int rows[DP_MAX_COLORS];
+        int cnt = 0;
+        for (int i = 0; i < K; ++i)
+            if (mask[i >> 5] >> (i & 31) & 1u) rows[cnt++] = i;
+        over = cnt > slots;
+        if (over) return 0u;
+        for (int i = 0; cnt < slots && i < K; ++i) {      // fill up with the lowest non-candidates
+            bool have = false;
+            for (int j = 0; j < cnt; ++j) have = have || rows[j] == i;
+            if (!have) rows[cnt++] = i;
+        }
+        std::sort(rows, rows + slots);
+        uint32_t e = 0;
+        for (int j = 0; j < slots; ++j) e |= (uint32_t)rows[j] << (8 * j);
+        if (slots == 3) e |= 0xff000000u;
+        return e;
+    };
+    (void)marker_top;
+    std::vector<uint32_t> t4(32768), sub;
+    std::vector<int> ocell;
+    for (int c = 0; c < 32768; ++c) {
+        bool over;
+        t4[c] = pack(&m3[(size_t)c * 8], over);
+        if (over) {
+            t4[c] = (uint32_t)ocell.size();     // < 0x03000000 (and < 0xff000000): the marker
+            ocell.push_back(c);
+        }
+    }
+    if (!ocell.empty()) {
+        uint32_t *dm2 = nullptr;
+        std::vector<uint32_t> m2((size_t)262144 * 8);
+        ok = cudaMalloc(&dm2, (size_t)262144 * 32) == cudaSuccess;
+        if (ok) {
+            k_thr_masks<<<262144, 64>>>(d_coef, K, 2, dm2, nearest_only);
+            ok = cudaMemcpy(m2.data(), dm2, (size_t)262144 * 32, cudaMemcpyDeviceToHost) == cudaSuccess;
+        }
+        if (dm2) cudaFree(dm2);
+        if (!ok) return false;
+        sub.resize(ocell.size() * 8);
+        for (size_t n = 0; n < ocell.size(); ++n) {
+            const int c = ocell[n], cr = c >> 10, cg = (c >> 5) & 31, cb = c & 31;
+            for (int s8 = 0; s8 < 8; ++s8) {
+                const int fr = cr * 2 + (s8 >> 2), fg = cg * 2 + ((s8 >> 1) & 1), fb = cb * 2 + (s8 & 1);
+                bool over;
+                sub[n * 8 + s8] = pack(&m2[((size_t)(fr * 64 + fg) * 64 + fb) * 8], over);   // 0 if still crowded
+            }
+        }
+    }
+    void *d4 = nullptr, *dsub = nullptr;
+    ok = cudaMalloc(&d4, 32768 * 4) == cudaSuccess &&
+         cudaMemcpy(d4, t4.data(), 32768 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMalloc(&dsub, sub.size() * 4 + 16) == cudaSuccess &&
+         (sub.empty() ||
+          cudaMemcpy(dsub, sub.data(), sub.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess);
+    if (!ok) {
+        if (d4) cudaFree(d4);
+        if (dsub) cudaFree(dsub);
+        return false;
+    }
+    *out_table = d4;
+    *out_sub = dsub;
+    *out_nsub = (int)ocell.size();
+    return true;
+}
+
 template <typename T>
 size_t put(std::vector<uint8_t> &buf, const T *src, size_t n, size_t align = 16)
 {
@@ -724,6 +806,29 @@ extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out
                 d.near3_nsub = ns;
                 h->near3_table = t;
                 h->near3_sub = sb;
+            }
+        } else {
+            // 31..256 colours: the same kernel with plain row numbers (PalDev::thr4_wide)
+            void *t = nullptr, *sb = nullptr, *t3 = nullptr, *sb3 = nullptr;
+            int ns = 0, ns3 = 0;
+            if (build_compact_table_wide(d.coef, K, 0, 4, &t, &sb, &ns) &&
+                build_compact_table_wide(d.coef, K, 1, 3, &t3, &sb3, &ns3)) {
+                d.thr4_table = static_cast<const uint32_t *>(t);
+                d.thr4_sub = static_cast<const uint32_t *>(sb);
+                d.thr4_nsub = ns;
+                d.near3_table = static_cast<const uint32_t *>(t3);
+                d.near3_sub = static_cast<const uint32_t *>(sb3);
+                d.near3_nsub = ns3;
+                d.thr4_wide = 1;
+                h->thr4_table = t;
+                h->thr4_sub = sb;
+                h->near3_table = t3;
+                h->near3_sub = sb3;
+            } else {
+                if (t) cudaFree(t);
+                if (sb) cudaFree(sb);
+                if (t3) cudaFree(t3);
+                if (sb3) cudaFree(sb3);
             }
         }
     }

@@ -80,6 +80,16 @@ struct PalDev {
     const uint32_t *near3_table;  // [32768] or null
     const uint32_t *near3_sub;    // [8 * near3_nsub]
     int near3_nsub;
+    // thr4_wide = 1 (31 <= K <= 256): the compact tables hold plain row numbers, one per byte.
+    //   top-2 table: four DISTINCT rows in ascending order (a cell with fewer candidates is filled
+    //     up with other rows -- harmless: a row that is not a candidate is never among the two
+    //     nearest anywhere in the cell), so the top byte is >= 3; an entry < 0x03000000 says "more
+    //     than four candidates" and holds the number n of its eight sub-cell entries in thr4_sub
+    //     (same format; a sub-cell entry < 0x03000000 still has more than four: exact path).
+    //   nearest table: three distinct ascending rows in bytes 0..2, top byte 0xff; an entry
+    //     < 0xff000000 is the refinement marker.
+    //   The sub-cell entries stay in global memory (L1).
+    int thr4_wide;
     // Exception table of the byte colours with an exact distance tie among their three nearest
     // rows (integral palettes): scipy's answers, replayed once at palette creation.
     //   x = colour (r | g<<8 | b<<16) | nearest row of query(k=1) << 24

@@ -72,6 +72,7 @@ struct ThreshParams {
     FastDiv dwm, dnpix;
     FastDiv dspr, dh;   // geom2: strips per row, rows per frame
     int geom_table;     // geom2: the compact candidate tables exist (K <= 30, integral, no LUT)
+    int wide;           // v4: the 31..256-colour table format (PalDev::thr4_wide)
 };
 
 // IGN threshold (:541-549): f32, one rounding per numpy ufunc, no contraction.
@@ -540,10 +541,11 @@ __global__ void __launch_bounds__(THREADS) k_thresh_fast(const ThreshParams p)
 // ---------------------------------------------------------------------------------------
 // 24 warps per SM for the threshold kinds (80 registers); plain quantisation needs fewer
 // registers and no matrix, so 32 warps fit beside the table
-template <int KIND>
+template <int KIND, bool WIDE = false>
 __host__ __device__ constexpr int v4_threads()
 {
-    return KIND == DP_THRESH_NONE ? 1024 : 768;
+    // (the 256-row tables of the wide format leave room for 31 warps beside the candidate table)
+    return KIND == DP_THRESH_NONE ? (WIDE ? 992 : 1024) : 768;
 }
 
 __device__ __forceinline__ unsigned smem_u32(const void *p)
@@ -616,9 +618,14 @@ struct V4Ctx {
 // the work.
 // TG = the table is read from global memory through L1 (kernels that cannot afford 128 KB of
 // shared memory for it, e.g. the fused geometry kernel) instead of from shared memory.
-template <int KIND, bool TG = false>
+// WIDE = the 31..256-colour table format (PalDev::thr4_wide): plain row numbers, fillers instead of
+// pad rows, sub-cell entries in global memory, and a factor test that tolerates the row bits in
+// the keys (see below).
+template <int KIND, bool TG = false, bool WIDE = false>
 __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float thr, bool &slow)
 {
+    constexpr unsigned AW = WIDE ? 8u : 1u;            // byte j of the entry -> row offset in the int2 array
+    constexpr unsigned MARK4 = WIDE ? 0x03000000u : 0xf8000000u;
     // byte offset of the pixel's cell in the u32 table: (r>>3)*4096 + (g>>3)*128 + (b>>3)*4
     const unsigned a5 = (v >> 3) & 0x1f1f1fu;
     const unsigned ta = (a5 & 0x1fu) * 4096u + __dp4a(a5, 0x00048000u, TG ? 0u : c.table_a);
@@ -627,30 +634,30 @@ __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float th
     if (KIND == DP_THRESH_NONE) {
         // plain quantisation: the table holds the rows that can be NEAREST in the cell, three
         // slots; the answer is the smallest key unless the two smallest tie
-        if (e >= 0xf8000000u) {
+        if (WIDE ? (e < 0xff000000u) : (e >= 0xf8000000u)) {
             const unsigned sc = ((v >> 2) & 1u) * 4u + ((v >> 10) & 1u) * 2u + ((v >> 18) & 1u);
             e = __ldg(c.sub_g + (e & 0xffffu) * 8u + sc);
         }
-        const int2 q0 = lds_s32x2(__dp4a(e, 0x00000001u, c.ent_a));
-        const int2 q1 = lds_s32x2(__dp4a(e, 0x00000100u, c.ent_a));
-        const int2 q2 = lds_s32x2(__dp4a(e, 0x00010000u, c.ent_a));
+        const int2 q0 = lds_s32x2(__dp4a(e, 0x00000001u * AW, c.ent_a));
+        const int2 q1 = lds_s32x2(__dp4a(e, 0x00000100u * AW, c.ent_a));
+        const int2 q2 = lds_s32x2(__dp4a(e, 0x00010000u * AW, c.ent_a));
         const int k0 = q0.y - 512 * (int)__dp4a(v, (unsigned)q0.x, 0u);
         const int k1 = q1.y - 512 * (int)__dp4a(v, (unsigned)q1.x, 0u);
         const int k2 = q2.y - 512 * (int)__dp4a(v, (unsigned)q2.x, 0u);
         const int m1 = min(min(k0, k1), k2);
         const int m3 = max(max(k0, k1), k2);
         const int m2 = (int)((unsigned)k0 + (unsigned)k1 + (unsigned)k2 - (unsigned)m1 - (unsigned)m3);
-        slow = (e >= 0xf8000000u) || ((unsigned)(m1 ^ m2) < 256u);
+        slow = (WIDE ? (e < 0xff000000u) : (e >= 0xf8000000u)) || ((unsigned)(m1 ^ m2) < 256u);
         return (unsigned)m1 & 255u;
     }
-    if (e >= 0xf8000000u) {   // more than four candidates in the 8^3 cell: refine to the 4^3 sub-cell
+    if (WIDE ? (e < MARK4) : (e >= MARK4)) {   // more than four candidates in the 8^3 cell: refine to the 4^3 sub-cell
         const unsigned sc = ((v >> 2) & 1u) * 4u + ((v >> 10) & 1u) * 2u + ((v >> 18) & 1u);
-        e = TG ? __ldg(c.subt_g + (e & 0xffffu) * 8u + sc) : lds_u32(c.sub_a + ((e & 0xffffu) * 8u + sc) * 4u);
+        e = (TG || WIDE) ? __ldg(c.subt_g + (e & 0xffffu) * 8u + sc) : lds_u32(c.sub_a + ((e & 0xffffu) * 8u + sc) * 4u);
     }
-    const int2 q0 = lds_s32x2(__dp4a(e, 0x00000001u, c.ent_a));   // base + byte j of e
-    const int2 q1 = lds_s32x2(__dp4a(e, 0x00000100u, c.ent_a));
-    const int2 q2 = lds_s32x2(__dp4a(e, 0x00010000u, c.ent_a));
-    const int2 q3 = lds_s32x2(__dp4a(e, 0x01000000u, c.ent_a));
+    const int2 q0 = lds_s32x2(__dp4a(e, 0x00000001u * AW, c.ent_a));   // base + row offset of byte j of e
+    const int2 q1 = lds_s32x2(__dp4a(e, 0x00000100u * AW, c.ent_a));
+    const int2 q2 = lds_s32x2(__dp4a(e, 0x00010000u * AW, c.ent_a));
+    const int2 q3 = lds_s32x2(__dp4a(e, 0x01000000u * AW, c.ent_a));
     const int k0 = q0.y - 512 * (int)__dp4a(v, (unsigned)q0.x, 0u);
     const int k1 = q1.y - 512 * (int)__dp4a(v, (unsigned)q1.x, 0u);
     const int k2 = q2.y - 512 * (int)__dp4a(v, (unsigned)q2.x, 0u);
@@ -660,13 +667,23 @@ __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float th
     const int m1 = min(lo01, lo23);
     const int x = max(lo01, lo23);
     const int m2 = min(min(x, hi01), hi23);
-    slow = e >= 0xf8000000u;                                    // still more than four candidates
+    slow = WIDE ? (e < MARK4) : (e >= MARK4);                   // still more than four candidates
     const int mx = max(max(x, hi01), hi23);
     // the median of {x, hi01, hi23}; modular arithmetic, the pad key 0x7fffffff may wrap
     const int m3 = (int)((unsigned)x + (unsigned)hi01 + (unsigned)hi23 - (unsigned)m2 - (unsigned)mx);
     slow = slow || (min((unsigned)(m1 ^ m2), (unsigned)(m2 ^ m3)) < 256u);
     const unsigned vm = v & 0xffffffu;
     const int vv = (int)__dp4a(vm, vm, 0u);
+    if (WIDE) {
+        // The keys keep their row bits: a1 = 256 n1 + row1, a12 = 256 (n1 + n2) + row1 + row2, and
+        //   s = T a12 - a1 = 256 (T (n1 + n2) - n1) + T (row1 + row2) - row1,
+        // whose last two terms are below 511 in magnitude; the two conversions (a1 < 2^27,
+        // a12 < 2^28) and the product add at most 8 + 16 + 16.  So |s| > 640 proves the sign of
+        // T (n1 + n2) - n1; anything closer (|T N - n1| < 2.5, a few pixels in 10^4) takes the exact path.
+        const float s = __fmaf_rn(thr, __int2float_rn(vv * 512 + m1 + m2), -__int2float_rn(vv * 256 + m1));
+        slow = slow || (fabsf(s) <= 640.0f);
+        return (unsigned)(s > 0.0f ? m1 : m2) & 255u;
+    }
     const int n1 = (vv * 256 + m1) >> 8;                        // exact squared distances
     const int nn = (vv * 512 + m1 + m2) >> 8;                   // n1 + n2 (row bits never carry: K <= 30)
     const float s = __fmaf_rn(thr, __int2float_rn(nn), -__int2float_rn(n1));
@@ -676,11 +693,18 @@ __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float th
 
 // exact decision for the pixels v4_pick flagged (rare): re-reads the pixel from global memory,
 // patches its output bytes in the warp's staging buffer and its index byte in global memory
-template <int KIND, bool WM_POW2>
+template <int KIND, bool WM_POW2, bool WIDE>
 __device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, long long gp, uint32_t x,
-                                    uint32_t y, unsigned ra, uint8_t *out_bytes, const unsigned *s_orgb)
+                                    uint32_t y, unsigned ra, uint8_t *out_bytes, const unsigned *s_orgb,
+                                    const int2 *s_ent)
 {
     const PalDev *P = p.P;
+    FastCtx fc;     // WIDE: the exact pick over the cell's full candidate list (a K-row scan is too long)
+    fc.table = P->thr_table;
+    fc.ovf = P->thr_ovf;
+    fc.ent = s_ent;
+    fc.shift = P->thr_shift;
+    fc.ncell = 256 >> fc.shift;
     while (slowmask) {
         const int j = __ffs(slowmask) - 1;
         slowmask &= slowmask - 1;
@@ -693,7 +717,8 @@ __device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, lo
         } else if (KIND == DP_THRESH_IGN) {
             thr = ign_threshold(p, (int)x + j, (int)y);
         }
-        const int idx = pick_int<KIND>(P, P->coef, p.K, q[0], q[1], q[2], thr);
+        const int idx = WIDE ? pick_fast<KIND>(P, fc, p.K, (unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16), thr)
+                             : pick_int<KIND>(P, P->coef, p.K, q[0], q[1], q[2], thr);
         const unsigned col = s_orgb[idx];
         out_bytes[3 * j] = (uint8_t)col;
         out_bytes[3 * j + 1] = (uint8_t)(col >> 8);
@@ -702,18 +727,22 @@ __device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, lo
     }
 }
 
-template <int KIND, bool WM_POW2>
-__global__ void __launch_bounds__(v4_threads<KIND>(), 1) k_thresh_v4(const ThreshParams p)
+__host__ __device__ constexpr int v4_ent_bytes(bool wide) { return wide ? 2048 : 272; }     // int2 [256] / [34]
+__host__ __device__ constexpr int v4_orgb_bytes(bool wide) { return wide ? 1024 : 128; }    // u32 [256] / [32]
+
+template <int KIND, bool WM_POW2, bool WIDE>
+__global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const ThreshParams p)
 {
-    constexpr int V4_THREADS = v4_threads<KIND>();
+    constexpr int V4_THREADS = v4_threads<KIND, WIDE>();
     constexpr int V4_WARPS = V4_THREADS / 32;
+    constexpr int ENTB = v4_ent_bytes(WIDE), ORGBB = v4_orgb_bytes(WIDE);
     extern __shared__ __align__(16) uint8_t smem[];
-    const int P_nsub = p.P->thr4_nsub;
+    const int P_nsub = WIDE ? 0 : p.P->thr4_nsub;          // WIDE: sub-cell entries stay in global memory
     uint32_t *s_table = reinterpret_cast<uint32_t *>(smem);                    // [32768]
-    int2 *s_ent = reinterpret_cast<int2 *>(smem + 131072);                     // [34]
-    unsigned *s_orgb = reinterpret_cast<unsigned *>(smem + 131072 + 272);      // [32]
-    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem + 131072 + 272 + 128);   // [warps][2]
-    uint4 *s_io = reinterpret_cast<uint4 *>(smem + 131072 + 272 + 128 + 512);  // [warps][2][96]
+    int2 *s_ent = reinterpret_cast<int2 *>(smem + 131072);                     // [34] / [256]
+    unsigned *s_orgb = reinterpret_cast<unsigned *>(smem + 131072 + ENTB);     // [32] / [256]
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem + 131072 + ENTB + ORGBB);   // [warps][2]
+    uint4 *s_io = reinterpret_cast<uint4 *>(smem + 131072 + ENTB + ORGBB + 512);  // [warps][2][96]
     uint32_t *s_sub = reinterpret_cast<uint32_t *>(s_io + V4_WARPS * 192);     // [8 * nsub]
     float *s_mat = reinterpret_cast<float *>(s_sub + (KIND == DP_THRESH_NONE ? 0 : ((8 * P_nsub + 3) & ~3)));   // [mh][wm]
 
@@ -728,7 +757,7 @@ __global__ void __launch_bounds__(v4_threads<KIND>(), 1) k_thresh_v4(const Thres
         if (KIND != DP_THRESH_NONE)
             for (int i = tid; i < 8 * P_nsub; i += V4_THREADS) s_sub[i] = __ldg(P->thr4_sub + i);
     }
-    if (tid < 34) {
+    if (tid < (WIDE ? 256 : 34)) {
         int2 en = make_int2(0, 0x7fffff00 | 255);       // pad rows never win
         if (tid < K) {
             const int4 cf = P->coef[tid];
@@ -737,7 +766,7 @@ __global__ void __launch_bounds__(v4_threads<KIND>(), 1) k_thresh_v4(const Thres
         }
         s_ent[tid] = en;
     }
-    if (tid < 32) {
+    if (tid < (WIDE ? 256 : 32)) {
         unsigned col = 0;
         if (tid < K) {
             const uint8_t *o = P->out_rgb + 4 * tid;
@@ -761,6 +790,8 @@ __global__ void __launch_bounds__(v4_threads<KIND>(), 1) k_thresh_v4(const Thres
     ctx.orgb_a = smem_u32(s_orgb);
     ctx.sub_a = smem_u32(s_sub);
     ctx.sub_g = P->near3_sub;
+    ctx.subt_g = P->thr4_sub;
+    ctx.table_g = nullptr;
     ctx.P = P;
     ctx.K = K;
     const unsigned mat_a = smem_u32(s_mat);
@@ -851,10 +882,10 @@ __global__ void __launch_bounds__(v4_threads<KIND>(), 1) k_thresh_v4(const Thres
                     t.w = ign_threshold(p, (int)x + 4 * gq + 3, (int)y);
                 }
                 bool s0, s1, s2, s3;
-                const unsigned i0 = v4_pick<KIND>(ctx, a, t.x, s0);
-                const unsigned i1 = v4_pick<KIND>(ctx, __funnelshift_r(a, b, 24), t.y, s1);
-                const unsigned i2 = v4_pick<KIND>(ctx, __funnelshift_r(b, cq, 16), t.z, s2);
-                const unsigned i3 = v4_pick<KIND>(ctx, cq >> 8, t.w, s3);
+                const unsigned i0 = v4_pick<KIND, false, WIDE>(ctx, a, t.x, s0);
+                const unsigned i1 = v4_pick<KIND, false, WIDE>(ctx, __funnelshift_r(a, b, 24), t.y, s1);
+                const unsigned i2 = v4_pick<KIND, false, WIDE>(ctx, __funnelshift_r(b, cq, 16), t.z, s2);
+                const unsigned i3 = v4_pick<KIND, false, WIDE>(ctx, cq >> 8, t.w, s3);
                 slowmask |= ((s0 ? 1u : 0u) | (s1 ? 2u : 0u) | (s2 ? 4u : 0u) | (s3 ? 8u : 0u)) << (4 * gq);
                 const unsigned c0 = lds_u32(ctx.orgb_a + 4u * i0), c1 = lds_u32(ctx.orgb_a + 4u * i1),
                                c2 = lds_u32(ctx.orgb_a + 4u * i2), c3 = lds_u32(ctx.orgb_a + 4u * i3);
@@ -870,8 +901,8 @@ __global__ void __launch_bounds__(v4_threads<KIND>(), 1) k_thresh_v4(const Thres
         cur[3 * lane + 1] = make_uint4(w[4], w[5], w[6], w[7]);
         cur[3 * lane + 2] = make_uint4(w[8], w[9], w[10], w[11]);
         if (slowmask)
-            v4_fix<KIND, WM_POW2>(p, slowmask, gp, x, y, ra, reinterpret_cast<uint8_t *>(cur + 3 * lane),
-                                  s_orgb);
+            v4_fix<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra, reinterpret_cast<uint8_t *>(cur + 3 * lane),
+                                        s_orgb, s_ent);
         // generic-proxy writes -> visible to the async proxy, then one bulk store by lane 0
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -1144,12 +1175,15 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
     size_t mat_bytes = (KIND == DP_THRESH_MATRIX && p.mh * p.mw <= 1024) ? (size_t)p.mh * p.mw * 4 : 0;
     if (!geom && p.fast == 4) {
         const bool pow2 = (p.wm & (p.wm - 1)) == 0;
-        constexpr int V4_THREADS = v4_threads<KIND>();
-        constexpr int V4_WARPS = V4_THREADS / 32;
-        const size_t smem = 131072 + 272 + 128 + 512 + (size_t)V4_WARPS * 3072 +
+        const bool wide = p.wide != 0;
+        const int V4_THREADS = wide ? v4_threads<KIND, true>() : v4_threads<KIND, false>();
+        const int V4_WARPS = V4_THREADS / 32;
+        const size_t smem = 131072 + v4_ent_bytes(wide) + v4_orgb_bytes(wide) + 512 + (size_t)V4_WARPS * 3072 +
                             (KIND == DP_THRESH_NONE ? 0 : (size_t)p.sub_bytes) +
                             (KIND == DP_THRESH_MATRIX ? (size_t)p.mh * p.wm * 4 : 0);
-        void (*kern)(ThreshParams) = pow2 ? k_thresh_v4<KIND, true> : k_thresh_v4<KIND, false>;
+        void (*kern)(ThreshParams) =
+            wide ? (pow2 ? k_thresh_v4<KIND, true, true> : k_thresh_v4<KIND, false, true>)
+                 : (pow2 ? k_thresh_v4<KIND, true, false> : k_thresh_v4<KIND, false, false>);
         DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const long long ntiles = ((long long)p.frames * p.npix + 511) >> 9;
         const long long want = (ntiles + V4_WARPS - 1) / V4_WARPS;   // frames * npix < 2^31 here
@@ -1273,7 +1307,8 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
         ((reinterpret_cast<uintptr_t>(src_rgb) | reinterpret_cast<uintptr_t>(dst_rgb)) & 15) == 0 &&
         p.npix % 16 == 0 && (!dst_idx || (reinterpret_cast<uintptr_t>(dst_idx) & 3) == 0))
         p.fast = (pal->dev.thr_cells <= 4096) ? 1 : 2;
-    if (p.fast && (kind == DP_THRESH_NONE ? pal->dev.near3_table : pal->dev.thr4_table) && pal->dev.K <= 30 && !pal->has_lut && geo->w % 16 == 0 &&
+    const bool wide = pal->dev.thr4_wide != 0;
+    if (p.fast && (kind == DP_THRESH_NONE ? pal->dev.near3_table : pal->dev.thr4_table) && (pal->dev.K <= 30 || wide) && !pal->has_lut && geo->w % 16 == 0 &&
         (!dst_idx || (reinterpret_cast<uintptr_t>(dst_idx) & 15) == 0) && !getenv("DP_THRESH_NO_V4")) {
         // widened matrix width: the smallest common multiple of mat_w and 16
         int wm = 16;
@@ -1282,20 +1317,21 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
             while (b) { int t = a % b; a = b; b = t; }
             wm = p.mw / a * 16;
         }
-        const int sub_bytes = ((8 * pal->dev.thr4_nsub + 3) & ~3) * 4;
-        const long long need = 131072 + 272 + 128 + 512 +
-                               (kind == DP_THRESH_NONE ? 32ll * 3072 : 24ll * 3072 + sub_bytes) +
+        const int sub_bytes = wide ? 0 : ((8 * pal->dev.thr4_nsub + 3) & ~3) * 4;
+        const long long need = 131072 + v4_ent_bytes(wide) + v4_orgb_bytes(wide) + 512 +
+                               (kind == DP_THRESH_NONE ? (wide ? 31ll : 32ll) * 3072 : 24ll * 3072 + sub_bytes) +
                                (kind == DP_THRESH_MATRIX ? (long long)p.mh * wm * 4 : 0);
         if (need <= 227 * 1024 && (long long)frames * p.npix < (1ll << 31) &&
             (kind != DP_THRESH_MATRIX || (long long)p.mh * wm <= 4096)) {
             p.fast = 4;
+            p.wide = wide ? 1 : 0;
             p.sub_bytes = sub_bytes;
             p.wm = wm;
             p.dwm = make_fastdiv((uint32_t)wm);
             p.dnpix = make_fastdiv((uint32_t)p.npix);
         }
     }
-    p.geom_table = (pal->dev.integral && pal->dev.K >= 2 && pal->dev.K <= 30 && !pal->has_lut &&
+    p.geom_table = (pal->dev.integral && pal->dev.K >= 2 && pal->dev.K <= 30 && !wide && !pal->has_lut &&
                     pal->dev.thr4_table && pal->dev.near3_table) ? 1 : 0;
     cudaStream_t st = dp_stream(stream);
     switch (kind) {

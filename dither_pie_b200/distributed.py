@@ -82,13 +82,13 @@ def nccl_comm():
     rank, world = init_process_group()
     if world == 1:
         return None
-    try:   # prefer the very file PyTorch loaded
-        import glob
-        import nvidia.nccl as _n
-        cands = glob.glob(os.path.join(os.path.dirname(_n.__file__), "lib", "libnccl.so*"))
-        check(lib().dp_nccl_load(cands[0].encode() if cands else None), "dp_nccl_load")
-    except ImportError:
-        check(lib().dp_nccl_load(None), "dp_nccl_load")
+    # prefer the very file PyTorch loaded (nvidia-nccl wheel; a namespace package without __file__)
+    import glob
+    import sys
+    cands = []
+    for base in sys.path:
+        cands += glob.glob(os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so*"))
+    check(lib().dp_nccl_load(cands[0].encode() if cands else None), "dp_nccl_load")
     ident = np.zeros(128, np.uint8)
     if rank == 0:
         check(lib().dp_nccl_unique_id(ident.ctypes.data), "dp_nccl_unique_id")

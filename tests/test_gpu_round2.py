@@ -443,3 +443,32 @@ def test_kmeans_4k_full_image_lloyd_vs_oracle():
             cnt += np.bincount(lab, minlength=16)
         ref = np.where(cnt[:, None] > 0, sums / np.maximum(cnt, 1)[:, None], ref)
     assert res[1] == 3 and np.abs(res[0] - ref).max() < 1e-9
+
+
+# ------------------------------------------------------------------ wide (31..256 colours) v4 kernel
+@pytest.mark.parametrize("k", [31, 40, 64, 100, 255, 256])
+def test_threshold_v4_wide_table_vs_oracle(k):
+    """k_thresh_v4 with the 31..256-colour table format (plain row numbers, filler rows, sub-cell
+    entries in global memory, exact path over the cell's candidate list): widths that are multiples
+    of 16 on gradient, noise and tie-heavy block images, colour and index output."""
+    pal = synth.random_palette(k, seed=100 + k)
+    imgs = [synth.frame(48, 160, 21), synth.noise_frame(40, 96, 22), synth.blocks_frame(64, 128, 23, 8, 6)]
+    modes = [("none", {}), ("bayer", {"size": "8x8"}), ("bayer", {"size": "2x2"}), ("IGN", {}),
+             ("blue_noise", {"size": 32, "seed": 5}), ("polka_dot", {"tile_size": 13, "gamma": 3.0})]
+    for img in imgs:
+        for mode, params in modes:
+            ref = O.apply_dithering(img, pal, mode, params)
+            out, idx = engine.dither_frames(img, pal, mode, params, return_indices=True)
+            assert mismatch(out, ref) == 0, (k, img.shape, mode, params, mismatch(out, ref))
+            assert np.array_equal(np.asarray(pal, np.uint8)[idx], out)
+    lat = synth.lattice_palette(64, 3, 51)          # exact ties everywhere
+    img = synth.blocks_frame(48, 96, 24, 4, 6)
+    for mode, params in modes:
+        assert mismatch(engine.dither_frames(img, lat, mode, params), O.apply_dithering(img, lat, mode, params)) == 0, mode
+
+
+def test_threshold_v4_wide_1080p_256_colours_vs_oracle():
+    img = synth.frame(1080, 1920, 0)
+    pal = synth.random_palette(256)
+    for mode, params in (("bayer", {"size": "8x8"}), ("none", {})):
+        assert mismatch(engine.dither_frames(img, pal, mode, params), O.apply_dithering(img, pal, mode, params)) == 0, mode
