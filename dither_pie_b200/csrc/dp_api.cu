@@ -401,6 +401,7 @@ __global__ void __launch_bounds__(256) k_tie_scan(const PalDev *__restrict__ P, 
 int build_tie_table(PalDev &d, dp_palette *h, const void *dev_paldev, int K)
 {
     d.tie_table = nullptr;
+    d.tie_idx = nullptr;
     d.tie_n = -1;
     const unsigned cap = 1u << 21;   // 2M tie colours (16 MB); beyond that replay in the kernels
     uint2 *dout = nullptr;
@@ -436,6 +437,20 @@ int build_tie_table(PalDev &d, dp_palette *h, const void *dev_paldev, int K)
     d.tie_table = static_cast<const uint2 *>(dt);
     d.tie_n = (int)n;
     h->tie_table = dt;
+    // bucket index by the two high bytes of the colour key (the table is sorted by the key)
+    if (n) {
+        std::vector<uint32_t> idx(65537, 0);
+        for (unsigned i = 0; i < n; ++i) idx[((host[i].x & 0xffffffu) >> 8) + 1]++;
+        for (int k = 0; k < 65536; ++k) idx[k + 1] += idx[k];
+        void *di = nullptr;
+        if (cudaMalloc(&di, idx.size() * 4) == cudaSuccess &&
+            cudaMemcpy(di, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess) {
+            d.tie_idx = static_cast<const uint32_t *>(di);
+            h->tie_idx = di;
+        } else if (di) {
+            cudaFree(di);
+        }
+    }
     return 0;
 }
 
@@ -833,6 +848,7 @@ extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out
         }
     }
     d.tie_table = nullptr;
+    d.tie_idx = nullptr;
     d.tie_n = -1;
     h->dev = d;
     if (cudaMemcpy(blob, &d, sizeof(d), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -862,6 +878,7 @@ extern "C" int dp_palette_destroy(dp_palette *pal)
     if (pal->ext_table) cudaFree(pal->ext_table);
     if (pal->ext_ovf) cudaFree(pal->ext_ovf);
     if (pal->ext_dev) cudaFree(pal->ext_dev);
+    if (pal->tie_idx) cudaFree(pal->tie_idx);
     if (pal->thr_table) cudaFree(pal->thr_table);
     if (pal->thr_ovf) cudaFree(pal->thr_ovf);
     if (pal->thr4_table) cudaFree(pal->thr4_table);

@@ -97,6 +97,11 @@ struct PalDev {
     // sorted by colour; tie_n < 0: not built (the kernels replay the KD-tree themselves).
     const uint2 *tie_table;
     int tie_n;
+    // bucket index of the tie table: entries whose colour key >> 8 (= g | b << 8) equals k are
+    // tie_table[tie_idx[k] .. tie_idx[k+1]) -- a lookup is one index load and a search among the
+    // (on average < 1) entries of the bucket instead of ~16 dependent loads of a whole-table
+    // binary search.  [65537] or null.
+    const uint32_t *tie_idx;
     // nearest-row candidates for arbitrary real values in [0,255]^3 (diffusion modes): 32^3 cells
     // of 8x8x8; a row is dropped from a cell only if another row is strictly nearer at EVERY
     // point of the cell's closed box (exact linear test).  Two levels, because few candidate
@@ -133,6 +138,7 @@ struct dp_palette {
     void *near3_table;
     void *near3_sub;
     void *tie_table;
+    void *tie_idx;
     void *ed_table;   // one allocation: level 1 | patterns | flat
     void *ed_ovf;     // one allocation: cells | offsets | lists
     // lazily built twin with unbounded outer cells (dp_palette_ext): tables, a device copy of

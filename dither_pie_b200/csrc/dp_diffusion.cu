@@ -228,17 +228,23 @@ __device__ __forceinline__ float acc_f64(float acc, double prod)
 // representable in f32, because f32<->f64 conversions issue at 1/8 rate on sm_100 (measured:
 // 8.7 cycles per warp instruction, 18 cycles latency; tools/ubench/lat.cu) and the reference's
 // `+=` needs two of them per tap and channel.  Rounding an f64 to the nearest f32 (ties to even)
-// without a conversion: add and subtract 2^(e+29), e = exponent of x -- the sum's last mantissa
-// bit is then the f32 ulp of x's binade and the f64 adder does the round-to-nearest-even.
-// Identical to (double)(float)x for every x whose magnitude is 0 or in the normal f32 range
-// (work values are bounded by a few hundred; |x| < 2^-126 would need three consecutive exact
-// cancellations).  The sign of a zero result may differ (+0 for -0), which no comparison,
-// clamp or product downstream can observe in the chosen palette rows.
+// without a conversion, in two fused multiply-adds (Veltkamp's splitting with the constant
+// 2^29 - 1):   t = fl(x * 2^29 - x),   r = x * 2^29 - t.
+// x * 2^29 is exact, t is x * (2^29 - 1) rounded to 53 bits, i.e. to a multiple of the f32 ulp of
+// x's binade (2^(e-23)), so r = x * 2^29 - t -- exact by Sterbenz -- is x rounded to that grid;
+// the tie rule is the adder's round-to-even (in a tie the low 29 bits of x are 10...0, so
+// x * 2^29 is an even multiple of the grid and the parity of t is the parity of r).  With the
+// MINUS sign the sum can only fall into the binade below (for mantissas within 2^-29 of 1.0), where
+// the finer grid still rounds such x to 2^e; the plus sign would spill into the binade above and
+// round too coarsely.  Checked against (double)(float)x on 8e7 adversarial doubles (ties, ties +- 1
+// ulp, mantissas next to 1 and 2, both signs): identical.  Valid for 0 and for magnitudes in the
+// normal f32 range (work values are bounded by a few hundred; |x| < 2^-126 would need three
+// consecutive exact cancellations).  The sign of a zero result may differ (+0 for -0), which no
+// comparison, clamp or product downstream can observe in the chosen palette rows.
 __device__ __forceinline__ double round_to_f32(double x)
 {
-    const int hi = __double2hiint(x);
-    const double m = __hiloint2double((hi & (int)0xfff00000) + 0x01d00000, 0);
-    return __dsub_rn(__dadd_rn(x, m), m);
+    const double t = __fma_rn(x, 536870912.0, -x);
+    return __fma_rn(x, 536870912.0, -t);
 }
 __device__ __forceinline__ double acc_r(double acc, double prod)
 {

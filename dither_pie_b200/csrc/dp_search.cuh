@@ -176,6 +176,11 @@ __device__ __forceinline__ void tie_answer(const PalDev *__restrict__ P, int r, 
     if (n > 0) {
         const unsigned key = (unsigned)r | ((unsigned)g << 8) | ((unsigned)b << 16);
         int lo = 0, hi = n - 1;
+        if (P->tie_idx) {          // the bucket of (g, b): usually zero or one entry
+            lo = (int)__ldg(P->tie_idx + (key >> 8));
+            hi = (int)__ldg(P->tie_idx + (key >> 8) + 1) - 1;
+            if (hi < lo) hi = lo = (lo < n ? lo : n - 1);   // empty bucket: one compare that fails
+        }
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if ((__ldg(&P->tie_table[mid].x) & 0xffffffu) < key) lo = mid + 1; else hi = mid;

@@ -619,8 +619,7 @@ struct V4Ctx {
 // TG = the table is read from global memory through L1 (kernels that cannot afford 128 KB of
 // shared memory for it, e.g. the fused geometry kernel) instead of from shared memory.
 // WIDE = the 31..256-colour table format (PalDev::thr4_wide): plain row numbers, fillers instead of
-// pad rows, sub-cell entries in global memory, and a factor test that tolerates the row bits in
-// the keys (see below).
+// pad rows, sub-cell entries in global memory.
 template <int KIND, bool TG = false, bool WIDE = false>
 __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float thr, bool &slow)
 {
@@ -675,13 +674,10 @@ __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float th
     const unsigned vm = v & 0xffffffu;
     const int vv = (int)__dp4a(vm, vm, 0u);
     if (WIDE) {
-        // The keys keep their row bits: a1 = 256 n1 + row1, a12 = 256 (n1 + n2) + row1 + row2, and
-        //   s = T a12 - a1 = 256 (T (n1 + n2) - n1) + T (row1 + row2) - row1,
-        // whose last two terms are below 511 in magnitude; the two conversions (a1 < 2^27,
-        // a12 < 2^28) and the product add at most 8 + 16 + 16.  So |s| > 640 proves the sign of
-        // T (n1 + n2) - n1; anything closer (|T N - n1| < 2.5, a few pixels in 10^4) takes the exact path.
-        const float s = __fmaf_rn(thr, __int2float_rn(vv * 512 + m1 + m2), -__int2float_rn(vv * 256 + m1));
-        slow = slow || (fabsf(s) <= 640.0f);
+        // rows up to 255: the two row bytes may carry when the keys are added, so shift first
+        const int n1w = (vv * 256 + m1) >> 8, n2w = (vv * 256 + m2) >> 8;
+        const float s = __fmaf_rn(thr, __int2float_rn(n1w + n2w), -__int2float_rn(n1w));
+        slow = slow || (s == 0.0f);
         return (unsigned)(s > 0.0f ? m1 : m2) & 255u;
     }
     const int n1 = (vv * 256 + m1) >> 8;                        // exact squared distances
