@@ -412,6 +412,15 @@ def run_gpu(args):
         except Exception as e:
             video = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    # ---- the one collective of the design: pixel-sharded k-means, NCCL all-reduce of the K x 4
+    # integer sums on the kernel stream (all ranks)
+    kmeans_line = None
+    if not args.no_video:
+        try:
+            kmeans_line = kmeans_sharded_line(torch, dist, synth, rank, world, dev, max_over_ranks, barrier)
+        except Exception as e:
+            kmeans_line = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -446,6 +455,8 @@ def run_gpu(args):
     }
     if video is not None:
         line["video"] = video
+    if kmeans_line is not None:
+        line["kmeans_sharded"] = kmeans_line
     if world == 1:
         # cpu baseline: bounded sample of the same workload on ALL host cores (undo the GPU-local
         # affinity first; worker threads inherit the mask when they are created)
@@ -468,6 +479,36 @@ def run_gpu(args):
     _emit(line, real_stdout)
     if world > 1:
         dist.destroy_process_group()
+
+
+def kmeans_sharded_line(torch, dist, synth, rank, world, dev, max_over_ranks, barrier):
+    """BASELINE configs[2], throughput mode, as a strong-scaling job: 20 Lloyd iterations (K=16) over
+    the 8.29 Mpx 4K frame, pixels sharded contiguously over the ranks, dp_kmeans_lloyd with the NCCL
+    all-reduce of the integer sums on the kernel stream and the stop test on the device (the host
+    looks once).  Wall clock of the synchronous call, max over ranks, best of 3.  The SHA-256 of the
+    final centres must be the same for every N (integer sums -> shard-count invariant)."""
+    import hashlib
+    from dither_pie_b200 import _capi, distributed as D, kmeans as KM
+    img = synth.frame(H4K, W4K, 2).reshape(-1, 3)
+    init = img[np.random.RandomState(0).choice(len(img), 16, replace=False)].astype(np.float64)
+    lo, hi = D.shard_pixels(len(img), rank, world)
+    comm = D.nccl_comm() if world > 1 else None
+    shard = _capi.DeviceBuffer((hi - lo) * 3).upload(np.ascontiguousarray(img[lo:hi]))
+    iters = 20
+    KM.lloyd_device(shard.ptr, hi - lo, init, -1.0, 2, comm=comm)          # warm-up (NCCL channels)
+    best, res = None, None
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        res = KM.lloyd_device(shard.ptr, hi - lo, init, -1.0, iters, comm=comm, check_every=iters)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        best = dt if best is None else min(best, dt)
+    shard.free()
+    return {"n_gpus": world, "scaling": "strong", "pixels": int(len(img)), "K": 16, "iterations": iters,
+            "ms": best * 1e3, "us_per_iteration": best / iters * 1e6,
+            "mpx_s": len(img) * iters / best / 1e6, "tied_samples": int(res.ties),
+            "centres_sha256_16": hashlib.sha256(np.ascontiguousarray(res[0]).tobytes()).hexdigest()[:16],
+            "collective": "ncclAllReduce(u64 x 65) per iteration on the kernel stream" if world > 1 else "none"}
 
 
 def video_lines(torch, dist, engine, synth, arena, in_bytes, rank, world, dev, sp, stream, barrier, max_over_ranks):
