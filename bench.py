@@ -359,7 +359,7 @@ def run_gpu(args):
     # results back; copy-in / kernels / copy-out overlap across batches and steps.
     nbytes = B * frame4k
     e2e_steps = max(3, min(args.steps, 6))
-    PB = min(B, 64)                    # frames per device batch inside the pipeline
+    PB = min(B, args.pipe_batch)       # frames per device batch inside the pipeline
 
     def e2e_leg(output, steps):
         if output == "index":
@@ -392,7 +392,8 @@ def run_gpu(args):
            "d2h_bytes_per_step": B * H4K * W4K * len(ED_VARIANTS), "steps": e2e_steps,
            "api": "dither_pie_b200.pipeline.FramePipeline.submit/flush (pinned host arrays, index-plane output)",
            "output": "palette-index plane, 1 B/pixel per variant",
-           "pipeline": f"copy-in + one kernel stream per variant + copy-out, {PB}-frame device batches, 2 slots",
+           "pipeline": f"copy-in + one kernel stream per variant + copy-out, {PB}-frame device batches, "
+                       f"{pipeline.FramePipeline.SLOTS} buffer sets",
            "h2d_gbs_per_rank": st_idx["h2d_gbs"], "d2h_gbs_per_rank": st_idx["d2h_gbs"],
            "host_affinity": numa, "pinned_arena_gb": arena.nbytes / 1e9, "pinned_alloc_s": arena.alloc_s}
     if not args.no_rgb_e2e:
@@ -806,6 +807,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="4K frames per step per GPU")
+    ap.add_argument("--pipe-batch", type=int, default=64, help="frames per device batch of the e2e pipeline")
     ap.add_argument("--no-extra", action="store_true", help="skip the per-mode entries")
     ap.add_argument("--no-video", action="store_true", help="skip the strong-scaling video configs")
     ap.add_argument("--no-rgb-e2e", action="store_true", help="skip the colour-byte variant of the e2e leg")

@@ -18,6 +18,7 @@ Everything goes through the C ABI (dp_stream_*, dp_event_*, dp_memcpy_*, the dit
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from typing import List, Optional, Sequence
 
@@ -97,7 +98,7 @@ class FramePipeline:
     returns while the GPU works, consecutive submits keep the three streams busy across calls) and
     ``flush()`` waits for everything submitted so far."""
 
-    SLOTS = 2
+    SLOTS = int(os.environ.get("DP_PIPE_SLOTS", "2"))    # device buffer sets in flight
 
     def __init__(self, plans: Sequence[engine.Plan], pal: engine.PaletteHandle, batch_frames: int,
                  output: str = "rgb"):
