@@ -687,6 +687,40 @@ __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float th
     return (unsigned)(s > 0.0f ? m1 : m2) & 255u;
 }
 
+// pick_int over the kernel's SHARED row table (packed rgb, |p|^2 << 8 | row): the exact top-3 of all
+// K rows without touching global memory; only a genuine distance tie goes to the exception table
+// (two dependent loads through its bucket index).
+template <int KIND>
+__device__ __forceinline__ int pick_int_ent(const PalDev *P, const int2 *s_ent, int K, unsigned v, float thr)
+{
+    if (K == 1) return 0;
+    Top3 t;
+    top3_init(t);
+#pragma unroll 4
+    for (int i = 0; i < K; ++i) {
+        const int2 e = s_ent[i];
+        top3_push(t, e.y - 512 * (int)__dp4a(v, (unsigned)e.x, 0u));
+    }
+    const int r = v & 255u, g = (v >> 8) & 255u, b = (v >> 16) & 255u;
+    int i1 = t.m1 & 255, i2 = t.m2 & 255;
+    const int s1 = t.m1 >> 8, s2 = t.m2 >> 8, s3 = t.m3 >> 8;
+    bool amb = (s1 == s2);
+    if (KIND != DP_THRESH_NONE) amb = amb || (K >= 3 && s2 == s3);
+    if (amb) {
+        int oi[2];
+        if (KIND == DP_THRESH_NONE)
+            tie_answer<1>(P, r, g, b, oi);
+        else
+            tie_answer<2>(P, r, g, b, oi);
+        i1 = oi[0];
+        if (KIND != DP_THRESH_NONE) i2 = oi[1];
+        // the multiset of distances is unchanged: (s1, s2) stay valid
+    }
+    if (KIND == DP_THRESH_NONE) return i1;
+    const int vv = r * r + g * g + b * b;
+    return factor_le_int(s1 + vv, s2 + vv, thr) ? i1 : i2;
+}
+
 // exact decision for the pixels v4_pick flagged (rare): re-reads the pixel from global memory,
 // patches its output bytes in the warp's staging buffer and its index byte in global memory
 template <int KIND, bool WM_POW2, bool WIDE>
@@ -713,8 +747,8 @@ __device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, lo
         } else if (KIND == DP_THRESH_IGN) {
             thr = ign_threshold(p, (int)x + j, (int)y);
         }
-        const int idx = WIDE ? pick_fast<KIND>(P, fc, p.K, (unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16), thr)
-                             : pick_int<KIND>(P, P->coef, p.K, q[0], q[1], q[2], thr);
+        const unsigned vq = (unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16);
+        const int idx = WIDE ? pick_fast<KIND>(P, fc, p.K, vq, thr) : pick_int_ent<KIND>(P, s_ent, p.K, vq, thr);
         const unsigned col = s_orgb[idx];
         out_bytes[3 * j] = (uint8_t)col;
         out_bytes[3 * j + 1] = (uint8_t)(col >> 8);

@@ -111,5 +111,13 @@ def kmeans_palette(arr_u8: np.ndarray, num_colors: int, random_state=42) -> List
     pix = np.asarray(arr_u8, np.uint8).reshape(-1, 3)
     if len(pix) > SAMPLE:
         pix = pix[random.sample(range(len(pix)), SAMPLE)]
-    centers, _ = kmeans_fit(pix, num_colors, random_state)
-    return [tuple(c) for c in centers.astype(int)]
+    res = kmeans_fit(pix, num_colors, random_state)
+    if getattr(res, "empty_iters", 0):
+        # sklearn relocates an empty cluster to the sample farthest from its centre
+        # (_relocate_empty_clusters_dense, an argpartition whose order is numpy's); here an empty
+        # cluster keeps its centre.  Only images with fewer distinct colours than clusters get here.
+        import warnings
+        warnings.warn("k-means: an empty cluster occurred (fewer distinct colours than clusters?); "
+                      "the palette can differ from scikit-learn's, which relocates empty clusters",
+                      RuntimeWarning, stacklevel=2)
+    return [tuple(c) for c in res[0].astype(int)]

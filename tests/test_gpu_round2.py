@@ -472,3 +472,21 @@ def test_threshold_v4_wide_1080p_256_colours_vs_oracle():
     pal = synth.random_palette(256)
     for mode, params in (("bayer", {"size": "8x8"}), ("none", {})):
         assert mismatch(engine.dither_frames(img, pal, mode, params), O.apply_dithering(img, pal, mode, params)) == 0, mode
+
+
+def test_kmeans_fewer_distinct_colours_than_clusters_is_reported():
+    """Flat art with fewer distinct colours than clusters: k-means++ draws duplicate seeds, some
+    clusters stay empty.  sklearn would relocate them (an argpartition-order dependent step); this
+    library keeps their centres and says so (LloydResult.empty_iters, a RuntimeWarning from the
+    palette call) -- the documented divergence of DESIGN.md section 3.4."""
+    from PIL import Image
+    img = synth.blocks_frame(64, 64, 5, 16, 2)          # at most 8 distinct colours
+    assert len(np.unique(img.reshape(-1, 3), axis=0)) < 12
+    res = kmeans.kmeans_fit(img.reshape(-1, 3), 12, 42)
+    assert res.empty_iters > 0
+    with pytest.warns(RuntimeWarning, match="empty cluster"):
+        pal = dp.ColorReducer.generate_kmeans_palette(Image.fromarray(img), 12)
+    assert len(pal) == 12
+    # same rule as the oracle's Lloyd (an empty cluster keeps its centre): identical centres
+    ref = O.kmeans_centers(img.reshape(-1, 3), 12, 42)
+    assert np.abs(res[0] - ref).max() < 1e-9
