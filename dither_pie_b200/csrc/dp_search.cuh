@@ -169,6 +169,33 @@ __device__ __noinline__ void kd_emulate(const PalDev *__restrict__ P, double x0,
 // Exact-tie answers for byte colours and integral palettes: binary search in the palette's
 // exception table (built by k_tie_scan at palette creation), KD-tree replay if there is none.
 // ---------------------------------------------------------------------------------------
+// Look a byte colour up in the exception table only: true (and scipy's answers in oi) if the
+// colour has an exact tie among its three nearest rows, false if it is not in the table or the
+// table was not built.
+template <int KQ>
+__device__ __forceinline__ bool tie_lookup(const PalDev *__restrict__ P, int r, int g, int b, int *oi)
+{
+    const int n = P->tie_n;
+    if (n <= 0 || !P->tie_idx) return false;
+    const unsigned key = (unsigned)r | ((unsigned)g << 8) | ((unsigned)b << 16);
+    int lo = (int)__ldg(P->tie_idx + (key >> 8));
+    int hi = (int)__ldg(P->tie_idx + (key >> 8) + 1) - 1;
+    if (hi < lo) return false;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((__ldg(&P->tie_table[mid].x) & 0xffffffu) < key) lo = mid + 1; else hi = mid;
+    }
+    const uint2 e = __ldg(P->tie_table + lo);
+    if ((e.x & 0xffffffu) != key) return false;
+    if (KQ == 1) {
+        oi[0] = (int)(e.x >> 24);
+    } else {
+        oi[0] = (int)(e.y & 255u);
+        oi[1] = (int)((e.y >> 8) & 255u);
+    }
+    return true;
+}
+
 template <int KQ>
 __device__ __forceinline__ void tie_answer(const PalDev *__restrict__ P, int r, int g, int b, int *oi)
 {

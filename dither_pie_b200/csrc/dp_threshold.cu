@@ -748,7 +748,23 @@ __device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, lo
             thr = ign_threshold(p, (int)x + j, (int)y);
         }
         const unsigned vq = (unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16);
-        const int idx = WIDE ? pick_fast<KIND>(P, fc, p.K, vq, thr) : pick_int_ent<KIND>(P, s_ent, p.K, vq, thr);
+        int idx;
+        int oi[2];
+        // most flagged pixels are exact distance ties: their answer is in the exception table
+        // (two dependent loads), no scan of the rows is needed
+        if (tie_lookup<KIND == DP_THRESH_NONE ? 1 : 2>(P, q[0], q[1], q[2], oi)) {
+            idx = oi[0];
+            if (KIND != DP_THRESH_NONE) {
+                const int vv = (int)q[0] * q[0] + (int)q[1] * q[1] + (int)q[2] * q[2];
+                const int2 ea = s_ent[oi[0]], eb = s_ent[oi[1]];
+                const int n0 = ((ea.y - 512 * (int)__dp4a(vq, (unsigned)ea.x, 0u)) >> 8) + vv;
+                const int n1 = ((eb.y - 512 * (int)__dp4a(vq, (unsigned)eb.x, 0u)) >> 8) + vv;
+                // the two smallest distances as a multiset do not depend on the tie order
+                idx = factor_le_int(min(n0, n1), max(n0, n1), thr) ? oi[0] : oi[1];
+            }
+        } else {
+            idx = WIDE ? pick_fast<KIND>(P, fc, p.K, vq, thr) : pick_int_ent<KIND>(P, s_ent, p.K, vq, thr);
+        }
         const unsigned col = s_orgb[idx];
         out_bytes[3 * j] = (uint8_t)col;
         out_bytes[3 * j + 1] = (uint8_t)(col >> 8);

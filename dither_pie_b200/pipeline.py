@@ -8,7 +8,7 @@ n is dithered:
     kernel stream    one launch per plan (several dither modes can share one upload)
     copy-out stream  D2H of every plan's result (colour bytes, or the 1-byte index plane)
 
-with two device buffer sets and CUDA events between the three streams.  Host arrays that are
+with three device buffer sets and CUDA events between the streams.  Host arrays that are
 page-locked (``pinned_empty`` / ``PinnedArray`` / ``dp_host_register``) are the DMA source and
 target themselves; ordinary numpy arrays are staged through a pinned ring by the calling thread
 (a host memcpy per batch, which then bounds the rate -- hand in pinned arrays for speed).
@@ -98,7 +98,7 @@ class FramePipeline:
     returns while the GPU works, consecutive submits keep the three streams busy across calls) and
     ``flush()`` waits for everything submitted so far."""
 
-    SLOTS = int(os.environ.get("DP_PIPE_SLOTS", "2"))    # device buffer sets in flight
+    SLOTS = int(os.environ.get("DP_PIPE_SLOTS", "3"))    # device buffer sets in flight
 
     def __init__(self, plans: Sequence[engine.Plan], pal: engine.PaletteHandle, batch_frames: int,
                  output: str = "rgb"):
