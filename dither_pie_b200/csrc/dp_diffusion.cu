@@ -347,16 +347,31 @@ __device__ __forceinline__ int nearest_screen(const Search &s, const uint4 e, fl
 {
     const unsigned off[7] = {e.x & 0xffffu, e.x >> 16, e.y & 0xffffu, e.y >> 16,
                              e.z & 0xffffu, e.z >> 16, e.w & 0xffffu};
-    int k1 = 0x7fffffff, k2 = 0x7fffffff;
+    int key[NSLOT];
 #pragma unroll
     for (int j = 0; j < NSLOT; ++j) {
         const float4 p = lds_f32x4(s.rows_a + off[j]);
         const float dr = __fsub_rn(r, p.x), dg = __fsub_rn(g, p.y), db = __fsub_rn(b, p.z);
         const float d = __fmaf_rn(db, db, __fmaf_rn(dg, dg, __fmul_rn(dr, dr)));
-        const int key = (__float_as_int(d) & (int)0xffffff00) | __float_as_int(p.w);
-        const int hi = max(k1, key);
-        k1 = min(k1, key);
-        k2 = min(k2, hi);
+        key[j] = (__float_as_int(d) & (int)0xffffff00) | __float_as_int(p.w);
+    }
+    // the two smallest keys as a tree (the running pair costs three dependent operations per key):
+    // pair the keys, then  smallest = min of the pair minima,  runner-up = min(second smallest of
+    // the pair minima, smallest pair maximum) -- a pair maximum of another pair is never below
+    // that pair's minimum, so taking all of them cannot undercut the true runner-up
+    int k1, k2;
+    if (NSLOT == 4) {
+        const int lo01 = min(key[0], key[1]), hi01 = max(key[0], key[1]);
+        const int lo23 = min(key[2], key[3]), hi23 = max(key[2], key[3]);
+        k1 = min(lo01, lo23);
+        k2 = min(max(lo01, lo23), min(hi01, hi23));
+    } else {
+        const int lo01 = min(key[0], key[1]), hi01 = max(key[0], key[1]);
+        const int lo23 = min(key[2], key[3]), hi23 = max(key[2], key[3]);
+        const int lo45 = min(key[4], key[5]), hi45 = max(key[4], key[5]);
+        const int a = min(lo01, lo23), bq = max(lo01, lo23), c = min(lo45, key[6]), dq = max(lo45, key[6]);
+        k1 = min(a, c);
+        k2 = min(min(max(a, c), min(bq, dq)), min(min(hi01, hi23), hi45));
     }
     sure = ((e.w >> 16) != DP_ED_OVERFLOW) && (k2 - k1 > 2048);
     if (NSLOT < 7) sure = sure && (off[NSLOT] == DP_ED_PAD);   // slots fill in order
