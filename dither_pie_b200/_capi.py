@@ -73,6 +73,13 @@ PROTOTYPES = {
     "dp_kmeans_update": [_vp, _i, _vp, _vp, _vp],
     "dp_kmeans_lloyd": [_vp, _i64, _vp, _i, _d, _i, _vp, _i, C.POINTER(_i), C.POINTER(_d),
                         C.POINTER(C.c_ulonglong), C.POINTER(_i), _vp],
+    "dp_kmeans_lloyd_p2p": [_vp, _i64, _vp, _i, _d, _i, _i, _i, _vp, C.c_ulonglong, _i, C.POINTER(_i),
+                            C.POINTER(_d), C.POINTER(C.c_ulonglong), C.POINTER(_i), _vp],
+    "dp_p2p_inbox_bytes": [],
+    "dp_p2p_alloc": [_sz, C.POINTER(_vp), _vp],
+    "dp_p2p_open": [_vp, C.POINTER(_vp)],
+    "dp_p2p_close": [_vp],
+    "dp_p2p_free": [_vp],
     "dp_nccl_load": [C.c_char_p],
     "dp_nccl_unique_id": [_vp],
     "dp_nccl_comm_create": [_vp, _i, _i, C.POINTER(_vp)],

@@ -24,6 +24,7 @@
 #include <dlfcn.h>
 
 #include <mutex>
+#include <vector>
 
 #include "dp_common.cuh"
 
@@ -41,15 +42,98 @@ struct KmState {
     int done;                  // stop flag (shift <= tol, or the iteration budget is used up)
     int n_iter;                // completed Lloyd iterations
     int empty;                 // iterations that saw an empty cluster (it keeps its centre)
-    int pad;
+    int error;                 // peer exchange timed out (dp_kmeans_lloyd_p2p)
     double shift2;             // squared centre shift of the last completed iteration
     unsigned long long ties;   // samples exactly equidistant from their two nearest centres
 };
 
+// ---- exchange of the integer sums over peer memory (NVLink), dp_kmeans_lloyd_p2p -----------------
+// Every rank owns an INBOX in its own memory that the peers can write (cudaIpc):
+//   sums  u64 [2 parities][KM_P2P_RANKS][KM_P2P_STRIDE]   slot [parity][r] <- rank r's K*4+1 sums
+//   flags u64 [2 parities][KM_P2P_RANKS]                  <- the iteration number, written last
+// The assignment kernel itself PUSHES: the block that finishes last (a ticket counter) stores the
+// rank's sums into slot [it & 1][rank] of every inbox (its own included) with plain stores over
+// NVLink, fences at system scope and then releases the flags; the
+// next prepare launch waits until all `world` flags of that parity show the iteration and adds the
+// slots up -- integers, so every rank obtains the same totals whatever the order.  No collective
+// launch and no reduction tree between the two kernels of an iteration: the message is 65 integers
+// and the cost is one NVLink store latency.
+// A parity is rewritten two iterations later, which a rank can only reach after it has seen every
+// peer's flag of the iteration in between -- and a peer raises that flag only after its own
+// prepare launch (the reader of the older parity) has completed: double buffering suffices.
+constexpr int KM_P2P_RANKS = 8;
+constexpr int KM_P2P_STRIDE = DP_MAX_COLORS * 4 + 8;      // u64 per slot (>= K*4+1)
+constexpr size_t KM_P2P_FLAGS_OFF = (size_t)2 * KM_P2P_RANKS * KM_P2P_STRIDE;   // in u64
+constexpr size_t KM_P2P_BYTES = (KM_P2P_FLAGS_OFF + 2 * KM_P2P_RANKS) * 8;
+
+struct KmPeers {
+    unsigned long long *inbox[KM_P2P_RANKS];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct KmPush {              // by-value kernel argument; world == 0: no exchange
+    KmPeers peers;
+    int rank, world, parity;
+    unsigned long long iter;   // the tag the flags receive
+    unsigned *ticket;          // blocks-finished counter (zero between launches)
+};
+
+__device__ __forceinline__ void km_push_sums(const unsigned long long *sums, int nsum, const KmPush &ps)
+{
+    // constant indices into the kernel argument (unrolled): it stays in the constant bank
+    const size_t slot = ((size_t)ps.parity * KM_P2P_RANKS + ps.rank) * KM_P2P_STRIDE;
+    for (int k = threadIdx.x; k < nsum; k += blockDim.x) {
+        const unsigned long long v = __ldcg(sums + k);
+#pragma unroll
+        for (int p = 0; p < KM_P2P_RANKS; ++p)
+            if (p < ps.world) ps.peers.inbox[p][slot + k] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    const size_t flag = KM_P2P_FLAGS_OFF + (size_t)ps.parity * KM_P2P_RANKS + ps.rank;
+#pragma unroll
+    for (int p = 0; p < KM_P2P_RANKS; ++p)
+        if ((int)threadIdx.x == p && p < ps.world) st_release_sys(ps.peers.inbox[p] + flag, ps.iter);
+}
+
+// tail of an assignment kernel: the block that takes the last ticket sees every block's atomics
+// (fence before the ticket, fence after) and pushes the totals of this rank
+__device__ __forceinline__ void km_push_tail(const unsigned long long *sums, int nsum, const KmPush &ps)
+{
+    if (ps.world == 0) return;
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ps.ticket, 1u) == gridDim.x - 1 ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) *ps.ticket = 0;
+    km_push_sums(sums, nsum, ps);
+}
+
+// a rank whose shard is empty launches no assignment kernel: it pushes its (zero) sums with this
+__global__ void __launch_bounds__(KM_THREADS) k_kmeans_push(const unsigned long long *__restrict__ sums, int nsum,
+                                                            KmPush ps, const KmState *__restrict__ state)
+{
+    if (state->done) return;
+    km_push_sums(sums, nsum, ps);
+}
+
 // ---- generic path (K > 32): one thread per pixel, shared atomics ----------------------------
 __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate(
     const uint8_t *__restrict__ px, long long n, const double *__restrict__ centers, int K,
-    unsigned long long *__restrict__ sums, const KmState *__restrict__ state)
+    unsigned long long *__restrict__ sums, const KmState *__restrict__ state, KmPush ps)
 {
     if (state && state->done) return;
     __shared__ double s_c[DP_MAX_COLORS * 3];
@@ -94,6 +178,7 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate(
         __syncthreads();
     }
     if (threadIdx.x == 0 && s_ties) atomicAdd(&sums[4 * K], (unsigned long long)s_ties);
+    km_push_tail(sums, K * 4 + 1, ps);
 }
 
 // ---- centres <- sums / count (every thread that calls it gets the same values) ---------------
@@ -173,17 +258,54 @@ __device__ void km_build_grid(const double *s_c, int K, uint32_t *__restrict__ g
 //   c_prev / c_next   f64 [K,3] ping-pong centre buffers
 //   sums_prev         u64 [K*4+1] of the iteration that just finished (null: first iteration)
 //   sums_next         zeroed here for the accumulate pass that follows (null: nothing follows)
+//   inbox / world / wait_iter   peer exchange: the previous iteration's sums are the total of the
+//                     `world` slots of parity wait_iter & 1 of this rank's inbox, valid once every
+//                     flag shows wait_iter (null / 0: sums_prev holds the totals already)
 __global__ void __launch_bounds__(KM_THREADS) k_kmeans_prepare(
-    const double *__restrict__ c_prev, double *__restrict__ c_next, const unsigned long long *__restrict__ sums_prev,
+    const double *__restrict__ c_prev, double *__restrict__ c_next, const unsigned long long *sums_prev,
     unsigned long long *__restrict__ sums_next, int K, double tol, int last, KmState *__restrict__ state,
-    uint32_t *__restrict__ grid, int4 *__restrict__ ent)
+    uint32_t *__restrict__ grid, int4 *__restrict__ ent, const unsigned long long *inbox = nullptr, int world = 0,
+    unsigned long long wait_iter = 0)
 {
     if (state->done) return;
     __shared__ double s_c[DP_MAX_COLORS * 3];
     __shared__ double s_d2[DP_MAX_COLORS * 3];
-    __shared__ int s_stop, s_empty;
-    if (threadIdx.x == 0) s_stop = s_empty = 0;
+    __shared__ unsigned long long s_tot[DP_MAX_COLORS * 4 + 1];
+    __shared__ int s_stop, s_empty, s_err;
+    if (threadIdx.x == 0) s_stop = s_empty = s_err = 0;
     __syncthreads();
+    if (inbox && sums_prev) {
+        const int parity = (int)(wait_iter & 1ull);
+        if ((int)threadIdx.x < world) {
+            const unsigned long long *f = inbox + KM_P2P_FLAGS_OFF + (size_t)parity * KM_P2P_RANKS + threadIdx.x;
+            unsigned spins = 0;
+            while (ld_acquire_sys(f) < wait_iter) {
+                __nanosleep(200);
+                if (++spins > (1u << 24)) {      // ~10 s: a peer died or never launched -> error, not a hang
+                    s_err = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        if (s_err) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                state->error = 1;
+                __threadfence();
+                state->done = 1;
+            }
+            return;
+        }
+        const int nsum = K * 4 + 1;
+        for (int k = threadIdx.x; k < nsum; k += KM_THREADS) {
+            unsigned long long t = 0;
+            for (int r = 0; r < world; ++r)
+                t += __ldcg(inbox + ((size_t)parity * KM_P2P_RANKS + r) * KM_P2P_STRIDE + k);
+            s_tot[k] = t;
+        }
+        __syncthreads();
+        sums_prev = s_tot;
+    }
     if (sums_prev) {
         for (int i = threadIdx.x; i < K * 3; i += KM_THREADS) {
             bool emp = false;
@@ -270,7 +392,7 @@ template <int KP>   // bins rows = KP + 1 (KP = 16 or 32 centres, + the dummy ro
 __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
     const uint8_t *__restrict__ px, long long n, const double *__restrict__ centers, int K,
     unsigned long long *__restrict__ sums, const uint32_t *__restrict__ grid, const int4 *__restrict__ ent,
-    const KmState *__restrict__ state)
+    const KmState *__restrict__ state, KmPush ps)
 {
     if (state && state->done) return;
     extern __shared__ __align__(16) unsigned char km_smem[];
@@ -471,6 +593,7 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
     __syncthreads();
     if (tid < K * 4 && s_tot[tid]) atomicAdd(&sums[tid], s_tot[tid]);
     if (tid == 0 && s_tot[32 * 4]) atomicAdd(&sums[4 * K], s_tot[32 * 4]);
+    km_push_tail(sums, K * 4 + 1, ps);
 }
 
 inline size_t km_accum_smem(int KP)
@@ -524,7 +647,7 @@ int km_scratch(KmScratch **out)
 // launch of the assignment pass: bins for 16 or 32 centres, as many resident blocks as fit
 template <int KP>
 int km_launch_accum_kp(const uint8_t *pixels, long long n, const double *centers, int K, unsigned long long *sums,
-                       const uint32_t *grid, const int4 *ent, const KmState *state, cudaStream_t st)
+                       const uint32_t *grid, const int4 *ent, const KmState *state, cudaStream_t st, const KmPush &ps)
 {
     static thread_local int per_sm[64] = {0};
     int dev = 0;
@@ -541,16 +664,24 @@ int km_launch_accum_kp(const uint8_t *pixels, long long n, const double *centers
     long long blocks = (tiles + KM_WARPS - 1) / KM_WARPS;
     if (blocks < 1) blocks = 1;
     k_kmeans_accum16<KP><<<(int)(blocks < cap ? blocks : cap), KM_THREADS, smem, st>>>(pixels, n, centers, K, sums, grid,
-                                                                                       ent, state);
+                                                                                       ent, state, ps);
     DP_LAUNCH_CHECK();
     return 0;
 }
 
-int km_launch_accum(const uint8_t *pixels, long long n, const double *centers, int K, unsigned long long *sums,
-                    const uint32_t *grid, const int4 *ent, const KmState *state, cudaStream_t st)
+KmPush km_no_push()
 {
-    return K <= 16 ? km_launch_accum_kp<16>(pixels, n, centers, K, sums, grid, ent, state, st)
-                   : km_launch_accum_kp<32>(pixels, n, centers, K, sums, grid, ent, state, st);
+    KmPush ps;
+    memset(&ps, 0, sizeof(ps));
+    return ps;
+}
+
+int km_launch_accum(const uint8_t *pixels, long long n, const double *centers, int K, unsigned long long *sums,
+                    const uint32_t *grid, const int4 *ent, const KmState *state, cudaStream_t st,
+                    const KmPush &ps = km_no_push())
+{
+    return K <= 16 ? km_launch_accum_kp<16>(pixels, n, centers, K, sums, grid, ent, state, st, ps)
+                   : km_launch_accum_kp<32>(pixels, n, centers, K, sums, grid, ent, state, st, ps);
 }
 
 // ---- NCCL, resolved at run time (the library has no link-time dependency on it) -----------------
@@ -658,7 +789,7 @@ extern "C" int dp_kmeans_accumulate(const uint8_t *pixels, int64_t n, const doub
     long long cap = (long long)dp_num_sms() * 8;
     long long chunks = (n + KM_PIX_PER_BLOCK - 1) / KM_PIX_PER_BLOCK;
     int grid = (int)(chunks < cap ? chunks : cap);
-    k_kmeans_accumulate<<<grid, KM_THREADS, 0, st>>>(pixels, n, centers, K, sums, nullptr);
+    k_kmeans_accumulate<<<grid, KM_THREADS, 0, st>>>(pixels, n, centers, K, sums, nullptr, km_no_push());
     DP_LAUNCH_CHECK();
     return 0;
 }
@@ -674,18 +805,55 @@ extern "C" int dp_kmeans_update(const unsigned long long *sums, int K, double *c
 }
 
 // The whole Lloyd loop (see the header).  Synchronous: returns when the loop has stopped.
-extern "C" int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers_host, int K, double tol,
-                               int max_iter, void *nccl_comm, int check_every, int *n_iter, double *shift2,
-                               unsigned long long *ties, int *empty_iters, void *stream)
+// Exchange of the sums between ranks: none, ncclAllReduce on the stream, or the peer-memory push.
+namespace {
+
+// small pool of pinned KmState blocks (one per concurrent Lloyd loop)
+std::mutex g_pin_mu;
+std::vector<KmState *> g_pin_free;
+
+KmState *km_pinned_state_get()
 {
-    DP_REQUIRE(pixels && centers_host, "null argument");
-    DP_REQUIRE(K >= 1 && K <= DP_MAX_COLORS && n >= 0 && max_iter >= 1, "bad size");
-    if (nccl_comm) DP_REQUIRE(g_nccl.handle, "NCCL communicator given but NCCL was never loaded");
-    cudaStream_t st = dp_stream(stream);
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (!g_pin_free.empty()) {
+            KmState *p = g_pin_free.back();
+            g_pin_free.pop_back();
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, 64, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return static_cast<KmState *>(p);
+}
+
+void km_pinned_state_put(KmState *p)
+{
+    std::lock_guard<std::mutex> lk(g_pin_mu);
+    g_pin_free.push_back(p);
+}
+
+struct KmExchange {
+    void *nccl_comm = nullptr;
+    int rank = 0, world = 1;            // peer exchange when inboxes != nullptr
+    void *const *inboxes = nullptr;
+    unsigned long long epoch = 0;       // tags = epoch << 32 | iteration (flags only ever grow)
+};
+
+int km_lloyd(const uint8_t *pixels, int64_t n, double *centers_host, int K, double tol, int max_iter,
+             const KmExchange &ex, int check_every, int *n_iter, double *shift2, unsigned long long *ties,
+             int *empty_iters, cudaStream_t st)
+{
     int dev = 0;
     DP_CUDA(cudaGetDevice(&dev));
     if (dp_retain_pool(dev)) return 1;
     if (check_every < 1) check_every = 4;
+    const bool p2p = ex.inboxes != nullptr && ex.world > 1;
+    KmPeers peers;
+    memset(&peers, 0, sizeof(peers));
+    if (p2p)
+        for (int r = 0; r < ex.world; ++r) peers.inbox[r] = static_cast<unsigned long long *>(ex.inboxes[r]);
+    const unsigned long long *my_inbox = p2p ? peers.inbox[ex.rank] : nullptr;
     const size_t nsum = (size_t)K * 4 + 1;
     const size_t off_c = 0, off_s = off_c + 2 * (size_t)K * 3 * 8, off_state = off_s + 2 * nsum * 8,
                  off_grid = off_state + 64, off_ent = off_grid + 4096 * 4, total = off_ent + 4 * 33 * 16;
@@ -695,14 +863,24 @@ extern "C" int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers
     unsigned long long *sums[2] = {reinterpret_cast<unsigned long long *>(ws + off_s),
                                    reinterpret_cast<unsigned long long *>(ws + off_s) + nsum};
     KmState *state = reinterpret_cast<KmState *>(ws + off_state);
+    unsigned *ticket = reinterpret_cast<unsigned *>(ws + off_state + 48);
+    static_assert(sizeof(KmState) <= 48, "the ticket lives behind the state in its 64-byte slot");
     uint32_t *grid = reinterpret_cast<uint32_t *>(ws + off_grid);
     int4 *ent = reinterpret_cast<int4 *>(ws + off_ent);
-    int rc = 0;
-    KmState host_state;
+    // the state is polled through PINNED memory: a copy to pageable memory blocks inside the driver,
+    // and with several ranks as threads of one process that stalls the other ranks' launches
+    KmState *pinned = km_pinned_state_get();
+    if (!pinned) {
+        cudaFreeAsync(ws, st);
+        dp_set_error("cudaHostAlloc failed for the k-means state");
+        return 1;
+    }
+    KmState &host_state = *pinned;
     memset(&host_state, 0, sizeof(host_state));
     auto finish = [&](int code) {
         cudaFreeAsync(ws, st);
         cudaStreamSynchronize(st);
+        km_pinned_state_put(pinned);
         return code;
     };
 #define KM_TRY(call)                                                                          \
@@ -718,27 +896,39 @@ extern "C" int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers
     const long long cap = (long long)dp_num_sms() * 8;
     const long long chunks = (n + KM_PIX_PER_BLOCK - 1) / KM_PIX_PER_BLOCK;
     const int ggrid = (int)(chunks < cap ? (chunks < 1 ? 1 : chunks) : cap);
+    const unsigned long long tag0 = ex.epoch << 32;
     int it = 1;
     bool stopped = false;
     while (!stopped) {
         const int upto = it + check_every - 1 < max_iter ? it + check_every - 1 : max_iter;
         for (; it <= upto; ++it) {
-            // prepare(it): centres C_{it-1} from sums of iteration it-1 (none for it == 1), stop
+            // prepare(it): centres C_{it-1} from the sums of iteration it-1 (none for it == 1), stop
             // test, grid; then the assignment pass of iteration `it` into sums[it & 1]
             k_kmeans_prepare<<<K <= 32 ? 512 : 1, KM_THREADS, 0, st>>>(
                 it == 1 ? cbuf[0] : cbuf[it & 1], cbuf[(it - 1) & 1], it > 1 ? sums[(it - 1) & 1] : nullptr,
-                sums[it & 1], K, tol, 0, state, grid, ent);
+                sums[it & 1], K, tol, 0, state, grid, ent, my_inbox, ex.world, tag0 + (unsigned long long)(it - 1));
+            KmPush ps = km_no_push();
+            if (p2p) {
+                ps.peers = peers;
+                ps.rank = ex.rank;
+                ps.world = ex.world;
+                ps.parity = it & 1;
+                ps.iter = tag0 + (unsigned long long)it;
+                ps.ticket = ticket;
+            }
             if (n > 0) {
+                // with peers the last block of the assignment kernel pushes the sums itself
                 if (K <= 32) {
-                    if (km_launch_accum(pixels, n, cbuf[(it - 1) & 1], K, sums[it & 1], grid, ent, state, st))
+                    if (km_launch_accum(pixels, n, cbuf[(it - 1) & 1], K, sums[it & 1], grid, ent, state, st, ps))
                         return finish(1);
                 } else
                     k_kmeans_accumulate<<<ggrid, KM_THREADS, 0, st>>>(pixels, n, cbuf[(it - 1) & 1], K, sums[it & 1],
-                                                                      state);
-            }
+                                                                      state, ps);
+            } else if (p2p)
+                k_kmeans_push<<<1, KM_THREADS, 0, st>>>(sums[it & 1], (int)nsum, ps, state);
             KM_TRY(cudaGetLastError());
-            if (nccl_comm) {
-                const int r = g_nccl.AllReduce(sums[it & 1], sums[it & 1], nsum, DP_NCCL_UINT64, DP_NCCL_SUM, nccl_comm, st);
+            if (!p2p && ex.nccl_comm) {
+                const int r = g_nccl.AllReduce(sums[it & 1], sums[it & 1], nsum, DP_NCCL_UINT64, DP_NCCL_SUM, ex.nccl_comm, st);
                 if (r != 0) {
                     dp_set_error("ncclAllReduce failed: %d (%s)", r, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
                     return finish(1);
@@ -748,12 +938,17 @@ extern "C" int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers
         if (it > max_iter) {
             // the iteration budget is used up: finalise C_{max_iter}
             k_kmeans_prepare<<<1, KM_THREADS, 0, st>>>(cbuf[it & 1], cbuf[(it - 1) & 1], sums[(it - 1) & 1], nullptr, K, tol,
-                                                      1, state, grid, ent);
+                                                      1, state, grid, ent, my_inbox, ex.world,
+                                                      tag0 + (unsigned long long)(it - 1));
             KM_TRY(cudaGetLastError());
         }
         KM_TRY(cudaMemcpyAsync(&host_state, state, sizeof(KmState), cudaMemcpyDeviceToHost, st));
         KM_TRY(cudaStreamSynchronize(st));
         stopped = host_state.done != 0 || it > max_iter;
+    }
+    if (host_state.error) {
+        dp_set_error("k-means peer exchange timed out: a rank did not deliver its sums");
+        return finish(3);
     }
     // final centres: C_{n_iter} lives in cbuf[n_iter & 1]
     KM_TRY(cudaMemcpyAsync(centers_host, cbuf[host_state.n_iter & 1], (size_t)K * 3 * 8, cudaMemcpyDeviceToHost, st));
@@ -763,5 +958,84 @@ extern "C" int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers
     if (shift2) *shift2 = host_state.shift2;
     if (ties) *ties = host_state.ties;
     if (empty_iters) *empty_iters = host_state.empty;
-    return finish(rc);
+    return finish(0);
+}
+
+}  // namespace
+
+extern "C" int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers_host, int K, double tol,
+                               int max_iter, void *nccl_comm, int check_every, int *n_iter, double *shift2,
+                               unsigned long long *ties, int *empty_iters, void *stream)
+{
+    DP_REQUIRE(pixels && centers_host, "null argument");
+    DP_REQUIRE(K >= 1 && K <= DP_MAX_COLORS && n >= 0 && max_iter >= 1, "bad size");
+    if (nccl_comm) DP_REQUIRE(g_nccl.handle, "NCCL communicator given but NCCL was never loaded");
+    KmExchange ex;
+    ex.nccl_comm = nccl_comm;
+    return km_lloyd(pixels, n, centers_host, K, tol, max_iter, ex, check_every, n_iter, shift2, ties, empty_iters,
+                    dp_stream(stream));
+}
+
+extern "C" int dp_kmeans_lloyd_p2p(const uint8_t *pixels, int64_t n, double *centers_host, int K, double tol,
+                                   int max_iter, int rank, int world, void *const *inboxes, unsigned long long epoch,
+                                   int check_every, int *n_iter, double *shift2, unsigned long long *ties,
+                                   int *empty_iters, void *stream)
+{
+    DP_REQUIRE(pixels && centers_host && inboxes, "null argument");
+    DP_REQUIRE(K >= 1 && K <= DP_MAX_COLORS && n >= 0 && max_iter >= 1, "bad size");
+    DP_REQUIRE(world >= 1 && world <= KM_P2P_RANKS && rank >= 0 && rank < world, "bad rank / world (at most 8 ranks)");
+    for (int r = 0; r < world; ++r) DP_REQUIRE(inboxes[r], "null inbox");
+    KmExchange ex;
+    ex.rank = rank;
+    ex.world = world;
+    ex.inboxes = inboxes;
+    ex.epoch = epoch;
+    return km_lloyd(pixels, n, centers_host, K, tol, max_iter, ex, check_every, n_iter, shift2, ties, empty_iters,
+                    dp_stream(stream));
+}
+
+// ---- peer-visible memory (cudaIpc) for the inboxes ------------------------------------------------
+extern "C" int dp_p2p_inbox_bytes(void) { return (int)KM_P2P_BYTES; }
+
+extern "C" int dp_p2p_alloc(size_t bytes, void **dptr, void *ipc_handle64)
+{
+    DP_REQUIRE(dptr && ipc_handle64 && bytes, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    void *p = nullptr;
+    DP_CUDA(cudaMalloc(&p, bytes));
+    DP_CUDA(cudaMemset(p, 0, bytes));
+    DP_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        dp_set_error("cudaIpcGetMemHandle -> %s", cudaGetErrorString(e));
+        return 1;
+    }
+    memcpy(ipc_handle64, &h, 64);
+    *dptr = p;
+    return 0;
+}
+
+extern "C" int dp_p2p_open(const void *ipc_handle64, void **dptr)
+{
+    DP_REQUIRE(dptr && ipc_handle64, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle64, 64);
+    DP_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int dp_p2p_close(void *dptr)
+{
+    if (!dptr) return 0;
+    DP_CUDA(cudaIpcCloseMemHandle(dptr));
+    return 0;
+}
+
+extern "C" int dp_p2p_free(void *dptr)
+{
+    if (!dptr) return 0;
+    DP_CUDA(cudaFree(dptr));
+    return 0;
 }

@@ -102,22 +102,71 @@ def nccl_comm():
     return _nccl_comm
 
 
+_p2p = None
+
+
+def p2p_exchange():
+    """(rank, world, inbox pointers, epoch) for ``kmeans.lloyd_device(p2p=...)``: every rank
+    allocates an inbox in its own device memory, the ranks all-gather the 64-byte cudaIpc handles
+    through ``torch.distributed`` and map each other's inboxes (peer access over NVLink).  Created
+    once per process; each call returns a fresh epoch and passes a barrier, as dp_kmeans_lloyd_p2p
+    requires between two uses of the same inboxes.  None for a single process."""
+    global _p2p
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from ._capi import check, lib
+    rank, world = init_process_group()
+    if world == 1:
+        return None
+    if world > 8:
+        raise RuntimeError("the peer-memory exchange covers one NVSwitch domain (<= 8 ranks)")
+    if _p2p is None:
+        L = lib()
+        mine = C.c_void_p()
+        handle = np.zeros(64, np.uint8)
+        check(L.dp_p2p_alloc(int(L.dp_p2p_inbox_bytes()), C.byref(mine), handle.ctypes.data), "dp_p2p_alloc")
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else "cpu"
+        t = torch.from_numpy(handle).to(dev)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        ptrs = []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(mine.value)
+            else:
+                h = np.ascontiguousarray(parts[r].cpu().numpy())
+                q = C.c_void_p()
+                check(L.dp_p2p_open(h.ctypes.data, C.byref(q)), "dp_p2p_open")
+                ptrs.append(q.value)
+        _p2p = {"rank": rank, "world": world, "ptrs": ptrs, "epoch": 0}
+    _p2p["epoch"] += 1
+    dist.barrier()
+    if dist.get_backend() == "nccl":
+        torch.cuda.synchronize()       # the barrier's own kernel has finished: every peer is past its last use
+    return (_p2p["rank"], _p2p["world"], _p2p["ptrs"], _p2p["epoch"])
+
+
 def kmeans_fit_sharded(pixels_u8: np.ndarray, init_centers: np.ndarray, tol: float,
-                       max_iter: int = kmeans.MAX_ITER, check_every: int = 8):
+                       max_iter: int = kmeans.MAX_ITER, check_every: int = 8, exchange: str = "p2p"):
     """Full-image Lloyd iterations with the pixels sharded over the ranks of the job
     (BASELINE config 3, throughput mode).  Every rank passes the SAME ``pixels_u8`` [N,3] and
-    initial centres; each uploads only its shard; ``dp_kmeans_lloyd`` accumulates exact integer
-    sums on its GPU and all-reduces them with ncclAllReduce on the kernel stream (no host
-    synchronisation per iteration).  Returns (centres f64 [K,3], iters) -- identical on all ranks."""
+    initial centres; each uploads only its shard; the Lloyd loop accumulates exact integer sums
+    on its GPU and exchanges them per iteration without host synchronisation -- ``exchange="p2p"``:
+    the kernels push the sums into the peers' inboxes over NVLink (dp_kmeans_lloyd_p2p);
+    ``"nccl"``: ncclAllReduce on the kernel stream.  Returns (centres f64 [K,3], iters) --
+    identical on all ranks."""
     from . import _capi
     rank, world = init_process_group()
     _capi.ensure_device()
     pix = np.ascontiguousarray(pixels_u8, np.uint8).reshape(-1, 3)
     lo, hi = shard_pixels(pix.shape[0], rank, world)
-    comm = nccl_comm()
     buf = _capi.DeviceBuffer(max((hi - lo) * 3, 16)).upload(np.ascontiguousarray(pix[lo:hi]))
     try:
-        return kmeans.lloyd_device(buf.ptr, hi - lo, init_centers, tol, max_iter, comm=comm,
+        if exchange == "p2p" and world <= 8:
+            return kmeans.lloyd_device(buf.ptr, hi - lo, init_centers, tol, max_iter, p2p=p2p_exchange(),
+                                       check_every=check_every)
+        return kmeans.lloyd_device(buf.ptr, hi - lo, init_centers, tol, max_iter, comm=nccl_comm(),
                                    check_every=check_every)
     finally:
         buf.free()

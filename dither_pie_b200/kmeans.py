@@ -69,21 +69,32 @@ class LloydResult(tuple):
 
 def lloyd_device(pixels_ptr: int, n: int, centers: np.ndarray, tol: float,
                  max_iter: int = MAX_ITER, comm: Optional[int] = None, stream=None,
-                 check_every: int = 4) -> Tuple[np.ndarray, int]:
+                 check_every: int = 4, p2p=None) -> Tuple[np.ndarray, int]:
     """Lloyd iterations on device-resident u8 pixels [n,3] through ``dp_kmeans_lloyd``: the whole
     loop runs on the stream with the stop test on the device; the host looks at the flag every
     ``check_every`` iterations.  ``centers`` f64 [K,3] (uncentred).  When the pixels are one shard
     of a multi-GPU job pass ``comm`` (a dp_nccl_comm_create handle): the K x 4 integer sums are
-    all-reduced with ncclAllReduce on the same stream, so every rank ends with identical centres.
+    all-reduced with ncclAllReduce on the same stream, so every rank ends with identical centres;
+    or ``p2p`` (from ``distributed.p2p_exchange()``): the kernels push the sums into the peers'
+    inboxes over NVLink themselves, no NCCL launch.
     Returns (centres, n_iter); the result also carries ``.ties`` (samples exactly equidistant from
     their two nearest centres, summed over the iterations), ``.shift2`` and ``.empty_iters``."""
     K = int(centers.shape[0])
     c_host = np.ascontiguousarray(centers, np.float64).copy()
     n_iter, shift2 = C.c_int(0), C.c_double(0.0)
     ties, empty = C.c_ulonglong(0), C.c_int(0)
-    check(lib().dp_kmeans_lloyd(pixels_ptr, int(n), c_host.ctypes.data, K, float(tol), int(max_iter),
-                                comm, int(check_every), C.byref(n_iter), C.byref(shift2),
-                                C.byref(ties), C.byref(empty), stream), "dp_kmeans_lloyd")
+    if p2p is not None:
+        # (rank, world, inbox pointers, epoch): the kernels exchange the sums over peer memory
+        rank, world, inboxes, epoch = p2p
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(x)) for x in inboxes])
+        check(lib().dp_kmeans_lloyd_p2p(pixels_ptr, int(n), c_host.ctypes.data, K, float(tol), int(max_iter),
+                                        int(rank), int(world), arr, int(epoch), int(check_every),
+                                        C.byref(n_iter), C.byref(shift2), C.byref(ties), C.byref(empty),
+                                        stream), "dp_kmeans_lloyd_p2p")
+    else:
+        check(lib().dp_kmeans_lloyd(pixels_ptr, int(n), c_host.ctypes.data, K, float(tol), int(max_iter),
+                                    comm, int(check_every), C.byref(n_iter), C.byref(shift2),
+                                    C.byref(ties), C.byref(empty), stream), "dp_kmeans_lloyd")
     return LloydResult(c_host, int(n_iter.value), float(shift2.value), int(ties.value),
                        int(empty.value))
 

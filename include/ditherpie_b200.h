@@ -287,6 +287,29 @@ int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers_host, int 
                     unsigned long long *ties, int *empty_iters, void *stream);
 
 /*
+ * dp_kmeans_lloyd_p2p -- the same loop with the exchange done by the kernels themselves over peer
+ * memory (NVLink) instead of an NCCL launch: after its assignment pass a rank stores its K*4+1
+ * integers into a slot of every rank's INBOX and releases a flag; the next "prepare" launch waits
+ * for the `world` flags and adds the slots up (integers: identical totals on every rank).
+ *   inboxes   HOST array of `world` DEVICE pointers; inboxes[rank] is this rank's own inbox
+ *             (dp_p2p_alloc(dp_p2p_inbox_bytes(), ...)), the others are the peers' inboxes opened
+ *             with dp_p2p_open from the handles the ranks exchanged
+ *   epoch     a counter the caller increments per call (same value on every rank): flags only grow.
+ *             The ranks must pass a barrier between two calls on the same inboxes.
+ * At most 8 ranks (one NVSwitch domain).  Returns 3 if a peer did not deliver within ~10 s.
+ */
+int dp_kmeans_lloyd_p2p(const uint8_t *pixels, int64_t n, double *centers_host, int K, double tol,
+                        int max_iter, int rank, int world, void *const *inboxes,
+                        unsigned long long epoch, int check_every, int *n_iter, double *shift2,
+                        unsigned long long *ties, int *empty_iters, void *stream);
+/* peer-visible device memory between the processes of one box (cudaIpc) */
+int dp_p2p_inbox_bytes(void);
+int dp_p2p_alloc(size_t bytes, void **dptr, void *ipc_handle64);
+int dp_p2p_open(const void *ipc_handle64, void **dptr);
+int dp_p2p_close(void *dptr);   /* a mapping from dp_p2p_open */
+int dp_p2p_free(void *dptr);    /* an allocation from dp_p2p_alloc */
+
+/*
  * NCCL plumbing for the sharded k-means (one process per GPU).  libnccl is resolved at run time
  * (dlopen: the copy the process already loaded -- e.g. PyTorch's -- or the system one), the
  * library has no link-time dependency on it.  Rank 0 creates the id and hands the 128 bytes to

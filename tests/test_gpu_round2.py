@@ -490,3 +490,56 @@ def test_kmeans_fewer_distinct_colours_than_clusters_is_reported():
     # same rule as the oracle's Lloyd (an empty cluster keeps its centre): identical centres
     ref = O.kmeans_centers(img.reshape(-1, 3), 12, 42)
     assert np.abs(res[0] - ref).max() < 1e-9
+
+
+@pytest.mark.parametrize("K,world", [(16, 2), (16, 3), (40, 2)])
+def test_kmeans_peer_memory_exchange_two_ranks_on_one_gpu(K, world):
+    """dp_kmeans_lloyd_p2p: the assignment kernel's last block pushes the rank's integer sums into
+    every inbox, the next prepare launch waits for the flags and adds the slots up.  Here the
+    `world` ranks are host threads with their own streams on ONE device (the inboxes are plain
+    device allocations; across processes they are cudaIpc mappings -- tools/multigpu_check.py):
+    same centres, iteration count and tie count as the unsharded loop, twice in a row (epochs)."""
+    import ctypes as C
+    import threading
+    from dither_pie_b200 import pipeline
+    from dither_pie_b200._capi import check, lib
+    img = synth.frame(540, 960, 4).reshape(-1, 3)
+    rs = np.random.RandomState(K)
+    init = img[rs.choice(len(img), K, replace=False)].astype(np.float64)
+    tol = float(np.mean(np.var(img.astype(np.float64), axis=0)) * 1e-4)
+    want = _lloyd_gpu(img, init, tol, 25)
+    L = lib()
+    inboxes = []
+    for _ in range(world):
+        p, h = C.c_void_p(), np.zeros(64, np.uint8)
+        check(L.dp_p2p_alloc(int(L.dp_p2p_inbox_bytes()), C.byref(p), h.ctypes.data), "dp_p2p_alloc")
+        inboxes.append(p.value)
+    bounds = [len(img) * r // world for r in range(world + 1)]
+    bounds[1] -= 5                                   # ragged, unaligned shards
+    bufs = [_capi.DeviceBuffer((bounds[r + 1] - bounds[r]) * 3).upload(np.ascontiguousarray(img[bounds[r]:bounds[r + 1]]))
+            for r in range(world)]
+    streams = [pipeline._Stream() for _ in range(world)]
+    try:
+        for epoch in (1, 2):
+            out, errs = [None] * world, []
+
+            def run(r):
+                try:
+                    _capi.ensure_device(0)
+                    out[r] = kmeans.lloyd_device(bufs[r].ptr, bounds[r + 1] - bounds[r], init, tol, 25,
+                                                 p2p=(r, world, inboxes, epoch), stream=streams[r].h, check_every=3)
+                except Exception as e:       # noqa: BLE001
+                    errs.append(e)
+
+            th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+            [t.start() for t in th]
+            [t.join(120) for t in th]
+            assert not errs, errs
+            for r in range(world):
+                assert out[r][1] == want[1] and np.array_equal(out[r][0], want[0]), (epoch, r)
+                assert out[r].ties == want.ties
+    finally:
+        for b in bufs:
+            b.free()
+        for p in inboxes:
+            check(L.dp_p2p_free(p), "dp_p2p_free")
