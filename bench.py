@@ -432,13 +432,13 @@ def run_gpu(args):
     alg_bytes = BYTES_PER_PX * B * H4K * W4K
     achieved = alg_bytes / (avg_kernel_ms * 1e-3) / 1e9
     # DRAM traffic per launch for 128 4K frames in the ncu --set full captures (profiles/):
-    # 7.795 GB for k_diffuse_wave<floyd_steinberg>, 8.194 GB for <jjn> (the two ends of the step's
-    # three launches), i.e. 7.3-7.7 B/pixel against 6 algorithmic -- hand-off streams + table
-    traffic = 0.5 * (7.794756e9 + 8.194386e9) / (128 * H4K * W4K) * (B * H4K * W4K)
+    # 7.617 GB for k_diffuse_wave<floyd_steinberg>, 7.761 GB for <jjn> (the two ends of the step's
+    # three launches), i.e. 7.2-7.3 B/pixel against 6 algorithmic -- hand-off streams + table
+    traffic = 0.5 * (7.616983e9 + 7.761e9) / (128 * H4K * W4K) * (B * H4K * W4K)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
-                                  "mean of profiles/r1l_diffuse_wave_{fs,jjn}_K256_4k_x128.txt "
+                                  "mean of profiles/r2k_diffuse_wave_{fs,jjn}_K256_4k_x128.txt "
                                   "(scaled by frames)",
                 "kernel": "k_diffuse_wave",
                 "peak_source": peak_src, "avg_launch_ms": avg_kernel_ms,
@@ -483,33 +483,55 @@ def run_gpu(args):
 
 
 def kmeans_sharded_line(torch, dist, synth, rank, world, dev, max_over_ranks, barrier):
-    """BASELINE configs[2], throughput mode, as a strong-scaling job: 20 Lloyd iterations (K=16) over
-    the 8.29 Mpx 4K frame, pixels sharded contiguously over the ranks, dp_kmeans_lloyd with the NCCL
-    all-reduce of the integer sums on the kernel stream and the stop test on the device (the host
-    looks once).  Wall clock of the synchronous call, max over ranks, best of 3.  The SHA-256 of the
-    final centres must be the same for every N (integer sums -> shard-count invariant)."""
+    """BASELINE configs[2], throughput mode, as a strong-scaling job: Lloyd iterations (K=16) over
+    the 8.29 Mpx 4K frame, pixels sharded contiguously over the ranks, stop test on the device
+    (the host looks once).  Exchange of the integer sums between the ranks: "p2p" -- the last
+    block of the assignment kernel pushes them into every rank's inbox over NVLink and the next
+    launch waits for the flags (dp_kmeans_lloyd_p2p) -- and, for comparison, ncclAllReduce on the
+    kernel stream.  Wall clock of the synchronous call (workspace allocation, centre upload and
+    the final read-back included), max over ranks, best of 3, at 20 and at 100 iterations; the
+    marginal cost per iteration is the difference.  The SHA-256 of the final centres must be the
+    same for every N and both exchanges (integer sums -> shard-count invariant)."""
     import hashlib
     from dither_pie_b200 import _capi, distributed as D, kmeans as KM
     img = synth.frame(H4K, W4K, 2).reshape(-1, 3)
     init = img[np.random.RandomState(0).choice(len(img), 16, replace=False)].astype(np.float64)
     lo, hi = D.shard_pixels(len(img), rank, world)
-    comm = D.nccl_comm() if world > 1 else None
     shard = _capi.DeviceBuffer((hi - lo) * 3).upload(np.ascontiguousarray(img[lo:hi]))
-    iters = 20
-    KM.lloyd_device(shard.ptr, hi - lo, init, -1.0, 2, comm=comm)          # warm-up (NCCL channels)
-    best, res = None, None
-    for _ in range(3):
-        barrier()
-        t0 = time.perf_counter()
-        res = KM.lloyd_device(shard.ptr, hi - lo, init, -1.0, iters, comm=comm, check_every=iters)
-        dt = max_over_ranks(time.perf_counter() - t0)
-        best = dt if best is None else min(best, dt)
+
+    def timed(iters, kw):
+        KM.lloyd_device(shard.ptr, hi - lo, init, -1.0, 2, **kw())          # warm-up
+        best, res = None, None
+        for _ in range(3):
+            args = kw()
+            barrier()
+            t0 = time.perf_counter()
+            res = KM.lloyd_device(shard.ptr, hi - lo, init, -1.0, iters, check_every=iters, **args)
+            dt = max_over_ranks(time.perf_counter() - t0)
+            best = dt if best is None else min(best, dt)
+        return best, res
+
+    def leg(kw):
+        t20, res = timed(20, kw)
+        t100, _ = timed(100, kw)
+        return {"ms_20_iterations": t20 * 1e3, "ms_100_iterations": t100 * 1e3,
+                "us_per_iteration": (t100 - t20) / 80 * 1e6, "fixed_ms": (t20 - (t100 - t20) / 4) * 1e3,
+                "mpx_s": len(img) * 80 / (t100 - t20) / 1e6, "tied_samples": int(res.ties),
+                "centres_sha256_16": hashlib.sha256(np.ascontiguousarray(res[0]).tobytes()).hexdigest()[:16]}
+
+    out = {"n_gpus": world, "scaling": "strong", "pixels": int(len(img)), "K": 16}
+    if world == 1:
+        out.update(leg(lambda: {}))
+        out["exchange"] = "none"
+    else:
+        out.update(leg(lambda: {"p2p": D.p2p_exchange()}))
+        out["exchange"] = ("peer memory: the assignment kernel's last block stores the 65 u64 sums into every "
+                           "rank's inbox over NVLink (cudaIpc mappings), the next launch waits for the flags")
+        comm = D.nccl_comm()
+        out["nccl"] = leg(lambda: {"comm": comm})
+        out["nccl"]["exchange"] = "ncclAllReduce(u64 x 65) per iteration on the kernel stream"
     shard.free()
-    return {"n_gpus": world, "scaling": "strong", "pixels": int(len(img)), "K": 16, "iterations": iters,
-            "ms": best * 1e3, "us_per_iteration": best / iters * 1e6,
-            "mpx_s": len(img) * iters / best / 1e6, "tied_samples": int(res.ties),
-            "centres_sha256_16": hashlib.sha256(np.ascontiguousarray(res[0]).tobytes()).hexdigest()[:16],
-            "collective": "ncclAllReduce(u64 x 65) per iteration on the kernel stream" if world > 1 else "none"}
+    return out
 
 
 def video_lines(torch, dist, engine, synth, arena, in_bytes, rank, world, dev, sp, stream, barrier, max_over_ranks):

@@ -72,12 +72,14 @@ def build_timing() -> str:
     counters (-DDP_WAVE_TIMING).  Written next to the objects, never loaded by the product."""
     build()
     out = os.path.join(OBJ_DIR, "libditherpie_b200_timing.so")
-    tobj = os.path.join(OBJ_DIR, "dp_diffusion_timing.o")
-    subprocess.check_call(["nvcc", *NVCC_FLAGS, "-DDP_WAVE_TIMING", "-c",
-                           os.path.join(CSRC, "dp_diffusion.cu"), "-o", tobj])
-    others = [os.path.join(OBJ_DIR, s[:-3] + ".o") for s in sources() if s != "dp_diffusion.cu"]
+    timed = {"dp_diffusion.cu": "-DDP_WAVE_TIMING", "dp_kmeans.cu": "-DDP_KM_TIMING"}   # tools/km_timing.py
+    tobjs = []
+    for src, flag in timed.items():
+        tobjs.append(os.path.join(OBJ_DIR, src[:-3] + "_timing.o"))
+        subprocess.check_call(["nvcc", *NVCC_FLAGS, flag, "-c", os.path.join(CSRC, src), "-o", tobjs[-1]])
+    others = [os.path.join(OBJ_DIR, s[:-3] + ".o") for s in sources() if s not in timed]
     subprocess.check_call(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a",
-                           "-o", out, tobj, *others, "-lcudart", "-ldl"])
+                           "-o", out, *tobjs, *others, "-lcudart", "-ldl"])
     return out
 
 

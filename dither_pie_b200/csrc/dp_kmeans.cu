@@ -61,6 +61,7 @@ struct KmState {
 // A parity is rewritten two iterations later, which a rank can only reach after it has seen every
 // peer's flag of the iteration in between -- and a peer raises that flag only after its own
 // prepare launch (the reader of the older parity) has completed: double buffering suffices.
+constexpr int KM_GRID_REPLICAS = 8;
 constexpr int KM_P2P_RANKS = 8;
 constexpr int KM_P2P_STRIDE = DP_MAX_COLORS * 4 + 8;      // u64 per slot (>= K*4+1)
 constexpr size_t KM_P2P_FLAGS_OFF = (size_t)2 * KM_P2P_RANKS * KM_P2P_STRIDE;   // in u64
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_push(const unsigned long 
 // ---- generic path (K > 32): one thread per pixel, shared atomics ----------------------------
 __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate(
     const uint8_t *__restrict__ px, long long n, const double *__restrict__ centers, int K,
-    unsigned long long *__restrict__ sums, const KmState *__restrict__ state, KmPush ps)
+    unsigned long long *__restrict__ sums, const KmState *__restrict__ state, KmPush ps, int chunk_px)
 {
     if (state && state->done) return;
     __shared__ double s_c[DP_MAX_COLORS * 3];
@@ -141,12 +142,12 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accumulate(
     __shared__ unsigned int s_ties;
     for (int i = threadIdx.x; i < K * 3; i += KM_THREADS) s_c[i] = centers[i];
     if (threadIdx.x == 0) s_ties = 0;
-    const long long nchunks = (n + KM_PIX_PER_BLOCK - 1) / KM_PIX_PER_BLOCK;
+    const long long nchunks = (n + chunk_px - 1) / chunk_px;
     for (long long chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         for (int i = threadIdx.x; i < K * 4; i += KM_THREADS) s_sum[i] = 0;
         __syncthreads();
-        const long long p0 = chunk * KM_PIX_PER_BLOCK;
-        const int cnt = (int)((n - p0) < KM_PIX_PER_BLOCK ? (n - p0) : KM_PIX_PER_BLOCK);
+        const long long p0 = chunk * chunk_px;
+        const int cnt = (int)((n - p0) < chunk_px ? (n - p0) : chunk_px);
         for (int j = threadIdx.x; j < cnt; j += KM_THREADS) {
             const uint8_t *q = px + (size_t)(p0 + j) * 3;
             const int r = q[0], g = q[1], b = q[2];
@@ -203,8 +204,10 @@ __device__ __forceinline__ double km_new_center(const unsigned long long *sums, 
 // A centre is dropped from a box when another centre is strictly nearer at EVERY point of the box:
 // the difference of two squared distances is linear in the point, so its maximum sits at a corner
 // (exact test in double with a 1e-6 margin).  One warp per box, lane = centre.
+// `replicas` copies of the grid, 4096 words apart (the persistent loop: its blocks all read the
+// grid at the same moment, copies spread that over more L2 lines)
 __device__ void km_build_grid(const double *s_c, int K, uint32_t *__restrict__ grid, int4 *__restrict__ ent,
-                              int first_box, int box_stride)
+                              int first_box, int box_stride, int replicas = 1)
 {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (blockIdx.x == 0 && threadIdx.x < 4 * 33) {
@@ -220,26 +223,38 @@ __device__ void km_build_grid(const double *s_c, int K, uint32_t *__restrict__ g
         }
         ent[threadIdx.x] = e;
     }
-    for (int cell = first_box + wib; cell < 4096; cell += box_stride) {
-        const double lo[3] = {16.0 * (cell & 15), 16.0 * ((cell >> 4) & 15), 16.0 * (cell >> 8)};
-        bool alive = false;
-        if (lane < K) {
-            const double ci[3] = {s_c[3 * lane], s_c[3 * lane + 1], s_c[3 * lane + 2]};
-            const double ni = ci[0] * ci[0] + ci[1] * ci[1] + ci[2] * ci[2];
-            alive = true;
-            for (int j = 0; j < K && alive; ++j) {
-                if (j == lane) continue;
-                const double cj[3] = {s_c[3 * j], s_c[3 * j + 1], s_c[3 * j + 2]};
-                double mx = (cj[0] * cj[0] + cj[1] * cj[1] + cj[2] * cj[2]) - ni;   // |c_j|^2 - |c_i|^2
-                for (int a = 0; a < 3; ++a) {
-                    const double dlt = ci[a] - cj[a];
-                    mx += 2.0 * (dlt > 0.0 ? lo[a] + 15.0 : lo[a]) * dlt;
-                }
-                if (mx < -1e-6) alive = false;   // centre j is strictly nearer everywhere in the box
-            }
+    // f32 with a margin that covers its rounding (|terms| < 4e5, a dozen operations: error < 0.2):
+    // a centre is dropped only if it loses by more than 2 everywhere -- a superset of the exact
+    // candidate set, which is all the assignment pass needs (its decisions are exact).
+    // K <= 16: half a warp per box (lanes 16..31 take the odd box), else a warp per box.
+    const int bpw = K <= 16 ? 2 : 1;
+    const int sub = bpw == 2 ? lane >> 4 : 0, li = bpw == 2 ? (lane & 15) : lane;
+    float cf[3] = {0.f, 0.f, 0.f}, nf = 0.f;
+    if (li < K) {
+        cf[0] = (float)s_c[3 * li];
+        cf[1] = (float)s_c[3 * li + 1];
+        cf[2] = (float)s_c[3 * li + 2];
+        nf = (float)(s_c[3 * li] * s_c[3 * li] + s_c[3 * li + 1] * s_c[3 * li + 1] + s_c[3 * li + 2] * s_c[3 * li + 2]);
+    }
+    for (int task = first_box + wib; task * bpw < 4096; task += box_stride) {
+        const int cell = task * bpw + sub;
+        const float lo[3] = {16.0f * (cell & 15), 16.0f * ((cell >> 4) & 15), 16.0f * (cell >> 8)};
+        bool alive = li < K;
+        for (int j = 0; j < K; ++j) {
+            // centre j's values come from lane j of this half (shuffles: no shared-memory traffic)
+            const int srcl = bpw == 2 ? (lane & 16) | j : j;
+            const float cj0 = __shfl_sync(0xffffffffu, cf[0], srcl), cj1 = __shfl_sync(0xffffffffu, cf[1], srcl),
+                        cj2 = __shfl_sync(0xffffffffu, cf[2], srcl), nj = __shfl_sync(0xffffffffu, nf, srcl);
+            const float d0 = cf[0] - cj0, d1 = cf[1] - cj1, d2 = cf[2] - cj2;
+            float mx = nj - nf;                                   // |c_j|^2 - |c_i|^2
+            mx = fmaf(2.0f * (d0 > 0.0f ? lo[0] + 15.0f : lo[0]), d0, mx);
+            mx = fmaf(2.0f * (d1 > 0.0f ? lo[1] + 15.0f : lo[1]), d1, mx);
+            mx = fmaf(2.0f * (d2 > 0.0f ? lo[2] + 15.0f : lo[2]), d2, mx);
+            if (j != li && mx < -2.0f) alive = false;             // centre j is nearer everywhere in the box
         }
-        unsigned m = __ballot_sync(0xffffffffu, alive);
-        if (lane == 0) {
+        const unsigned mall = __ballot_sync(0xffffffffu, alive);
+        unsigned m = bpw == 2 ? (mall >> (16 * sub)) & 0xffffu : mall;
+        if (li == 0) {
             uint32_t e = 0xffffffffu;
             if (__popc(m) <= 4) {
                 e = 0;
@@ -249,7 +264,7 @@ __device__ void km_build_grid(const double *s_c, int K, uint32_t *__restrict__ g
                     e |= idx << (8 * k);
                 }
             }
-            grid[cell] = e;
+            for (int r = 0; r < replicas; ++r) grid[r * 4096 + cell] = e;
         }
     }
 }
@@ -388,29 +403,69 @@ struct KmWarpShared {
     unsigned pad[3];
 };
 
-template <int KP>   // bins rows = KP + 1 (KP = 16 or 32 centres, + the dummy row)
-__global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
-    const uint8_t *__restrict__ px, long long n, const double *__restrict__ centers, int K,
-    unsigned long long *__restrict__ sums, const uint32_t *__restrict__ grid, const int4 *__restrict__ ent,
-    const KmState *__restrict__ state, KmPush ps)
+// shared memory of the assignment pass (KP = 16 or 32 centres; bins rows = KP + 1 with the dummy row)
+template <int KP>
+struct KmSmem {
+    uint2 *bins;                 // [warps][KP+1][32]
+    uint32_t *grid;              // [4096]
+    int4 *ent;                   // [4][33]
+    double *c;                   // [32*3]
+    KmWarpShared *w;             // [warps]
+    unsigned long long *tot;     // [32*4+1]
+    unsigned char *end;
+};
+
+template <int KP>
+__device__ __forceinline__ KmSmem<KP> km_carve(unsigned char *base)
 {
-    if (state && state->done) return;
-    extern __shared__ __align__(16) unsigned char km_smem[];
-    uint2 *s_bins = reinterpret_cast<uint2 *>(km_smem);                         // [warps][KP+1][32]
-    uint32_t *s_grid = reinterpret_cast<uint32_t *>(s_bins + KM_WARPS * (KP + 1) * 32);   // [4096]
-    int4 *s_ent = reinterpret_cast<int4 *>(s_grid + 4096);                      // [4][33]
-    double *s_c = reinterpret_cast<double *>(s_ent + 4 * 33);                   // [32*3]
-    KmWarpShared *s_w = reinterpret_cast<KmWarpShared *>(s_c + 32 * 3);         // [warps]
-    unsigned long long *s_tot = reinterpret_cast<unsigned long long *>(s_w + KM_WARPS);   // [32*4+1]
+    KmSmem<KP> m;
+    m.bins = reinterpret_cast<uint2 *>(base);
+    m.grid = reinterpret_cast<uint32_t *>(m.bins + KM_WARPS * (KP + 1) * 32);
+    m.ent = reinterpret_cast<int4 *>(m.grid + 4096);
+    m.c = reinterpret_cast<double *>(m.ent + 4 * 33);
+    m.w = reinterpret_cast<KmWarpShared *>(m.c + 32 * 3);
+    m.tot = reinterpret_cast<unsigned long long *>(m.w + KM_WARPS);
+    m.end = reinterpret_cast<unsigned char *>(m.tot + 32 * 4 + 1);
+    return m;
+}
+
+// grid + table into shared memory (ld.global.cg: inside the persistent loop kernel the tables
+// were written by other blocks of the SAME launch)
+template <int KP>
+__device__ __forceinline__ void km_accum_tables(const KmSmem<KP> &m, const uint32_t *grid, const int4 *ent)
+{
+    const int tid = threadIdx.x;
+    if (tid < 4 * 33) m.ent[tid] = __ldcg(ent + tid);
+    static_assert(4096 / 4 == 4 * KM_THREADS, "four 16-byte words per thread");
+    uint4 g[4];   // all four loads in flight before the first store (one L2 round trip, not four)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g[i] = __ldcg(reinterpret_cast<const uint4 *>(grid) + tid + i * KM_THREADS);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) reinterpret_cast<uint4 *>(m.grid)[tid + i * KM_THREADS] = g[i];
+}
+
+// bins, block totals and slow lists cleared -- once per launch: the assignment pass leaves them zero
+template <int KP>
+__device__ __forceinline__ void km_accum_zero(const KmSmem<KP> &m)
+{
+    const int tid = threadIdx.x;
+    for (int i = tid; i < KM_WARPS * (KP + 1) * 32; i += KM_THREADS) m.bins[i] = make_uint2(0u, 0u);
+    if (tid < 32 * 4 + 1) m.tot[tid] = 0ull;
+    if ((tid & 31) == 0) m.w[tid >> 5].nslow = 0u;
+}
+
+// the assignment pass proper: this block's tiles -> atomics into sums[K*4+1]
+template <int KP>
+__device__ __forceinline__ void km_accum_body(const KmSmem<KP> &m, const uint8_t *__restrict__ px, long long n, int K,
+                                              unsigned long long *__restrict__ sums)
+{
+    uint2 *s_bins = m.bins;
+    uint32_t *s_grid = m.grid;
+    int4 *s_ent = m.ent;
+    double *s_c = m.c;
+    unsigned long long *s_tot = m.tot;
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    if (tid < K * 3) s_c[tid] = centers[tid];
-    if (tid < 4 * 33) s_ent[tid] = ent[tid];
-    for (int i = tid; i < 4096; i += KM_THREADS) s_grid[i] = grid[i];
-    for (int i = tid; i < KM_WARPS * (KP + 1) * 32; i += KM_THREADS) s_bins[i] = make_uint2(0u, 0u);
-    if (tid < 32 * 4 + 1) s_tot[tid] = 0ull;
-    KmWarpShared &ws = s_w[wib];
-    if (lane == 0) ws.nslow = 0u;
-    __syncthreads();
+    KmWarpShared &ws = m.w[wib];
 
     const unsigned FULL = 0xffffffffu;
     const unsigned ent_a = (unsigned)__cvta_generic_to_shared(s_ent);
@@ -480,8 +535,10 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
 
     const uint4 *g4 = reinterpret_cast<const uint4 *>(px + 3 * head);
     const long long ntiles = (ngroups + 31) >> 5;             // 32 groups = 512 pixels per warp tile
+    // consecutive tiles go to different BLOCKS (then to the warps of a block): a short input
+    // spreads over all SMs instead of filling the first blocks' eight warps
     const long long wstride = (long long)gridDim.x * KM_WARPS;
-    long long t = (long long)blockIdx.x * KM_WARPS + wib;
+    long long t = (long long)blockIdx.x + (long long)gridDim.x * wib;
     uint4 nx0 = make_uint4(0, 0, 0, 0), nx1 = nx0, nx2 = nx0;
     auto fetch = [&](long long tile) {
         const long long grp = tile * 32 + lane;
@@ -591,10 +648,240 @@ __global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
     }
     if (lane == 0 && nties) atomicAdd(&s_tot[32 * 4], (unsigned long long)nties);
     __syncthreads();
-    if (tid < K * 4 && s_tot[tid]) atomicAdd(&sums[tid], s_tot[tid]);
-    if (tid == 0 && s_tot[32 * 4]) atomicAdd(&sums[4 * K], s_tot[32 * 4]);
+    // (every word that was used goes back to zero: the persistent loop comes here again)
+    if (tid < K * 4) {
+        const unsigned long long v = s_tot[tid];
+        if (v) {
+            atomicAdd(&sums[tid], v);
+            s_tot[tid] = 0ull;
+        }
+    }
+    if (tid == 0) {
+        const unsigned long long v = s_tot[32 * 4];
+        if (v) {
+            atomicAdd(&sums[4 * K], v);
+            s_tot[32 * 4] = 0ull;
+        }
+    }
+}
+
+template <int KP>
+__global__ void __launch_bounds__(KM_THREADS) k_kmeans_accum16(
+    const uint8_t *__restrict__ px, long long n, const double *__restrict__ centers, int K,
+    unsigned long long *__restrict__ sums, const uint32_t *__restrict__ grid, const int4 *__restrict__ ent,
+    const KmState *__restrict__ state, KmPush ps)
+{
+    if (state && state->done) return;
+    extern __shared__ __align__(16) unsigned char km_smem[];
+    const KmSmem<KP> m = km_carve<KP>(km_smem);
+    if (threadIdx.x < K * 3) m.c[threadIdx.x] = centers[threadIdx.x];
+    km_accum_tables<KP>(m, grid, ent);
+    km_accum_zero<KP>(m);
+    __syncthreads();
+    km_accum_body<KP>(m, px, n, K, sums);
     km_push_tail(sums, K * 4 + 1, ps);
 }
+
+// ---- the whole Lloyd loop as ONE persistent launch (K <= 32) -------------------------------------
+// All blocks are resident (grid = SMs x occupancy) and meet at a grid barrier twice per iteration:
+//   prepare(it)   every block: totals of iteration it-1 (own sums, or the ranks' inbox slots once
+//                 their flags show the tag), new centres, shift, stop test -- all blocks compute
+//                 the same values, so the decision to leave the loop needs no broadcast; block 0
+//                 records the state and clears the sums; the 4096 grid boxes are spread over the
+//                 warps of the whole grid
+//   -- barrier --
+//   assign(it)    as k_kmeans_accum16
+//   -- barrier --  then block 0 pushes the rank's sums to the peers (peer exchange)
+// Two launches and their gaps per iteration (~22 us on this stack) become two barriers (~3 us).
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// barrier over all blocks of the launch: bar[0] counts arrivals and is never reset -- barrier
+// number g (0, 1, ...) is complete when the count reaches (g + 1) * blocks, and the block that
+// makes it so publishes g + 1 in bar[1].  One release (the arriving atomic) and one acquire (the
+// poll) per block.  Returns false after ~10 s without release (a block never became resident):
+// callers bail out.
+__device__ __forceinline__ bool km_grid_barrier(unsigned *bar, unsigned &gen)
+{
+    __shared__ int s_ok;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s_ok = 1;
+        unsigned old;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(bar) : "memory");
+        if (old + 1u == (gen + 1u) * gridDim.x) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1u) : "memory");
+        } else {
+            unsigned spins = 0;
+            while (ld_acquire_gpu_u32(bar + 1) == gen) {
+                if (++spins > 64u) __nanosleep(32);
+                if (spins > (1u << 26)) {
+                    s_ok = 0;
+                    break;
+                }
+            }
+        }
+    }
+    ++gen;
+    __syncthreads();
+    return s_ok != 0;
+}
+
+#ifdef DP_KM_TIMING
+__device__ unsigned long long g_km_timing[8];
+#define KM_TICK(k)                                                             \
+    do {                                                                       \
+        const long long _now = clock64();                                      \
+        if (blockIdx.x == 1 && threadIdx.x == 0) g_km_timing[(k)] += (unsigned long long)(_now - _tick); \
+        _tick = _now;                                                          \
+    } while (0)
+#else
+#define KM_TICK(k) do { } while (0)
+#endif
+
+template <int KP>
+__global__ void __launch_bounds__(KM_THREADS, 3) k_kmeans_loop(
+    const uint8_t *__restrict__ px, long long n, double *__restrict__ c_io, int K, double tol, int max_iter,
+    unsigned long long *__restrict__ sums2, KmState *__restrict__ state, uint32_t *__restrict__ grid,
+    int4 *__restrict__ ent, unsigned *__restrict__ bar, KmPush ps, const unsigned long long *inbox)
+{
+    extern __shared__ __align__(16) unsigned char km_smem[];
+    const KmSmem<KP> m = km_carve<KP>(km_smem);
+    double *s_new = reinterpret_cast<double *>(m.end + 8 - ((uintptr_t)m.end & 7));   // [32*3]
+    double *s_d2 = s_new + 32 * 3;                                                    // [32*3]
+    unsigned long long *s_prev = reinterpret_cast<unsigned long long *>(s_d2 + 32 * 3);   // [32*4+1]
+    __shared__ int s_stop, s_empty, s_err;
+    const int tid = threadIdx.x;
+    const int nsum = K * 4 + 1;
+    if (tid < K * 3) m.c[tid] = c_io[tid];
+    if (tid == 0) s_stop = s_empty = s_err = 0;
+    km_accum_zero<KP>(m);
+    __syncthreads();
+    // this block's share of the assignment pass (same tiling as k_kmeans_accum16)
+    const unsigned mis = (unsigned)(reinterpret_cast<uintptr_t>(px) & 15u);
+    long long head = mis ? (long long)((16u - mis) * 11u & 15u) : 0;
+    if (head > n) head = n;
+    const long long ntiles = (((n - head) >> 4) + 31) >> 5;
+    const bool has_work = blockIdx.x == 0 || (long long)blockIdx.x < ntiles;
+    const unsigned long long tag0 = ps.iter;
+    bool failed = false;
+    unsigned bar_gen = 0;
+    unsigned long long ties_acc = 0;
+    int empty_acc = 0;
+#ifdef DP_KM_TIMING
+    long long _tick = clock64();
+#endif
+    for (int it = 1;; ++it) {
+        KM_TICK(6);
+        unsigned long long *sums_cur = sums2 + (size_t)(it & 1) * nsum;
+        if (it > 1) {
+            // ---- totals of iteration it-1
+            if (inbox) {
+                const int parity = (it - 1) & 1;
+                if (tid < ps.world) {
+                    const unsigned long long *f = inbox + KM_P2P_FLAGS_OFF + (size_t)parity * KM_P2P_RANKS + tid;
+                    const unsigned long long want = tag0 + (unsigned long long)(it - 1);
+                    unsigned spins = 0;
+                    while (ld_acquire_sys(f) < want) {
+                        __nanosleep(100);
+                        if (++spins > (1u << 25)) {
+                            s_err = 1;
+                            break;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (s_err) {
+                    failed = true;
+                    break;
+                }
+                for (int k = tid; k < nsum; k += KM_THREADS) {
+                    unsigned long long t = 0;
+                    for (int r = 0; r < ps.world; ++r)
+                        t += __ldcg(inbox + ((size_t)parity * KM_P2P_RANKS + r) * KM_P2P_STRIDE + k);
+                    s_prev[k] = t;
+                }
+            } else {
+                const unsigned long long *sp = sums2 + (size_t)((it - 1) & 1) * nsum;
+                for (int k = tid; k < nsum; k += KM_THREADS) s_prev[k] = __ldcg(sp + k);
+            }
+            __syncthreads();
+            // ---- centres, shift, stop test (same code and order as k_kmeans_prepare)
+            if (tid < K * 3) {
+                bool emp = false;
+                const double nw = km_new_center(s_prev, m.c, tid / 3, tid % 3, &emp);
+                const double d = nw - m.c[tid];
+                s_new[tid] = nw;
+                s_d2[tid] = __dmul_rn(d, d);
+                if (emp) s_empty = 1;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                double tot = 0.0;
+                for (int i = 0; i < K * 3; ++i) tot = __dadd_rn(tot, s_d2[i]);
+                const int stop = (tot <= tol || it - 1 >= max_iter) ? 1 : 0;
+                s_stop = stop;
+                if (blockIdx.x == 0) {
+                    // stores only (the counters live in registers): no global round trip on the
+                    // path every other block waits for at the barrier
+                    for (int i = 0; i < K * 3; ++i) c_io[i] = s_new[i];
+                    ties_acc += s_prev[4 * K];
+                    empty_acc += s_empty ? 1 : 0;
+                    state->n_iter = it - 1;
+                    state->shift2 = tot;
+                    state->ties = ties_acc;
+                    state->empty = empty_acc;
+                }
+                s_empty = 0;
+            }
+            __syncthreads();
+            if (tid < K * 3) m.c[tid] = s_new[tid];
+            __syncthreads();
+            if (s_stop) break;
+        }
+        KM_TICK(0);
+        // ---- tables for the new centres; clear the sums of this iteration
+        if (blockIdx.x == 0)
+            for (int k = tid; k < nsum; k += KM_THREADS) sums_cur[k] = 0ull;
+        km_build_grid(m.c, K, grid, ent, blockIdx.x * KM_WARPS, gridDim.x * KM_WARPS, KM_GRID_REPLICAS);
+        KM_TICK(1);
+        if (!km_grid_barrier(bar, bar_gen)) {
+            failed = true;
+            break;
+        }
+        KM_TICK(2);
+        // ---- assignment pass
+        if (has_work) {
+            km_accum_tables<KP>(m, grid + (blockIdx.x % KM_GRID_REPLICAS) * 4096, ent);
+            __syncthreads();
+            KM_TICK(3);
+            km_accum_body<KP>(m, px, n, K, sums_cur);
+        }
+        KM_TICK(4);
+        if (!km_grid_barrier(bar, bar_gen)) {
+            failed = true;
+            break;
+        }
+        KM_TICK(5);
+        if (inbox && blockIdx.x == 0) {
+            KmPush q = ps;
+            q.parity = it & 1;
+            q.iter = tag0 + (unsigned long long)it;
+            km_push_sums(sums_cur, nsum, q);
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        if (failed) state->error = 1;
+        __threadfence();
+        state->done = 1;
+    }
+}
+
+inline size_t km_loop_smem(int KP);
 
 inline size_t km_accum_smem(int KP)
 {
@@ -644,6 +931,37 @@ int km_scratch(KmScratch **out)
     return 0;
 }
 
+inline size_t km_loop_smem(int KP) { return km_accum_smem(KP) + 8 + 2 * 32 * 3 * 8 + (32 * 4 + 1) * 8; }
+
+// launch of the persistent Lloyd loop: every block must be resident (they meet at grid barriers),
+// so the grid is the occupancy of an idle device -- DP_KMEANS_LOOP_BLOCKS lowers it (tests that run
+// several ranks as streams of ONE device need all their kernels resident side by side)
+template <int KP>
+int km_launch_loop_kp(const uint8_t *pixels, long long n, double *c_io, int K, double tol, int max_iter,
+                      unsigned long long *sums2, KmState *state, uint32_t *grid, int4 *ent, unsigned *bar,
+                      const KmPush &ps, const unsigned long long *inbox, cudaStream_t st)
+{
+    static thread_local int per_sm[64] = {0};
+    int dev = 0;
+    DP_CUDA(cudaGetDevice(&dev));
+    const size_t smem = km_loop_smem(KP);
+    if (dev >= 0 && dev < 64 && !per_sm[dev]) {
+        DP_CUDA(cudaFuncSetAttribute(k_kmeans_loop<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_kmeans_loop<KP>, KM_THREADS, smem));
+        per_sm[dev] = occ < 1 ? 1 : occ;
+    }
+    long long blocks = (long long)dp_num_sms() * (dev >= 0 && dev < 64 ? per_sm[dev] : 1);
+    if (const char *ev = getenv("DP_KMEANS_LOOP_BLOCKS")) {
+        const long long b = atoll(ev);
+        if (b >= 1 && b < blocks) blocks = b;
+    }
+    k_kmeans_loop<KP><<<(int)blocks, KM_THREADS, smem, st>>>(pixels, n, c_io, K, tol, max_iter, sums2, state, grid, ent,
+                                                             bar, ps, inbox);
+    DP_LAUNCH_CHECK();
+    return 0;
+}
+
 // launch of the assignment pass: bins for 16 or 32 centres, as many resident blocks as fit
 template <int KP>
 int km_launch_accum_kp(const uint8_t *pixels, long long n, const double *centers, int K, unsigned long long *sums,
@@ -667,6 +985,20 @@ int km_launch_accum_kp(const uint8_t *pixels, long long n, const double *centers
                                                                                        ent, state, ps);
     DP_LAUNCH_CHECK();
     return 0;
+}
+
+// pixels per block of the generic pass: at most KM_PIX_PER_BLOCK (exact u32 partials), less when
+// the input is short so that it still spreads over the whole device (the reference's k-means
+// sees 10 000 samples: one 16 384-pixel chunk would be ONE block)
+inline int km_generic_chunk(long long n, long long cap, int *grid)
+{
+    long long chunk = (n + cap - 1) / cap;
+    chunk = (chunk + KM_THREADS - 1) / KM_THREADS * KM_THREADS;
+    if (chunk < KM_THREADS) chunk = KM_THREADS;
+    if (chunk > KM_PIX_PER_BLOCK) chunk = KM_PIX_PER_BLOCK;
+    const long long chunks = (n + chunk - 1) / chunk;
+    *grid = (int)(chunks < 1 ? 1 : (chunks < cap ? chunks : cap));
+    return (int)chunk;
 }
 
 KmPush km_no_push()
@@ -786,10 +1118,9 @@ extern "C" int dp_kmeans_accumulate(const uint8_t *pixels, int64_t n, const doub
         DP_LAUNCH_CHECK();
         return km_launch_accum(pixels, n, centers, K, sums, sc->grid, sc->ent, nullptr, st);
     }
-    long long cap = (long long)dp_num_sms() * 8;
-    long long chunks = (n + KM_PIX_PER_BLOCK - 1) / KM_PIX_PER_BLOCK;
-    int grid = (int)(chunks < cap ? chunks : cap);
-    k_kmeans_accumulate<<<grid, KM_THREADS, 0, st>>>(pixels, n, centers, K, sums, nullptr, km_no_push());
+    int grid = 1;
+    const int chunk_px = km_generic_chunk(n, (long long)dp_num_sms() * 8, &grid);
+    k_kmeans_accumulate<<<grid, KM_THREADS, 0, st>>>(pixels, n, centers, K, sums, nullptr, km_no_push(), chunk_px);
     DP_LAUNCH_CHECK();
     return 0;
 }
@@ -856,7 +1187,7 @@ int km_lloyd(const uint8_t *pixels, int64_t n, double *centers_host, int K, doub
     const unsigned long long *my_inbox = p2p ? peers.inbox[ex.rank] : nullptr;
     const size_t nsum = (size_t)K * 4 + 1;
     const size_t off_c = 0, off_s = off_c + 2 * (size_t)K * 3 * 8, off_state = off_s + 2 * nsum * 8,
-                 off_grid = off_state + 64, off_ent = off_grid + 4096 * 4, total = off_ent + 4 * 33 * 16;
+                 off_grid = off_state + 64, off_ent = off_grid + 4096 * 4 * KM_GRID_REPLICAS, total = off_ent + 4 * 33 * 16;
     char *ws = nullptr;
     DP_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&ws), total, st));
     double *cbuf[2] = {reinterpret_cast<double *>(ws + off_c), reinterpret_cast<double *>(ws + off_c) + (size_t)K * 3};
@@ -893,12 +1224,41 @@ int km_lloyd(const uint8_t *pixels, int64_t n, double *centers_host, int K, doub
     } while (0)
     KM_TRY(cudaMemsetAsync(ws + off_s, 0, 2 * nsum * 8 + 64, st));
     KM_TRY(cudaMemcpyAsync(cbuf[0], centers_host, (size_t)K * 3 * 8, cudaMemcpyHostToDevice, st));
-    const long long cap = (long long)dp_num_sms() * 8;
-    const long long chunks = (n + KM_PIX_PER_BLOCK - 1) / KM_PIX_PER_BLOCK;
-    const int ggrid = (int)(chunks < cap ? (chunks < 1 ? 1 : chunks) : cap);
+    int ggrid = 1;
+    const int gchunk = km_generic_chunk(n, (long long)dp_num_sms() * 8, &ggrid);
     const unsigned long long tag0 = ex.epoch << 32;
     int it = 1;
     bool stopped = false;
+    // K <= 32 without an NCCL communicator: the whole loop is one persistent launch
+    bool persistent = K <= 32 && !ex.nccl_comm;
+    if (const char *ev = getenv("DP_KMEANS_LOOP")) persistent = persistent && atoi(ev) != 0;
+    if (persistent) {
+        KmPush ps = km_no_push();
+        if (p2p) {
+            ps.peers = peers;
+            ps.rank = ex.rank;
+            ps.world = ex.world;
+        }
+        ps.iter = tag0;
+        const int rc = K <= 16 ? km_launch_loop_kp<16>(pixels, n, cbuf[0], K, tol, max_iter, sums[0], state, grid, ent,
+                                                        ticket, ps, my_inbox, st)
+                               : km_launch_loop_kp<32>(pixels, n, cbuf[0], K, tol, max_iter, sums[0], state, grid, ent,
+                                                        ticket, ps, my_inbox, st);
+        if (rc) return finish(1);
+        KM_TRY(cudaMemcpyAsync(&host_state, state, sizeof(KmState), cudaMemcpyDeviceToHost, st));
+        KM_TRY(cudaStreamSynchronize(st));
+        if (host_state.error) {
+            dp_set_error("k-means loop kernel gave up at a barrier or waiting for a peer's sums");
+            return finish(3);
+        }
+        KM_TRY(cudaMemcpyAsync(centers_host, cbuf[0], (size_t)K * 3 * 8, cudaMemcpyDeviceToHost, st));
+        KM_TRY(cudaStreamSynchronize(st));
+        if (n_iter) *n_iter = host_state.n_iter;
+        if (shift2) *shift2 = host_state.shift2;
+        if (ties) *ties = host_state.ties;
+        if (empty_iters) *empty_iters = host_state.empty;
+        return finish(0);
+    }
     while (!stopped) {
         const int upto = it + check_every - 1 < max_iter ? it + check_every - 1 : max_iter;
         for (; it <= upto; ++it) {
@@ -923,7 +1283,7 @@ int km_lloyd(const uint8_t *pixels, int64_t n, double *centers_host, int K, doub
                         return finish(1);
                 } else
                     k_kmeans_accumulate<<<ggrid, KM_THREADS, 0, st>>>(pixels, n, cbuf[(it - 1) & 1], K, sums[it & 1],
-                                                                      state, ps);
+                                                                      state, ps, gchunk);
             } else if (p2p)
                 k_kmeans_push<<<1, KM_THREADS, 0, st>>>(sums[it & 1], (int)nsum, ps, state);
             KM_TRY(cudaGetLastError());
@@ -1039,3 +1399,15 @@ extern "C" int dp_p2p_free(void *dptr)
     DP_CUDA(cudaFree(dptr));
     return 0;
 }
+
+#ifdef DP_KM_TIMING
+extern "C" int dp_debug_km_timing(unsigned long long *out, int reset)
+{
+    DP_CUDA(cudaMemcpyFromSymbol(out, g_km_timing, sizeof(unsigned long long) * 8));
+    if (reset) {
+        static unsigned long long zeros[8];
+        DP_CUDA(cudaMemcpyToSymbol(g_km_timing, zeros, sizeof(zeros)));
+    }
+    return 0;
+}
+#endif

@@ -383,11 +383,15 @@ def _lloyd_gpu(pix, init, tol, max_iter, offset=0, **kw):
         buf.free()
 
 
+@pytest.mark.parametrize("persistent", ["1", "0"])
 @pytest.mark.parametrize("K", [2, 5, 16, 32, 40])
-def test_kmeans_lloyd_device_loop_vs_oracle(K):
-    """dp_kmeans_lloyd (stop test on the device, host polls every few iterations) against the
-    oracle's f64 Lloyd: same iteration count, centres to 1e-9 -- for aligned and unaligned pixel
-    pointers, pixel counts that are not multiples of 16, and K beyond the 32-centre fast kernel."""
+def test_kmeans_lloyd_device_loop_vs_oracle(K, persistent, monkeypatch):
+    """dp_kmeans_lloyd against the oracle's f64 Lloyd: same iteration count, centres to 1e-9 -- for
+    aligned and unaligned pixel pointers, pixel counts that are not multiples of 16, and K beyond
+    the 32-centre fast kernels.  Both forms of the loop: one persistent launch with grid barriers
+    (K <= 32, the default) and a prepare + assignment launch per iteration with the stop flag on
+    the device and the host looking every few iterations (DP_KMEANS_LOOP=0; always for K > 32)."""
+    monkeypatch.setenv("DP_KMEANS_LOOP", persistent)
     rs = np.random.RandomState(K)
     for n, off in ((10000, 0), (70001, 3), (517, 7), (15, 1)):
         pix = np.ascontiguousarray(synth.frame(300, 400, 5).reshape(-1, 3)[:n]) if n > 600 else \
@@ -492,10 +496,11 @@ def test_kmeans_fewer_distinct_colours_than_clusters_is_reported():
     assert np.abs(res[0] - ref).max() < 1e-9
 
 
-@pytest.mark.parametrize("K,world", [(16, 2), (16, 3), (40, 2)])
-def test_kmeans_peer_memory_exchange_two_ranks_on_one_gpu(K, world):
+@pytest.mark.parametrize("K,world,persistent", [(16, 2, "1"), (16, 3, "1"), (32, 2, "1"), (16, 2, "0"), (40, 2, "0")])
+def test_kmeans_peer_memory_exchange_two_ranks_on_one_gpu(K, world, persistent, monkeypatch):
     """dp_kmeans_lloyd_p2p: the assignment kernel's last block pushes the rank's integer sums into
-    every inbox, the next prepare launch waits for the flags and adds the slots up.  Here the
+    every inbox, the next prepare step waits for the flags and adds the slots up (in the persistent
+    loop kernel: block 0 pushes after the grid barrier that ends the assignment pass).  Here the
     `world` ranks are host threads with their own streams on ONE device (the inboxes are plain
     device allocations; across processes they are cudaIpc mappings -- tools/multigpu_check.py):
     same centres, iteration count and tie count as the unsharded loop, twice in a row (epochs)."""
@@ -503,6 +508,9 @@ def test_kmeans_peer_memory_exchange_two_ranks_on_one_gpu(K, world):
     import threading
     from dither_pie_b200 import pipeline
     from dither_pie_b200._capi import check, lib
+    # persistent loop kernels of several ranks must all be resident on the one device: 64 blocks each
+    monkeypatch.setenv("DP_KMEANS_LOOP", persistent)
+    monkeypatch.setenv("DP_KMEANS_LOOP_BLOCKS", "64")
     img = synth.frame(540, 960, 4).reshape(-1, 3)
     rs = np.random.RandomState(K)
     init = img[rs.choice(len(img), K, replace=False)].astype(np.float64)
