@@ -1160,9 +1160,12 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
 }
 
 // ---------------------------------------------------------------------------------------
-// Serpentine (or any) scan, serial per frame: one warp per frame, lane 0 walks the reference's
-// loop on a 3-row f32 ring kept in global memory (L1/L2 resident); the other lanes only help
-// moving rows in and out.  Correct for every variant; throughput comes from frames in flight.
+// Serpentine (or any) scan, serial per frame: row y+1 starts where row y ends, so there is no
+// wavefront -- one WARP per frame walks the reference's loop pixel by pixel and spends its lanes
+// inside the pixel: lane j evaluates candidate j of the pixel's cell in f64 (warp minimum, lowest
+// lane among equals = first index), lane k applies tap k.  The 3-row f32 work ring lives in shared
+// memory (in global memory for rows wider than ~6000 pixels).  Throughput comes from frames in
+// flight; a single frame runs at the latency of this chain (~0.4 us per pixel).
 // ---------------------------------------------------------------------------------------
 struct SerialParams {
     const PalDev *P;
@@ -1170,15 +1173,85 @@ struct SerialParams {
     uint8_t *dst;
     uint8_t *dst_idx;
     int frames, h, w, K, serpentine, variant;
-    float *ring;           // [frames][3][w][3]
+    float *ring;           // [frames][3][w][3], or null: the ring is in shared memory
     const float *ostro_w;  // ostromoukhov only
     double hyb_lum, hyb_col;   // hybrid only
     const float *plane;        // weighted only
 };
 
-template <bool OSTRO>
+__device__ __forceinline__ double warp_min_f64(double v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// nearest_first_exact by the whole warp: strict '<' in ascending candidate order = the minimum,
+// lowest position among equals.  Every lane returns the row.
+__device__ __forceinline__ int nearest_first_exact_warp(const Search &s, int cell, const uint4 e, double r, double g,
+                                                        double b, int lane)
+{
+    const CandList L = cand_list(s, cell, e);
+    double best = 1e20;
+    int bi = 0;
+    for (int base = 0; base < L.n; base += 32) {
+        const int j = base + lane;
+        int row = 0;
+        double d = 1e300;
+        if (j < L.n) {
+            row = cand_at(L, j);
+            d = dist_numba(s.s_pal + 3 * row, r, g, b);
+        }
+        const double m = warp_min_f64(d);
+        if (m < best) {
+            const unsigned eq = __ballot_sync(0xffffffffu, d == m);
+            bi = __shfl_sync(0xffffffffu, row, __ffs(eq) - 1);
+            best = m;
+        }
+    }
+    return bi;
+}
+
+// nearest_kd_exact / nearest_kd_full by the whole warp: unique minimum, else scipy's traversal.
+// `L` null: every palette row (points outside the colour cube).
+__device__ __forceinline__ int nearest_kd_warp(const PalDev *P, const Search &s, const CandList *L, int K, double r,
+                                               double g, double b, int lane)
+{
+    const int n = L ? L->n : K;
+    double best = DP_INF_F64;
+    int bi = 0;
+    bool tie = false;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane;
+        int row = 0;
+        double d = DP_INF_F64;
+        if (j < n) {
+            row = L ? cand_at(*L, j) : j;
+            d = dist_scipy(s.s_pal + 3 * row, r, g, b);
+        }
+        const double m = warp_min_f64(d);
+        const unsigned eq = __ballot_sync(0xffffffffu, j < n && d == m);
+        if (m < best) {
+            bi = __shfl_sync(0xffffffffu, row, __ffs(eq) - 1);
+            best = m;
+            tie = __popc(eq) > 1;
+        } else if (m == best && eq) {
+            tie = true;
+        }
+    }
+    if (tie) {
+        int oi[1];
+        double os[1];
+        kd_emulate<1>(P, r, g, b, oi, os);
+        bi = oi[0];
+    }
+    return bi;
+}
+
+template <bool OSTRO, bool RING_SMEM>
 __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
 {
+    extern __shared__ __align__(16) float s_ring[];
     __shared__ double s_pal[DP_MAX_COLORS * 3];
     __shared__ float s_palf[DP_MAX_COLORS * 3];
     __shared__ uint8_t s_orgb[DP_MAX_COLORS * 4];
@@ -1221,7 +1294,7 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
         const uint8_t *src_f = p.src + frame_px * 3 * f;
         uint8_t *dst_f = p.dst + frame_px * 3 * f;
         uint8_t *idx_f = p.dst_idx ? p.dst_idx + frame_px * f : nullptr;
-        float *ring = p.ring + (size_t)f * 3 * W * 3;
+        float *ring = RING_SMEM ? s_ring : p.ring + (size_t)f * 3 * W * 3;
         // rows 0..2 into the ring
         for (int rr = 0; rr < 3 && rr < H; ++rr)
             for (int i = lane; i < W * 3; i += 32)
@@ -1231,90 +1304,90 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
             float *r0 = ring + (size_t)(y % 3) * W * 3;
             float *r1 = ring + (size_t)((y + 1) % 3) * W * 3;
             float *r2 = ring + (size_t)((y + 2) % 3) * W * 3;
-            if (lane == 0) {
-                const int dir = (p.serpentine && (y & 1)) ? -1 : 1;
-                int x = dir > 0 ? 0 : W - 1;
-                for (int n = 0; n < W; ++n, x += dir) {
-                    float *px = r0 + 3 * x;
-                    int bi;
-                    if (!OSTRO && p.variant == V_WEIGHTED) {
-                        // perceptual (:1042-1063), see the wavefront kernel
-                        float ov[3], er[3];
-                        for (int c = 0; c < 3; ++c) ov[c] = px[c];
-                        const bool inside = ov[0] >= 0.f && ov[0] <= 255.f && ov[1] >= 0.f && ov[1] <= 255.f &&
-                                            ov[2] >= 0.f && ov[2] <= 255.f;
-                        const int wcell = inside ? cell_of(ov[0], ov[1], ov[2]) : 0;
-                        bi = inside ? nearest_kd_exact(P, srch, wcell, fetch_pattern(srch, wcell), (double)ov[0],
-                                                       (double)ov[1], (double)ov[2])
-                                    : nearest_kd_full(P, s_pal, p.K, (double)ov[0], (double)ov[1], (double)ov[2]);
-                        for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], s_palf[3 * bi + c]);
-                        const float fac = p.plane[((size_t)f * H + y) * W + x];
-                        const float w0 = __fmul_rn(0.4375f, fac), w1 = __fmul_rn(0.1875f, fac),
-                                    w2 = __fmul_rn(0.3125f, fac), w3 = __fmul_rn(0.0625f, fac);
-                        for (int c = 0; c < 3; ++c) {
-                            if (x + 1 < W) r0[3 * (x + 1) + c] = __fadd_rn(r0[3 * (x + 1) + c], __fmul_rn(er[c], w0));
-                            if (y + 1 < H) {
-                                if (x > 0) r1[3 * (x - 1) + c] = __fadd_rn(r1[3 * (x - 1) + c], __fmul_rn(er[c], w1));
-                                r1[3 * x + c] = __fadd_rn(r1[3 * x + c], __fmul_rn(er[c], w2));
-                                if (x + 1 < W) r1[3 * (x + 1) + c] = __fadd_rn(r1[3 * (x + 1) + c], __fmul_rn(er[c], w3));
-                            }
-                        }
-                    } else if (!OSTRO) {
-                        double v[3], e[3];
-                        for (int c = 0; c < 3; ++c) {
-                            double tv = (double)px[c];
-                            v[c] = tv < 0.0 ? 0.0 : (tv > 255.0 ? 255.0 : tv);
-                        }
-                        const int scell = cell_of((float)v[0], (float)v[1], (float)v[2]);
-                        bi = nearest_first_exact(srch, scell, fetch_pattern(srch, scell), v[0], v[1], v[2]);
-                        for (int c = 0; c < 3; ++c) e[c] = __dsub_rn(v[c], (double)s_palf[3 * bi + c]);
-                        if (p.variant == V_HYBRID) {   // _hybrid_numba :1447-1455
-                            const double lum = __dadd_rn(
-                                __dadd_rn(__dmul_rn(0.299, e[0]), __dmul_rn(0.587, e[1])),
-                                __dmul_rn(0.114, e[2]));
-                            const double cf[3] = {0.299, 0.587, 0.114};
-                            for (int c = 0; c < 3; ++c) {
-                                const double l = __dmul_rn(cf[c], lum);
-                                e[c] = __dadd_rn(__dmul_rn(p.hyb_lum, l), __dmul_rn(p.hyb_col, __dsub_rn(e[c], l)));
-                            }
-                        }
-                        for (int k = 0; k < ntaps; ++k) {
-                            const int nx = x + s_tdx[k] * dir;
-                            const int dy = s_tdy[k];
-                            if (nx < 0 || nx >= W || y + dy >= H) continue;
-                            float *q = (dy == 0 ? r0 : dy == 1 ? r1 : r2) + 3 * nx;
-                            for (int c = 0; c < 3; ++c) q[c] = acc_f64(q[c], __dmul_rn(e[c], s_tw[k]));
-                        }
+            const int dir = (p.serpentine && (y & 1)) ? -1 : 1;
+            int x = dir > 0 ? 0 : W - 1;
+            // every lane walks the row; the values it reads are the same in all lanes
+            for (int n = 0; n < W; ++n, x += dir) {
+                const float *px = r0 + 3 * x;
+                const float pv[3] = {px[0], px[1], px[2]};
+                int bi;
+                if (!OSTRO && p.variant == V_WEIGHTED) {
+                    // perceptual (:1042-1063), see the wavefront kernel
+                    float er[3];
+                    const bool inside = pv[0] >= 0.f && pv[0] <= 255.f && pv[1] >= 0.f && pv[1] <= 255.f &&
+                                        pv[2] >= 0.f && pv[2] <= 255.f;
+                    if (inside) {
+                        const int wcell = cell_of(pv[0], pv[1], pv[2]);
+                        const CandList L = cand_list(srch, wcell, __ldg(srch.flat + wcell));
+                        bi = nearest_kd_warp(P, srch, &L, p.K, (double)pv[0], (double)pv[1], (double)pv[2], lane);
                     } else {
-                        float ov[3], er[3];
-                        for (int c = 0; c < 3; ++c) {
-                            float a = px[c];
-                            ov[c] = a < 0.f ? 0.f : (a > 255.f ? 255.f : a);
-                        }
-                        const int ocell = cell_of(ov[0], ov[1], ov[2]);
-                        bi = nearest_kd_exact(P, srch, ocell, fetch_pattern(srch, ocell), (double)ov[0],
-                                              (double)ov[1], (double)ov[2]);
-                        for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], s_palf[3 * bi + c]);
-                        float lum = __fmul_rn(0.299f, ov[0]);
-                        lum = __fadd_rn(lum, __fmul_rn(0.587f, ov[1]));
-                        lum = __fadd_rn(lum, __fmul_rn(0.114f, ov[2]));
-                        lum = lum < 0.f ? 0.f : (lum > 255.f ? 255.f : lum);
-                        const int li = (int)lum;
-                        const float w0 = p.ostro_w[4 * li], w1 = p.ostro_w[4 * li + 1],
-                                    w2 = p.ostro_w[4 * li + 2];
-                        int nx = x + dir;
-                        if (nx >= 0 && nx < W)
-                            for (int c = 0; c < 3; ++c)
-                                r0[3 * nx + c] = __fadd_rn(r0[3 * nx + c], __fmul_rn(er[c], w0));
-                        if (y + 1 < H) {
-                            nx = x - dir;
-                            if (nx >= 0 && nx < W)
-                                for (int c = 0; c < 3; ++c)
-                                    r1[3 * nx + c] = __fadd_rn(r1[3 * nx + c], __fmul_rn(er[c], w1));
-                            for (int c = 0; c < 3; ++c)
-                                r1[3 * x + c] = __fadd_rn(r1[3 * x + c], __fmul_rn(er[c], w2));
+                        bi = nearest_kd_warp(P, srch, nullptr, p.K, (double)pv[0], (double)pv[1], (double)pv[2], lane);
+                    }
+                    for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(pv[c], s_palf[3 * bi + c]);
+                    const float fac = p.plane[((size_t)f * H + y) * W + x];
+                    // lane t applies tap t: (x+1, y) 7/16, (x-1, y+1) 3/16, (x, y+1) 5/16, (x+1, y+1) 1/16
+                    if (lane < 4) {
+                        const float wt = __fmul_rn(lane == 0 ? 0.4375f : lane == 1 ? 0.1875f : lane == 2 ? 0.3125f : 0.0625f,
+                                                   fac);
+                        const int nx = lane == 1 ? x - 1 : lane == 2 ? x : x + 1;
+                        const bool ok = nx >= 0 && nx < W && (lane == 0 || y + 1 < H);
+                        if (ok) {
+                            float *q = (lane == 0 ? r0 : r1) + 3 * nx;
+                            for (int c = 0; c < 3; ++c) q[c] = __fadd_rn(q[c], __fmul_rn(er[c], wt));
                         }
                     }
+                } else if (!OSTRO) {
+                    double v[3], e[3];
+                    for (int c = 0; c < 3; ++c) {
+                        const double tv = (double)pv[c];
+                        v[c] = tv < 0.0 ? 0.0 : (tv > 255.0 ? 255.0 : tv);
+                    }
+                    const int scell = cell_of((float)v[0], (float)v[1], (float)v[2]);
+                    bi = nearest_first_exact_warp(srch, scell, __ldg(srch.flat + scell), v[0], v[1], v[2], lane);
+                    for (int c = 0; c < 3; ++c) e[c] = __dsub_rn(v[c], (double)s_palf[3 * bi + c]);
+                    if (p.variant == V_HYBRID) {   // _hybrid_numba :1447-1455
+                        const double lum = __dadd_rn(
+                            __dadd_rn(__dmul_rn(0.299, e[0]), __dmul_rn(0.587, e[1])),
+                            __dmul_rn(0.114, e[2]));
+                        const double cf[3] = {0.299, 0.587, 0.114};
+                        for (int c = 0; c < 3; ++c) {
+                            const double l = __dmul_rn(cf[c], lum);
+                            e[c] = __dadd_rn(__dmul_rn(p.hyb_lum, l), __dmul_rn(p.hyb_col, __dsub_rn(e[c], l)));
+                        }
+                    }
+                    if (lane < ntaps) {   // the taps of one pixel hit distinct pixels: one lane each
+                        const int nx = x + s_tdx[lane] * dir;
+                        const int dy = s_tdy[lane];
+                        if (nx >= 0 && nx < W && y + dy < H) {
+                            float *q = (dy == 0 ? r0 : dy == 1 ? r1 : r2) + 3 * nx;
+                            const double tw = s_tw[lane];
+                            for (int c = 0; c < 3; ++c) q[c] = acc_f64(q[c], __dmul_rn(e[c], tw));
+                        }
+                    }
+                } else {
+                    float ov[3], er[3];
+                    for (int c = 0; c < 3; ++c) ov[c] = pv[c] < 0.f ? 0.f : (pv[c] > 255.f ? 255.f : pv[c]);
+                    const int ocell = cell_of(ov[0], ov[1], ov[2]);
+                    const CandList L = cand_list(srch, ocell, __ldg(srch.flat + ocell));
+                    bi = nearest_kd_warp(P, srch, &L, p.K, (double)ov[0], (double)ov[1], (double)ov[2], lane);
+                    for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], s_palf[3 * bi + c]);
+                    float lum = __fmul_rn(0.299f, ov[0]);
+                    lum = __fadd_rn(lum, __fmul_rn(0.587f, ov[1]));
+                    lum = __fadd_rn(lum, __fmul_rn(0.114f, ov[2]));
+                    lum = lum < 0.f ? 0.f : (lum > 255.f ? 255.f : lum);
+                    const int li = (int)lum;
+                    // lane t applies tap t: (x+dir, y) c0, (x-dir, y+1) c1, (x, y+1) c2
+                    if (lane < 3) {
+                        const float wt = p.ostro_w[4 * li + lane];
+                        const int nx = lane == 0 ? x + dir : lane == 1 ? x - dir : x;
+                        const bool ok = nx >= 0 && nx < W && (lane == 0 || y + 1 < H);
+                        if (ok) {
+                            float *q = (lane == 0 ? r0 : r1) + 3 * nx;
+                            for (int c = 0; c < 3; ++c) q[c] = __fadd_rn(q[c], __fmul_rn(er[c], wt));
+                        }
+                    }
+                }
+                if (lane == 0) {
                     if (p.dst) {   // (null: index-plane-only output)
                         uint8_t *o = dst_f + ((size_t)y * W + x) * 3;
                         o[0] = s_orgb[4 * bi];
@@ -1323,8 +1396,8 @@ __global__ void __launch_bounds__(32) k_diffuse_serial(const SerialParams p)
                     }
                     if (idx_f) idx_f[(size_t)y * W + x] = (uint8_t)bi;
                 }
+                __syncwarp();   // the taps are in the ring before any lane reads the next pixel
             }
-            __syncwarp();
             // row y's slot becomes row y+3
             if (y + 3 < H)
                 for (int i = lane; i < W * 3; i += 32)
@@ -1499,14 +1572,31 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
         sp.hyb_lum = hyb_lum;
         sp.hyb_col = hyb_col;
         sp.plane = plane;
+        // the 3-row ring in shared memory when it fits beside the kernel's static tables
+        const size_t ring_bytes = (size_t)3 * w * 3 * sizeof(float);
+        const bool ring_smem = ring_bytes <= 200 * 1024;
         Workspace ring;
-        if (ring.alloc((size_t)frames * 3 * w * 3 * sizeof(float), st)) return 1;
-        sp.ring = static_cast<float *>(ring.ptr);
+        if (!ring_smem) {
+            if (ring.alloc((size_t)frames * ring_bytes, st)) return 1;
+            sp.ring = static_cast<float *>(ring.ptr);
+        }
+        const size_t smem = ring_smem ? ring_bytes : 0;
         int grid = frames < dp_num_sms() * 16 ? frames : dp_num_sms() * 16;
-        if (ostro)
-            k_diffuse_serial<true><<<grid, 32, 0, st>>>(sp);
-        else
-            k_diffuse_serial<false><<<grid, 32, 0, st>>>(sp);
+        if (ring_smem) {
+            if (ostro) {
+                DP_CUDA(cudaFuncSetAttribute(k_diffuse_serial<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             200 * 1024));
+                k_diffuse_serial<true, true><<<grid, 32, smem, st>>>(sp);
+            } else {
+                DP_CUDA(cudaFuncSetAttribute(k_diffuse_serial<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             200 * 1024));
+                k_diffuse_serial<false, true><<<grid, 32, smem, st>>>(sp);
+            }
+        } else if (ostro) {
+            k_diffuse_serial<true, false><<<grid, 32, 0, st>>>(sp);
+        } else {
+            k_diffuse_serial<false, false><<<grid, 32, 0, st>>>(sp);
+        }
         DP_LAUNCH_CHECK();
         return 0;
     }

@@ -403,6 +403,71 @@ struct KmWarpShared {
     unsigned pad[3];
 };
 
+// One lane screens ALL centres for a pixel with the fixed-point scores (slot 0's copy of the
+// table) and keeps the two smallest.  Returns the label, or `undecided` when the runner-up is
+// within the margin.
+__device__ __noinline__ unsigned km_scan_all(unsigned v, unsigned ent_a, int K, unsigned undecided)
+{
+    const int vr = (int)(v & 255u), vg = (int)((v >> 8) & 255u), vb = (int)((v >> 16) & 255u);
+    int best = 0x7fffffff, second = 0x7fffffff;
+    unsigned bi = 0;
+    // four centres per round, their loads in flight together (entries K..32 are pads that never win)
+    for (int k0 = 0; k0 < K; k0 += 4) {
+        int sc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int4 en;
+            asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(en.x), "=r"(en.y), "=r"(en.z), "=r"(en.w)
+                : "r"(ent_a + 16u * (k0 + u)));
+            sc[u] = vb * en.z + (vg * en.y + (vr * en.x + en.w));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (sc[u] < best) {
+                second = best;
+                best = sc[u];
+                bi = (unsigned)(k0 + u);
+            } else if (sc[u] < second) {
+                second = sc[u];
+            }
+        }
+    }
+    return (second - best <= KM_MARGIN) ? undecided : bi;
+}
+
+// Undecided pixels inside a box that keeps more than four candidates (grid word 0xffffffff; early
+// Lloyd iterations put whole image regions there): every lane screens its own such pixels against
+// all centres -- 32 lanes side by side -- and adds the decided ones to its bins; what is left goes
+// to the warp's list as usual.  The pixels are read again (their first pass went to the dummy row).
+// (Measured: 20 iterations over a 4K frame 1.87 -> 0.83 ms; a single first-iteration-like pass over
+// 16 frames 0.41 -> 0.45 ms, the lane-serial scan being slower than the warp when such pixels are few.)
+__device__ __noinline__ unsigned km_lane_overflow(unsigned slowmask, const uint8_t *lane_px, unsigned grid_a,
+                                                  unsigned ent_a, unsigned bins_a, int K, unsigned undecided)
+{
+    unsigned m = slowmask;
+    while (m) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const uint8_t *q = lane_px + 3 * j;
+        const unsigned v = (unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16);
+        const unsigned a4 = (v >> 4) & 0x0f0f0fu;
+        unsigned e;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(__dp4a(a4, 0x00004004u, grid_a) + ((a4 >> 6) & 0x3c00u)));
+        if (e != 0xffffffffu) continue;
+        const unsigned label = km_scan_all(v, ent_a, K, undecided);
+        if (label != undecided) {
+            slowmask &= ~(1u << j);
+            const unsigned ba = bins_a + 256u * label;
+            uint2 bin;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bin.x), "=r"(bin.y) : "r"(ba));
+            bin.x += __byte_perm(v, 0u, 0x4140);
+            bin.y += __byte_perm(v, 1u, 0x7472);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ba), "r"(bin.x), "r"(bin.y) : "memory");
+        }
+    }
+    return slowmask;
+}
+
 // shared memory of the assignment pass (KP = 16 or 32 centres; bins rows = KP + 1 with the dummy row)
 template <int KP>
 struct KmSmem {
@@ -497,6 +562,32 @@ __device__ __forceinline__ void km_accum_body(const KmSmem<KP> &m, const uint8_t
             an += 1;
         }
     };
+    // an undecided pixel, by the whole warp.  If its box keeps more than four candidates (grid word
+    // 0xffffffff) the warp first screens ALL centres with the fixed-point scores, lane = centre
+    // (two integer warp reductions); only a runner-up within the margin needs the f64 resolution.
+    auto resolve_any = [&](unsigned v) {
+        const unsigned a4 = (v >> 4) & 0x0f0f0fu;
+        if (s_grid[(a4 & 15u) | ((a4 >> 4) & 0xf0u) | ((a4 >> 8) & 0xf00u)] == 0xffffffffu) {
+            int sc = 0x7fffffff;
+            if (lane < K) {
+                const int4 en = s_ent[lane];   // slot 0's copy of the table
+                sc = (int)(v >> 16) * en.z + ((int)((v >> 8) & 255u) * en.y + ((int)(v & 255u) * en.x + en.w));
+            }
+            const int m1 = __reduce_min_sync(FULL, sc);
+            const int win = __ffs(__ballot_sync(FULL, sc == m1)) - 1;
+            const int m2 = __reduce_min_sync(FULL, lane == win ? 0x7fffffff : sc);
+            if (m2 - m1 > KM_MARGIN) {
+                if (lane == win) {
+                    ar += v & 255u;
+                    ag += (v >> 8) & 255u;
+                    ab += (v >> 16) & 255u;
+                    an += 1;
+                }
+                return;
+            }
+        }
+        resolve(v);
+    };
     // fold the lanes' private bins into the 64-bit totals (lane k owns centre k)
     auto drain = [&]() {
         for (int k = 0; k < K; ++k) {
@@ -588,6 +679,10 @@ __device__ __forceinline__ void km_accum_body(const KmSmem<KP> &m, const uint8_t
             bin.y += __byte_perm(v, 1u, 0x7472);
             asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ba), "r"(bin.x), "r"(bin.y) : "memory");
         }
+        // undecided pixels of boxes with more than four candidates: the lanes first screen their own
+        if (live && slowmask)
+            slowmask = km_lane_overflow(slowmask, px + 3 * (head + t * 512 + lane * 16), grid_a, ent_a, bins_a, K,
+                                        (unsigned)KP);
         // undecided pixels of the tile: onto the warp's list, then the warp resolves them one by one
         if (live && slowmask) {
             unsigned m = slowmask;
@@ -605,7 +700,7 @@ __device__ __forceinline__ void km_accum_body(const KmSmem<KP> &m, const uint8_t
             if (ns <= KM_SLOW_CAP) {
                 for (unsigned i = 0; i < ns; ++i) {
                     const uint8_t *q = tile_px + 3 * ws.slow[i];
-                    resolve((unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16));
+                    resolve_any((unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16));
                 }
             } else {
                 // list overflow (pathological inputs): redo the tile's undecided pixels by
@@ -625,7 +720,7 @@ __device__ __forceinline__ void km_accum_body(const KmSmem<KP> &m, const uint8_t
                     const int lo01 = min(sc[0], sc[1]), hi01 = max(sc[0], sc[1]);
                     const int lo23 = min(sc[2], sc[3]), hi23 = max(sc[2], sc[3]);
                     const int m1 = min(lo01, lo23), m2 = min(max(lo01, lo23), min(hi01, hi23));
-                    if ((e == 0xffffffffu) || (m2 - m1 <= KM_MARGIN)) resolve(v);
+                    if ((e == 0xffffffffu) || (m2 - m1 <= KM_MARGIN)) resolve_any(v);
                 }
             }
             __syncwarp();

@@ -266,11 +266,12 @@ int dp_kmeans_update(const unsigned long long *sums, int K, double *centers, dou
 
 /*
  * dp_kmeans_lloyd -- the whole Lloyd loop of KMeans.fit (sklearn _kmeans.py:630-760 as called from
- * dithering_lib.py:1854-1855) from a given initialisation, with the stop test kept on the device:
- * per iteration one "prepare" launch (centres from the previous sums, squared centre shift, stop
- * flag, candidate grid for the new centres) and one assignment launch; with a communicator the
- * K*4+1 integer sums are all-reduced (ncclAllReduce, same stream) between them -- the only
- * collective of the hot path.  The host reads the flag every `check_every` iterations only.
+ * dithering_lib.py:1854-1855) from a given initialisation, with the stop test kept on the device.
+ * K <= 32 without a communicator: ONE persistent launch runs the loop (centres from the previous
+ * sums, squared centre shift, stop decision, candidate grid, assignment pass; the blocks meet at
+ * grid barriers).  Otherwise per iteration one "prepare" launch and one assignment launch; with
+ * a communicator the K*4+1 integer sums are all-reduced (ncclAllReduce, same stream) between
+ * them, and the host reads the stop flag every `check_every` iterations only.
  *   pixels        DEVICE u8 [n,3] -- this rank's shard of the pixels
  *   centers_host  HOST f64 [K,3], in: initial centres, out: final centres (identical on all ranks)
  *   tol           stop when the squared centre shift is <= tol (sklearn: tol * mean variance)
@@ -289,8 +290,9 @@ int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers_host, int 
 /*
  * dp_kmeans_lloyd_p2p -- the same loop with the exchange done by the kernels themselves over peer
  * memory (NVLink) instead of an NCCL launch: after its assignment pass a rank stores its K*4+1
- * integers into a slot of every rank's INBOX and releases a flag; the next "prepare" launch waits
- * for the `world` flags and adds the slots up (integers: identical totals on every rank).
+ * integers into a slot of every rank's INBOX and releases a flag; the next "prepare" step waits
+ * for the `world` flags and adds the slots up (integers: identical totals on every rank).  For
+ * K <= 32 this happens inside the persistent loop kernel, else in the launch pair's kernels.
  *   inboxes   HOST array of `world` DEVICE pointers; inboxes[rank] is this rank's own inbox
  *             (dp_p2p_alloc(dp_p2p_inbox_bytes(), ...)), the others are the peers' inboxes opened
  *             with dp_p2p_open from the handles the ranks exchanged

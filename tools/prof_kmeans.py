@@ -17,6 +17,8 @@ def main():
     ap.add_argument("--frames", type=int, default=16, help="distinct 4K frames in the pixel array")
     ap.add_argument("--k", type=int, default=16)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--loop", type=int, default=0, help="instead: the persistent Lloyd loop, this many iterations "
+                                                        "over ALL the pixels")
     a = ap.parse_args()
     from dither_pie_b200 import _capi, synth
     from dither_pie_b200._capi import DeviceBuffer, check, lib
@@ -26,6 +28,19 @@ def main():
     rs = np.random.RandomState(0)
     init = px[rs.choice(n, a.k, replace=False)].astype(np.float64)
     buf = DeviceBuffer(px.nbytes).upload(np.ascontiguousarray(px))
+    if a.loop:
+        from dither_pie_b200 import kmeans
+        kmeans.lloyd_device(buf.ptr, n, init, -1.0, 2)
+        ts = []
+        for _ in range(a.reps):
+            _capi.sync()
+            t0 = time.perf_counter()
+            kmeans.lloyd_device(buf.ptr, n, init, -1.0, a.loop)
+            ts.append(time.perf_counter() - t0)
+        dt = sorted(ts)[len(ts) // 2]
+        print(f"kmeans Lloyd loop K={a.k} {n/1e6:.1f} Mpx x {a.loop} iterations: median {dt*1e3:.3f} ms  "
+              f"{dt/a.loop*1e6:.1f} us/iteration  {3*n*a.loop/dt/1e9:.0f} GB/s(alg)")
+        return
     cent = DeviceBuffer(init.nbytes).upload(init)
     sums = DeviceBuffer((a.k * 4 + 1) * 8)
     ts = []
