@@ -492,6 +492,348 @@ __global__ void __launch_bounds__(256) k_ht_select4(const HtParams p)
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// v2 kernels (round 2): rows of a multiple of 16 pixels, 16-byte aligned buffers, cell_size <= 14,
+// tile cell range within HT_CAP.  Three more frame-invariant maps make the per-pixel work
+// branch-free and keep every cell look-up in shared memory:
+//   tgeo  [tiles]     int4 (base cell id, local grid width, local grid height) of a 64 x 128 tile
+//   loc16 [npix] u16  4 * (tile-local cell number ly * lw + lx): the byte offset of the cell's
+//                     entry in the select kernel's colour table, half the offset of its sums entry
+//   bmask [npix/16]   bit k: pixel k of the 16-pixel strip starts a new run of equal cells
+// Global sums are ONE u64 per cell (r | g << 16 | b << 32 | n << 48; a cell of size <= 14 holds at
+// most 225 pixels), the cells kernel leaves rgb | row << 24 per cell.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ht_tilegeo(const HtParams p, int tiles_x, int ntiles, int4 *tgeo)
+{
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= ntiles) return;
+    const int ty = t / tiles_x, tx = t - ty * tiles_x;
+    const int x0 = tx * HT_TW, y0 = ty * HT_TH;
+    const int x1 = min(x0 + HT_TW, p.w) - 1, y1 = min(y0 + HT_TH, p.h) - 1;
+    int cxl = 0, cxh = 0, cyl = 0, cyh = 0;
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        int cx, cy;
+        ht_cell_xy(p, (k & 1) ? x1 : x0, (k & 2) ? y1 : y0, cx, cy);
+        if (k == 0) {
+            cxl = cxh = cx;
+            cyl = cyh = cy;
+        } else {
+            cxl = min(cxl, cx); cxh = max(cxh, cx);
+            cyl = min(cyl, cy); cyh = max(cyh, cy);
+        }
+    }
+    tgeo[t] = make_int4((cyl - p.cy_min) * p.ncx + (cxl - p.cx_min), cxh - cxl + 1, cyh - cyl + 1, 0);
+}
+
+// one thread per 16-pixel strip: tile-local cell offsets and the run-start mask from the cell map
+__global__ void __launch_bounds__(256) k_ht_locmap(const HtParams p, int tiles_x, const int4 *__restrict__ tgeo,
+                                                   uint16_t *__restrict__ loc16, uint16_t *__restrict__ bmask)
+{
+    const int spr = p.w >> 4;
+    const int s = blockIdx.x * 256 + threadIdx.x;
+    if (s >= spr * p.h) return;
+    const int y = s / spr, xs = (s - y * spr) << 4;
+    const int4 geo = __ldg(tgeo + (y / HT_TH) * tiles_x + xs / HT_TW);
+    const int i0 = y * p.w + xs;
+    unsigned packed[8];
+    unsigned mask = 0;
+    int prev = -1;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int d = __ldg(p.cell + i0 + k) - geo.x;
+        const int ly = d / p.ncx, lx = d - ly * p.ncx;
+        const int loc = ly * geo.y + lx;
+        if (d < 0 || lx >= geo.y || ly >= geo.z || loc >= HT_CAP) __trap();   // never: the corners bound the range
+        if (k && loc != prev) mask |= 1u << k;
+        prev = loc;
+        const unsigned v = (unsigned)(loc * 4) & 0xffffu;
+        if (k & 1) packed[k >> 1] |= v << 16;
+        else packed[k >> 1] = v;
+    }
+    uint4 *o = reinterpret_cast<uint4 *>(loc16 + i0);
+    o[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    o[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    bmask[i0 >> 4] = (uint16_t)mask;
+}
+
+// 128-bit loads as volatile asm: they keep their program order, so a strip's loads are all in
+// flight before the first use (left to itself the compiler threads them through the pixel loop
+// to save registers and every pixel group waits for its own load)
+__device__ __forceinline__ uint4 ht_ld_stream(const void *q)
+{
+    uint4 v;
+    asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(q));
+    return v;
+}
+__device__ __forceinline__ uint4 ht_ld_map(const void *q)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(q));
+    return v;
+}
+
+// bytes 3k .. 3k+2 of a 48-byte strip held in twelve words, as r | g << 16 and b | 1 << 16
+__device__ __forceinline__ void ht_px_packed(const unsigned (&w)[12], int k, unsigned &prg, unsigned &pbn)
+{
+    const int o = 3 * k, j = o >> 2, sh = o & 3;
+    if (sh == 0) {
+        prg = __byte_perm(w[j], 0u, 0x4140);
+        pbn = __byte_perm(w[j], 1u, 0x5452);
+    } else if (sh == 1) {
+        prg = __byte_perm(w[j], 0u, 0x4241);
+        pbn = __byte_perm(w[j], 1u, 0x5453);
+    } else if (sh == 2) {
+        prg = __byte_perm(w[j], 0u, 0x4342);
+        pbn = __byte_perm(w[j + 1], 1u, 0x5450);
+    } else {
+        const unsigned v = __funnelshift_r(w[j], w[j + 1], 24);
+        prg = __byte_perm(v, 0u, 0x4140);
+        pbn = __byte_perm(v, 1u, 0x5452);
+    }
+}
+
+__device__ __forceinline__ unsigned ht_byte(const unsigned (&w)[12], int b)
+{
+    return (w[b >> 2] >> (8 * (b & 3))) & 255u;
+}
+
+template <bool LUT, int OCC>
+__global__ void __launch_bounds__(256, OCC) k_ht_sums_v2(const HtParams p, int tiles_x, const int4 *__restrict__ tgeo,
+                                                    const uint16_t *__restrict__ loc16,
+                                                    const uint16_t *__restrict__ bmask,
+                                                    unsigned long long *__restrict__ sums64)
+{
+    __shared__ uint8_t s_lut[256];
+    __shared__ __align__(16) unsigned s_grid[HT_CAP * 2];
+    if (LUT) s_lut[threadIdx.x] = p.P->in_lut[threadIdx.x];
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int x0 = tx * HT_TW, y0 = ty * HT_TH;
+    const int x1 = min(x0 + HT_TW, p.w) - 1, y1 = min(y0 + HT_TH, p.h) - 1;
+    const int4 geo = __ldg(tgeo + blockIdx.x);
+    const int nloc = geo.y * geo.z;
+    for (int i = threadIdx.x; i < nloc * 2; i += 256) s_grid[i] = 0;
+    __syncthreads();
+
+    const int f = blockIdx.y;
+    const uint8_t *src = p.src + (size_t)f * p.npix * 3;
+    char *grid = reinterpret_cast<char *>(s_grid);
+    constexpr int SPR = HT_TW / 16;
+#pragma unroll 1
+    for (int sidx = threadIdx.x; sidx < HT_TH * SPR; sidx += 256) {
+        const int r = sidx / SPR, y = y0 + r;
+        const int xs = x0 + (sidx - r * SPR) * 16;
+        if (y > y1 || xs > x1) continue;
+        const int i0 = y * p.w + xs;
+        unsigned w[12], lo[8];
+        {
+            const uint4 *q = reinterpret_cast<const uint4 *>(src + (size_t)i0 * 3);
+            const uint4 a = ht_ld_stream(q), b = ht_ld_stream(q + 1), c = ht_ld_stream(q + 2);
+            const uint4 *lq = reinterpret_cast<const uint4 *>(loc16 + i0);
+            const uint4 l0 = ht_ld_map(lq), l1 = ht_ld_map(lq + 1);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+            w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+            w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+            lo[0] = l0.x; lo[1] = l0.y; lo[2] = l0.z; lo[3] = l0.w;
+            lo[4] = l1.x; lo[5] = l1.y; lo[6] = l1.z; lo[7] = l1.w;
+        }
+        const unsigned m = __ldg(bmask + (i0 >> 4));
+        unsigned rg = 0, bn = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            unsigned prg, pbn;
+            if (LUT) {
+                prg = (unsigned)s_lut[ht_byte(w, 3 * k)] | ((unsigned)s_lut[ht_byte(w, 3 * k + 1)] << 16);
+                pbn = (unsigned)s_lut[ht_byte(w, 3 * k + 2)] | 0x10000u;
+            } else {
+                ht_px_packed(w, k, prg, pbn);
+            }
+            if (k && ((m >> k) & 1u)) {
+                // the run that ended at pixel k-1: entry at 2 * loc16 bytes
+                const unsigned off = ((k - 1) & 1) ? (lo[(k - 1) >> 1] >> 16) : (lo[(k - 1) >> 1] & 0xffffu);
+                unsigned *g = reinterpret_cast<unsigned *>(grid + 2 * off);
+                atomicAdd(g, rg);
+                atomicAdd(g + 1, bn);
+                rg = 0;
+                bn = 0;
+            }
+            rg += prg;
+            bn += pbn;
+        }
+        {
+            unsigned *g = reinterpret_cast<unsigned *>(grid + 2 * (lo[7] >> 16));
+            atomicAdd(g, rg);
+            atomicAdd(g + 1, bn);
+        }
+    }
+    __syncthreads();
+    unsigned long long *gs = sums64 + (size_t)f * p.ncells;
+    for (int i = threadIdx.x; i < nloc; i += 256) {
+        const uint2 t = reinterpret_cast<const uint2 *>(s_grid)[i];
+        if (!(t.y >> 16)) continue;
+        const int ly = i / geo.y, lx = i - ly * geo.y;
+        atomicAdd(gs + (size_t)(geo.x + ly * p.ncx + lx), (unsigned long long)t.x | ((unsigned long long)t.y << 32));
+    }
+}
+
+// per cell: mean colour in f64 -> nearest palette row (scipy query(k=1) semantics), stored as
+// out_rgb | row << 24.  All K distances are screened in f32 first: with palette and mean in
+// [0, 255] the absolute error of an f32 squared distance is below 0.1, so a runner-up more than
+// 0.5 above the minimum makes the minimum the exact (and untied) answer; otherwise the exact f64
+// search with the KD-tree tie replay decides.
+__global__ void __launch_bounds__(128) k_ht_cells_v2(const HtParams p, const unsigned long long *__restrict__ sums64,
+                                                     unsigned *__restrict__ cell_col)
+{
+    __shared__ float4 s_pal[DP_MAX_COLORS];
+    for (int i = threadIdx.x; i < p.K; i += 128) {
+        const float *q = p.P->pal_f32 + 3 * i;
+        s_pal[i] = make_float4(q[0], q[1], q[2], 0.f);
+    }
+    __syncthreads();
+    const int f = blockIdx.y;
+    const unsigned long long *sums = sums64 + (size_t)f * p.ncells;
+    unsigned *cc = cell_col + (size_t)f * p.ncells;
+    for (int c = blockIdx.x * 128 + threadIdx.x; c < p.ncells; c += gridDim.x * 128) {
+        const unsigned long long s = sums[c];
+        const unsigned n = (unsigned)(s >> 48);
+        if (!n) continue;
+        const double dn = (double)n;
+        const double m0 = __ddiv_rn((double)(unsigned)(s & 0xffffu), dn);
+        const double m1 = __ddiv_rn((double)(unsigned)((s >> 16) & 0xffffu), dn);
+        const double m2 = __ddiv_rn((double)(unsigned)((s >> 32) & 0xffffu), dn);
+        const float x0 = (float)m0, x1 = (float)m1, x2 = (float)m2;
+        float b1 = 3.0e38f, b2 = 3.0e38f;
+        int bi = 0;
+        for (int i = 0; i < p.K; ++i) {
+            const float4 q = s_pal[i];
+            const float d0 = q.x - x0, d1 = q.y - x1, d2 = q.z - x2;
+            const float d = fmaf(d2, d2, fmaf(d1, d1, d0 * d0));
+            if (d < b1) {
+                b2 = b1;
+                b1 = d;
+                bi = i;
+            } else if (d < b2) {
+                b2 = d;
+            }
+        }
+        if (!(b2 - b1 > 0.5f)) bi = nearest_kd_f64(p.P, m0, m1, m2);
+        const uint8_t *o = p.P->out_rgb + 4 * bi;
+        cc[c] = (unsigned)o[0] | ((unsigned)o[1] << 8) | ((unsigned)o[2] << 16) | ((unsigned)bi << 24);
+    }
+}
+
+// ink / paper per pixel: a block owns a 64 x 128 tile, the tile's cell colours sit in shared
+// memory (one LDS per pixel at the offset the loc16 map holds), a thread owns 16-pixel strips
+// (three 128-bit loads, three 128-bit stores, four + two for the maps).
+template <bool LUT, bool RGB, bool IDX, int OCC>
+__global__ void __launch_bounds__(256, OCC) k_ht_select_v2(const HtParams p, int tiles_x, const int4 *__restrict__ tgeo,
+                                                      const uint16_t *__restrict__ loc16,
+                                                      const unsigned *__restrict__ cell_col)
+{
+    __shared__ uint8_t s_lut[256];
+    __shared__ __align__(16) unsigned s_col[HT_CAP];
+    __shared__ unsigned s_paper;
+    if (LUT) s_lut[threadIdx.x] = p.P->in_lut[threadIdx.x];
+    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
+    const int x0 = tx * HT_TW, y0 = ty * HT_TH;
+    const int x1 = min(x0 + HT_TW, p.w) - 1, y1 = min(y0 + HT_TH, p.h) - 1;
+    const int4 geo = __ldg(tgeo + blockIdx.x);
+    const int nloc = geo.y * geo.z;
+    const int f = blockIdx.y;
+    const unsigned *cc = cell_col + (size_t)f * p.ncells;
+    for (int i = threadIdx.x; i < nloc; i += 256) {
+        const int ly = i / geo.y, lx = i - ly * geo.y;
+        s_col[i] = __ldg(cc + (geo.x + ly * p.ncx + lx));
+    }
+    if (threadIdx.x == 0) {
+        const uint8_t *o = p.P->out_rgb + 4 * p.paper;
+        s_paper = (unsigned)o[0] | ((unsigned)o[1] << 8) | ((unsigned)o[2] << 16) | ((unsigned)p.paper << 24);
+    }
+    __syncthreads();
+    const unsigned paper = s_paper;
+    const uint8_t *src = p.src + (size_t)f * p.npix * 3;
+    uint8_t *dst = RGB ? p.dst + (size_t)f * p.npix * 3 : nullptr;
+    uint8_t *dix = IDX ? p.dst_idx + (size_t)f * p.npix : nullptr;
+    const char *colt = reinterpret_cast<const char *>(s_col);
+    constexpr int SPR = HT_TW / 16;
+#pragma unroll 1
+    for (int sidx = threadIdx.x; sidx < HT_TH * SPR; sidx += 256) {
+        const int r = sidx / SPR, y = y0 + r;
+        const int xs = x0 + (sidx - r * SPR) * 16;
+        if (y > y1 || xs > x1) continue;
+        const int i0 = y * p.w + xs;
+        unsigned w[12], lo[8];
+        float th[16];
+        {
+            const uint4 *q = reinterpret_cast<const uint4 *>(src + (size_t)i0 * 3);
+            const uint4 a = ht_ld_stream(q), b = ht_ld_stream(q + 1), c = ht_ld_stream(q + 2);
+            const uint4 *lq = reinterpret_cast<const uint4 *>(loc16 + i0);
+            const uint4 l0 = ht_ld_map(lq), l1 = ht_ld_map(lq + 1);
+            const uint4 *tq = reinterpret_cast<const uint4 *>(p.screen + i0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint4 t = ht_ld_map(tq + k);
+                th[4 * k] = __uint_as_float(t.x); th[4 * k + 1] = __uint_as_float(t.y);
+                th[4 * k + 2] = __uint_as_float(t.z); th[4 * k + 3] = __uint_as_float(t.w);
+            }
+            // every load of the strip is issued before the first use
+            asm volatile("" ::"r"(a.x), "r"(b.x), "r"(c.x), "r"(l0.x), "r"(l1.x), "f"(th[0]), "f"(th[4]), "f"(th[8]),
+                         "f"(th[12]));
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+            w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+            w[8] = c.x; w[9] = c.y; w[10] = c.z; w[11] = c.w;
+            lo[0] = l0.x; lo[1] = l0.y; lo[2] = l0.z; lo[3] = l0.w;
+            lo[4] = l1.x; lo[5] = l1.y; lo[6] = l1.z; lo[7] = l1.w;
+        }
+        unsigned col[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            unsigned mr, mg, mb;   // 2^23 + byte as a float bit pattern
+            if (LUT) {
+                mr = 0x4b000000u | s_lut[ht_byte(w, 3 * k)];
+                mg = 0x4b000000u | s_lut[ht_byte(w, 3 * k + 1)];
+                mb = 0x4b000000u | s_lut[ht_byte(w, 3 * k + 2)];
+            } else {
+                mr = __byte_perm(w[(3 * k) >> 2], 0x4b000000u, 0x7540 + ((3 * k) & 3));
+                mg = __byte_perm(w[(3 * k + 1) >> 2], 0x4b000000u, 0x7540 + ((3 * k + 1) & 3));
+                mb = __byte_perm(w[(3 * k + 2) >> 2], 0x4b000000u, 0x7540 + ((3 * k + 2) & 3));
+            }
+            // (:1605-1606, :1638-1639) f32, one rounding per operation: fl(c * byte) as one fma
+            const float gray = __fadd_rn(
+                __fadd_rn(__fmaf_rn(0.299f, __uint_as_float(mr), -0.299f * 8388608.0f),
+                          __fmaf_rn(0.587f, __uint_as_float(mg), -0.587f * 8388608.0f)),
+                __fmaf_rn(0.114f, __uint_as_float(mb), -0.114f * 8388608.0f));
+            const unsigned off = (k & 1) ? (lo[k >> 1] >> 16) : (lo[k >> 1] & 0xffffu);
+            unsigned c = paper;
+            if (gray < th[k]) c = *reinterpret_cast<const unsigned *>(colt + off);
+            col[k] = c;
+        }
+        if (RGB) {
+            uint4 *o = reinterpret_cast<uint4 *>(dst + (size_t)i0 * 3);
+            unsigned ow[12];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                ow[3 * g] = __byte_perm(col[4 * g], col[4 * g + 1], 0x4210);
+                ow[3 * g + 1] = __byte_perm(col[4 * g + 1], col[4 * g + 2], 0x5421);
+                ow[3 * g + 2] = __byte_perm(col[4 * g + 2], col[4 * g + 3], 0x6542);
+            }
+            __stcs(o, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+            __stcs(o + 1, make_uint4(ow[4], ow[5], ow[6], ow[7]));
+            __stcs(o + 2, make_uint4(ow[8], ow[9], ow[10], ow[11]));
+        }
+        if (IDX) {
+            unsigned iw[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const unsigned t01 = __byte_perm(col[4 * g], col[4 * g + 1], 0x0073);
+                const unsigned t23 = __byte_perm(col[4 * g + 2], col[4 * g + 3], 0x0073);
+                iw[g] = __byte_perm(t01, t23, 0x5410);
+            }
+            __stcs(reinterpret_cast<uint4 *>(dix + i0), make_uint4(iw[0], iw[1], iw[2], iw[3]));
+        }
+    }
+}
+
 struct Ws {
     void *ptr = nullptr;
     cudaStream_t st = nullptr;
@@ -510,8 +852,15 @@ struct MapEntry {
     double ca, sa, min_dot, span, sharp;
     float *gthr;
     int *cell;
+    // v2 maps (null until a call that can use them asks)
+    uint16_t *loc16, *bmask;
+    int4 *tgeo;
     cudaEvent_t ready;
     unsigned long long stamp;
+};
+struct V2Maps {
+    uint16_t *loc16 = nullptr, *bmask = nullptr;
+    int4 *tgeo = nullptr;
 };
 struct MapCache {
     std::mutex mu;
@@ -525,8 +874,20 @@ MapCache &map_cache()
 }
 constexpr size_t HT_MAP_CACHE = 4;
 
-// returns 0 and fills p.screen / p.cell; launches k_ht_maps on `st` on a miss
-int cached_maps(HtParams &p, cudaStream_t st)
+// tile geometry, tile-local cell offsets and run-start masks from the cell map (on `st`)
+int build_v2_maps(const HtParams &p, const V2Maps &v, int tiles_x, int ntiles, cudaStream_t st)
+{
+    k_ht_tilegeo<<<(ntiles + 255) / 256, 256, 0, st>>>(p, tiles_x, ntiles, v.tgeo);
+    DP_LAUNCH_CHECK();
+    const int strips = p.npix / 16;
+    k_ht_locmap<<<(strips + 255) / 256, 256, 0, st>>>(p, tiles_x, v.tgeo, v.loc16, v.bmask);
+    DP_LAUNCH_CHECK();
+    return 0;
+}
+
+// returns 0 and fills p.screen / p.cell (and `v2` when asked); launches the map kernels on `st`
+// on a miss
+int cached_maps(HtParams &p, cudaStream_t st, V2Maps *v2, int tiles_x, int ntiles)
 {
     int dev = 0;
     DP_CUDA(cudaGetDevice(&dev));
@@ -540,6 +901,22 @@ int cached_maps(HtParams &p, cudaStream_t st)
             p.screen = e.gthr;
             p.cell = e.cell;
             DP_CUDA(cudaStreamWaitEvent(st, e.ready, 0));
+            if (v2) {
+                if (!e.loc16) {
+                    V2Maps n;
+                    DP_CUDA(cudaMalloc(&n.loc16, (size_t)p.npix * 2));
+                    DP_CUDA(cudaMalloc(&n.bmask, (size_t)(p.npix / 16) * 2));
+                    DP_CUDA(cudaMalloc(&n.tgeo, (size_t)ntiles * sizeof(int4)));
+                    if (build_v2_maps(p, n, tiles_x, ntiles, st)) return 1;
+                    DP_CUDA(cudaEventRecord(e.ready, st));
+                    e.loc16 = n.loc16;
+                    e.bmask = n.bmask;
+                    e.tgeo = n.tgeo;
+                }
+                v2->loc16 = e.loc16;
+                v2->bmask = e.bmask;
+                v2->tgeo = e.tgeo;
+            }
             return 0;
         }
     }
@@ -550,6 +927,9 @@ int cached_maps(HtParams &p, cudaStream_t st)
         // cudaFree waits for the device: no in-flight kernel can still read the evicted maps
         cudaFree(mc.ent[v].gthr);
         cudaFree(mc.ent[v].cell);
+        cudaFree(mc.ent[v].loc16);
+        cudaFree(mc.ent[v].bmask);
+        cudaFree(mc.ent[v].tgeo);
         cudaEventDestroy(mc.ent[v].ready);
         mc.ent.erase(mc.ent.begin() + v);
     }
@@ -558,6 +938,8 @@ int cached_maps(HtParams &p, cudaStream_t st)
     e.ca = p.ca; e.sa = p.sa; e.min_dot = p.min_dot; e.span = p.span; e.sharp = p.sharp;
     e.gthr = nullptr;
     e.cell = nullptr;
+    e.loc16 = e.bmask = nullptr;
+    e.tgeo = nullptr;
     e.stamp = ++mc.clock;
     DP_CUDA(cudaMalloc(&e.gthr, (size_t)p.npix * 4));
     if (cudaMalloc(&e.cell, (size_t)p.npix * 4) != cudaSuccess) {
@@ -569,6 +951,16 @@ int cached_maps(HtParams &p, cudaStream_t st)
     p.cell = e.cell;
     k_ht_maps<<<(p.npix + 255) / 256, 256, 0, st>>>(p);
     DP_LAUNCH_CHECK();
+    if (v2) {
+        V2Maps n;
+        DP_CUDA(cudaMalloc(&n.loc16, (size_t)p.npix * 2));
+        DP_CUDA(cudaMalloc(&n.bmask, (size_t)(p.npix / 16) * 2));
+        DP_CUDA(cudaMalloc(&n.tgeo, (size_t)ntiles * sizeof(int4)));
+        if (build_v2_maps(p, n, tiles_x, ntiles, st)) return 1;
+        e.loc16 = v2->loc16 = n.loc16;
+        e.bmask = v2->bmask = n.bmask;
+        e.tgeo = v2->tgeo = n.tgeo;
+    }
     DP_CUDA(cudaEventRecord(e.ready, st));
     mc.ent.push_back(e);
     return 0;
@@ -657,11 +1049,24 @@ extern "C" int dp_halftone(const dp_palette *pal, const uint8_t *src_rgb, int fr
         p.paper = best;
     }
 
-    Ws w_screen, w_cell, w_sums, w_cp;
-    w_screen.st = w_cell.st = w_sums.st = w_cp.st = st;
+    Ws w_screen, w_cell, w_sums, w_cp, w_loc, w_mask, w_geo;
+    w_screen.st = w_cell.st = w_sums.st = w_cp.st = w_loc.st = w_mask.st = w_geo.st = st;
     const int sms = dp_num_sms();
+    // worst-case cell range of a tile: |d(xr)| <= TW |cos| + TH |sin| across a tile (+2 for
+    // the floor at both ends and rounding), likewise yr
+    const double ex = (HT_TW * fabs(cos_a) + HT_TH * fabs(sin_a)) / cell_size + 2.0;
+    const double ey = (HT_TW * fabs(sin_a) + HT_TH * fabs(cos_a)) / cell_size + 2.0;
+    const int tiles_x = (w + HT_TW - 1) / HT_TW, tiles_y = (h + HT_TH - 1) / HT_TH;
+    const int ntiles = tiles_x * tiles_y;
+    int mode = (ceil(ex) * ceil(ey) <= (double)HT_CAP) ? (cell_size <= 14 ? 1 : 0) : 2;
+    if (const char *ev = getenv("DP_HT_MODE")) mode = atoi(ev);   // tuning knob (tools/)
+    // the v2 kernels: 16-pixel strips, 128-bit accesses, 16-bit sums per tile cell
+    const bool v2 = mode == 1 && cell_size <= 14 && ceil(ex) * ceil(ey) <= (double)HT_CAP && p.vec16 &&
+                    ((reinterpret_cast<uintptr_t>(dst_rgb) | reinterpret_cast<uintptr_t>(dst_idx)) & 15) == 0 &&
+                    !getenv("DP_HT_V1");
+    V2Maps vm;
     if (p.make_screen && !getenv("DP_HT_NO_MAP_CACHE")) {
-        if (cached_maps(p, st)) return 1;
+        if (cached_maps(p, st, v2 ? &vm : nullptr, tiles_x, ntiles)) return 1;
     } else {
         DP_CUDA(cudaMallocAsync(&w_screen.ptr, (size_t)p.npix * 4, st));
         p.screen = static_cast<float *>(w_screen.ptr);
@@ -670,6 +1075,56 @@ extern "C" int dp_halftone(const dp_palette *pal, const uint8_t *src_rgb, int fr
         p.cell = static_cast<int *>(w_cell.ptr);
         k_ht_maps<<<(p.npix + 255) / 256, 256, 0, st>>>(p);
         DP_LAUNCH_CHECK();
+        if (v2) {
+            DP_CUDA(cudaMallocAsync(&w_loc.ptr, (size_t)p.npix * 2, st));
+            DP_CUDA(cudaMallocAsync(&w_mask.ptr, (size_t)(p.npix / 16) * 2, st));
+            DP_CUDA(cudaMallocAsync(&w_geo.ptr, (size_t)ntiles * sizeof(int4), st));
+            vm.loc16 = static_cast<uint16_t *>(w_loc.ptr);
+            vm.bmask = static_cast<uint16_t *>(w_mask.ptr);
+            vm.tgeo = static_cast<int4 *>(w_geo.ptr);
+            if (build_v2_maps(p, vm, tiles_x, ntiles, st)) return 1;
+        }
+    }
+    if (v2) {
+        const size_t sums_bytes = (size_t)frames * p.ncells * sizeof(unsigned long long);
+        DP_CUDA(cudaMallocAsync(&w_sums.ptr, sums_bytes, st));
+        unsigned long long *sums64 = static_cast<unsigned long long *>(w_sums.ptr);
+        DP_CUDA(cudaMallocAsync(&w_cp.ptr, (size_t)frames * p.ncells * 4, st));
+        unsigned *cell_col = static_cast<unsigned *>(w_cp.ptr);
+        DP_CUDA(cudaMemsetAsync(sums64, 0, sums_bytes, st));
+        const dim3 tg(ntiles, frames);
+        // OCC: blocks per SM the register allocation aims at (4: a strip's loads all in flight before
+        // the first use, 6: ptxas threads the loads through the pixel loop to save registers)
+        int occ_sums = 6, occ_sel = 4;
+        if (const char *ev = getenv("DP_HT_OCC")) {   // tuning knob (tools/): "<sums><select>", e.g. 64
+            if (ev[0] == '4' || ev[0] == '6') occ_sums = ev[0] - '0';
+            if (ev[0] && (ev[1] == '4' || ev[1] == '6')) occ_sel = ev[1] - '0';
+        }
+        if (p.has_lut) k_ht_sums_v2<true, 6><<<tg, 256, 0, st>>>(p, tiles_x, vm.tgeo, vm.loc16, vm.bmask, sums64);
+        else if (occ_sums == 4) k_ht_sums_v2<false, 4><<<tg, 256, 0, st>>>(p, tiles_x, vm.tgeo, vm.loc16, vm.bmask, sums64);
+        else k_ht_sums_v2<false, 6><<<tg, 256, 0, st>>>(p, tiles_x, vm.tgeo, vm.loc16, vm.bmask, sums64);
+        DP_LAUNCH_CHECK();
+        int gc = (p.ncells + 127) / 128;
+        if (gc > sms * 8) gc = sms * 8;
+        k_ht_cells_v2<<<dim3(gc, frames), 128, 0, st>>>(p, sums64, cell_col);
+        DP_LAUNCH_CHECK();
+#define HT_SEL(L, R, I)                                                                              \
+    do {                                                                                             \
+        if (occ_sel == 4) k_ht_select_v2<L, R, I, 4><<<tg, 256, 0, st>>>(p, tiles_x, vm.tgeo, vm.loc16, cell_col); \
+        else k_ht_select_v2<L, R, I, 6><<<tg, 256, 0, st>>>(p, tiles_x, vm.tgeo, vm.loc16, cell_col);              \
+    } while (0)
+        const int variant = (p.has_lut ? 4 : 0) | (dst_rgb ? 2 : 0) | (dst_idx ? 1 : 0);
+        switch (variant) {
+        case 1: HT_SEL(false, false, true); break;
+        case 2: HT_SEL(false, true, false); break;
+        case 3: HT_SEL(false, true, true); break;
+        case 5: HT_SEL(true, false, true); break;
+        case 6: HT_SEL(true, true, false); break;
+        default: HT_SEL(true, true, true); break;
+        }
+#undef HT_SEL
+        DP_LAUNCH_CHECK();
+        return 0;
     }
     size_t sums_bytes = (size_t)frames * p.ncells * 2 * sizeof(unsigned long long);
     DP_CUDA(cudaMallocAsync(&w_sums.ptr, sums_bytes, st));
@@ -681,14 +1136,7 @@ extern "C" int dp_halftone(const dp_palette *pal, const uint8_t *src_rgb, int fr
     int gx = (p.npix + 255) / 256;
     if (gx > sms * 8) gx = sms * 8;
     {
-        // worst-case cell range of a tile: |d(xr)| <= TW |cos| + TH |sin| across a tile (+2 for
-        // the floor at both ends and rounding), likewise yr
-        const double ex = (HT_TW * fabs(cos_a) + HT_TH * fabs(sin_a)) / cell_size + 2.0;
-        const double ey = (HT_TW * fabs(sin_a) + HT_TH * fabs(cos_a)) / cell_size + 2.0;
-        const int tiles_x = (w + HT_TW - 1) / HT_TW, tiles_y = (h + HT_TH - 1) / HT_TH;
-        const dim3 tg(tiles_x * tiles_y, frames);
-        int mode = (ceil(ex) * ceil(ey) <= (double)HT_CAP) ? (cell_size <= 14 ? 1 : 0) : 2;
-        if (const char *ev = getenv("DP_HT_MODE")) mode = atoi(ev);   // tuning knob (tools/)
+        const dim3 tg(ntiles, frames);
         if (mode == 0) k_ht_sums_tile<0><<<tg, 256, 0, st>>>(p, tiles_x);
         else if (mode == 1) k_ht_sums_tile<1><<<tg, 256, 0, st>>>(p, tiles_x);
         else if (mode == 2) k_ht_sums_tile<2><<<tg, 256, 0, st>>>(p, tiles_x);

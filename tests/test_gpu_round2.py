@@ -166,6 +166,34 @@ def test_index_only_with_fused_geometry_and_null_outputs_refused():
     buf.free()
 
 
+def test_halftone_v2_kernels_multi_tile_gamma_and_old_kernels_agree(monkeypatch):
+    """Rows of a multiple of 16 pixels take the v2 halftone kernels (tile-local cell maps, one u64 of
+    sums per cell, colour table in shared memory): several tiles in both directions, partial tiles,
+    cell sizes up to the 16-bit limit, gamma LUT, colour + index output -- against the oracle, and
+    against the old kernels (DP_HT_V1)."""
+    cases = [{}, {"cell_size": 5, "angle": 30.0, "shape": "diamond"},
+             {"cell_size": 14, "angle": 75.0, "shape": "square"}, {"cell_size": 3, "angle": 90.0},
+             {"cell_size": 8, "angle": 45.0, "dot_gain": 1.3, "min_dot_size": 0.1, "max_dot_size": 0.9},
+             {"cell_size": 2, "angle": 10.0}, {"cell_size": 20, "angle": 60.0}]
+    frames = np.stack([synth.frame(200, 272, 90 + t) if t != 1 else synth.noise_frame(200, 272, 91)
+                       for t in range(3)])
+    for pal, gamma in ((PICO, False), (synth.random_palette(64), False), (PICO, True)):
+        rows = np.asarray(pal, np.uint8)
+        for params in cases:
+            rgb, idx = engine.dither_frames(frames, pal, "halftone", params, use_gamma=gamma, return_indices=True)
+            only = engine.dither_frames(frames, pal, "halftone", params, use_gamma=gamma, indices_only=True)
+            assert np.array_equal(idx, only), (params, gamma)
+            if not gamma:
+                assert np.array_equal(rows[idx], rgb), (params, gamma)
+            refs = oracle_many([(frames[t], pal, "halftone", params, gamma) for t in range(3)])
+            for t in range(3):
+                assert mismatch(rgb[t], refs[t]) == 0, (params, gamma, t)
+            monkeypatch.setenv("DP_HT_V1", "1")
+            old = engine.dither_frames(frames, pal, "halftone", params, use_gamma=gamma)
+            monkeypatch.delenv("DP_HT_V1")
+            assert np.array_equal(old, rgb), (params, gamma)
+
+
 # ------------------------------------------------------------------ host-buffer entry point
 def test_threshold_dither_host_entry_point():
     """dp_threshold_dither_host -- the call INTEGRATION.md's example binding uses."""
