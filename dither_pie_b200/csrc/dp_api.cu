@@ -678,6 +678,10 @@ extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out
     std::vector<uint8_t> orgb(K * 4, 0);
     for (int i = 0; i < K; ++i)
         for (int c = 0; c < 3; ++c) orgb[4 * i + c] = out_rgb[3 * i + c];
+    h->pal_is_out = 1;
+    for (int i = 0; i < K; ++i)
+        for (int c = 0; c < 3; ++c)
+            if (palette[3 * i + c] != (float)out_rgb[3 * i + c]) h->pal_is_out = 0;
     uint8_t lut[256];
     h->has_lut = 0;
     for (int i = 0; i < 256; ++i) {

@@ -129,6 +129,7 @@ struct PalDev {
 struct dp_palette {
     PalDev dev;
     int has_lut;   // in_lut is not the identity
+    int pal_is_out;   // every palette value equals the row's output byte (plain byte palettes)
     int device;
     void *blob;    // single device allocation backing the palette arrays and the KD-tree
     void *thr_table;

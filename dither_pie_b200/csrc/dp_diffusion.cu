@@ -172,6 +172,7 @@ struct WaveParams {
     uint8_t *dst;
     uint8_t *dst_idx;
     int frames, h, w, nbands, total_units, has_lut, K;
+    int bytes;          // identity input LUT and palette rows == output bytes: BYTES instantiation
     float *hand;        // [units][6 planes][TPAD] f32 hand-off streams (index = consumer step)
     int *progress;      // [units]
     int *qctrl;         // [0] queue head (consumers), [1] queue tail (producers)
@@ -307,6 +308,20 @@ __device__ __forceinline__ uint4 lds_u32x4(unsigned a)
     uint4 v;
     asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
     return v;
+}
+
+// Byte -> work value without a table (BYTES instantiations: identity input LUT, palette rows equal
+// to their output bytes).  The shared-memory pipe is the busiest unit of the wavefront kernel
+// (ncu: l1tex data-pipe wavefronts 68-74 % of peak, profiles/r2p_*): the byte -> double LUT and
+// the f64 palette rows cost ~21 of its ~99 wavefronts per warp step, all of them bank-conflicted
+// gathers.  2^52 + b is exact and so is the subtraction (one DADD / FADD on an idle pipe).
+__device__ __forceinline__ double byte_f64(unsigned b)
+{
+    return __dsub_rn(__hiloint2double(0x43300000, (int)b), 4503599627370496.0);
+}
+__device__ __forceinline__ float byte_f32(unsigned b)
+{
+    return __fsub_rn(__int_as_float((int)(0x4b000000u | b)), 8388608.0f);
 }
 
 struct Search {
@@ -668,7 +683,7 @@ __host__ __device__ constexpr int wave_step_unroll(int v)
     return (v == DP_ED_JJN || v == DP_ED_STUCKI) ? DP_WAVE_UNROLL_5X5 : DP_WAVE_UNROLL_OTHER;
 }
 
-template <int V, bool BIG, int NSLOT>
+template <int V, bool BIG, int NSLOT, bool BYTES>
 __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wave(const WaveParams p)
 {
     using SP = Spec<V>;
@@ -952,13 +967,13 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                         for (int c = 0; c < 3; ++c) d1[SP::W1 - 1][c] = fb[c];
                     }
                     if constexpr (sizeof(T) == 8) {
-                        top[0] = lds_f64(lut_a + 8u * pb[0]);
-                        top[1] = lds_f64(lut_a + 8u * pb[1]);
-                        top[2] = lds_f64(lut_a + 8u * pb[2]);
+                        top[0] = BYTES ? byte_f64(pb[0]) : lds_f64(lut_a + 8u * pb[0]);
+                        top[1] = BYTES ? byte_f64(pb[1]) : lds_f64(lut_a + 8u * pb[1]);
+                        top[2] = BYTES ? byte_f64(pb[2]) : lds_f64(lut_a + 8u * pb[2]);
                     } else {
-                        top[0] = lds_f32(lut_a + 4u * pb[0]);
-                        top[1] = lds_f32(lut_a + 4u * pb[1]);
-                        top[2] = lds_f32(lut_a + 4u * pb[2]);
+                        top[0] = BYTES ? byte_f32(pb[0]) : lds_f32(lut_a + 4u * pb[0]);
+                        top[1] = BYTES ? byte_f32(pb[1]) : lds_f32(lut_a + 4u * pb[1]);
+                        top[2] = BYTES ? byte_f32(pb[2]) : lds_f32(lut_a + 4u * pb[2]);
                     }
                 }
 
@@ -966,6 +981,7 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                 const bool active = rowok && x >= 0 && x < W;
                 if (active) {
                     int bi;
+                    unsigned oc;   // the row's output bytes (BYTES: also its palette values)
                     if constexpr (!SP::F32) {
                         double v[3], e[3];
                         float vf[3];
@@ -980,8 +996,11 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                         DP_STICK(1);
                         bi = nearest_row<false, NSLOT>(P, srch, vf[0], vf[1], vf[2], v[0], v[1], v[2]);
                         DP_STICK(2);
+                        oc = lds_u32(orgb_a + 4u * bi);
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) e[c] = __dsub_rn(v[c], lds_f64(pal_a + 24u * bi + 8u * c));
+                        for (int c = 0; c < 3; ++c)
+                            e[c] = __dsub_rn(v[c], BYTES ? byte_f64(__byte_perm(oc, 0u, 0x4440u + c))
+                                                         : lds_f64(pal_a + 24u * bi + 8u * c));
                         if constexpr (V == V_HYBRID) {
                             // _hybrid_numba :1447-1455, one rounding per operation, in its order
                             const double lum = __dadd_rn(
@@ -1009,8 +1028,11 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                             P, srch, cell_of(fminf(fmaxf(ov[0], 0.f), 255.f), fminf(fmaxf(ov[1], 0.f), 255.f),
                                              fminf(fmaxf(ov[2], 0.f), 255.f)),
                             ov[0], ov[1], ov[2], (double)ov[0], (double)ov[1], (double)ov[2], p.K);
+                        oc = lds_u32(orgb_a + 4u * bi);
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], lds_f32(palf_a + 12u * bi + 4u * c));
+                        for (int c = 0; c < 3; ++c)
+                            er[c] = __fsub_rn(ov[c], BYTES ? byte_f32(__byte_perm(oc, 0u, 0x4440u + c))
+                                                           : lds_f32(palf_a + 12u * bi + 4u * c));
                         const float w0 = __fmul_rn(0.4375f, fac), w1 = __fmul_rn(0.1875f, fac),
                                     w2 = __fmul_rn(0.3125f, fac), w3 = __fmul_rn(0.0625f, fac);
 #pragma unroll
@@ -1029,8 +1051,11 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                         }
                         bi = nearest_row<true, NSLOT>(P, srch, ov[0], ov[1], ov[2], (double)ov[0],
                                                (double)ov[1], (double)ov[2]);
+                        oc = lds_u32(orgb_a + 4u * bi);
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) er[c] = __fsub_rn(ov[c], lds_f32(palf_a + 12u * bi + 4u * c));
+                        for (int c = 0; c < 3; ++c)
+                            er[c] = __fsub_rn(ov[c], BYTES ? byte_f32(__byte_perm(oc, 0u, 0x4440u + c))
+                                                           : lds_f32(palf_a + 12u * bi + 4u * c));
                         float lum = __fmul_rn(0.299f, ov[0]);
                         lum = __fadd_rn(lum, __fmul_rn(0.587f, ov[1]));
                         lum = __fadd_rn(lum, __fmul_rn(0.114f, ov[2]));
@@ -1045,7 +1070,6 @@ __global__ void __launch_bounds__(wave_max_warps<V, BIG>() * 32, 1) k_diffuse_wa
                             d1[0][c] = __fadd_rn(d1[0][c], __fmul_rn(er[c], w1));
                         }
                     }
-                    const unsigned oc = lds_u32(orgb_a + 4u * bi);
                     ob[3 * sidx] = (unsigned char)oc;
                     ob[3 * sidx + 1] = (unsigned char)(oc >> 8);
                     ob[3 * sidx + 2] = (unsigned char)(oc >> 16);
@@ -1439,7 +1463,7 @@ __global__ void k_wave_init(int *progress, int *qctrl, int *queue, int units, in
 
 // BIG selects the kernel instantiation (register budget); `big` the launch shape; NSLOT the
 // number of candidate slots the screening pass evaluates.
-template <int V, bool BIG, int NSLOT>
+template <int V, bool BIG, int NSLOT, bool BYTES>
 int launch_wave_as(const WaveParams &p0, cudaStream_t st, int npat, bool big)
 {
     using Stage = WarpStageT<typename StateOf<V>::T, Spec<V>::ROWS3 ? 6 : 3>;
@@ -1464,10 +1488,10 @@ int launch_wave_as(const WaveParams &p0, cudaStream_t st, int npat, bool big)
     // the patterns join it when they fit beside the stages
     p.pat_smem = (p.l1_smem && fixed + sizeof(Stage) * warps + (size_t)npat * 16 <= limit) ? npat : 0;
     const size_t smem = fixed + sizeof(Stage) * warps + (size_t)p.pat_smem * 16;
-    DP_CUDA(cudaFuncSetAttribute(k_diffuse_wave<V, BIG, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DP_CUDA(cudaFuncSetAttribute(k_diffuse_wave<V, BIG, NSLOT, BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));
     int per_sm = 0;
-    DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_diffuse_wave<V, BIG, NSLOT>, warps * 32,
+    DP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_diffuse_wave<V, BIG, NSLOT, BYTES>, warps * 32,
                                                           smem));
     if (per_sm < 1) per_sm = 1;
     long long blocks = ((long long)p.total_units + warps - 1) / warps;
@@ -1477,7 +1501,7 @@ int launch_wave_as(const WaveParams &p0, cudaStream_t st, int npat, bool big)
         const int g = atoi(ev);
         if (g >= 1 && g < grid) grid = g;
     }
-    k_diffuse_wave<V, BIG, NSLOT><<<grid, warps * 32, smem, st>>>(p);
+    k_diffuse_wave<V, BIG, NSLOT, BYTES><<<grid, warps * 32, smem, st>>>(p);
     DP_LAUNCH_CHECK();
     return 0;
 }
@@ -1486,22 +1510,27 @@ int launch_wave_as(const WaveParams &p0, cudaStream_t st, int npat, bool big)
 // sub-partitions (a lone warp is latency-bound).  Many bands: one block per SM with as many
 // warps as registers (wave_max_warps) and shared memory allow.  Only the 5x5 footprints are
 // compiled differently for the two regimes; for the others BIG merely selects the launch shape.
-template <int V, int NSLOT>
+template <int V, int NSLOT, bool BYTES>
 int launch_wave_n(const WaveParams &p, cudaStream_t st, int npat)
 {
     const bool big = p.total_units > dp_num_sms() * 8;
     if constexpr (V == DP_ED_JJN || V == DP_ED_STUCKI) {
-        return big ? launch_wave_as<V, true, NSLOT>(p, st, npat, true)
-                   : launch_wave_as<V, false, NSLOT>(p, st, npat, false);
+        return big ? launch_wave_as<V, true, NSLOT, BYTES>(p, st, npat, true)
+                   : launch_wave_as<V, false, NSLOT, BYTES>(p, st, npat, false);
     } else {
-        return launch_wave_as<V, true, NSLOT>(p, st, npat, big);
+        return launch_wave_as<V, true, NSLOT, BYTES>(p, st, npat, big);
     }
 }
 
+// p.bytes: identity input LUT and palette rows equal to their output bytes (every plain byte
+// palette without gamma): the BYTES instantiations form work values and palette values from the
+// bytes themselves instead of gathering them from shared-memory tables.
 template <int V>
 int launch_wave(const WaveParams &p, cudaStream_t st, int npat, bool four_slots)
 {
-    return four_slots ? launch_wave_n<V, 4>(p, st, npat) : launch_wave_n<V, 7>(p, st, npat);
+    if (p.bytes)
+        return four_slots ? launch_wave_n<V, 4, true>(p, st, npat) : launch_wave_n<V, 7, true>(p, st, npat);
+    return four_slots ? launch_wave_n<V, 4, false>(p, st, npat) : launch_wave_n<V, 7, false>(p, st, npat);
 }
 
 template <int V>
@@ -1614,6 +1643,7 @@ int run_diffusion(const dp_palette *pal, const uint8_t *src, int frames, int h, 
     DP_REQUIRE(units < (1ll << 30), "too many row bands in one call");
     p.total_units = (int)units;
     p.has_lut = pal->has_lut;
+    p.bytes = (!pal->has_lut && pal->pal_is_out && !getenv("DP_WAVE_NO_BYTES")) ? 1 : 0;
     p.K = pal->dev.K;
     p.ostro_w = ostro_w;
     p.hyb_lum = hyb_lum;

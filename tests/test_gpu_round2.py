@@ -236,6 +236,33 @@ def test_wavefront_handoff_stress_tiny_frames_two_blocks(monkeypatch):
             assert not bad, (mode, params, rep, bad[:5])
 
 
+def test_wavefront_byte_and_table_instantiations_agree(monkeypatch):
+    """Plain byte palettes without gamma take the BYTES instantiations of the wavefront kernel
+    (work values and palette values formed from the bytes themselves); gamma palettes and
+    DP_WAVE_NO_BYTES take the shared-memory tables.  Both against the oracle, every state type
+    (f64 numba variants, hybrid, f32 Ostromoukhov / perceptual), 4- and 7-slot screening."""
+    frames = np.stack([synth.frame(75, 133, 700 + t) if t else synth.noise_frame(75, 133, 700)
+                       for t in range(3)])
+    cases = (("error_diffusion", {"variant": "floyd_steinberg"}), ("error_diffusion", {"variant": "stucki"}),
+             ("error_diffusion", {"variant": "sierra_lite"}), ("ostromoukhov", {}), ("hybrid", {}),
+             ("perceptual", {}))
+    for pal in (PICO, synth.random_palette(256)):
+        for mode, params in cases:
+            refs = oracle_many([(f, pal, mode, params) for f in frames])
+            out = engine.dither_frames(frames, pal, mode, params)
+            monkeypatch.setenv("DP_WAVE_NO_BYTES", "1")
+            tab = engine.dither_frames(frames, pal, mode, params)
+            monkeypatch.delenv("DP_WAVE_NO_BYTES")
+            assert np.array_equal(out, tab), (mode, params, len(pal))
+            for t in range(3):
+                assert mismatch(out[t], refs[t]) == 0, (mode, params, len(pal), t)
+    for mode, params in cases[:4]:     # gamma: the table instantiations by themselves
+        refs = oracle_many([(f, PICO, mode, params, True) for f in frames])
+        out = engine.dither_frames(frames, PICO, mode, params, use_gamma=True)
+        for t in range(3):
+            assert mismatch(out[t], refs[t]) == 0, (mode, params, "gamma", t)
+
+
 # ------------------------------------------------------------------ frame pipeline
 def test_frame_pipeline_matches_direct_calls_pinned_and_pageable():
     frames = np.stack([synth.frame(120, 208, 60 + t) for t in range(11)])
