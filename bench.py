@@ -5,7 +5,8 @@
 
 Headline workload (BASELINE.json configs[1]): 3840x2160 RGB frames, error diffusion with the
 Floyd-Steinberg + Atkinson + JJN kernels, 256-colour palette.  One "step" is one pass of the three
-kernels over a batch of 128 synthetic 4K frames (3.2 GB, far larger than L2).
+kernels over a device-resident batch of 256 synthetic 4K frames (6.4 GB, far larger than L2); the
+three kernels are independent and run on three streams.
 Metric: Mpixels/s (input pixels x dither passes per second), whole job over all ranks.
 N > 1: one process per GPU (torchrun), every rank owns its own batch of frames (frames are
 independent -> weak scaling, no data-path collective); time = max over ranks.
@@ -125,7 +126,10 @@ def workload_config(n_gpus, batch):
             "frames_per_step_per_gpu": batch, "passes_per_frame": len(ED_VARIANTS),
             "palette": "first 256 unique rows of RandomState(2024).randint(0,256)",
             "frame": "synth.frame(2160,3840,seed) gradient + uniform noise [-16,16]",
-            "l2_policy": "inputs larger than L2 (a batch of 128 4K frames is 3.2 GB in, 3x that out)",
+            "l2_policy": f"inputs larger than L2 (a batch of {batch} 4K frames is "
+                         f"{(batch or 0) * H4K * W4K * 3 / 1e9:.1f} GB in, 3x that out)",
+            "streams": "the three variants of a step run on three streams (independent kernels over the "
+                       "same batch; the next kernel's ramp-up fills the previous kernel's drain tail)",
             "parallelism": f"frame-sharded x{n_gpus}, no data-path collective"}
 
 
@@ -312,18 +316,38 @@ def run_gpu(args):
     base = np.stack([synth.frame(H4K, W4K, 1 + rank * 16 + t) for t in range(4)])
     for t in range(B):       # per-rank synthetic frames: 4 seeds, the rest rolled copies (new bytes)
         host_in[t] = base[t % 4] if t < 4 else np.roll(base[t % 4], 7 * t, axis=1)
-    src = torch.empty((B, H4K, W4K, 3), dtype=torch.uint8, device=dev)
+    # device-resident batch: DB frames (the wavefront kernel loses its ramp-up and drain tail once
+    # per launch, so larger batches amortise them: 128 -> 256 frames is worth ~10 %); the first B
+    # are the host frames of the e2e legs, the rest rolled copies (new bytes)
+    DB = max(B, args.dev_batch)
+    src = torch.empty((DB, H4K, W4K, 3), dtype=torch.uint8, device=dev)
+    src[:B].copy_(torch.from_numpy(host_in))
+    for t0 in range(B, DB, B):
+        n = min(B, DB - t0)
+        src[t0:t0 + n].copy_(torch.roll(src[:n], shifts=11 * (t0 // B), dims=2))
     dst = [torch.empty_like(src) for _ in ED_VARIANTS]
-    src.copy_(torch.from_numpy(host_in))
     plans = [engine.Plan("error_diffusion", {"variant": v}, H4K, W4K) for v in ED_VARIANTS]
     px_per_step = B * H4K * W4K * len(ED_VARIANTS)
+    dev_px_per_step = DB * H4K * W4K * len(ED_VARIANTS)
     launches = 0
+    # one stream per variant: the three kernels of a step are independent (same input, own output);
+    # the longest (JJN) is launched first
+    vstreams = [torch.cuda.Stream(device=dev) for _ in ED_VARIANTS]
+    vsp = [C.c_void_p(v.cuda_stream) for v in vstreams]
+    order = sorted(range(len(ED_VARIANTS)), key=lambda i: ED_VARIANTS[i] != "jjn")
+    fork = torch.cuda.Event()
+    joins = [torch.cuda.Event() for _ in ED_VARIANTS]
 
     def step():
         nonlocal launches
-        for pl, d in zip(plans, dst):
-            pl.run(pal, src.data_ptr(), B, d.data_ptr(), None, sp)
+        fork.record(stream)
+        for i in order:
+            vstreams[i].wait_event(fork)
+            plans[i].run(pal, src.data_ptr(), DB, dst[i].data_ptr(), None, vsp[i])
+            joins[i].record(vstreams[i])
             launches += 2  # k_wave_init + k_diffuse_wave per call
+        for i in order:
+            stream.wait_event(joins[i])
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -332,26 +356,31 @@ def run_gpu(args):
     if rank == 0:
         sampler.start()
     launches = 0
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps * len(ED_VARIANTS))]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    k = 0
     for _ in range(args.steps):
-        for pl, d in zip(plans, dst):
-            ev[k][0].record(stream)
-            pl.run(pal, src.data_ptr(), B, d.data_ptr(), None, sp)
-            ev[k][1].record(stream)
-            launches += 2
-            k += 1
+        step()
     e1.record(stream)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    value = world * dev_px_per_step * args.steps / (ms_total * 1e-3) / 1e6
+    # the same launches one after the other on ONE stream (not part of `value`): the duration of
+    # each kernel by itself, for the roofline line and for comparison with the ncu launch list
+    iso_steps = max(2, min(args.steps, 4))
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(iso_steps * len(ED_VARIANTS))]
+    k = 0
+    for _ in range(iso_steps):
+        for pl, d in zip(plans, dst):
+            ev[k][0].record(stream)
+            pl.run(pal, src.data_ptr(), DB, d.data_ptr(), None, sp)
+            ev[k][1].record(stream)
+            k += 1
+    barrier()
     kernel_ms = [a.elapsed_time(b) for a, b in ev]
     per_variant_ms = {v: statistics.mean(kernel_ms[i::len(ED_VARIANTS)]) for i, v in enumerate(ED_VARIANTS)}
-    value = world * px_per_step * args.steps / (ms_total * 1e-3) / 1e6
     del dst
 
     # ---- e2e: pinned HOST arrays through pipeline.FramePipeline (the engine under
@@ -428,13 +457,15 @@ def run_gpu(args):
         return
 
     peak, peak_src = peaks()
-    avg_kernel_ms = sum(kernel_ms) / len(kernel_ms)
-    alg_bytes = BYTES_PER_PX * B * H4K * W4K
+    # the three launches of a step overlap on three streams: the average launch duration inside
+    # the timed region is the step time / 3 (each kernel by itself: launch_ms_isolated)
+    avg_kernel_ms = ms_total / args.steps / len(ED_VARIANTS)
+    alg_bytes = BYTES_PER_PX * DB * H4K * W4K
     achieved = alg_bytes / (avg_kernel_ms * 1e-3) / 1e9
     # DRAM traffic per launch for 128 4K frames in the ncu --set full captures (profiles/):
     # 7.617 GB for k_diffuse_wave<floyd_steinberg>, 7.761 GB for <jjn> (the two ends of the step's
     # three launches), i.e. 7.2-7.3 B/pixel against 6 algorithmic -- hand-off streams + table
-    traffic = 0.5 * (7.616983e9 + 7.761e9) / (128 * H4K * W4K) * (B * H4K * W4K)
+    traffic = 0.5 * (7.616983e9 + 7.761e9) / (128 * H4K * W4K) * (DB * H4K * W4K)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic,
                 "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
@@ -442,7 +473,11 @@ def run_gpu(args):
                                   "(scaled by frames)",
                 "kernel": "k_diffuse_wave",
                 "peak_source": peak_src, "avg_launch_ms": avg_kernel_ms,
-                "launch_ms": per_variant_ms,
+                "avg_launch_note": "the step's three launches overlap on three streams: step time / 3, "
+                                   "measured with CUDA events on the stream that forks and joins them",
+                "launch_ms_isolated": per_variant_ms,
+                "launch_isolated_note": "each kernel by itself, one stream, CUDA events around the launch "
+                                        "(a separate pass after the timed region)",
                 "note": "error diffusion is bounded by its per-pixel dependency chain (~1100 cycles "
                         "per wavefront step) and by instruction issue, not by HBM; see DESIGN.md"}
 
@@ -450,7 +485,7 @@ def run_gpu(args):
         "metric": "Mpixels/s", "value": value, "unit": "Mpx/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": workload_config(world, B),
+        "data": "synthetic", "config": workload_config(world, DB),
         "clocks": clocks, "gpu_launches": launches,
         "e2e": e2e, "roofline": roofline,
     }
@@ -842,7 +877,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="4K frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=128, help="4K host frames per e2e step per GPU")
+    ap.add_argument("--dev-batch", type=int, default=256,
+                    help="4K frames per device-resident step per GPU (>= --batch)")
     ap.add_argument("--pipe-batch", type=int, default=64, help="frames per device batch of the e2e pipeline")
     ap.add_argument("--no-extra", action="store_true", help="skip the per-mode entries")
     ap.add_argument("--no-video", action="store_true", help="skip the strong-scaling video configs")
