@@ -25,6 +25,9 @@ WANT = [
     "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
     "lts__t_sectors_op_read.sum", "lts__t_sectors_op_write.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_lgds.sum", "l1tex__t_sector_hit_rate.pct",
 ]
 
 
