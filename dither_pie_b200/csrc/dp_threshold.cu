@@ -73,6 +73,7 @@ struct ThreshParams {
     FastDiv dspr, dh;   // geom2: strips per row, rows per frame
     int geom_table;     // geom2: the compact candidate tables exist (K <= 30, integral, no LUT)
     int wide;           // v4: the 31..256-colour table format (PalDev::thr4_wide)
+    int defer;          // v4 wide thresholds: flagged pixels are listed per warp and fixed 32 at a time
 };
 
 // IGN threshold (:541-549): f32, one rounding per numpy ufunc, no contraction.
@@ -721,6 +722,30 @@ __device__ __forceinline__ int pick_int_ent(const PalDev *P, const int2 *s_ent, 
     return factor_le_int(s1 + vv, s2 + vv, thr) ? i1 : i2;
 }
 
+// exact decision for one pixel v4_pick flagged: most flagged pixels are exact distance ties, whose
+// answer is in the exception table (two dependent loads), no scan of the rows is needed
+template <int KIND, bool WIDE>
+__device__ __forceinline__ int v4_exact_idx(const ThreshParams &p, const FastCtx &fc, const int2 *s_ent,
+                                            unsigned r, unsigned g, unsigned b, float thr)
+{
+    const PalDev *P = p.P;
+    const unsigned vq = r | (g << 8) | (b << 16);
+    int oi[2];
+    if (tie_lookup<KIND == DP_THRESH_NONE ? 1 : 2>(P, (int)r, (int)g, (int)b, oi)) {
+        int idx = oi[0];
+        if (KIND != DP_THRESH_NONE) {
+            const int vv = (int)(r * r + g * g + b * b);
+            const int2 ea = s_ent[oi[0]], eb = s_ent[oi[1]];
+            const int n0 = ((ea.y - 512 * (int)__dp4a(vq, (unsigned)ea.x, 0u)) >> 8) + vv;
+            const int n1 = ((eb.y - 512 * (int)__dp4a(vq, (unsigned)eb.x, 0u)) >> 8) + vv;
+            // the two smallest distances as a multiset do not depend on the tie order
+            idx = factor_le_int(min(n0, n1), max(n0, n1), thr) ? oi[0] : oi[1];
+        }
+        return idx;
+    }
+    return WIDE ? pick_fast<KIND>(P, fc, p.K, vq, thr) : pick_int_ent<KIND>(P, s_ent, p.K, vq, thr);
+}
+
 // exact decision for the pixels v4_pick flagged (rare): re-reads the pixel from global memory,
 // patches its output bytes in the warp's staging buffer and its index byte in global memory
 template <int KIND, bool WM_POW2, bool WIDE>
@@ -747,24 +772,7 @@ __device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, lo
         } else if (KIND == DP_THRESH_IGN) {
             thr = ign_threshold(p, (int)x + j, (int)y);
         }
-        const unsigned vq = (unsigned)q[0] | ((unsigned)q[1] << 8) | ((unsigned)q[2] << 16);
-        int idx;
-        int oi[2];
-        // most flagged pixels are exact distance ties: their answer is in the exception table
-        // (two dependent loads), no scan of the rows is needed
-        if (tie_lookup<KIND == DP_THRESH_NONE ? 1 : 2>(P, q[0], q[1], q[2], oi)) {
-            idx = oi[0];
-            if (KIND != DP_THRESH_NONE) {
-                const int vv = (int)q[0] * q[0] + (int)q[1] * q[1] + (int)q[2] * q[2];
-                const int2 ea = s_ent[oi[0]], eb = s_ent[oi[1]];
-                const int n0 = ((ea.y - 512 * (int)__dp4a(vq, (unsigned)ea.x, 0u)) >> 8) + vv;
-                const int n1 = ((eb.y - 512 * (int)__dp4a(vq, (unsigned)eb.x, 0u)) >> 8) + vv;
-                // the two smallest distances as a multiset do not depend on the tie order
-                idx = factor_le_int(min(n0, n1), max(n0, n1), thr) ? oi[0] : oi[1];
-            }
-        } else {
-            idx = WIDE ? pick_fast<KIND>(P, fc, p.K, vq, thr) : pick_int_ent<KIND>(P, s_ent, p.K, vq, thr);
-        }
+        const int idx = v4_exact_idx<KIND, WIDE>(p, fc, s_ent, q[0], q[1], q[2], thr);
         const unsigned col = s_orgb[idx];
         out_bytes[3 * j] = (uint8_t)col;
         out_bytes[3 * j + 1] = (uint8_t)(col >> 8);
@@ -773,10 +781,53 @@ __device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, lo
     }
 }
 
+// The wide format flags ~1 % of the pixels (distance ties and crowded sub-cells of a 256-colour
+// palette), i.e. a few per 512-pixel tile: fixed tile by tile (v4_fix), almost every tile pays a
+// chain of five dependent global loads for one or two pixels of one or two lanes, a third of the
+// kernel's time.  Instead the warp collects the flagged pixels of its tiles (batch pixel index)
+// in a small shared list and fixes them 32 at a time, one per lane, directly in global memory --
+// after the bulk stores of their tiles have completed.
+#define V4_DEFER_CAP 64
+template <int KIND, bool WM_POW2, bool WIDE>
+__device__ __noinline__ void v4_fix_deferred(const ThreshParams &p, const uint32_t *list, int n, int lane,
+                                             const float *s_mat, const unsigned *s_orgb, const int2 *s_ent)
+{
+    const PalDev *P = p.P;
+    FastCtx fc;
+    fc.table = P->thr_table;
+    fc.ovf = P->thr_ovf;
+    fc.ent = s_ent;
+    fc.shift = P->thr_shift;
+    fc.ncell = 256 >> fc.shift;
+    for (int i = lane; i < n; i += 32) {
+        const uint32_t gpp = list[i];
+        const uint8_t *q = p.src + (size_t)gpp * 3;
+        const uint32_t pin = gpp - fd_div(p.dnpix, gpp) * (uint32_t)p.npix;
+        const uint32_t y = fd_div(p.dw, pin), x = pin - y * p.w;
+        float thr = 0.0f;
+        if (KIND == DP_THRESH_MATRIX) {
+            const uint32_t ym = y - fd_div(p.dmh, y) * p.mh;
+            const uint32_t xm = WM_POW2 ? (x & (uint32_t)(p.wm - 1)) : (x - fd_div(p.dwm, x) * p.wm);
+            thr = s_mat[ym * p.wm + xm];
+        } else if (KIND == DP_THRESH_IGN) {
+            thr = ign_threshold(p, (int)x, (int)y);
+        }
+        const int idx = v4_exact_idx<KIND, WIDE>(p, fc, s_ent, q[0], q[1], q[2], thr);
+        const unsigned col = s_orgb[idx];
+        if (p.dst) {
+            uint8_t *o = p.dst + (size_t)gpp * 3;
+            o[0] = (uint8_t)col;
+            o[1] = (uint8_t)(col >> 8);
+            o[2] = (uint8_t)(col >> 16);
+        }
+        if (p.dst_idx) p.dst_idx[gpp] = (uint8_t)idx;
+    }
+}
+
 __host__ __device__ constexpr int v4_ent_bytes(bool wide) { return wide ? 2048 : 272; }     // int2 [256] / [34]
 __host__ __device__ constexpr int v4_orgb_bytes(bool wide) { return wide ? 1024 : 128; }    // u32 [256] / [32]
 
-template <int KIND, bool WM_POW2, bool WIDE>
+template <int KIND, bool WM_POW2, bool WIDE, bool DEFER>
 __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const ThreshParams p)
 {
     constexpr int V4_THREADS = v4_threads<KIND, WIDE>();
@@ -791,6 +842,8 @@ __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const
     uint4 *s_io = reinterpret_cast<uint4 *>(smem + 131072 + ENTB + ORGBB + 512);  // [warps][2][96]
     uint32_t *s_sub = reinterpret_cast<uint32_t *>(s_io + V4_WARPS * 192);     // [8 * nsub]
     float *s_mat = reinterpret_cast<float *>(s_sub + (KIND == DP_THRESH_NONE ? 0 : ((8 * P_nsub + 3) & ~3)));   // [mh][wm]
+    // DEFER instantiations: per-warp list of flagged pixels (the launch found room for it)
+    uint32_t *s_defer = reinterpret_cast<uint32_t *>(s_mat + (KIND == DP_THRESH_MATRIX ? p.mh * p.wm : 0));
 
     const PalDev *P = p.P;
     const int tid = threadIdx.x;
@@ -876,6 +929,8 @@ __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const
     uint32_t wt = blockIdx.x * V4_WARPS + wib;
     int buf = 0;
     unsigned it = 0;    // tiles done by this warp: buffer it & 1, barrier parity (it >> 1) & 1
+    uint32_t *dlist = s_defer + wib * V4_DEFER_CAP;
+    int ndefer = 0;     // warp-uniform
     if (wt < ntiles) issue(wt, 0);
     // position of this lane's first pixel inside its frame, advanced incrementally
     uint32_t pin = 0, pstep = 0;
@@ -946,9 +1001,46 @@ __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const
         cur[3 * lane] = make_uint4(w[0], w[1], w[2], w[3]);      // own slots: no hazard with other lanes
         cur[3 * lane + 1] = make_uint4(w[4], w[5], w[6], w[7]);
         cur[3 * lane + 2] = make_uint4(w[8], w[9], w[10], w[11]);
-        if (slowmask)
+        if (DEFER) {
+            // (inline on purpose: as a function called on almost every tile this costs more than
+            // it saves -- IGN K=256: 0.66 ms against 0.56 ms)
+            if (__ballot_sync(0xffffffffu, slowmask != 0)) {
+                const int cnt = __popc(slowmask);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total > V4_DEFER_CAP) {     // pathological tile: fixed in place, lane by lane
+                    if (slowmask)
+                        v4_fix<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra,
+                                                    reinterpret_cast<uint8_t *>(cur + 3 * lane), s_orgb, s_ent);
+                } else {
+                    if (ndefer + total > V4_DEFER_CAP) {
+                        // every listed pixel belongs to an earlier tile: wait until the bulk stores
+                        // of those tiles have completed (this tile's store is not issued yet), then
+                        // patch them in global memory
+                        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                        __syncwarp();
+                        v4_fix_deferred<KIND, WM_POW2, WIDE>(p, dlist, ndefer, lane, s_mat, s_orgb, s_ent);
+                        __syncwarp();
+                        ndefer = 0;
+                    }
+                    int pos = ndefer + incl - cnt;
+                    unsigned m = slowmask;
+                    while (m) {
+                        dlist[pos++] = gp + (uint32_t)(__ffs(m) - 1);
+                        m &= m - 1;
+                    }
+                    ndefer += total;
+                }
+            }
+        } else if (slowmask) {
             v4_fix<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra, reinterpret_cast<uint8_t *>(cur + 3 * lane),
                                         s_orgb, s_ent);
+        }
         // generic-proxy writes -> visible to the async proxy, then one bulk store by lane 0
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -958,6 +1050,10 @@ __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const
         }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (DEFER) {
+        __syncwarp();
+        v4_fix_deferred<KIND, WM_POW2, WIDE>(p, dlist, ndefer, lane, s_mat, s_orgb, s_ent);
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1224,17 +1320,34 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
         const bool wide = p.wide != 0;
         const int V4_THREADS = wide ? v4_threads<KIND, true>() : v4_threads<KIND, false>();
         const int V4_WARPS = V4_THREADS / 32;
-        const size_t smem = 131072 + v4_ent_bytes(wide) + v4_orgb_bytes(wide) + 512 + (size_t)V4_WARPS * 3072 +
-                            (KIND == DP_THRESH_NONE ? 0 : (size_t)p.sub_bytes) +
-                            (KIND == DP_THRESH_MATRIX ? (size_t)p.mh * p.wm * 4 : 0);
-        void (*kern)(ThreshParams) =
-            wide ? (pow2 ? k_thresh_v4<KIND, true, true> : k_thresh_v4<KIND, false, true>)
-                 : (pow2 ? k_thresh_v4<KIND, true, false> : k_thresh_v4<KIND, false, false>);
+        size_t smem = 131072 + v4_ent_bytes(wide) + v4_orgb_bytes(wide) + 512 + (size_t)V4_WARPS * 3072 +
+                      (KIND == DP_THRESH_NONE ? 0 : (size_t)p.sub_bytes) +
+                      (KIND == DP_THRESH_MATRIX ? (size_t)p.mh * p.wm * 4 : 0);
+        ThreshParams q = p;
+        // wide thresholds: deferred fixes when the per-warp lists fit beside everything else
+        const size_t defer_bytes = (size_t)V4_WARPS * V4_DEFER_CAP * 4;
+        // (the narrow format flags too few pixels for it to pay: PICO-8 0.367 -> 0.383 ms; only a
+        // tie-heavy palette like the C64's gains, 0.476 -> 0.455 ms; DP_THRESH_DEFER_ALL for tools/)
+        q.defer = ((wide || getenv("DP_THRESH_DEFER_ALL")) && KIND != DP_THRESH_NONE &&
+                   smem + defer_bytes <= 227 * 1024 && !getenv("DP_THRESH_NO_DEFER")) ? 1 : 0;
+        if (q.defer) smem += defer_bytes;
+        void (*kern)(ThreshParams);
+        if constexpr (KIND != DP_THRESH_NONE) {
+            if (q.defer)
+                kern = wide ? (pow2 ? k_thresh_v4<KIND, true, true, true> : k_thresh_v4<KIND, false, true, true>)
+                            : (pow2 ? k_thresh_v4<KIND, true, false, true> : k_thresh_v4<KIND, false, false, true>);
+            else
+                kern = wide ? (pow2 ? k_thresh_v4<KIND, true, true, false> : k_thresh_v4<KIND, false, true, false>)
+                            : (pow2 ? k_thresh_v4<KIND, true, false, false> : k_thresh_v4<KIND, false, false, false>);
+        } else {
+            kern = wide ? (pow2 ? k_thresh_v4<KIND, true, true, false> : k_thresh_v4<KIND, false, true, false>)
+                        : (pow2 ? k_thresh_v4<KIND, true, false, false> : k_thresh_v4<KIND, false, false, false>);
+        }
         DP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const long long ntiles = ((long long)p.frames * p.npix + 511) >> 9;
         const long long want = (ntiles + V4_WARPS - 1) / V4_WARPS;   // frames * npix < 2^31 here
         const int grid = (int)(want < sms ? want : sms);
-        kern<<<grid, V4_THREADS, smem, st>>>(p);
+        kern<<<grid, V4_THREADS, smem, st>>>(q);
     } else if (!geom && p.fast) {
         const bool tsm = p.fast == 1;
         const bool pow2 = ((p.mw & (p.mw - 1)) == 0) && ((p.mh & (p.mh - 1)) == 0);

@@ -526,6 +526,32 @@ def test_threshold_v4_wide_table_vs_oracle(k):
         assert mismatch(engine.dither_frames(img, lat, mode, params), O.apply_dithering(img, lat, mode, params)) == 0, mode
 
 
+def test_threshold_v4_wide_deferred_fixes_vs_oracle_and_in_place_fixes(monkeypatch):
+    """Wide-format threshold launches list their flagged pixels per warp and fix them 32 at a time
+    in global memory, after the bulk stores of their tiles (DP_THRESH_NO_DEFER: tile by tile, in the
+    staging buffer).  A batch large enough that every warp runs many tiles (lists fill up and are
+    flushed mid-run and at the end), a lattice palette whose tiles overflow the list (fixed in
+    place), colour + index and index-only output; both paths against the oracle."""
+    frames = np.stack([synth.frame(360, 640, 40 + t) if t % 2 else synth.noise_frame(360, 640, 40 + t)
+                       for t in range(12)])
+    big = np.concatenate([frames] * 16)     # 86 400 tiles of 512 pixels: ~24 per resident warp
+    cases = [(synth.random_palette(256), ("bayer", {"size": "8x8"})), (synth.random_palette(256), ("IGN", {})),
+             (synth.random_palette(100, seed=7), ("blue_noise", {"size": 64, "seed": 42})),
+             (synth.lattice_palette(64, 3, 51), ("bayer", {"size": "4x4"}))]
+    for pal, (mode, params) in cases:
+        refs = oracle_many([(f, pal, mode, params) for f in frames])
+        rgb, idx = engine.dither_frames(big, pal, mode, params, return_indices=True)
+        only = engine.dither_frames(big, pal, mode, params, indices_only=True)
+        monkeypatch.setenv("DP_THRESH_NO_DEFER", "1")
+        old = engine.dither_frames(big, pal, mode, params)
+        monkeypatch.delenv("DP_THRESH_NO_DEFER")
+        assert np.array_equal(old, rgb), (mode, len(pal))
+        assert np.array_equal(idx, only), (mode, len(pal))
+        assert np.array_equal(np.asarray(pal, np.uint8)[idx], rgb), (mode, len(pal))
+        for t in range(len(big)):
+            assert mismatch(rgb[t], refs[t % len(frames)]) == 0, (mode, len(pal), t)
+
+
 def test_threshold_v4_wide_1080p_256_colours_vs_oracle():
     img = synth.frame(1080, 1920, 0)
     pal = synth.random_palette(256)
