@@ -1326,7 +1326,9 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
         ThreshParams q = p;
         // wide thresholds: deferred fixes when the per-warp lists fit beside everything else
         const size_t defer_bytes = (size_t)V4_WARPS * V4_DEFER_CAP * 4;
-        // (the narrow format flags too few pixels for it to pay: PICO-8 0.367 -> 0.383 ms; only a
+        // (plain quantisation flags nearest-row ties only: deferring them costs more than it saves,
+        // K=256 0.407 -> 0.421 ms;
+        // the narrow format flags too few pixels for it to pay: PICO-8 0.367 -> 0.383 ms; only a
         // tie-heavy palette like the C64's gains, 0.476 -> 0.455 ms; DP_THRESH_DEFER_ALL for tools/)
         q.defer = ((wide || getenv("DP_THRESH_DEFER_ALL")) && KIND != DP_THRESH_NONE &&
                    smem + defer_bytes <= 227 * 1024 && !getenv("DP_THRESH_NO_DEFER")) ? 1 : 0;
