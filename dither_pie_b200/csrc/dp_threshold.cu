@@ -1329,8 +1329,9 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
         // (plain quantisation flags nearest-row ties only: deferring them costs more than it saves,
         // K=256 0.407 -> 0.421 ms;
         // the narrow format flags too few pixels for it to pay: PICO-8 0.367 -> 0.383 ms; only a
-        // tie-heavy palette like the C64's gains, 0.476 -> 0.455 ms; DP_THRESH_DEFER_ALL for tools/)
-        q.defer = ((wide || getenv("DP_THRESH_DEFER_ALL")) && KIND != DP_THRESH_NONE &&
+        // tie-heavy palette like the C64's gains, 0.476 -> 0.455 ms: p.defer says which;
+        // DP_THRESH_DEFER_ALL / DP_THRESH_NO_DEFER for tools/ and tests)
+        q.defer = ((p.defer || getenv("DP_THRESH_DEFER_ALL")) && KIND != DP_THRESH_NONE &&
                    smem + defer_bytes <= 227 * 1024 && !getenv("DP_THRESH_NO_DEFER")) ? 1 : 0;
         if (q.defer) smem += defer_bytes;
         void (*kern)(ThreshParams);
@@ -1486,6 +1487,9 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
             (kind != DP_THRESH_MATRIX || (long long)p.mh * wm <= 4096)) {
             p.fast = 4;
             p.wide = wide ? 1 : 0;
+            // deferred fixes: always for the wide format; for the narrow one only when the palette
+            // is tie-heavy (>= 0.2 % of the byte colours in its exception table, e.g. the C64's)
+            p.defer = (wide || pal->dev.tie_n >= 32768) ? 1 : 0;
             p.sub_bytes = sub_bytes;
             p.wm = wm;
             p.dwm = make_fastdiv((uint32_t)wm);

@@ -527,7 +527,7 @@ def test_threshold_v4_wide_table_vs_oracle(k):
 
 
 def test_threshold_v4_wide_deferred_fixes_vs_oracle_and_in_place_fixes(monkeypatch):
-    """Wide-format threshold launches list their flagged pixels per warp and fix them 32 at a time
+    """Wide-format threshold launches (and tie-heavy narrow ones) list their flagged pixels per warp and fix them 32 at a time
     in global memory, after the bulk stores of their tiles (DP_THRESH_NO_DEFER: tile by tile, in the
     staging buffer).  A batch large enough that every warp runs many tiles (lists fill up and are
     flushed mid-run and at the end), a lattice palette whose tiles overflow the list (fixed in
@@ -537,7 +537,8 @@ def test_threshold_v4_wide_deferred_fixes_vs_oracle_and_in_place_fixes(monkeypat
     big = np.concatenate([frames] * 16)     # 86 400 tiles of 512 pixels: ~24 per resident warp
     cases = [(synth.random_palette(256), ("bayer", {"size": "8x8"})), (synth.random_palette(256), ("IGN", {})),
              (synth.random_palette(100, seed=7), ("blue_noise", {"size": 64, "seed": 42})),
-             (synth.lattice_palette(64, 3, 51), ("bayer", {"size": "4x4"}))]
+             (synth.lattice_palette(64, 3, 51), ("bayer", {"size": "4x4"})),
+             (synth.hex_palette(synth.C64), ("bayer", {"size": "8x8"}))]   # narrow format, tie-heavy: deferred too
     for pal, (mode, params) in cases:
         refs = oracle_many([(f, pal, mode, params) for f in frames])
         rgb, idx = engine.dither_frames(big, pal, mode, params, return_indices=True)
