@@ -17,7 +17,8 @@ modes = [("none", {}), ("bayer", {"size": "8x8"}), ("bayer", {"size": "16x16"}),
          ("blue_noise", {"size": 32, "seed": 5}), ("polka_dot", {"tile_size": 6})]
 pals = {"pico8": synth.hex_palette(synth.PICO8), "c64": synth.hex_palette(synth.C64),
         "r30": synth.random_palette(30, seed=9), "r31": synth.random_palette(31, seed=9),
-        "lat27": synth.lattice_palette(27, 1, 127)}
+        "lat27": synth.lattice_palette(27, 1, 127),
+        "r100": synth.random_palette(100, seed=9), "r256": synth.random_palette(256)}   # wide format: deferred fixes
 for pname, pal in pals.items():
     for (h, w, nf) in ((1080, 1920, 3), (720, 1296, 5), (33, 48, 7)):
         frames = np.stack([synth.noise_frame(h, w, 300 + t) if t % 2 else synth.frame(h, w, 400 + t)
