@@ -749,9 +749,9 @@ __device__ __forceinline__ int v4_exact_idx(const ThreshParams &p, const FastCtx
 // exact decision for the pixels v4_pick flagged (rare): re-reads the pixel from global memory,
 // patches its output bytes in the warp's staging buffer and its index byte in global memory
 template <int KIND, bool WM_POW2, bool WIDE>
-__device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, long long gp, uint32_t x,
-                                    uint32_t y, unsigned ra, uint8_t *out_bytes, const unsigned *s_orgb,
-                                    const int2 *s_ent)
+__device__ __forceinline__ void v4_fix_body(const ThreshParams &p, unsigned slowmask, long long gp, uint32_t x,
+                                            uint32_t y, unsigned ra, uint8_t *out_bytes, const unsigned *s_orgb,
+                                            const int2 *s_ent)
 {
     const PalDev *P = p.P;
     FastCtx fc;     // WIDE: the exact pick over the cell's full candidate list (a K-row scan is too long)
@@ -781,6 +781,14 @@ __device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, lo
     }
 }
 
+template <int KIND, bool WM_POW2, bool WIDE>
+__device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, long long gp, uint32_t x,
+                                    uint32_t y, unsigned ra, uint8_t *out_bytes, const unsigned *s_orgb,
+                                    const int2 *s_ent)
+{
+    v4_fix_body<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra, out_bytes, s_orgb, s_ent);
+}
+
 // The wide format flags ~1 % of the pixels (distance ties and crowded sub-cells of a 256-colour
 // palette), i.e. a few per 512-pixel tile: fixed tile by tile (v4_fix), almost every tile pays a
 // chain of five dependent global loads for one or two pixels of one or two lanes, a third of the
@@ -789,7 +797,7 @@ __device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, lo
 // after the bulk stores of their tiles have completed.
 #define V4_DEFER_CAP 64
 template <int KIND, bool WM_POW2, bool WIDE>
-__device__ __noinline__ void v4_fix_deferred(const ThreshParams &p, const uint32_t *list, int n, int lane,
+__device__ __forceinline__ void v4_fix_deferred(const ThreshParams &p, const uint32_t *list, int n, int lane,
                                              const float *s_mat, const unsigned *s_orgb, const int2 *s_ent)
 {
     const PalDev *P = p.P;
@@ -1002,8 +1010,10 @@ __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const
         cur[3 * lane + 1] = make_uint4(w[4], w[5], w[6], w[7]);
         cur[3 * lane + 2] = make_uint4(w[8], w[9], w[10], w[11]);
         if (DEFER) {
-            // (inline on purpose: as a function called on almost every tile this costs more than
-            // it saves -- IGN K=256: 0.66 ms against 0.56 ms)
+            // (inline on purpose, and so are the fix functions it uses: any call in the tile loop
+            // makes ptxas keep the loop's state on the stack -- five exposed local-memory loads per
+            // tile, 10 % of the stall samples.  IGN K=256: everything behind one call 0.66 ms, the
+            // fix functions called 0.554 ms, all inline 0.520 ms)
             if (__ballot_sync(0xffffffffu, slowmask != 0)) {
                 const int cnt = __popc(slowmask);
                 int incl = cnt;
@@ -1015,7 +1025,7 @@ __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 if (total > V4_DEFER_CAP) {     // pathological tile: fixed in place, lane by lane
                     if (slowmask)
-                        v4_fix<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra,
+                        v4_fix_body<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra,
                                                     reinterpret_cast<uint8_t *>(cur + 3 * lane), s_orgb, s_ent);
                 } else {
                     if (ndefer + total > V4_DEFER_CAP) {
@@ -1038,8 +1048,15 @@ __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const
                 }
             }
         } else if (slowmask) {
-            v4_fix<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra, reinterpret_cast<uint8_t *>(cur + 3 * lane),
-                                        s_orgb, s_ent);
+            // (a call in the tile loop makes ptxas keep the loop's state on the stack: inline where
+            // the registers allow it -- the wide threshold kinds; plain quantisation at 64 registers
+            // and the narrow format, whose fix is a K-row scan, keep the call)
+            if (WIDE && KIND != DP_THRESH_NONE)
+                v4_fix_body<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra,
+                                                 reinterpret_cast<uint8_t *>(cur + 3 * lane), s_orgb, s_ent);
+            else
+                v4_fix<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra, reinterpret_cast<uint8_t *>(cur + 3 * lane),
+                                            s_orgb, s_ent);
         }
         // generic-proxy writes -> visible to the async proxy, then one bulk store by lane 0
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
