@@ -749,7 +749,7 @@ __device__ __forceinline__ int v4_exact_idx(const ThreshParams &p, const FastCtx
 // exact decision for the pixels v4_pick flagged (rare): re-reads the pixel from global memory,
 // patches its output bytes in the warp's staging buffer and its index byte in global memory
 template <int KIND, bool WM_POW2, bool WIDE>
-__device__ __forceinline__ void v4_fix_body(const ThreshParams &p, unsigned slowmask, long long gp, uint32_t x,
+__device__ __forceinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, long long gp, uint32_t x,
                                             uint32_t y, unsigned ra, uint8_t *out_bytes, const unsigned *s_orgb,
                                             const int2 *s_ent)
 {
@@ -779,14 +779,6 @@ __device__ __forceinline__ void v4_fix_body(const ThreshParams &p, unsigned slow
         out_bytes[3 * j + 2] = (uint8_t)(col >> 16);
         if (p.dst_idx) p.dst_idx[gp + j] = (uint8_t)idx;
     }
-}
-
-template <int KIND, bool WM_POW2, bool WIDE>
-__device__ __noinline__ void v4_fix(const ThreshParams &p, unsigned slowmask, long long gp, uint32_t x,
-                                    uint32_t y, unsigned ra, uint8_t *out_bytes, const unsigned *s_orgb,
-                                    const int2 *s_ent)
-{
-    v4_fix_body<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra, out_bytes, s_orgb, s_ent);
 }
 
 // The wide format flags ~1 % of the pixels (distance ties and crowded sub-cells of a 256-colour
@@ -1025,7 +1017,7 @@ __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
                 if (total > V4_DEFER_CAP) {     // pathological tile: fixed in place, lane by lane
                     if (slowmask)
-                        v4_fix_body<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra,
+                        v4_fix<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra,
                                                     reinterpret_cast<uint8_t *>(cur + 3 * lane), s_orgb, s_ent);
                 } else {
                     if (ndefer + total > V4_DEFER_CAP) {
@@ -1048,15 +1040,11 @@ __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const
                 }
             }
         } else if (slowmask) {
-            // (a call in the tile loop makes ptxas keep the loop's state on the stack: inline where
-            // the registers allow it -- the wide threshold kinds; plain quantisation at 64 registers
-            // and the narrow format, whose fix is a K-row scan, keep the call)
-            if (WIDE && KIND != DP_THRESH_NONE)
-                v4_fix_body<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra,
-                                                 reinterpret_cast<uint8_t *>(cur + 3 * lane), s_orgb, s_ent);
-            else
-                v4_fix<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra, reinterpret_cast<uint8_t *>(cur + 3 * lane),
-                                            s_orgb, s_ent);
+            // (inline: a call in the tile loop makes ptxas keep the loop's state on the stack and
+            // costs more than the fix's registers -- measured for every kind and both formats:
+            // `none` K=16 0.296 -> 0.277 ms, K=256 0.408 -> 0.389 ms, Bayer K=16 0.365 -> 0.359 ms)
+            v4_fix<KIND, WM_POW2, WIDE>(p, slowmask, gp, x, y, ra, reinterpret_cast<uint8_t *>(cur + 3 * lane),
+                                        s_orgb, s_ent);
         }
         // generic-proxy writes -> visible to the async proxy, then one bulk store by lane 0
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
