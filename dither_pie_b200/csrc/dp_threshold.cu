@@ -545,9 +545,18 @@ __global__ void __launch_bounds__(THREADS) k_thresh_fast(const ThreshParams p)
 template <int KIND, bool WIDE = false>
 __host__ __device__ constexpr int v4_threads()
 {
-    // (the 256-row tables of the wide format leave room for 31 warps beside the candidate table)
-    return KIND == DP_THRESH_NONE ? (WIDE ? 992 : 1024) : 768;
+    // (the skewed candidate table and the 256-row tables of the wide format leave room for 31 / 30
+    // warps)
+    return KIND == DP_THRESH_NONE ? (WIDE ? 960 : 992) : 768;
 }
+// The 32^3 cell table in shared memory, SKEWED: the entry of cell (r5, g5, b5) sits at word
+// r5 * 1057 + g5 * 33 + b5, so that its bank is (r5 + g5 + b5) mod 32 instead of b5.  Neighbouring
+// lanes hold similar colours: with the plain layout the gather of the cell entries was ~7-way
+// bank-conflicted (ncu: 6.9 wavefronts per LDS, profiles/r2t_thresh_v4_none_K16.txt), the largest
+// item on the kernel's busiest unit.  The address stays linear in the three 5-bit fields -- the
+// same IMAD + IDP.4A, other constants -- and the table grows by 4 KB (33 822 words).
+#define V4_TABLE_WORDS 33824                    /* 31 * 1057 + 31 * 33 + 31 + 1, rounded up to 16 bytes */
+#define V4_TABLE_BYTES (V4_TABLE_WORDS * 4)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p)
 {
@@ -626,9 +635,11 @@ __device__ __forceinline__ unsigned v4_pick(const V4Ctx &c, unsigned v, float th
 {
     constexpr unsigned AW = WIDE ? 8u : 1u;            // byte j of the entry -> row offset in the int2 array
     constexpr unsigned MARK4 = WIDE ? 0x03000000u : 0xf8000000u;
-    // byte offset of the pixel's cell in the u32 table: (r>>3)*4096 + (g>>3)*128 + (b>>3)*4
+    // byte offset of the pixel's cell in the u32 table: (r>>3)*4096 + (g>>3)*128 + (b>>3)*4 in global
+    // memory (TG), (r>>3)*4228 + (g>>3)*132 + (b>>3)*4 in the skewed shared copy (V4_TABLE_WORDS)
     const unsigned a5 = (v >> 3) & 0x1f1f1fu;
-    const unsigned ta = (a5 & 0x1fu) * 4096u + __dp4a(a5, 0x00048000u, TG ? 0u : c.table_a);
+    const unsigned ta = TG ? (a5 & 0x1fu) * 4096u + __dp4a(a5, 0x00048000u, 0u)
+                           : (a5 & 0x1fu) * 4228u + __dp4a(a5, 0x00048400u, c.table_a);
     unsigned e = TG ? __ldg(reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(c.table_g) + ta))
                     : lds_u32(ta);
     if (KIND == DP_THRESH_NONE) {
@@ -835,11 +846,11 @@ __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const
     constexpr int ENTB = v4_ent_bytes(WIDE), ORGBB = v4_orgb_bytes(WIDE);
     extern __shared__ __align__(16) uint8_t smem[];
     const int P_nsub = WIDE ? 0 : p.P->thr4_nsub;          // WIDE: sub-cell entries stay in global memory
-    uint32_t *s_table = reinterpret_cast<uint32_t *>(smem);                    // [32768]
-    int2 *s_ent = reinterpret_cast<int2 *>(smem + 131072);                     // [34] / [256]
-    unsigned *s_orgb = reinterpret_cast<unsigned *>(smem + 131072 + ENTB);     // [32] / [256]
-    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem + 131072 + ENTB + ORGBB);   // [warps][2]
-    uint4 *s_io = reinterpret_cast<uint4 *>(smem + 131072 + ENTB + ORGBB + 512);  // [warps][2][96]
+    uint32_t *s_table = reinterpret_cast<uint32_t *>(smem);                    // [V4_TABLE_WORDS], skewed
+    int2 *s_ent = reinterpret_cast<int2 *>(smem + V4_TABLE_BYTES);             // [34] / [256]
+    unsigned *s_orgb = reinterpret_cast<unsigned *>(smem + V4_TABLE_BYTES + ENTB);     // [32] / [256]
+    unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem + V4_TABLE_BYTES + ENTB + ORGBB);   // [warps][2]
+    uint4 *s_io = reinterpret_cast<uint4 *>(smem + V4_TABLE_BYTES + ENTB + ORGBB + 512);  // [warps][2][96]
     uint32_t *s_sub = reinterpret_cast<uint32_t *>(s_io + V4_WARPS * 192);     // [8 * nsub]
     float *s_mat = reinterpret_cast<float *>(s_sub + (KIND == DP_THRESH_NONE ? 0 : ((8 * P_nsub + 3) & ~3)));   // [mh][wm]
     // DEFER instantiations: per-warp list of flagged pixels (the launch found room for it)
@@ -851,8 +862,14 @@ __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const
     {
         const uint4 *src4 = reinterpret_cast<const uint4 *>(KIND == DP_THRESH_NONE ? P->near3_table
                                                                                    : P->thr4_table);
-        uint4 *dst4 = reinterpret_cast<uint4 *>(s_table);
-        for (int i = tid; i < 8192; i += V4_THREADS) dst4[i] = __ldg(src4 + i);
+        // four consecutive cells (b5 = 4k .. 4k+3 of one (r5, g5)) per load, scattered to the skewed
+        // positions r5 * 1057 + g5 * 33 + b5
+        for (int i = tid; i < 8192; i += V4_THREADS) {
+            const uint4 e4 = __ldg(src4 + i);
+            const int r5 = i >> 8, g5 = (i >> 3) & 31, b5 = (i & 7) << 2;
+            uint32_t *d = s_table + r5 * 1057 + g5 * 33 + b5;
+            d[0] = e4.x; d[1] = e4.y; d[2] = e4.z; d[3] = e4.w;
+        }
         if (KIND != DP_THRESH_NONE)
             for (int i = tid; i < 8 * P_nsub; i += V4_THREADS) s_sub[i] = __ldg(P->thr4_sub + i);
     }
@@ -1325,7 +1342,7 @@ int launch_kind(const ThreshParams &p, bool geom, cudaStream_t st)
         const bool wide = p.wide != 0;
         const int V4_THREADS = wide ? v4_threads<KIND, true>() : v4_threads<KIND, false>();
         const int V4_WARPS = V4_THREADS / 32;
-        size_t smem = 131072 + v4_ent_bytes(wide) + v4_orgb_bytes(wide) + 512 + (size_t)V4_WARPS * 3072 +
+        size_t smem = V4_TABLE_BYTES + v4_ent_bytes(wide) + v4_orgb_bytes(wide) + 512 + (size_t)V4_WARPS * 3072 +
                       (KIND == DP_THRESH_NONE ? 0 : (size_t)p.sub_bytes) +
                       (KIND == DP_THRESH_MATRIX ? (size_t)p.mh * p.wm * 4 : 0);
         ThreshParams q = p;
@@ -1485,8 +1502,8 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
             wm = p.mw / a * 16;
         }
         const int sub_bytes = wide ? 0 : ((8 * pal->dev.thr4_nsub + 3) & ~3) * 4;
-        const long long need = 131072 + v4_ent_bytes(wide) + v4_orgb_bytes(wide) + 512 +
-                               (kind == DP_THRESH_NONE ? (wide ? 31ll : 32ll) * 3072 : 24ll * 3072 + sub_bytes) +
+        const long long need = V4_TABLE_BYTES + v4_ent_bytes(wide) + v4_orgb_bytes(wide) + 512 +
+                               (kind == DP_THRESH_NONE ? (wide ? 30ll : 31ll) * 3072 : 24ll * 3072 + sub_bytes) +
                                (kind == DP_THRESH_MATRIX ? (long long)p.mh * wm * 4 : 0);
         if (need <= 227 * 1024 && (long long)frames * p.npix < (1ll << 31) &&
             (kind != DP_THRESH_MATRIX || (long long)p.mh * wm <= 4096)) {
