@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(THREADS) k_thresh_fast(const ThreshParams p)
 // owns 16 consecutive pixels (48 bytes) in registers.
 // ---------------------------------------------------------------------------------------
 // 24 warps per SM for the threshold kinds (80 registers); plain quantisation needs fewer
-// registers and no matrix, so 32 warps fit beside the table
+// registers and no matrix, so 31 warps fit beside the table (30 with the wide format's row tables)
 template <int KIND, bool WIDE = false>
 __host__ __device__ constexpr int v4_threads()
 {
