@@ -1043,6 +1043,8 @@ __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const
                         // patch them in global memory
                         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                         __syncwarp();
+                        // the patches are generic-proxy stores to bytes the async proxy wrote
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
                         v4_fix_deferred<KIND, WM_POW2, WIDE>(p, dlist, ndefer, lane, s_mat, s_orgb, s_ent);
                         __syncwarp();
                         ndefer = 0;
@@ -1074,6 +1076,7 @@ __global__ void __launch_bounds__(v4_threads<KIND, WIDE>(), 1) k_thresh_v4(const
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (DEFER) {
         __syncwarp();
+        asm volatile("fence.proxy.async.global;" ::: "memory");
         v4_fix_deferred<KIND, WM_POW2, WIDE>(p, dlist, ndefer, lane, s_mat, s_orgb, s_ent);
     }
 }
