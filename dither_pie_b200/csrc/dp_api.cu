@@ -632,6 +632,7 @@ extern "C" int dp_palette_create(const float *palette, int K, const uint8_t *out
                                  const int32_t *kd_indices, const double *kd_mins,
                                  const double *kd_maxes, dp_palette **out)
 {
+    DP_RANGE("dp_palette_create");
     DP_REQUIRE(palette && out_rgb && out, "null argument");
     DP_REQUIRE(K >= 1 && K <= DP_MAX_COLORS, "palette size must be 1..256");
     DP_REQUIRE(kd_nodes >= 1 && kd_split_dim && kd_split && kd_start_idx && kd_end_idx &&

@@ -6,7 +6,18 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/ditherpie_b200.h"
+
+// NVTX range around an entry point of the C ABI (host side; a no-op unless a profiler is attached)
+struct DpRange {
+    explicit DpRange(const char *name) { nvtxRangePushA(name); }
+    ~DpRange() { nvtxRangePop(); }
+    DpRange(const DpRange &) = delete;
+    DpRange &operator=(const DpRange &) = delete;
+};
+#define DP_RANGE(name) DpRange dp_range_guard_(name)
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
 #error "libditherpie_b200 targets sm_100a (B200) only"

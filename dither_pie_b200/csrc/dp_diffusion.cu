@@ -1701,6 +1701,7 @@ extern "C" int dp_error_diffusion(const dp_palette *pal, const uint8_t *src_rgb,
                                   int w, int variant, int serpentine, uint8_t *dst_rgb,
                                   uint8_t *dst_idx, void *stream)
 {
+    DP_RANGE("dp_error_diffusion");
     DP_REQUIRE(pal && src_rgb, "null argument");
     DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
@@ -1715,6 +1716,7 @@ extern "C" int dp_ostromoukhov(const dp_palette *pal, const uint8_t *src_rgb, in
                                int w, const int32_t *coeffs, int serpentine, uint8_t *dst_rgb,
                                uint8_t *dst_idx, void *stream)
 {
+    DP_RANGE("dp_ostromoukhov");
     DP_REQUIRE(pal && src_rgb && coeffs, "null argument");
     DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
@@ -1738,6 +1740,7 @@ extern "C" int dp_hybrid(const dp_palette *pal, const uint8_t *src_rgb, int fram
                          double lum_factor, double col_factor, uint8_t *dst_rgb, uint8_t *dst_idx,
                          void *stream)
 {
+    DP_RANGE("dp_hybrid");
     DP_REQUIRE(pal && src_rgb, "null argument");
     DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
@@ -1769,6 +1772,7 @@ __global__ void __launch_bounds__(256) k_perceptual_plane(const PalDev *P, const
 extern "C" int dp_perceptual(const dp_palette *pal, const uint8_t *src_rgb, int frames, int h, int w,
                              uint8_t *dst_rgb, uint8_t *dst_idx, void *stream)
 {
+    DP_RANGE("dp_perceptual");
     DP_REQUIRE(pal && src_rgb, "null argument");
     DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
@@ -1922,6 +1926,7 @@ extern "C" int dp_adaptive_variance(const dp_palette *pal, const uint8_t *src_rg
                                     double var_threshold, int window_radius, uint8_t *dst_rgb,
                                     uint8_t *dst_idx, void *stream)
 {
+    DP_RANGE("dp_adaptive_variance");
     DP_REQUIRE(pal && src_rgb, "null argument");
     DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");

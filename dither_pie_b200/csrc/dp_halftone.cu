@@ -973,6 +973,7 @@ extern "C" int dp_halftone(const dp_palette *pal, const uint8_t *src_rgb, int fr
                            double min_dot, double max_dot, int shape, double sharpness,
                            const float *screen, uint8_t *dst_rgb, uint8_t *dst_idx, void *stream)
 {
+    DP_RANGE("dp_halftone");
     DP_REQUIRE(pal && src_rgb, "null argument");
     DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0 && cell_size >= 1, "bad size");

@@ -1202,6 +1202,7 @@ extern "C" int dp_nccl_allreduce_u64(void *buf, size_t count, void *comm, void *
 extern "C" int dp_kmeans_accumulate(const uint8_t *pixels, int64_t n, const double *centers,
                                     int K, unsigned long long *sums, void *stream)
 {
+    DP_RANGE("dp_kmeans_accumulate");
     DP_REQUIRE(pixels && centers && sums, "null argument");
     DP_REQUIRE(K >= 1 && K <= DP_MAX_COLORS && n >= 0, "bad size");
     if (n == 0) return 0;
@@ -1223,6 +1224,7 @@ extern "C" int dp_kmeans_accumulate(const uint8_t *pixels, int64_t n, const doub
 extern "C" int dp_kmeans_update(const unsigned long long *sums, int K, double *centers,
                                 double *shift2, void *stream)
 {
+    DP_RANGE("dp_kmeans_update");
     DP_REQUIRE(sums && centers && shift2, "null argument");
     DP_REQUIRE(K >= 1 && K <= DP_MAX_COLORS, "bad size");
     k_kmeans_update<<<1, 32, 0, dp_stream(stream)>>>(sums, K, centers, shift2);
@@ -1422,6 +1424,7 @@ extern "C" int dp_kmeans_lloyd(const uint8_t *pixels, int64_t n, double *centers
                                int max_iter, void *nccl_comm, int check_every, int *n_iter, double *shift2,
                                unsigned long long *ties, int *empty_iters, void *stream)
 {
+    DP_RANGE("dp_kmeans_lloyd");
     DP_REQUIRE(pixels && centers_host, "null argument");
     DP_REQUIRE(K >= 1 && K <= DP_MAX_COLORS && n >= 0 && max_iter >= 1, "bad size");
     if (nccl_comm) DP_REQUIRE(g_nccl.handle, "NCCL communicator given but NCCL was never loaded");
@@ -1436,6 +1439,7 @@ extern "C" int dp_kmeans_lloyd_p2p(const uint8_t *pixels, int64_t n, double *cen
                                    int check_every, int *n_iter, double *shift2, unsigned long long *ties,
                                    int *empty_iters, void *stream)
 {
+    DP_RANGE("dp_kmeans_lloyd_p2p");
     DP_REQUIRE(pixels && centers_host && inboxes, "null argument");
     DP_REQUIRE(K >= 1 && K <= DP_MAX_COLORS && n >= 0 && max_iter >= 1, "bad size");
     DP_REQUIRE(world >= 1 && world <= KM_P2P_RANKS && rank >= 0 && rank < world, "bad rank / world (at most 8 ranks)");

@@ -71,6 +71,7 @@ inline void insert_clean(uint32_t *table, size_t mask, uint32_t c, uint64_t hash
 extern "C" int dp_unique_colors_pyset_order(const uint8_t *rgb, int64_t npix, uint8_t *out_rgb,
                                             int64_t *n_unique)
 {
+    DP_RANGE("dp_unique_colors_pyset_order");
     DP_REQUIRE(rgb && out_rgb && n_unique && npix >= 0, "bad argument");
     size_t mask = 7;   // PySet_MINSIZE - 1
     uint32_t *table = static_cast<uint32_t *>(calloc(mask + 1, sizeof(uint32_t)));
@@ -153,6 +154,7 @@ extern "C" int dp_unique_colors_pyset_order(const uint8_t *rgb, int64_t npix, ui
 // with numpy's RandomState, as the reference does).
 extern "C" int dp_blue_noise_from_order(const int32_t *order, int size, float *out)
 {
+    DP_RANGE("dp_blue_noise_from_order");
     DP_REQUIRE(order && out && size >= 1 && size <= 1024, "bad argument");
     const int n = size * size;
     int32_t *rr = static_cast<int32_t *>(malloc(sizeof(int32_t) * 3 * (size_t)n));

@@ -39,6 +39,7 @@ extern "C" int dp_resample_nearest(const uint8_t *src_rgb, int frames, int src_h
                                    const int32_t *ytab, const int32_t *xtab, int dst_h,
                                    int dst_w, uint8_t *dst_rgb, void *stream)
 {
+    DP_RANGE("dp_resample_nearest");
     DP_REQUIRE(src_rgb && dst_rgb && ytab && xtab, "null argument");
     DP_REQUIRE(frames >= 0 && src_h > 0 && src_w > 0 && dst_h >= 0 && dst_w >= 0, "bad size");
     long long rows = (long long)frames * dst_h;

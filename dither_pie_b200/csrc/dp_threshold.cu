@@ -1444,6 +1444,7 @@ extern "C" int dp_threshold_dither(const dp_palette *pal, const uint8_t *src_rgb
                                    float ign_scale, uint8_t *dst_rgb, uint8_t *dst_idx,
                                    void *stream)
 {
+    DP_RANGE("dp_threshold_dither");
     DP_REQUIRE(pal && src_rgb && geo, "null argument");
     DP_REQUIRE(dst_rgb || dst_idx, "no output: dst_rgb and dst_idx are both null");
     DP_REQUIRE(frames >= 0 && geo->h >= 0 && geo->w >= 0, "negative size");
@@ -1541,6 +1542,7 @@ extern "C" int dp_threshold_dither_host(const dp_palette *pal, const uint8_t *sr
                                         float ign_xoff, float ign_yoff, float ign_scale,
                                         uint8_t *dst_rgb_host)
 {
+    DP_RANGE("dp_threshold_dither_host");
     DP_REQUIRE(pal && src_rgb_host && dst_rgb_host, "null argument");
     DP_REQUIRE(frames >= 0 && h >= 0 && w >= 0, "negative size");
     if (kind == DP_THRESH_MATRIX) DP_REQUIRE(matrix_host && mat_h > 0 && mat_w > 0, "threshold matrix missing");
