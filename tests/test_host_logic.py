@@ -1,6 +1,7 @@
 """CPU: host-side logic of the package (tables, geometry, sharding, API surface)."""
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -226,3 +227,24 @@ def test_reference_cli_imports_against_the_drop_in_modules():
         "print('ok', sorted(cfg)[:3])\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.startswith("ok"), (r.stdout, r.stderr[-800:])
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` (the oracle's C port on the host cores) runs without a GPU and
+    prints ONE JSON line with the keys the driver reads: same metric / unit / config as the GPU arm,
+    `impl`, a `cpu_baseline` describing the run and an `e2e` that repeats the line's value."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [ln for ln in out.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "Mpixels/s" and d["unit"] == "Mpx/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["value"] > 0 and d["e2e"] == {"value": d["value"], "unit": "Mpx/s", "h2d_bytes_per_step": 0,
+                                           "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert "configs[1]" in d["config"]["workload"]
