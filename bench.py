@@ -110,7 +110,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / max(args.steps, 1) * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus, None),
+        # the GPU arm's config: each step of this arm is a bounded SAMPLE of that workload
+        # (cpu_baseline.sample says which)
+        "config": workload_config(args.gpus, max(args.batch, args.dev_batch)),
         "cpu_baseline": {"value": val, "unit": "Mpx/s", "cores": cores, "kind": "port",
                          "sample": sample,
                          "note": "C port of the reference's numba loop on ALL cores; the reference's own "
