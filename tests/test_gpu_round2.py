@@ -633,3 +633,18 @@ def test_kmeans_peer_memory_exchange_two_ranks_on_one_gpu(K, world, persistent, 
             b.free()
         for p in inboxes:
             check(L.dp_p2p_free(p), "dp_p2p_free")
+
+
+# ------------------------------------------------------------------ the rest of the mode list at size
+def test_golden_big_cases2_from_the_live_reference():
+    """540x960 outputs of the reference itself for the modes big_cases.npz does not hold (nearest
+    colour, Bayer / IGN / blue noise / polka dot at 16-256 colours, halftone, the other diffusion
+    kernels, serpentine, hybrid; tools/make_golden.py --big2): colour bytes and index plane."""
+    from test_oracle_golden import BIG2
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "big_cases2.npz"))
+    img = g["img"]
+    for key, pk, mode, params, crop in BIG2:
+        arr = img if crop is None else np.ascontiguousarray(img[:crop[0], :crop[1]])
+        rgb, idx = engine.dither_frames(arr, g[pk], mode, params, return_indices=True)
+        assert np.array_equal(idx, g[key]), (key, int((idx != g[key]).sum()))
+        assert np.array_equal(rgb, np.asarray(g[pk], np.uint8)[g[key]]), key

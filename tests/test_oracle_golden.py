@@ -168,3 +168,33 @@ def test_big_cases_from_the_live_reference():
                                   ("blue", "pal16", "blue_noise", {"size": 64, "seed": 42})):
         assert np.array_equal(O.apply_dithering(img, g[pk], mode, params), g[key]), key
     assert np.array_equal(O.apply_dithering(g["ostro_img"], g["pal64"], "ostromoukhov"), g["ostro"])
+
+
+BIG2 = [("none16", "pal16", "none", {}, None), ("none256", "pal256", "none", {}, None),
+        ("bayer8_256", "pal256", "bayer", {"size": "8x8"}, None),
+        ("bayer16_64", "pal64", "bayer", {"size": "16x16"}, None),
+        ("ign16", "pal16", "IGN", {"scale": 1.0, "seed": 0}, None),
+        ("ign256", "pal256", "IGN", {"scale": 2.5, "seed": 17}, None),
+        ("blue256", "pal256", "blue_noise", {"size": 64, "seed": 42}, None),
+        ("polka16", "pal16", "polka_dot", {"tile_size": 8, "gamma": 1.5}, None),
+        ("halftone16", "pal16", "halftone", {}, None),
+        ("halftone64", "pal64", "halftone", {"cell_size": 5, "angle": 30.0, "shape": "diamond"}, None),
+        ("ed_fs256", "pal256", "error_diffusion", {"variant": "floyd_steinberg"}, None),
+        ("ed_stucki64", "pal64", "error_diffusion", {"variant": "stucki"}, None),
+        ("ed_burkes16", "pal16", "error_diffusion", {"variant": "burkes"}, None),
+        ("ed_two_row64", "pal64", "error_diffusion", {"variant": "sierra_two_row"}, None),
+        ("ed_lite256", "pal256", "error_diffusion", {"variant": "sierra_lite"}, None),
+        ("ed_fs64_serp", "pal64", "error_diffusion", {"variant": "floyd_steinberg", "serpentine": "true"}, (270, 480)),
+        ("hybrid64", "pal64", "hybrid", {}, None)]
+
+
+def test_big_cases2_from_the_live_reference():
+    """The rest of the mode list at 540x960 from the reference itself (tools/make_golden.py --big2):
+    nearest colour, Bayer / IGN / blue noise / polka dot at 16-256 colours, halftone, the other
+    diffusion kernels, serpentine, hybrid -- stored as palette-index planes."""
+    g = load_golden("big_cases2.npz")
+    img = g["img"]
+    for key, pk, mode, params, crop in BIG2:
+        arr = img if crop is None else np.ascontiguousarray(img[:crop[0], :crop[1]])
+        out = O.apply_dithering(arr, g[pk], mode, params)
+        assert np.array_equal(out, np.asarray(g[pk], np.uint8)[g[key]]), key

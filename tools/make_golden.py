@@ -376,8 +376,59 @@ def big_golden(dl):
     print("big_cases.npz:", os.path.getsize(os.path.join(OUT, "big_cases.npz")), "bytes")
 
 
+BIG2_CASES = [
+    # key, palette key, mode, params, crop (rows, cols) of the 540x960 image
+    ("none16", "pal16", "none", {}, None),
+    ("none256", "pal256", "none", {}, None),
+    ("bayer8_256", "pal256", "bayer", {"size": "8x8"}, None),
+    ("bayer16_64", "pal64", "bayer", {"size": "16x16"}, None),
+    ("ign16", "pal16", "IGN", {"scale": 1.0, "seed": 0}, None),
+    ("ign256", "pal256", "IGN", {"scale": 2.5, "seed": 17}, None),
+    ("blue256", "pal256", "blue_noise", {"size": 64, "seed": 42}, None),
+    ("polka16", "pal16", "polka_dot", {"tile_size": 8, "gamma": 1.5}, None),
+    ("halftone16", "pal16", "halftone", {}, None),
+    ("halftone64", "pal64", "halftone", {"cell_size": 5, "angle": 30.0, "shape": "diamond"}, None),
+    ("ed_fs256", "pal256", "error_diffusion", {"variant": "floyd_steinberg"}, None),
+    ("ed_stucki64", "pal64", "error_diffusion", {"variant": "stucki"}, None),
+    ("ed_burkes16", "pal16", "error_diffusion", {"variant": "burkes"}, None),
+    ("ed_two_row64", "pal64", "error_diffusion", {"variant": "sierra_two_row"}, None),
+    ("ed_lite256", "pal256", "error_diffusion", {"variant": "sierra_lite"}, None),
+    ("ed_fs64_serp", "pal64", "error_diffusion", {"variant": "floyd_steinberg", "serpentine": "true"}, (270, 480)),
+    ("hybrid64", "pal64", "hybrid", {}, None),
+]
+
+
+def big2_golden(dl):
+    """The rest of the mode list at 540x960 from the live reference (big_cases.npz holds the BASELINE
+    configs' kernels): nearest colour, Bayer / IGN / blue noise / polka dot at 16-256 colours,
+    halftone, the other diffusion kernels, serpentine, hybrid.  Outputs are stored as palette-index
+    planes (the palettes are duplicate-free).  tests/golden/big_cases2.npz."""
+    img = synth.frame(1080, 1920, 3)[:540, :960].copy()
+    pals = {"pal16": synth.hex_palette(synth.PICO8), "pal64": synth.random_palette(64),
+            "pal256": synth.random_palette(256)}
+    store = {"img": img, **pals}
+    for key, pk, mode, params, crop in BIG2_CASES:
+        pal = pals[pk]
+        arr = img if crop is None else img[:crop[0], :crop[1]].copy()
+        d = dl.ImageDitherer(num_colors=len(pal), dither_mode=dl.DitherMode(mode),
+                             palette=[tuple(int(v) for v in c) for c in pal], dither_params=dict(params))
+        out = np.array(d.apply_dithering(Image.fromarray(arr, "RGB")))
+        code = {tuple(int(v) for v in c): i for i, c in enumerate(np.asarray(pal, np.uint8))}
+        assert len(code) == len(pal)
+        packed = out[..., 0].astype(np.int32) | (out[..., 1].astype(np.int32) << 8) | (out[..., 2].astype(np.int32) << 16)
+        lut = {(r | (g << 8) | (b << 16)): i for (r, g, b), i in code.items()}
+        idx = np.vectorize(lut.__getitem__, otypes=[np.uint8])(packed)
+        assert np.array_equal(np.asarray(pal, np.uint8)[idx], out)
+        store[key] = idx
+        print(key, out.shape)
+    np.savez_compressed(os.path.join(OUT, "big_cases2.npz"), **store)
+    print("big_cases2.npz:", os.path.getsize(os.path.join(OUT, "big_cases2.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    if "--big" in sys.argv:               # adds big_cases.npz without touching the other files
+    if "--big2" in sys.argv:              # adds big_cases2.npz without touching the other files
+        big2_golden(load()[0])
+    elif "--big" in sys.argv:             # adds big_cases.npz without touching the other files
         big_golden(load()[0])
     elif "--median-cut-only" in sys.argv:   # adds median_cut.json without touching the other files
         median_cut_golden(load()[0])
