@@ -198,3 +198,16 @@ def test_big_cases2_from_the_live_reference():
         arr = img if crop is None else np.ascontiguousarray(img[:crop[0], :crop[1]])
         out = O.apply_dithering(arr, g[pk], mode, params)
         assert np.array_equal(out, np.asarray(g[pk], np.uint8)[g[key]]), key
+
+
+def test_big_cases3_perceptual_and_adaptive_variance_from_the_live_reference():
+    """The reference's two pure-Python diffusion modes on a 270x480 crop (tools/make_golden.py
+    --big3): nine row bands, unclamped look-ups, the variance map."""
+    g = load_golden("big_cases3.npz")
+    img = g["img"]
+    for key, pk, mode, params in (("perceptual64", "pal64", "perceptual", {}),
+                                  ("perceptual16", "pal16", "perceptual", {}),
+                                  ("adaptive16", "pal16", "adaptive_variance", {}),
+                                  ("adaptive64", "pal64", "adaptive_variance", {"var_threshold": 60.0})):
+        out = O.apply_dithering(img, g[pk], mode, params)
+        assert np.array_equal(out, np.asarray(g[pk], np.uint8)[g[key]]), key

@@ -425,8 +425,37 @@ def big2_golden(dl):
     print("big_cases2.npz:", os.path.getsize(os.path.join(OUT, "big_cases2.npz")), "bytes")
 
 
+BIG3_CASES = [("perceptual64", "pal64", "perceptual", {}), ("perceptual16", "pal16", "perceptual", {}),
+              ("adaptive16", "pal16", "adaptive_variance", {}),
+              ("adaptive64", "pal64", "adaptive_variance", {"var_threshold": 60.0})]
+
+
+def big3_golden(dl):
+    """The two pure-Python diffusion modes of the reference (~14 kpx/s) on a 270x480 crop: nine
+    row bands, the unclamped look-ups of `perceptual`, the variance map of `adaptive_variance`.
+    Index planes.  tests/golden/big_cases3.npz."""
+    img = synth.frame(1080, 1920, 4)[:270, :480].copy()
+    pals = {"pal16": synth.hex_palette(synth.PICO8), "pal64": synth.random_palette(64)}
+    store = {"img": img, **pals}
+    for key, pk, mode, params in BIG3_CASES:
+        pal = pals[pk]
+        d = dl.ImageDitherer(num_colors=len(pal), dither_mode=dl.DitherMode(mode),
+                             palette=[tuple(int(v) for v in c) for c in pal], dither_params=dict(params))
+        out = np.array(d.apply_dithering(Image.fromarray(img, "RGB")))
+        lut = {(int(c[0]) | (int(c[1]) << 8) | (int(c[2]) << 16)): i for i, c in enumerate(np.asarray(pal, np.uint8))}
+        packed = out[..., 0].astype(np.int32) | (out[..., 1].astype(np.int32) << 8) | (out[..., 2].astype(np.int32) << 16)
+        idx = np.vectorize(lut.__getitem__, otypes=[np.uint8])(packed)
+        assert np.array_equal(np.asarray(pal, np.uint8)[idx], out)
+        store[key] = idx
+        print(key, out.shape)
+    np.savez_compressed(os.path.join(OUT, "big_cases3.npz"), **store)
+    print("big_cases3.npz:", os.path.getsize(os.path.join(OUT, "big_cases3.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    if "--big2" in sys.argv:              # adds big_cases2.npz without touching the other files
+    if "--big3" in sys.argv:              # adds big_cases3.npz without touching the other files
+        big3_golden(load()[0])
+    elif "--big2" in sys.argv:            # adds big_cases2.npz without touching the other files
         big2_golden(load()[0])
     elif "--big" in sys.argv:             # adds big_cases.npz without touching the other files
         big_golden(load()[0])
