@@ -211,3 +211,18 @@ def test_big_cases3_perceptual_and_adaptive_variance_from_the_live_reference():
                                   ("adaptive64", "pal64", "adaptive_variance", {"var_threshold": 60.0})):
         out = O.apply_dithering(img, g[pk], mode, params)
         assert np.array_equal(out, np.asarray(g[pk], np.uint8)[g[key]]), key
+
+
+def test_kmeans_config3_4k_frame_from_the_live_reference():
+    """BASELINE configs[2]: the reference's own k-means palette of the seed-2 4K frame
+    (random.seed(7) subsample, k=16, random_state=42; tools/make_golden.py --kmeans4k)."""
+    import random
+    from dither_pie_b200 import synth
+    g = load_golden("kmeans_4k.npz")
+    flat = synth.frame(2160, 3840, 2).reshape(-1, 3)
+    random.seed(7)
+    sample = flat[random.sample(range(len(flat)), 10000)]
+    assert np.array_equal(sample, g["sample"])          # the subsample is the reference's
+    c = O.kmeans_centers(sample, 16, 42)
+    assert np.abs(c - g["centers"]).max() <= 1e-3       # north_star tolerance
+    assert np.array_equal(c.astype(int), g["palette"])

@@ -452,8 +452,27 @@ def big3_golden(dl):
     print("big_cases3.npz:", os.path.getsize(os.path.join(OUT, "big_cases3.npz")), "bytes")
 
 
+def kmeans4k_golden(dl):
+    """BASELINE configs[2] exactly: k-means (k=16, random_state=42) on the seed-2 3840x2160 frame
+    with random.seed(7) for the reference's 10 000-pixel subsample (dithering_lib.py:1845-1857).
+    tests/golden/kmeans_4k.npz."""
+    from sklearn.cluster import KMeans
+    img = synth.frame(2160, 3840, 2)
+    pix = img.reshape(-1, 3)
+    random.seed(7)
+    sample = pix[random.sample(range(len(pix)), 10000)]
+    km = KMeans(n_clusters=16, random_state=42).fit(sample)
+    random.seed(7)
+    pal = dl.ColorReducer.generate_kmeans_palette(Image.fromarray(img, "RGB"), 16, 42)
+    np.savez_compressed(os.path.join(OUT, "kmeans_4k.npz"), sample=sample, centers=km.cluster_centers_,
+                        palette=np.asarray(pal, np.int64), niter=np.asarray(km.n_iter_))
+    print("kmeans_4k.npz: n_iter", km.n_iter_, "palette", [tuple(map(int, c)) for c in pal][:3], "...")
+
+
 if __name__ == "__main__":
-    if "--big3" in sys.argv:              # adds big_cases3.npz without touching the other files
+    if "--kmeans4k" in sys.argv:          # adds kmeans_4k.npz without touching the other files
+        kmeans4k_golden(load()[0])
+    elif "--big3" in sys.argv:              # adds big_cases3.npz without touching the other files
         big3_golden(load()[0])
     elif "--big2" in sys.argv:            # adds big_cases2.npz without touching the other files
         big2_golden(load()[0])
