@@ -196,8 +196,10 @@ class VideoProcessor:
     def _setup(self, frames, ditherer, pixelize_func):
         max_size = _unpack_pixelize(pixelize_func)
         if ditherer.palette is None:
-            # palette fixed from the first frame of the clip (dither_cli.py:619-654); every rank
-            # derives the same one from the same frame
+            # one palette for the clip, fixed from its (pixelized) first frame; every rank derives
+            # the same one from the same frame.  (The reference's CLI passes in a palette computed
+            # from the FULL first frame, dither_cli.py:619-654; its workers, given None, would each
+            # derive their own per frame.)
             first = frames[0]
             if max_size:
                 first = pixelize_regular_array(first, max_size)
@@ -383,8 +385,10 @@ class VideoProcessor:
         memory, dithered in chunks by the frame pipeline and written to the encoder's stdin -- no
         PNG files.  In a torchrun job every rank decodes and dithers its own contiguous frame
         range into ``<output>.parts/part_<rank>.rgb``; after a barrier rank 0 feeds the parts to
-        the encoder in order.  ``palette=None``: the palette comes from frame 0 (as the CLI does
-        for videos, dither_cli.py:619-654), identically on every rank."""
+        the encoder in order.  ``palette=None``: one palette for the clip, from frame 0 after
+        pixelization, identically on every rank (the reference's CLI passes a palette it computed
+        from the full first frame, dither_cli.py:619-654; the reference's workers, given None, each
+        derive their own per frame -- see INTEGRATION.md)."""
         try:
             if not shutil.which("ffmpeg") or not shutil.which("ffprobe"):
                 raise RuntimeError("ffmpeg/ffprobe not found (video I/O is a subprocess)")
