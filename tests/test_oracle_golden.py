@@ -226,3 +226,26 @@ def test_kmeans_config3_4k_frame_from_the_live_reference():
     c = O.kmeans_centers(sample, 16, 42)
     assert np.abs(c - g["centers"]).max() <= 1e-3       # north_star tolerance
     assert np.array_equal(c.astype(int), g["palette"])
+
+
+def test_config4_as_the_reference_cli_runs_it():
+    """BASELINE configs[3] from the live reference (tools/make_golden.py --config4): palette by
+    median cut from the FULL first 1080p frame (dither_cli.py:619-654), then pixelize 270 -> blue
+    noise (64, 42) / IGN (1.0, 0) with that palette -> x4.  The drop-in ColorReducer (host code of the
+    library) must find the same palette, the oracle the same frames."""
+    from PIL import Image
+    import dither_pie_b200 as dp
+    from dither_pie_b200 import synth
+    g = load_golden("config4.npz")
+    frames = [synth.frame(1080, 1920, 1000 + t) for t in range(2)]
+    pal = dp.ColorReducer.reduce_colors(Image.fromarray(frames[0], "RGB"), 16)
+    assert [tuple(int(v) for v in c) for c in pal] == [tuple(int(v) for v in c) for c in g["palette"]]
+    pal_u8 = np.asarray(g["palette"], np.uint8)
+    for name, mode, params in (("blue", "blue_noise", {"size": 64, "seed": 42}),
+                               ("ign", "IGN", {"scale": 1.0, "seed": 0})):
+        for t, f in enumerate(frames):
+            small = O.pixelize_regular(f, 270)
+            out = O.apply_dithering(small, g["palette"], mode, params)
+            assert np.array_equal(out, pal_u8[g[f"{name}_{t}"]]), (name, t)
+            if name == "blue" and t == 1:
+                assert np.array_equal(O.final_resize(out, 4, True), g["blue_1_x4"])

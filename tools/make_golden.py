@@ -469,8 +469,40 @@ def kmeans4k_golden(dl):
     print("kmeans_4k.npz: n_iter", km.n_iter_, "palette", [tuple(map(int, c)) for c in pal][:3], "...")
 
 
+def config4_golden(dl):
+    """BASELINE configs[3] as the reference's CLI runs it (dither_cli.py:619-690): the palette by
+    median cut from the FULL first frame (1080p, seed 1000), then per frame pixelize_regular(270)
+    -> dither with the fixed palette -> x4 final resize; frames 0 and 1, blue noise (64, 42) and
+    IGN (1.0, 0).  Stored: the palette, the dithered 480x270 frames as index planes and one
+    up-scaled output.  tests/golden/config4.npz."""
+    vp = load()[1]
+    frames = [synth.frame(1080, 1920, 1000 + t) for t in range(2)]
+    pal = dl.ColorReducer.reduce_colors(Image.fromarray(frames[0], "RGB"), 16)
+    pal_u8 = np.asarray(pal, np.uint8)
+    assert len({tuple(c) for c in pal}) == len(pal)
+    lut = {(int(c[0]) | (int(c[1]) << 8) | (int(c[2]) << 16)): i for i, c in enumerate(pal_u8)}
+    store = {"palette": np.asarray(pal, np.int64)}
+    for name, mode, params in (("blue", "blue_noise", {"size": 64, "seed": 42}),
+                               ("ign", "IGN", {"scale": 1.0, "seed": 0})):
+        d = dl.ImageDitherer(num_colors=len(pal), dither_mode=dl.DitherMode(mode), palette=pal,
+                             dither_params=dict(params))
+        for t, f in enumerate(frames):
+            small = vp.pixelize_regular(Image.fromarray(f, "RGB"), 270)
+            out = d.apply_dithering(small)
+            arr = np.array(out)
+            packed = arr[..., 0].astype(np.int32) | (arr[..., 1].astype(np.int32) << 8) | (arr[..., 2].astype(np.int32) << 16)
+            store[f"{name}_{t}"] = np.vectorize(lut.__getitem__, otypes=[np.uint8])(packed)
+            if t == 1 and name == "blue":
+                store["blue_1_x4"] = np.array(vp._apply_final_resize_to_frame(out, 4))
+            print(name, t, arr.shape)
+    np.savez_compressed(os.path.join(OUT, "config4.npz"), **store)
+    print("config4.npz:", os.path.getsize(os.path.join(OUT, "config4.npz")), "bytes")
+
+
 if __name__ == "__main__":
-    if "--kmeans4k" in sys.argv:          # adds kmeans_4k.npz without touching the other files
+    if "--config4" in sys.argv:           # adds config4.npz without touching the other files
+        config4_golden(load()[0])
+    elif "--kmeans4k" in sys.argv:          # adds kmeans_4k.npz without touching the other files
         kmeans4k_golden(load()[0])
     elif "--big3" in sys.argv:              # adds big_cases3.npz without touching the other files
         big3_golden(load()[0])
