@@ -249,3 +249,26 @@ def test_config4_as_the_reference_cli_runs_it():
             assert np.array_equal(out, pal_u8[g[f"{name}_{t}"]]), (name, t)
             if name == "blue" and t == 1:
                 assert np.array_equal(O.final_resize(out, 4, True), g["blue_1_x4"])
+
+
+def test_baseline_configs_at_full_size_hashes_of_the_live_reference():
+    """SHA-256 of the reference's own outputs at the BASELINE configs' FULL sizes (tools/make_golden.py
+    --hashes): 4K Floyd-Steinberg / Atkinson / JJN with 256 colours (configs[1]), 4K Sierra with 64
+    colours (configs[4]), 1080p Bayer 8x8 with 16 colours (configs[0]).  The oracle's C port must
+    produce the same bytes; the GPU tests compare the CUDA path with the oracle at these sizes."""
+    import hashlib
+    import json
+    from concurrent.futures import ThreadPoolExecutor
+    from dither_pie_b200 import synth
+    want = json.load(open(os.path.join(GOLDEN, "baseline_hashes.json")))
+    img4k = synth.frame(2160, 3840, 1)
+    jobs = {f"config2_{v}": (img4k, synth.random_palette(256), "error_diffusion", {"variant": v})
+            for v in ("floyd_steinberg", "atkinson", "jjn")}
+    jobs["config5_sierra_frame2000"] = (synth.frame(2160, 3840, 2000), synth.random_palette(64),
+                                        "error_diffusion", {"variant": "sierra"})
+    jobs["config1_bayer8x8"] = (synth.frame(1080, 1920, 0), synth.hex_palette(synth.PICO8), "bayer",
+                                {"size": "8x8"})
+    with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:   # the C port releases the GIL
+        got = dict(zip(jobs, ex.map(lambda j: hashlib.sha256(
+            np.ascontiguousarray(O.apply_dithering(*j)).tobytes()).hexdigest(), jobs.values())))
+    assert got == want

@@ -499,8 +499,36 @@ def config4_golden(dl):
     print("config4.npz:", os.path.getsize(os.path.join(OUT, "config4.npz")), "bytes")
 
 
+def baseline_hashes(dl):
+    """SHA-256 of the live reference's outputs at the BASELINE configurations' FULL sizes (too large
+    to store): configs[1] 3840x2160 seed 1, 256 colours, Floyd-Steinberg / Atkinson / JJN;
+    configs[4] 3840x2160 seed 2000, 64 colours, Sierra; configs[0] 1920x1080 seed 0, Bayer 8x8,
+    PICO-8.  tests/golden/baseline_hashes.json."""
+    import hashlib
+    res = {}
+
+    def run(img, pal, mode, params):
+        d = dl.ImageDitherer(num_colors=len(pal), dither_mode=dl.DitherMode(mode),
+                             palette=[tuple(int(v) for v in c) for c in pal], dither_params=dict(params))
+        out = np.ascontiguousarray(np.array(d.apply_dithering(Image.fromarray(img, "RGB"))))
+        return hashlib.sha256(out.tobytes()).hexdigest()
+
+    img4k = synth.frame(2160, 3840, 1)
+    for v in ("floyd_steinberg", "atkinson", "jjn"):
+        res[f"config2_{v}"] = run(img4k, synth.random_palette(256), "error_diffusion", {"variant": v})
+        print(v, res[f"config2_{v}"][:16])
+    res["config5_sierra_frame2000"] = run(synth.frame(2160, 3840, 2000), synth.random_palette(64),
+                                          "error_diffusion", {"variant": "sierra"})
+    res["config1_bayer8x8"] = run(synth.frame(1080, 1920, 0), synth.hex_palette(synth.PICO8), "bayer",
+                                  {"size": "8x8"})
+    json.dump(res, open(os.path.join(OUT, "baseline_hashes.json"), "w"), indent=1)
+    print(res)
+
+
 if __name__ == "__main__":
-    if "--config4" in sys.argv:           # adds config4.npz without touching the other files
+    if "--hashes" in sys.argv:            # adds baseline_hashes.json without touching the other files
+        baseline_hashes(load()[0])
+    elif "--config4" in sys.argv:           # adds config4.npz without touching the other files
         config4_golden(load()[0])
     elif "--kmeans4k" in sys.argv:          # adds kmeans_4k.npz without touching the other files
         kmeans4k_golden(load()[0])
