@@ -254,7 +254,8 @@ def test_config4_as_the_reference_cli_runs_it():
 def test_baseline_configs_at_full_size_hashes_of_the_live_reference():
     """SHA-256 of the reference's own outputs at the BASELINE configs' FULL sizes (tools/make_golden.py
     --hashes): 4K Floyd-Steinberg / Atkinson / JJN with 256 colours (configs[1]), 4K Sierra with 64
-    colours (configs[4]), 1080p Bayer 8x8 with 16 colours (configs[0]).  The oracle's C port must
+    colours (configs[4]), 1080p Bayer 8x8 with 16 colours (configs[0]), 4K nearest colour with config
+    3's k-means palette, and the threshold family / nearest colour at 1080p.  The oracle must
     produce the same bytes; the GPU tests compare the CUDA path with the oracle at these sizes."""
     import hashlib
     import json
@@ -266,8 +267,16 @@ def test_baseline_configs_at_full_size_hashes_of_the_live_reference():
             for v in ("floyd_steinberg", "atkinson", "jjn")}
     jobs["config5_sierra_frame2000"] = (synth.frame(2160, 3840, 2000), synth.random_palette(64),
                                         "error_diffusion", {"variant": "sierra"})
-    jobs["config1_bayer8x8"] = (synth.frame(1080, 1920, 0), synth.hex_palette(synth.PICO8), "bayer",
-                                {"size": "8x8"})
+    f1080, pico, r256 = synth.frame(1080, 1920, 0), synth.hex_palette(synth.PICO8), synth.random_palette(256)
+    jobs["config1_bayer8x8"] = (f1080, pico, "bayer", {"size": "8x8"})
+    jobs["1080p_halftone_pico8"] = (f1080, pico, "halftone", {})
+    jobs["1080p_ign_pico8"] = (f1080, pico, "IGN", {"scale": 1.0, "seed": 0})
+    jobs["1080p_blue_noise_pico8"] = (f1080, pico, "blue_noise", {"size": 64, "seed": 42})
+    jobs["1080p_none_pico8"] = (f1080, pico, "none", {})
+    jobs["1080p_none_r256"] = (f1080, r256, "none", {})
+    jobs["1080p_bayer8x8_r256"] = (f1080, r256, "bayer", {"size": "8x8"})
+    jobs["config3_4k_none_kmeans_palette"] = (synth.frame(2160, 3840, 2), load_golden("kmeans_4k.npz")["palette"],
+                                              "none", {})
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:   # the C port releases the GIL
         got = dict(zip(jobs, ex.map(lambda j: hashlib.sha256(
             np.ascontiguousarray(O.apply_dithering(*j)).tobytes()).hexdigest(), jobs.values())))

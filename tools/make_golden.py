@@ -521,6 +521,17 @@ def baseline_hashes(dl):
                                           "error_diffusion", {"variant": "sierra"})
     res["config1_bayer8x8"] = run(synth.frame(1080, 1920, 0), synth.hex_palette(synth.PICO8), "bayer",
                                   {"size": "8x8"})
+    # the threshold family and nearest colour at full size
+    f1080 = synth.frame(1080, 1920, 0)
+    pico, r256 = synth.hex_palette(synth.PICO8), synth.random_palette(256)
+    res["1080p_halftone_pico8"] = run(f1080, pico, "halftone", {})
+    res["1080p_ign_pico8"] = run(f1080, pico, "IGN", {"scale": 1.0, "seed": 0})
+    res["1080p_blue_noise_pico8"] = run(f1080, pico, "blue_noise", {"size": 64, "seed": 42})
+    res["1080p_none_pico8"] = run(f1080, pico, "none", {})
+    res["1080p_none_r256"] = run(f1080, r256, "none", {})
+    res["1080p_bayer8x8_r256"] = run(f1080, r256, "bayer", {"size": "8x8"})
+    km = np.load(os.path.join(OUT, "kmeans_4k.npz"))["palette"]
+    res["config3_4k_none_kmeans_palette"] = run(synth.frame(2160, 3840, 2), km, "none", {})
     json.dump(res, open(os.path.join(OUT, "baseline_hashes.json"), "w"), indent=1)
     print(res)
 
