@@ -368,11 +368,24 @@ def test_video_processor_frames():
 
 
 # ------------------------------------------------------------------ full-size checks
+def reference_hash(key):
+    """SHA-256 of the LIVE reference's output for a full-size BASELINE case
+    (tests/golden/baseline_hashes.json, tools/make_golden.py --hashes)."""
+    import json
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "baseline_hashes.json")))[key]
+
+
+def sha(arr):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
+
+
 def test_full_size_1080p_bayer_vs_oracle_and_properties():
     img = synth.frame(1080, 1920, 0)
     pal = PALS["pico8"]
     out, idx = gpu(img, pal, "bayer", {"size": "8x8"}, return_indices=True)
     assert mismatch(out, O.apply_dithering(img, pal, "bayer", {"size": "8x8"})) == 0
+    assert sha(out) == reference_hash("config1_bayer8x8")        # the reference's own bytes
     assert np.array_equal(pal[idx].astype(np.uint8), out)       # every pixel is a palette row
     near = gpu(img, pal, "none")
     assert np.array_equal(gpu(near, pal, "none"), near)          # nearest-colour is idempotent
@@ -389,6 +402,7 @@ def test_full_size_4k_error_diffusion_256_colours_vs_oracle():
     out = gpu(img, pal, "error_diffusion", {"variant": "floyd_steinberg"})
     ref = O.apply_dithering(img, pal, "error_diffusion", {"variant": "floyd_steinberg"})
     assert mismatch(out, ref) == 0
+    assert sha(out) == reference_hash("config2_floyd_steinberg")   # the reference's own bytes
     # a constant image whose colour is in the palette is a fixed point of error diffusion
     flat = np.broadcast_to(pal[7].astype(np.uint8), (64, 64, 3)).copy()
     assert np.array_equal(gpu(flat, pal, "error_diffusion", {"variant": "jjn"}), flat)

@@ -44,9 +44,14 @@ def test_config2_4k_atkinson_and_jjn_256_colours_vs_oracle():
     pal = synth.random_palette(256)
     jobs = [(img, pal, "error_diffusion", {"variant": v}) for v in ("atkinson", "jjn")]
     refs = oracle_many(jobs)
+    import hashlib
+    import json
+    want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "baseline_hashes.json")))
     for (_, _, mode, params), ref in zip(jobs, refs):
         out = engine.dither_frames(img, pal, mode, params)
         assert mismatch(out, ref) == 0, params
+        # ... and the LIVE reference's own bytes (tools/make_golden.py --hashes)
+        assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == want["config2_" + params["variant"]]
 
 
 def test_config5_4k_ostromoukhov_and_sierra_64_colours_multi_frame_vs_oracle():
@@ -59,6 +64,11 @@ def test_config5_4k_ostromoukhov_and_sierra_64_colours_multi_frame_vs_oracle():
         out = engine.dither_frames(frames, pal, mode, params)
         for t in range(3):
             assert mismatch(out[t], refs[t]) == 0, (mode, t)
+        if mode == "error_diffusion":      # frame 2000 under Sierra: the LIVE reference's own bytes
+            import hashlib
+            import json
+            want = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "baseline_hashes.json")))
+            assert hashlib.sha256(np.ascontiguousarray(out[0]).tobytes()).hexdigest() == want["config5_sierra_frame2000"]
 
 
 def test_config4_1080p_video_pixelize270_blue_noise_ign_x4_as_written():
