@@ -277,6 +277,12 @@ def test_baseline_configs_at_full_size_hashes_of_the_live_reference():
     jobs["1080p_bayer8x8_r256"] = (f1080, r256, "bayer", {"size": "8x8"})
     jobs["config3_4k_none_kmeans_palette"] = (synth.frame(2160, 3840, 2), load_golden("kmeans_4k.npz")["palette"],
                                               "none", {})
+    g540, r64 = np.ascontiguousarray(synth.frame(1080, 1920, 5)[:540, :960]), synth.random_palette(64)
+    jobs["gamma_540p_bayer8x8_pico8"] = (g540, pico, "bayer", {"size": "8x8"}, True)      # use_gamma=True
+    jobs["gamma_540p_none_r64"] = (g540, r64, "none", {}, True)
+    jobs["gamma_540p_halftone_pico8"] = (g540, pico, "halftone", {}, True)
+    jobs["gamma_540p_fs_r64"] = (g540, r64, "error_diffusion", {"variant": "floyd_steinberg"}, True)
+    jobs["gamma_540p_jjn_pico8"] = (g540, pico, "error_diffusion", {"variant": "jjn"}, True)
     with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:   # the C port releases the GIL
         got = dict(zip(jobs, ex.map(lambda j: hashlib.sha256(
             np.ascontiguousarray(O.apply_dithering(*j)).tobytes()).hexdigest(), jobs.values())))

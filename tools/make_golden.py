@@ -532,6 +532,20 @@ def baseline_hashes(dl):
     res["1080p_bayer8x8_r256"] = run(f1080, r256, "bayer", {"size": "8x8"})
     km = np.load(os.path.join(OUT, "kmeans_4k.npz"))["palette"]
     res["config3_4k_none_kmeans_palette"] = run(synth.frame(2160, 3840, 2), km, "none", {})
+    # gamma correction (use_gamma=True) at 540x960
+    def run_gamma(img, pal, mode, params):
+        d = dl.ImageDitherer(num_colors=len(pal), dither_mode=dl.DitherMode(mode), use_gamma=True,
+                             palette=[tuple(int(v) for v in c) for c in pal], dither_params=dict(params))
+        out = np.ascontiguousarray(np.array(d.apply_dithering(Image.fromarray(img, "RGB"))))
+        return hashlib.sha256(out.tobytes()).hexdigest()
+
+    g540 = synth.frame(1080, 1920, 5)[:540, :960].copy()
+    r64 = synth.random_palette(64)
+    res["gamma_540p_bayer8x8_pico8"] = run_gamma(g540, pico, "bayer", {"size": "8x8"})
+    res["gamma_540p_none_r64"] = run_gamma(g540, r64, "none", {})
+    res["gamma_540p_halftone_pico8"] = run_gamma(g540, pico, "halftone", {})
+    res["gamma_540p_fs_r64"] = run_gamma(g540, r64, "error_diffusion", {"variant": "floyd_steinberg"})
+    res["gamma_540p_jjn_pico8"] = run_gamma(g540, pico, "error_diffusion", {"variant": "jjn"})
     json.dump(res, open(os.path.join(OUT, "baseline_hashes.json"), "w"), indent=1)
     print(res)
 
