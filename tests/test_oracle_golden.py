@@ -277,6 +277,13 @@ def test_baseline_configs_at_full_size_hashes_of_the_live_reference():
     jobs["1080p_bayer8x8_r256"] = (f1080, r256, "bayer", {"size": "8x8"})
     jobs["config3_4k_none_kmeans_palette"] = (synth.frame(2160, 3840, 2), load_golden("kmeans_4k.npz")["palette"],
                                               "none", {})
+    f4k = synth.frame(2160, 3840, 2001)
+    for v in ("stucki", "burkes", "sierra_two_row", "sierra_lite"):
+        jobs[f"4k_{v}_r64"] = (f4k, synth.random_palette(64), "error_diffusion", {"variant": v})
+    jobs["1080p_fs_serpentine_r64"] = (f1080, synth.random_palette(64), "error_diffusion",
+                                       {"variant": "floyd_steinberg", "serpentine": "true"})
+    jobs["540p_ostromoukhov_r64"] = (np.ascontiguousarray(synth.frame(1080, 1920, 6)[:540, :960]),
+                                     synth.random_palette(64), "ostromoukhov", {})
     g540, r64 = np.ascontiguousarray(synth.frame(1080, 1920, 5)[:540, :960]), synth.random_palette(64)
     jobs["gamma_540p_bayer8x8_pico8"] = (g540, pico, "bayer", {"size": "8x8"}, True)      # use_gamma=True
     jobs["gamma_540p_none_r64"] = (g540, r64, "none", {}, True)

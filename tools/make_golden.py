@@ -532,6 +532,14 @@ def baseline_hashes(dl):
     res["1080p_bayer8x8_r256"] = run(f1080, r256, "bayer", {"size": "8x8"})
     km = np.load(os.path.join(OUT, "kmeans_4k.npz"))["palette"]
     res["config3_4k_none_kmeans_palette"] = run(synth.frame(2160, 3840, 2), km, "none", {})
+    # the other diffusion kernels at 4K (64 colours), serpentine at 1080p, Ostromoukhov at 540x960
+    r64b = synth.random_palette(64)
+    f4k = synth.frame(2160, 3840, 2001)
+    for v in ("stucki", "burkes", "sierra_two_row", "sierra_lite"):
+        res[f"4k_{v}_r64"] = run(f4k, r64b, "error_diffusion", {"variant": v})
+    res["1080p_fs_serpentine_r64"] = run(f1080, r64b, "error_diffusion",
+                                         {"variant": "floyd_steinberg", "serpentine": "true"})
+    res["540p_ostromoukhov_r64"] = run(synth.frame(1080, 1920, 6)[:540, :960].copy(), r64b, "ostromoukhov", {})
     # gamma correction (use_gamma=True) at 540x960
     def run_gamma(img, pal, mode, params):
         d = dl.ImageDitherer(num_colors=len(pal), dither_mode=dl.DitherMode(mode), use_gamma=True,
